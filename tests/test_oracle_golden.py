@@ -1,0 +1,93 @@
+"""Pin the CPU oracle against outputs of the unmodified reference (tests/golden/*.npz)."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import ml100k, optim, index, interactions as I
+
+MODELS = ["lr", "mf", "deepfm", "nfm", "afm", "ffm", "pnn_in", "pnn_out", "din", "dien", "neuralcf"]
+RTOL, ATOL = 1e-5, 1e-6       # north star: 1e-5 relative (fp32) for logits, loss, gradients
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_forward_loss_grads(name):
+    ins, y, sd0, z = load_golden(name)
+    pred, loss, grads = ml100k.loss_and_grads(name, sd0, ins, y)
+    assert pred.shape == z["pred"].shape            # MF is (B,), everything else (B,1)
+    np.testing.assert_allclose(pred.numpy(), z["pred"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(loss.item(), z["loss"], rtol=RTOL)
+    for k in sd0:
+        np.testing.assert_allclose(grads[k].numpy(), z[f"grad/{k}"], rtol=RTOL, atol=ATOL, err_msg=k)
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_two_adam_steps(name):
+    """oracle fwd/bwd + oracle dense Adam == reference Trainer.train_loop x2 with Adam(1e-3, wd=1e-5)."""
+    ins, y, sd0, z = load_golden(name)
+    sd = {k: v.clone() for k, v in sd0.items()}
+    m = {k: torch.zeros_like(v) for k, v in sd.items()}
+    v = {k: torch.zeros_like(t) for k, t in sd.items()}
+    losses = []
+    for step in (1, 2):
+        _, loss, g = ml100k.loss_and_grads(name, sd, ins, y)
+        losses.append(loss.item())
+        for k in sd:
+            sd[k], m[k], v[k] = optim.adam_dense(sd[k], g[k], m[k], v[k], step, lr=1e-3, wd=1e-5)
+    np.testing.assert_allclose(losses, z["losses"], rtol=RTOL)
+    for k in sd:
+        np.testing.assert_allclose(sd[k].numpy(), z[f"sd2/{k}"], rtol=1e-5, atol=2e-6, err_msg=k)
+    with torch.no_grad():
+        np.testing.assert_allclose(ml100k.forward(name, sd, *ins).numpy(), z["pred_after"], rtol=1e-4, atol=1e-6)
+
+
+def test_pnn_out_requires_b_eq_d():
+    ins, y, sd0, _ = load_golden("pnn_out")
+    with pytest.raises(RuntimeError):
+        ml100k.forward("pnn_out", sd0, ins[0][:7])
+
+
+def test_sampler_stream():
+    z = np.load(__import__("os").path.join(__import__("conftest").GOLDEN, "sampler.npz"))
+    excl = {tuple(p) for p in z["excl"].tolist()}
+    random.seed(123)
+    u1, i1 = index.negative_draws(20, 30, excl, 5)
+    u2, i2 = index.negative_draws(20, 30, excl, 2)
+    assert u1 == z["u1"].tolist() and i1 == z["i1"].tolist()
+    assert u1 + u2 == z["u2"].tolist() and i1 + i2 == z["i2"].tolist()      # state accumulates
+    random.seed(321)
+    u3, i3 = index.negative_draws(20, 30, excl, 3)
+    assert u3 == z["df_user"].tolist() and i3 == z["df_item"].tolist()
+
+
+def test_dedup_matches_torch_unique():
+    g = torch.Generator().manual_seed(0)
+    ids = torch.randint(0, 50, (1000,), generator=g)
+    u, inv, cnt = index.dedup(ids.numpy())
+    tu, tinv, tcnt = torch.unique(ids, sorted=True, return_inverse=True, return_counts=True)
+    assert np.array_equal(u, tu.numpy()) and np.array_equal(inv, tinv.numpy()) and np.array_equal(cnt, tcnt.numpy())
+    order = index.stable_order(ids.numpy())
+    assert np.array_equal(ids.numpy()[order], np.sort(ids.numpy()))
+
+
+def test_interaction_identities():
+    """FM sum-square == sum of pairwise dots; bi-interaction summed over d == FM; fast FFM == loop FFM."""
+    torch.manual_seed(0)
+    E = torch.randn(5, 7, 8)
+    np.testing.assert_allclose(I.fm_second_order(E).numpy(), I.inner_products(E).sum(1).numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(I.bi_interaction(E).sum(1).numpy(), I.fm_second_order(E).numpy(), rtol=1e-4, atol=1e-5)
+    T = torch.randn(4, 6, 6, 4)
+    np.testing.assert_allclose(I.ffm_cross(T).numpy(), I.ffm_cross_fast(T).numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_sparse_sgd_equals_dense_sgd():
+    torch.manual_seed(1)
+    table = torch.randn(20, 4)
+    ids = torch.randint(0, 20, (64,))
+    G = torch.randn(64, 4)
+    dense = torch.zeros_like(table).index_add_(0, ids, G)
+    want = table - 0.1 * dense
+    got = optim.sgd_rows(table.clone(), ids, G, 0.1)
+    assert torch.equal(got, want)
