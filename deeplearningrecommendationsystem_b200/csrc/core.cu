@@ -1,0 +1,156 @@
+// Error reporting, device queries, gather (pure copy) and small utility kernels.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace rs {
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int num_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
+}  // namespace rs
+
+RS_API int rs_version(void) { return 100; }
+RS_API const char *rs_last_error(void) { return rs::g_err; }
+
+// ------------------------------------------------------------------ gather
+struct GatherParams {
+  const float *base[RS_MAX_FIELDS];
+  int64_t rows[RS_MAX_FIELDS];
+};
+
+// One 16-byte element per thread-iteration; consecutive threads walk one row, so a warp reads
+// (32 / (W/4)) rows of one sample at a time with fully coalesced 128-bit loads.
+__global__ void __launch_bounds__(256) gather_rows_kernel(const __grid_constant__ GatherParams P, const int64_t *__restrict__ ids,
+                                                         int64_t n_lookups, int F, int wv /* float4 per row */,
+                                                         float *__restrict__ out, int32_t *status) {
+  __shared__ const float *s_base[RS_MAX_FIELDS];
+  __shared__ int64_t s_rows[RS_MAX_FIELDS];
+  for (int i = threadIdx.x; i < F; i += blockDim.x) {
+    s_base[i] = P.base[i];
+    s_rows[i] = P.rows[i];
+  }
+  __syncthreads();
+  int64_t total = n_lookups * wv;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = e / wv;
+    int v = (int)(e - p * wv);
+    int f = (int)(p % F);
+    int64_t id = rs::clamp_id(ids[p], s_rows[f], status);
+    float4 val = rs::ldg_nc_f4(s_base[f] + (id * wv + v) * 4);
+    rs::stg_f4(out + e * 4, val);
+  }
+}
+
+__global__ void gather_rows_scalar_kernel(const __grid_constant__ GatherParams P, const int64_t *__restrict__ ids, int64_t n_lookups,
+                                          int F, int W, float *__restrict__ out, int32_t *status) {
+  int64_t total = n_lookups * W;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = e / W;
+    int v = (int)(e - p * W);
+    int f = (int)(p % F);
+    int64_t id = rs::clamp_id(ids[p], P.rows[f], status);
+    out[e] = P.base[f][id * W + v];
+  }
+}
+
+RS_API int rs_gather_rows(const rs_tables *T, const int64_t *ids, int64_t B, float *out, int32_t *status, void *stream) {
+  RS_CHECK_ARG(T && ids && out, RS_E_ARG, "rs_gather_rows: null argument");
+  RS_CHECK_ARG(T->num_fields >= 1 && T->num_fields <= RS_MAX_FIELDS && T->width >= 1, RS_E_SHAPE, "rs_gather_rows: bad F/width");
+  if (B == 0) return RS_OK;
+  GatherParams P;
+  for (int f = 0; f < T->num_fields; ++f) {
+    P.base[f] = T->base[f];
+    P.rows[f] = T->rows[f];
+  }
+  int64_t n = B * T->num_fields;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (T->width % 4 == 0) {
+    int wv = T->width / 4;
+    int64_t total = n * wv;
+    int blocks = (int)((total + 255) / 256);
+    int cap = rs::num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    gather_rows_kernel<<<blocks, 256, 0, st>>>(P, ids, n, T->num_fields, wv, out, status);
+  } else {
+    int64_t total = n * T->width;
+    int blocks = (int)((total + 255) / 256);
+    int cap = rs::num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    gather_rows_scalar_kernel<<<blocks, 256, 0, st>>>(P, ids, n, T->num_fields, T->width, out, status);
+  }
+  RS_CHECK_LAUNCH();
+  return RS_OK;
+}
+
+// ------------------------------------------------------------------ x[:, col].long()
+__global__ void xcol_to_ids_kernel(const float *__restrict__ x, int64_t B, int xcols, int col, int64_t *__restrict__ ids) {
+  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) ids[b] = (int64_t)x[b * xcols + col];  // truncation toward zero == Tensor.long()
+}
+RS_API int rs_xcol_to_ids(const float *x, int64_t B, int32_t xcols, int32_t col, int64_t *ids, void *stream) {
+  RS_CHECK_ARG(x && ids && col >= 0 && col < xcols, RS_E_ARG, "rs_xcol_to_ids: bad argument");
+  if (B == 0) return RS_OK;
+  xcol_to_ids_kernel<<<(int)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, B, xcols, col, ids);
+  RS_CHECK_LAUNCH();
+  return RS_OK;
+}
+
+// ------------------------------------------------------------------ sigmoid + BCE (mean) fwd/bwd
+// pass 1: per-block partial sums in a fixed tree order; pass 2: one block sums the partials in index order.
+__global__ void __launch_bounds__(256) sigmoid_bce_kernel(const float *__restrict__ logit, const float *__restrict__ y, int64_t B,
+                                                         float *__restrict__ pred, float *__restrict__ g_logit,
+                                                         float *__restrict__ partial) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  float invB = 1.0f / (float)B;
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (int64_t)gridDim.x * blockDim.x) {
+    float z = logit[b];
+    float p = 1.0f / (1.0f + expf(-z));
+    float t = y[b];
+    float lp = fmaxf(logf(p), -100.f);
+    float l1p = fmaxf(logf(1.0f - p), -100.f);
+    acc -= t * lp + (1.0f - t) * l1p;
+    if (pred) pred[b] = p;
+    if (g_logit) g_logit[b] = (p - t) * invB;
+  }
+  acc = rs::warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    partial[blockIdx.x] = s;
+  }
+}
+__global__ void bce_finish_kernel(const float *__restrict__ partial, int nparts, int64_t B, float *__restrict__ loss) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < nparts; ++i) s += partial[i];
+    *loss = s / (float)B;
+  }
+}
+RS_API int rs_sigmoid_bce(const float *logit, const float *y, int64_t B, float *pred, float *g_logit, float *loss_mean, float *ws,
+                          void *stream) {
+  RS_CHECK_ARG(logit && y && loss_mean && ws && B > 0, RS_E_ARG, "rs_sigmoid_bce: bad argument");
+  int blocks = (int)((B + 255) / 256);
+  if (blocks > 1024) blocks = 1024;
+  cudaStream_t st = (cudaStream_t)stream;
+  sigmoid_bce_kernel<<<blocks, 256, 0, st>>>(logit, y, B, pred, g_logit, ws);
+  RS_CHECK_LAUNCH();
+  bce_finish_kernel<<<1, 32, 0, st>>>(ws, blocks, B, loss_mean);
+  RS_CHECK_LAUNCH();
+  return RS_OK;
+}

@@ -1,0 +1,223 @@
+// Field-aware factorisation machine: lookup + pairwise field-aware interaction (reference model/ffm.py:46-82,
+// generalised from the six MovieLens features to F id-fields).
+//
+// rs_ffm_fwd -- HBM-bound streaming kernel.  A sample needs F table rows of F*D floats (43 KB at F=26, D=16).
+// A persistent CTA per SM runs a producer warp that issues one cp.async.bulk (TMA bulk copy, SASS UBLKCP) per
+// row into a ring of shared-memory stages guarded by full/empty mbarriers; four consumer warps reduce
+// sum_{i<j} <T[i][j], T[j][i]> from shared memory and stream out the transposed tile
+// stash[b][i][j] = T[j][i] (the Jacobian d cross / d v_{i,j}) that the segment-reduce/update kernel later
+// scales by dL/dcross[b].  Rows are padded in shared memory so the transposed reads are bank-conflict free.
+#include "common.cuh"
+
+namespace {
+
+constexpr int NCW = 4;                 // consumer warps
+constexpr int NTHREADS = (NCW + 1) * 32;
+constexpr int MAX_STAGES = 8;
+
+struct FfmParams {
+  const float *base[RS_MAX_FIELDS];
+  int64_t rows[RS_MAX_FIELDS];
+  const int64_t *ids;
+  float *cross, *stash;
+  int64_t B;
+  int F, D, dv, dvs;
+  int rowv;    // float4 per table row = F*dv
+  int pitchv;  // float4 per padded row in shared memory
+  int nst;     // ring stages
+  int32_t *status;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1) ffm_fwd_kernel(const __grid_constant__ FfmParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES];
+  __shared__ float s_part[MAX_STAGES][NCW];
+  __shared__ const float *s_base[RS_MAX_FIELDS];
+  __shared__ int64_t s_rows[RS_MAX_FIELDS];
+  for (int i = threadIdx.x; i < P.F; i += blockDim.x) {
+    s_base[i] = P.base[i];
+    s_rows[i] = P.rows[i];
+  }
+  float4 *tiles = reinterpret_cast<float4 *>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int stage_v = P.F * P.pitchv;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P.nst; ++s) {
+      rs::mbar_init(&full_bar[s], 1);
+      rs::mbar_init(&empty_bar[s], NCW);
+    }
+    rs::mbar_fence_init();
+  }
+  __syncthreads();
+  const uint32_t row_bytes = (uint32_t)P.rowv * 16u;
+
+  if (warp == 0) {
+    // ===== producer: one bulk copy per table row =====
+    int k = 0;
+    for (int64_t b = blockIdx.x; b < P.B; b += gridDim.x, ++k) {
+      const int s = k % P.nst;
+      const uint32_t ph = (uint32_t)(k / P.nst) & 1u;
+      rs::mbar_wait(&empty_bar[s], ph ^ 1u);
+      if (lane == 0) rs::mbar_arrive_expect_tx(&full_bar[s], row_bytes * (uint32_t)P.F);
+      __syncwarp();
+      float4 *dst = tiles + (size_t)s * stage_v;
+      for (int f = lane; f < P.F; f += 32) {
+        const int64_t id = rs::clamp_id(P.ids[b * P.F + f], s_rows[f], P.status);
+        rs::bulk_g2s(dst + (size_t)f * P.pitchv, s_base[f] + id * (int64_t)P.rowv * 4, row_bytes, &full_bar[s]);
+      }
+    }
+  } else {
+    // ===== consumers =====
+    const int cw = warp - 1;
+    const int ct = threadIdx.x - 32;
+    int k = 0;
+    for (int64_t b = blockIdx.x; b < P.B; b += gridDim.x, ++k) {
+      const int s = k % P.nst;
+      const uint32_t ph = (uint32_t)(k / P.nst) & 1u;
+      rs::mbar_wait(&full_bar[s], ph);
+      const float4 *T = tiles + (size_t)s * stage_v;
+      float4 *st_out = P.stash ? reinterpret_cast<float4 *>(P.stash) + b * (int64_t)P.F * P.rowv : nullptr;
+      float acc = 0.f;
+      for (int i = cw; i < P.F; i += NCW) {
+        const float4 *Ti = T + (size_t)i * P.pitchv;
+        for (int w = lane; w < P.rowv; w += 32) {
+          const int j = w >> P.dvs, d4 = w & (P.dv - 1);
+          float4 tr = T[(size_t)j * P.pitchv + i * P.dv + d4];  // v_{j,i}
+          if (j == i) tr = rs::f4_zero();
+          if (j > i) acc += rs::f4_dot(Ti[w], tr);
+          if (st_out) rs::stg_cs_f4(reinterpret_cast<float *>(st_out + (size_t)i * P.rowv + w), tr);
+        }
+      }
+      acc = rs::warp_sum(acc);
+      if (lane == 0) s_part[s][cw] = acc;
+      // all four consumer warps: partials visible, tile reads done
+      asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory");
+      if (ct == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCW; ++c) t += s_part[s][c];
+        P.cross[b] = t;
+      }
+      if (lane == 0) rs::mbar_arrive(&empty_bar[s]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ dense small-F variant (MovieLens FFM)
+struct FieldOf {
+  int32_t fo[RS_MAX_FIELDS];
+};
+
+// warp per sample; Tin (B, F, NF, D).  mode 0: cross;  mode 1: dT = g * d cross / dT
+__global__ void __launch_bounds__(256) ffm_dense_kernel(const float *__restrict__ Tin, const float *__restrict__ g_cross, int64_t B, int F,
+                                                       int NF, int D, const __grid_constant__ FieldOf FO, float *__restrict__ cross,
+                                                       float *__restrict__ dT) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t tile = (int64_t)F * NF * D;
+  for (int64_t b = warp_global; b < B; b += nwarps) {
+    const float *T = Tin + b * tile;
+    if (cross) {
+      float acc = 0.f;
+      for (int i = 0; i < F; ++i)
+        for (int j = i + 1; j < F; ++j) {
+          const float *a = T + ((int64_t)i * NF + FO.fo[j]) * D;
+          const float *c = T + ((int64_t)j * NF + FO.fo[i]) * D;
+          for (int d = lane; d < D; d += 32) acc = fmaf(a[d], c[d], acc);
+        }
+      acc = rs::warp_sum(acc);
+      if (lane == 0) cross[b] = acc;
+    }
+    if (dT) {
+      const float g = g_cross[b];
+      for (int i = 0; i < F; ++i)
+        for (int c = 0; c < NF; ++c)
+          for (int d = lane; d < D; d += 32) {
+            float acc = 0.f;
+            for (int j = 0; j < F; ++j)
+              if (j != i && FO.fo[j] == c) acc += T[((int64_t)j * NF + FO.fo[i]) * D + d];
+            dT[b * tile + ((int64_t)i * NF + c) * D + d] = g * acc;
+          }
+    }
+  }
+}
+
+int dense_launch(const float *Tin, const float *g, int64_t B, int F, int NF, int D, const int32_t *field_of, float *cross, float *dT,
+                 void *stream) {
+  RS_CHECK_ARG(Tin && field_of, RS_E_ARG, "rs_ffm_dense: null argument");
+  RS_CHECK_ARG(F >= 2 && F <= RS_MAX_FIELDS && NF >= 1 && NF <= RS_MAX_FIELDS && D >= 1, RS_E_SHAPE, "rs_ffm_dense: bad shape");
+  FieldOf FO;
+  for (int f = 0; f < RS_MAX_FIELDS; ++f) FO.fo[f] = 0;
+  for (int f = 0; f < F; ++f) {
+    RS_CHECK_ARG(field_of[f] >= 0 && field_of[f] < NF, RS_E_ARG, "rs_ffm_dense: field_of[%d] out of range", f);
+    FO.fo[f] = field_of[f];
+  }
+  if (B == 0) return RS_OK;
+  int64_t blocks64 = (B + 7) / 8;
+  int cap = rs::num_sms() * 8;
+  int blocks = (int)(blocks64 < cap ? blocks64 : cap);
+  ffm_dense_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(Tin, g, B, F, NF, D, FO, cross, dT);
+  RS_CHECK_LAUNCH();
+  return RS_OK;
+}
+
+}  // namespace
+
+RS_API int rs_ffm_fwd(const rs_tables *T, const int64_t *ids, int64_t B, int32_t D, float *cross, float *stash, int32_t *status,
+                      void *stream) {
+  RS_CHECK_ARG(T && ids && cross, RS_E_ARG, "rs_ffm_fwd: null argument");
+  const int F = T->num_fields;
+  RS_CHECK_ARG(F >= 2 && F <= RS_MAX_FIELDS, RS_E_SHAPE, "rs_ffm_fwd: F=%d out of range", F);
+  RS_CHECK_ARG(D >= 4 && D <= 256 && (D & (D - 1)) == 0, RS_E_UNSUPPORTED, "rs_ffm_fwd: D=%d must be a power of two in [4,256]", D);
+  RS_CHECK_ARG(T->width == F * D, RS_E_SHAPE, "rs_ffm_fwd: table width %d != F*D = %d", T->width, F * D);
+  if (B == 0) return RS_OK;
+  FfmParams P = {};
+  for (int f = 0; f < F; ++f) {
+    RS_CHECK_ARG(T->base[f] && T->rows[f] > 0, RS_E_ARG, "rs_ffm_fwd: table %d missing", f);
+    P.base[f] = T->base[f];
+    P.rows[f] = T->rows[f];
+  }
+  P.ids = ids;
+  P.cross = cross;
+  P.stash = stash;
+  P.B = B;
+  P.F = F;
+  P.D = D;
+  P.dv = D / 4;
+  P.dvs = 0;
+  while ((1 << P.dvs) < P.dv) ++P.dvs;
+  P.rowv = F * P.dv;
+  const int row_bytes = P.rowv * 16;
+  int pad = 0;
+  if (P.dv < 8) pad = (((P.dv * 16 - row_bytes) % 128) + 128) % 128;  // rows of consecutive j land 16*dv bytes apart mod 128
+  P.pitchv = (row_bytes + pad) / 16;
+  const size_t stage_bytes = (size_t)F * P.pitchv * 16;
+  int nst = (int)((200 * 1024) / stage_bytes);
+  RS_CHECK_ARG(nst >= 2, RS_E_UNSUPPORTED, "rs_ffm_fwd: F*F*D tile (%zu B) too large for a 2-stage ring", stage_bytes);
+  if (nst > MAX_STAGES) nst = MAX_STAGES;
+  P.nst = nst;
+  P.status = status;
+  const size_t smem = stage_bytes * nst;
+  RS_CUDA(cudaFuncSetAttribute(ffm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ffm_fwd_kernel, NTHREADS, smem);
+  if (per_sm < 1) per_sm = 1;
+  int64_t cap = (int64_t)rs::num_sms() * per_sm;
+  int grid = (int)(B < cap ? B : cap);
+  ffm_fwd_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(P);
+  RS_CHECK_LAUNCH();
+  return RS_OK;
+}
+
+RS_API int rs_ffm_dense_fwd(const float *Tin, int64_t B, int32_t F, int32_t NF, int32_t D, const int32_t *field_of, float *cross,
+                            void *stream) {
+  RS_CHECK_ARG(cross, RS_E_ARG, "rs_ffm_dense_fwd: null output");
+  return dense_launch(Tin, nullptr, B, F, NF, D, field_of, cross, nullptr, stream);
+}
+
+RS_API int rs_ffm_dense_bwd(const float *Tin, const float *g_cross, int64_t B, int32_t F, int32_t NF, int32_t D,
+                            const int32_t *field_of, float *dT, void *stream) {
+  RS_CHECK_ARG(g_cross && dT, RS_E_ARG, "rs_ffm_dense_bwd: null argument");
+  return dense_launch(Tin, g_cross, B, F, NF, D, field_of, nullptr, dT, stream);
+}

@@ -1,0 +1,504 @@
+// Deterministic dedup (stable radix sort + segment boundaries) and the segment-reduce fused with the
+// embedding row update (dense-grad / SGD / lazy Adam).  Replaces autograd's embedding_dense_backward and
+// optimizer.step() for embedding tables (reference trainer/trainer.py:38-39).
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "common.cuh"
+
+namespace {
+
+struct Offsets {
+  int64_t off[RS_MAX_FIELDS];
+};
+
+__global__ void __launch_bounds__(256) make_keys_kernel(const int64_t *__restrict__ ids, int64_t n, int F, const __grid_constant__ Offsets O,
+                                                       int64_t total_rows, uint32_t *__restrict__ keys, int32_t *__restrict__ pos,
+                                                       int32_t *status) {
+  __shared__ int64_t s_off[RS_MAX_FIELDS + 1];
+  for (int i = threadIdx.x; i < F; i += blockDim.x) s_off[i] = O.off[i];
+  if (threadIdx.x == 0) s_off[F] = total_rows;
+  __syncthreads();
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  int f = (int)(p % F);
+  int64_t lo = s_off[f];
+  int64_t hi = (f + 1 < F ? s_off[f + 1] : total_rows);
+  int64_t id = rs::clamp_id(ids[p], hi - lo, status);
+  keys[p] = (uint32_t)(lo + id);
+  pos[p] = (int32_t)p;
+}
+
+__global__ void __launch_bounds__(256) head_flags_kernel(const uint32_t *__restrict__ k, int64_t n, int32_t *__restrict__ head) {
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  head[s] = (s == 0 || k[s] != k[s - 1]) ? 1 : 0;
+}
+
+// segidx1 = inclusive scan of head flags (1-based segment index)
+__global__ void __launch_bounds__(256) seg_scatter_kernel(const uint32_t *__restrict__ k, const int32_t *__restrict__ pos,
+                                                         const int32_t *__restrict__ head, const int32_t *__restrict__ segidx1, int64_t n,
+                                                         int64_t *__restrict__ uniq, int32_t *__restrict__ seg_start,
+                                                         int32_t *__restrict__ inverse, int32_t *__restrict__ n_uniq) {
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  int g = segidx1[s] - 1;
+  if (head[s]) {
+    uniq[g] = (int64_t)k[s];
+    seg_start[g] = (int32_t)s;
+  }
+  inverse[pos[s]] = g;
+  if (s == n - 1) {
+    *n_uniq = g + 1;
+    seg_start[g + 1] = (int32_t)n;
+  }
+}
+
+__global__ void __launch_bounds__(256) chunk_flags_kernel(const int32_t *__restrict__ head, const int32_t *__restrict__ segidx1,
+                                                         const int32_t *__restrict__ seg_start, int64_t n, int32_t *__restrict__ chead,
+                                                         int32_t *__restrict__ counts) {
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  int g = segidx1[s] - 1;
+  int st = seg_start[g];
+  chead[s] = (((int)s - st) % RS_CHUNK == 0) ? 1 : 0;
+  if (head[s]) counts[g] = seg_start[g + 1] - st;
+}
+
+__global__ void __launch_bounds__(256) chunk_scatter_kernel(const int32_t *__restrict__ head, const int32_t *__restrict__ segidx1,
+                                                           const int32_t *__restrict__ chead, const int32_t *__restrict__ chunkidx1,
+                                                           int64_t n, int32_t *__restrict__ chunk_start, int32_t *__restrict__ chunk_seg,
+                                                           int32_t *__restrict__ seg_first_chunk, int32_t *__restrict__ n_chunks) {
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  int g = segidx1[s] - 1;
+  int c = chunkidx1[s] - 1;
+  if (chead[s]) {
+    chunk_start[c] = (int32_t)s;
+    chunk_seg[c] = g;
+    if (head[s]) seg_first_chunk[g] = c;
+  }
+  if (s == n - 1) {
+    *n_chunks = c + 1;
+    chunk_start[c + 1] = (int32_t)n;
+    seg_first_chunk[g + 1] = c + 1;
+  }
+}
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+struct WsLayout {
+  size_t sorted_key, sorted_pos, uniq, inverse, counts, seg_start, seg_first_chunk, chunk_start, chunk_seg, scalars;
+  size_t keys_in, pos_in, head, segidx1, chead, chunkidx1, cub, partial, total;
+  size_t cub_bytes, partial_floats;
+};
+
+WsLayout layout(int64_t n, int max_width) {
+  WsLayout L;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    size_t at = o;
+    o += align_up(bytes);
+    return at;
+  };
+  size_t n1 = (size_t)n + 1;
+  L.sorted_key = take(n * 4);
+  L.sorted_pos = take(n * 4);
+  L.uniq = take(n * 8);
+  L.inverse = take(n * 4);
+  L.counts = take(n * 4);
+  L.seg_start = take(n1 * 4);
+  L.seg_first_chunk = take(n1 * 4);
+  L.chunk_start = take(n1 * 4);
+  L.chunk_seg = take(n * 4);
+  L.scalars = take(64);
+  L.keys_in = take(n * 4);
+  L.pos_in = take(n * 4);
+  L.head = take(n * 4);
+  L.segidx1 = take(n * 4);
+  L.chead = take(n * 4);
+  L.chunkidx1 = take(n * 4);
+  size_t sort_b = 0, scan_b = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_b, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const int32_t *)nullptr,
+                                  (int32_t *)nullptr, (int)n, 0, 32);
+  cub::DeviceScan::InclusiveSum(nullptr, scan_b, (const int32_t *)nullptr, (int32_t *)nullptr, (int)n);
+  L.cub_bytes = sort_b > scan_b ? sort_b : scan_b;
+  L.cub = take(L.cub_bytes);
+  // Only chunks of multi-chunk segments store a partial.  Such chunks are all full (RS_CHUNK lookups) except the
+  // tail of each segment, so slot = 2*(chunk_start/RS_CHUNK) + is_tail is injective and < 2*(n/RS_CHUNK + 1)
+  // (see partial_slot below).
+  L.partial_floats = (size_t)(2 * (n / RS_CHUNK + 2)) * (size_t)max_width;
+  L.partial = take(L.partial_floats * 4);
+  L.total = o;
+  return L;
+}
+
+}  // namespace
+
+RS_API int rs_dedup_workspace_bytes(int64_t n, int32_t max_width, size_t *bytes) {
+  RS_CHECK_ARG(bytes && n >= 0 && n < (1ll << 31) && max_width >= 1, RS_E_ARG, "rs_dedup_workspace_bytes: bad argument");
+  *bytes = layout(n > 0 ? n : 1, max_width).total;
+  return RS_OK;
+}
+
+RS_API int rs_dedup_sort(const int64_t *ids, int64_t n, int32_t F, const int64_t *row_offset, int64_t total_rows, void *ws,
+                         size_t ws_bytes, rs_segments *seg, int32_t *status, void *stream) {
+  RS_CHECK_ARG(ids && ws && seg, RS_E_ARG, "rs_dedup_sort: null argument");
+  RS_CHECK_ARG(n > 0 && n < (1ll << 31), RS_E_SHAPE, "rs_dedup_sort: n must be in [1, 2^31)");
+  RS_CHECK_ARG(F >= 1 && F <= RS_MAX_FIELDS && n % F == 0, RS_E_SHAPE, "rs_dedup_sort: bad F");
+  RS_CHECK_ARG(total_rows > 0 && total_rows < (1ll << 32), RS_E_SHAPE, "rs_dedup_sort: total_rows must be < 2^32");
+  // recover max_width from the workspace size is not possible; the caller sized ws with its own max_width, so
+  // recompute the layout with width 1 for the fixed part and give the remainder to the partial buffer.
+  WsLayout L = layout(n, 1);
+  RS_CHECK_ARG(ws_bytes >= L.total, RS_E_WORKSPACE, "rs_dedup_sort: workspace too small (%zu < %zu)", ws_bytes, L.total);
+  char *w = (char *)ws;
+  seg->sorted_key = (uint32_t *)(w + L.sorted_key);
+  seg->sorted_pos = (int32_t *)(w + L.sorted_pos);
+  seg->uniq = (int64_t *)(w + L.uniq);
+  seg->inverse = (int32_t *)(w + L.inverse);
+  seg->counts = (int32_t *)(w + L.counts);
+  seg->seg_start = (int32_t *)(w + L.seg_start);
+  seg->seg_first_chunk = (int32_t *)(w + L.seg_first_chunk);
+  seg->chunk_start = (int32_t *)(w + L.chunk_start);
+  seg->chunk_seg = (int32_t *)(w + L.chunk_seg);
+  seg->n_uniq = (int32_t *)(w + L.scalars);
+  seg->n_chunks = seg->n_uniq + 1;
+  seg->partial = (float *)(w + L.partial);
+  seg->partial_floats = (int64_t)((ws_bytes - L.partial) / 4);
+  uint32_t *keys_in = (uint32_t *)(w + L.keys_in);
+  int32_t *pos_in = (int32_t *)(w + L.pos_in);
+  int32_t *head = (int32_t *)(w + L.head);
+  int32_t *segidx1 = (int32_t *)(w + L.segidx1);
+  int32_t *chead = (int32_t *)(w + L.chead);
+  int32_t *chunkidx1 = (int32_t *)(w + L.chunkidx1);
+  void *cub_ws = w + L.cub;
+  size_t cub_bytes = L.cub_bytes;
+
+  Offsets O;
+  for (int f = 0; f < RS_MAX_FIELDS; ++f) O.off[f] = (row_offset && f < F) ? row_offset[f] : 0;
+  if (!row_offset) RS_CHECK_ARG(F == 1, RS_E_ARG, "rs_dedup_sort: row_offset required when F > 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  int blocks = (int)((n + 255) / 256);
+  make_keys_kernel<<<blocks, 256, 0, st>>>(ids, n, F, O, total_rows, keys_in, pos_in, status);
+  RS_CHECK_LAUNCH();
+  int end_bit = 1;
+  while (end_bit < 32 && (1ull << end_bit) < (uint64_t)total_rows) ++end_bit;
+  RS_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, keys_in, seg->sorted_key, pos_in, seg->sorted_pos, (int)n, 0, end_bit, st));
+  head_flags_kernel<<<blocks, 256, 0, st>>>(seg->sorted_key, n, head);
+  RS_CHECK_LAUNCH();
+  RS_CUDA(cub::DeviceScan::InclusiveSum(cub_ws, cub_bytes, head, segidx1, (int)n, st));
+  seg_scatter_kernel<<<blocks, 256, 0, st>>>(seg->sorted_key, seg->sorted_pos, head, segidx1, n, seg->uniq, seg->seg_start,
+                                             seg->inverse, seg->n_uniq);
+  RS_CHECK_LAUNCH();
+  chunk_flags_kernel<<<blocks, 256, 0, st>>>(head, segidx1, seg->seg_start, n, chead, seg->counts);
+  RS_CHECK_LAUNCH();
+  RS_CUDA(cub::DeviceScan::InclusiveSum(cub_ws, cub_bytes, chead, chunkidx1, (int)n, st));
+  chunk_scatter_kernel<<<blocks, 256, 0, st>>>(head, segidx1, chead, chunkidx1, n, seg->chunk_start, seg->chunk_seg,
+                                               seg->seg_first_chunk, seg->n_chunks);
+  RS_CHECK_LAUNCH();
+  return RS_OK;
+}
+
+// =================================================================== segment reduce + update
+namespace {
+
+struct UpdParams {
+  const int32_t *sorted_pos, *seg_start, *seg_first_chunk, *chunk_start, *chunk_seg, *n_uniq, *n_chunks;
+  const int64_t *uniq;
+  float *partial;
+  const float *stash, *scale, *dense;
+  float *table, *m, *v, *dense_grad;
+  int W, F, scale_width;
+  float lr, wd, beta1, beta2, eps, step_size, inv_sqrt_bc2;
+};
+
+// Slot of a chunk's partial sum.  Full chunks are disjoint runs of RS_CHUNK sorted lookups, so start/RS_CHUNK is
+// unique among them; a tail chunk (len < RS_CHUNK) is preceded by at least one full chunk of its own segment, so
+// start/RS_CHUNK is unique among tails as well.  Even slots hold full chunks, odd slots tails.
+__device__ __forceinline__ int partial_slot(int start, int len) { return 2 * (start / RS_CHUNK) + (len < RS_CHUNK ? 1 : 0); }
+
+template <int VEC>
+struct Vec;
+template <>
+struct Vec<4> {
+  using T = float4;
+  static __device__ __forceinline__ T zero() { return rs::f4_zero(); }
+  static __device__ __forceinline__ T ld(const float *p) { return rs::ldg_f4(p); }
+  static __device__ __forceinline__ T ldnc(const float *p) { return rs::ldg_nc_f4(p); }
+  static __device__ __forceinline__ void st(float *p, T v) { rs::stg_f4(p, v); }
+  static __device__ __forceinline__ T add(T a, T b) { return rs::f4_add(a, b); }
+  static __device__ __forceinline__ T mul(T a, T b) { return rs::f4_mul(a, b); }
+  static __device__ __forceinline__ T scale(T a, float s) { return rs::f4_scale(a, s); }
+};
+template <>
+struct Vec<1> {
+  using T = float;
+  static __device__ __forceinline__ T zero() { return 0.f; }
+  static __device__ __forceinline__ T ld(const float *p) { return *p; }
+  static __device__ __forceinline__ T ldnc(const float *p) { return __ldg(p); }
+  static __device__ __forceinline__ void st(float *p, T v) { *p = v; }
+  static __device__ __forceinline__ T add(T a, T b) { return a + b; }
+  static __device__ __forceinline__ T mul(T a, T b) { return a * b; }
+  static __device__ __forceinline__ T scale(T a, float s) { return a * s; }
+};
+
+__device__ __forceinline__ float upd_sgd(float w, float g, const UpdParams &P) { return w - P.lr * (g + P.wd * w); }
+__device__ __forceinline__ float4 upd_sgd(float4 w, float4 g, const UpdParams &P) {
+  return make_float4(upd_sgd(w.x, g.x, P), upd_sgd(w.y, g.y, P), upd_sgd(w.z, g.z, P), upd_sgd(w.w, g.w, P));
+}
+// torch.optim.Adam single-tensor arithmetic on one element
+__device__ __forceinline__ void adam1(float &w, float &m, float &v, float g, const UpdParams &P) {
+  g = g + P.wd * w;
+  m = m + (1.0f - P.beta1) * (g - m);               // lerp_(g, 1-beta1)
+  v = P.beta2 * v + (1.0f - P.beta2) * g * g;
+  float denom = sqrtf(v) * P.inv_sqrt_bc2 + P.eps;
+  w = w - P.step_size * (m / denom);
+}
+
+template <int VEC, int MODE>
+__device__ __forceinline__ void apply_row(const UpdParams &P, int64_t row, int e /* element (in VEC units) */, typename Vec<VEC>::T g) {
+  using V = Vec<VEC>;
+  int64_t off = (row * P.W) + (int64_t)e * VEC;
+  if (MODE == RS_UPD_GRAD) {
+    V::st(P.dense_grad + off, g);
+  } else if (MODE == RS_UPD_SGD) {
+    typename V::T w = V::ld(P.table + off);
+    V::st(P.table + off, upd_sgd(w, g, P));
+  } else {
+    float wv[VEC], mv[VEC], vv[VEC], gv[VEC];
+    *reinterpret_cast<typename V::T *>(wv) = V::ld(P.table + off);
+    *reinterpret_cast<typename V::T *>(mv) = V::ld(P.m + off);
+    *reinterpret_cast<typename V::T *>(vv) = V::ld(P.v + off);
+    *reinterpret_cast<typename V::T *>(gv) = g;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) adam1(wv[i], mv[i], vv[i], gv[i], P);
+    V::st(P.table + off, *reinterpret_cast<typename V::T *>(wv));
+    V::st(P.m + off, *reinterpret_cast<typename V::T *>(mv));
+    V::st(P.v + off, *reinterpret_cast<typename V::T *>(vv));
+  }
+}
+
+// One lane group (GS lanes, NA elements of VEC floats per lane) per chunk.  Lookups of the chunk are visited in
+// sorted (= ascending position) order; loads for UNR lookups are issued before their adds so the dependent FADD
+// chain does not serialise the memory latency.
+template <int VEC, int GS, int NA, int MODE>
+__global__ void __launch_bounds__(256) seg_chunk_kernel(const __grid_constant__ UpdParams P, int64_t n) {
+  using V = Vec<VEC>;
+  constexpr int GPB = 256 / GS;
+  const int lane = threadIdx.x % GS;
+  const int WV = P.W / VEC;
+  const int nchunks = *P.n_chunks;
+  for (int64_t c = (int64_t)blockIdx.x * GPB + threadIdx.x / GS; c < nchunks; c += (int64_t)gridDim.x * GPB) {
+    const int s0 = P.chunk_start[c], s1 = P.chunk_start[c + 1];
+    const int g = P.chunk_seg[c];
+    typename V::T acc[NA];
+#pragma unroll
+    for (int a = 0; a < NA; ++a) acc[a] = V::zero();
+    constexpr int UNR = (NA <= 2) ? 4 : (NA <= 4 ? 2 : 1);
+    for (int s = s0; s < s1; s += UNR) {
+      typename V::T val[UNR][NA];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const bool live = s + u < s1;
+        const int p = live ? P.sorted_pos[s + u] : 0;
+        const int b = p / P.F;
+#pragma unroll
+        for (int a = 0; a < NA; ++a) {
+          const int e = lane + a * GS;
+          typename V::T x = V::zero();
+          if (live && e < WV) {
+            if (P.stash) {
+              x = V::ldnc(P.stash + (int64_t)p * P.W + e * VEC);
+              if (P.scale) {
+                if (P.scale_width == 1)
+                  x = V::scale(x, __ldg(P.scale + b));
+                else
+                  x = V::mul(x, V::ldnc(P.scale + (int64_t)b * P.scale_width + e * VEC));
+              }
+            }
+            if (P.dense) x = V::add(x, V::ldnc(P.dense + (int64_t)p * P.W + e * VEC));
+          }
+          val[u][a] = x;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u)
+#pragma unroll
+        for (int a = 0; a < NA; ++a) acc[a] = V::add(acc[a], val[u][a]);
+    }
+    const bool single = (P.seg_first_chunk[g + 1] - P.seg_first_chunk[g]) == 1;
+    if (single) {
+      const int64_t row = P.uniq[g];
+#pragma unroll
+      for (int a = 0; a < NA; ++a) {
+        const int e = lane + a * GS;
+        if (e < WV) apply_row<VEC, MODE>(P, row, e, acc[a]);
+      }
+    } else {
+      float *dst = P.partial + (int64_t)partial_slot(s0, s1 - s0) * P.W;
+#pragma unroll
+      for (int a = 0; a < NA; ++a) {
+        const int e = lane + a * GS;
+        if (e < WV) V::st(dst + e * VEC, acc[a]);
+      }
+    }
+  }
+}
+
+// One lane group per segment that has more than one chunk: add the chunk partials in chunk order, apply.
+template <int VEC, int GS, int NA, int MODE>
+__global__ void __launch_bounds__(256) seg_combine_kernel(const __grid_constant__ UpdParams P, int64_t n) {
+  using V = Vec<VEC>;
+  constexpr int GPB = 256 / GS;
+  const int lane = threadIdx.x % GS;
+  const int WV = P.W / VEC;
+  const int nu = *P.n_uniq;
+  for (int64_t g = (int64_t)blockIdx.x * GPB + threadIdx.x / GS; g < nu; g += (int64_t)gridDim.x * GPB) {
+    const int c0 = P.seg_first_chunk[g], c1 = P.seg_first_chunk[g + 1];
+    if (c1 - c0 <= 1) continue;
+    typename V::T acc[NA];
+#pragma unroll
+    for (int a = 0; a < NA; ++a) acc[a] = V::zero();
+    for (int c = c0; c < c1; ++c) {
+      const int s0 = P.chunk_start[c], s1 = P.chunk_start[c + 1];
+      const float *src = P.partial + (int64_t)partial_slot(s0, s1 - s0) * P.W;
+#pragma unroll
+      for (int a = 0; a < NA; ++a) {
+        const int e = lane + a * GS;
+        if (e < WV) acc[a] = V::add(acc[a], V::ld(src + e * VEC));
+      }
+    }
+    const int64_t row = P.uniq[g];
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+      const int e = lane + a * GS;
+      if (e < WV) apply_row<VEC, MODE>(P, row, e, acc[a]);
+    }
+  }
+}
+
+template <int VEC, int GS, int NA, int MODE>
+int launch_update(const UpdParams &P, int64_t n, cudaStream_t st) {
+  constexpr int GPB = 256 / GS;
+  int64_t blocks64 = (n + GPB - 1) / GPB;
+  int cap = rs::num_sms() * 64;
+  int blocks = (int)(blocks64 < cap ? blocks64 : cap);
+  seg_chunk_kernel<VEC, GS, NA, MODE><<<blocks, 256, 0, st>>>(P, n);
+  RS_CHECK_LAUNCH();
+  seg_combine_kernel<VEC, GS, NA, MODE><<<blocks, 256, 0, st>>>(P, n);
+  RS_CHECK_LAUNCH();
+  return RS_OK;
+}
+
+template <int VEC, int GS, int NA>
+int launch_mode(const UpdParams &P, int mode, int64_t n, cudaStream_t st) {
+  switch (mode) {
+    case RS_UPD_GRAD: return launch_update<VEC, GS, NA, RS_UPD_GRAD>(P, n, st);
+    case RS_UPD_SGD: return launch_update<VEC, GS, NA, RS_UPD_SGD>(P, n, st);
+    case RS_UPD_ADAM: return launch_update<VEC, GS, NA, RS_UPD_ADAM>(P, n, st);
+  }
+  rs::set_error("rs_segment_update: bad mode %d", mode);
+  return RS_E_ARG;
+}
+
+}  // namespace
+
+RS_API int rs_segment_update(const rs_segments *seg, int64_t n, const rs_update *u, void *stream) {
+  RS_CHECK_ARG(seg && u, RS_E_ARG, "rs_segment_update: null argument");
+  RS_CHECK_ARG(n > 0 && n < (1ll << 31), RS_E_SHAPE, "rs_segment_update: bad n");
+  RS_CHECK_ARG(u->width >= 1 && u->width <= 2048 && u->F >= 1 && n % u->F == 0, RS_E_SHAPE, "rs_segment_update: bad width/F");
+  RS_CHECK_ARG(u->stash || u->dense, RS_E_ARG, "rs_segment_update: need stash and/or dense gradient source");
+  RS_CHECK_ARG(!u->scale || (u->stash && (u->scale_width == 1 || u->scale_width == u->width)), RS_E_ARG,
+               "rs_segment_update: scale needs stash and scale_width in {1,width}");
+  if (u->mode == RS_UPD_GRAD) RS_CHECK_ARG(u->dense_grad, RS_E_ARG, "rs_segment_update: dense_grad is NULL");
+  if (u->mode != RS_UPD_GRAD) RS_CHECK_ARG(u->table, RS_E_ARG, "rs_segment_update: table is NULL");
+  if (u->mode == RS_UPD_ADAM) RS_CHECK_ARG(u->m && u->v && u->step >= 1, RS_E_ARG, "rs_segment_update: Adam needs m, v, step>=1");
+  RS_CHECK_ARG((int64_t)(2 * (n / RS_CHUNK + 2)) * u->width <= seg->partial_floats, RS_E_WORKSPACE,
+               "rs_segment_update: dedup workspace was sized for a narrower row (need %lld floats of partials, have %lld)",
+               (long long)((int64_t)(2 * (n / RS_CHUNK + 2)) * u->width), (long long)seg->partial_floats);
+  UpdParams P;
+  P.sorted_pos = seg->sorted_pos;
+  P.seg_start = seg->seg_start;
+  P.seg_first_chunk = seg->seg_first_chunk;
+  P.chunk_start = seg->chunk_start;
+  P.chunk_seg = seg->chunk_seg;
+  P.n_uniq = seg->n_uniq;
+  P.n_chunks = seg->n_chunks;
+  P.uniq = seg->uniq;
+  P.partial = seg->partial;
+  P.stash = u->stash;
+  P.scale = u->scale;
+  P.dense = u->dense;
+  P.table = u->table;
+  P.m = u->m;
+  P.v = u->v;
+  P.dense_grad = u->dense_grad;
+  P.W = u->width;
+  P.F = u->F;
+  P.scale_width = u->scale_width;
+  P.lr = u->lr;
+  P.wd = u->wd;
+  P.beta1 = u->beta1;
+  P.beta2 = u->beta2;
+  P.eps = u->eps;
+  double bc1 = 1.0 - pow((double)u->beta1, (double)u->step);
+  double bc2 = 1.0 - pow((double)u->beta2, (double)u->step);
+  P.step_size = (float)((double)u->lr / (bc1 > 0 ? bc1 : 1.0));
+  P.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2 > 0 ? bc2 : 1.0));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int W = u->width, mode = u->mode;
+  if (W % 4 == 0) {
+    const int wv = W / 4;
+    if (wv <= 1) return launch_mode<4, 1, 1>(P, mode, n, st);
+    if (wv <= 2) return launch_mode<4, 2, 1>(P, mode, n, st);
+    if (wv <= 4) return launch_mode<4, 4, 1>(P, mode, n, st);
+    if (wv <= 8) return launch_mode<4, 8, 1>(P, mode, n, st);
+    if (wv <= 16) return launch_mode<4, 16, 1>(P, mode, n, st);
+    if (wv <= 32) return launch_mode<4, 32, 1>(P, mode, n, st);
+    if (wv <= 64) return launch_mode<4, 32, 2>(P, mode, n, st);
+    if (wv <= 128) return launch_mode<4, 32, 4>(P, mode, n, st);
+    if (wv <= 256) return launch_mode<4, 32, 8>(P, mode, n, st);
+    return launch_mode<4, 32, 16>(P, mode, n, st);
+  }
+  if (W == 1) return launch_mode<1, 1, 1>(P, mode, n, st);
+  if (W <= 32) return launch_mode<1, 32, 1>(P, mode, n, st);
+  if (W <= 128) return launch_mode<1, 32, 4>(P, mode, n, st);
+  if (W <= 512) return launch_mode<1, 32, 16>(P, mode, n, st);
+  rs::set_error("rs_segment_update: width %d not a multiple of 4 and > 512", W);
+  return RS_E_UNSUPPORTED;
+}
+
+// =================================================================== dense Adam sweep
+__global__ void __launch_bounds__(256) adam_dense_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
+                                                        float *__restrict__ v, int64_t numel, float wd, float beta1, float beta2, float eps,
+                                                        float step_size, float inv_sqrt_bc2) {
+  UpdParams P;
+  P.wd = wd;
+  P.beta1 = beta1;
+  P.beta2 = beta2;
+  P.eps = eps;
+  P.step_size = step_size;
+  P.inv_sqrt_bc2 = inv_sqrt_bc2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += (int64_t)gridDim.x * blockDim.x) {
+    float w = p[i], mm = m[i], vv = v[i];
+    adam1(w, mm, vv, g[i], P);
+    p[i] = w;
+    m[i] = mm;
+    v[i] = vv;
+  }
+}
+
+RS_API int rs_adam_dense(float *p, const float *g, float *m, float *v, int64_t numel, float lr, float wd, float beta1, float beta2,
+                         float eps, int32_t step, void *stream) {
+  RS_CHECK_ARG(p && g && m && v && step >= 1, RS_E_ARG, "rs_adam_dense: bad argument");
+  if (numel == 0) return RS_OK;
+  double bc1 = 1.0 - pow((double)beta1, (double)step);
+  double bc2 = 1.0 - pow((double)beta2, (double)step);
+  int64_t blocks64 = (numel + 255) / 256;
+  int cap = rs::num_sms() * 16;
+  int blocks = (int)(blocks64 < cap ? blocks64 : cap);
+  adam_dense_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, numel, wd, beta1, beta2, eps, (float)((double)lr / bc1),
+                                                              (float)(1.0 / sqrt(bc2)));
+  RS_CHECK_LAUNCH();
+  return RS_OK;
+}

@@ -1,0 +1,364 @@
+"""Thin tensor-level wrappers over the C ABI (include/recsys_b200.h).  torch is plumbing only: it owns the
+device memory and the stream; every op below is one call into librecsys_b200.so.  No CPU fallback."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import RS_MAX_FIELDS, RS_UPD_ADAM, RS_UPD_GRAD, RS_UPD_SGD  # noqa: F401
+
+_status = {}
+_launches = 0
+
+
+def launches():
+    """Number of C-ABI calls that launched kernels since import (bench.py reports it)."""
+    return _launches
+
+
+def _count(n=1):
+    global _launches
+    _launches += n
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("deeplearningrecommendationsystem_b200 ops need CUDA tensors (there is no CPU fallback)")
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _f32(t):
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        raise TypeError(f"expected float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def _i64(t):
+    if t.dtype != torch.int64:
+        raise TypeError(f"ids must be int64, got {t.dtype}")
+    return t.contiguous()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def status_word(device):
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _status:
+        _status[key] = torch.zeros(1, dtype=torch.int32, device=f"cuda:{key}")
+    return _status[key]
+
+
+def check_status(device=None):
+    """Synchronising check of the out-of-range-id flag; raises IndexError like nn.Embedding does on CPU."""
+    w = status_word(device if device is not None else torch.cuda.current_device())
+    v = int(w.item())
+    if v:
+        w.zero_()
+        raise IndexError("index out of range in embedding lookup")
+
+
+def make_tables(weights, width=None):
+    """rs_tables from a list of (rows_f, W) fp32 CUDA tensors (one per field)."""
+    T = _lib.rs_tables()
+    if len(weights) > RS_MAX_FIELDS:
+        raise ValueError(f"at most {RS_MAX_FIELDS} fields")
+    T.num_fields = len(weights)
+    T.width = int(width if width is not None else weights[0].shape[1])
+    for f, w in enumerate(weights):
+        _need_cuda(w)
+        if w.dtype != torch.float32 or not w.is_contiguous() or w.shape[1] != T.width:
+            raise ValueError("tables must be contiguous float32 (rows, width)")
+        T.base[f] = w.data_ptr()
+        T.rows[f] = w.shape[0]
+    return T
+
+
+def tables_from_concat(weight, offsets, rows):
+    """rs_tables over ONE concatenated (total_rows, W) tensor: field f starts at row offsets[f]."""
+    T = _lib.rs_tables()
+    T.num_fields = len(rows)
+    T.width = weight.shape[1]
+    base = weight.data_ptr()
+    for f, (o, r) in enumerate(zip(offsets, rows)):
+        T.base[f] = base + int(o) * T.width * 4
+        T.rows[f] = int(r)
+    return T
+
+
+def dummy_tables(F, D):
+    T = _lib.rs_tables()
+    T.num_fields, T.width = F, D
+    return T
+
+
+def gather_rows(T, ids):
+    """out[..., f, :] = table_f[ids[..., f]]; ids (B, F) -> (B, F, W).  Bit-exact row copy."""
+    ids = _i64(ids)
+    _need_cuda(ids)
+    B = ids.numel() // T.num_fields
+    out = torch.empty(B, T.num_fields, T.width, dtype=torch.float32, device=ids.device)
+    _lib.check(_lib.load().rs_gather_rows(C.byref(T), ids.data_ptr(), B, out.data_ptr(), status_word(ids.device).data_ptr(), _stream()),
+               "rs_gather_rows")
+    _count()
+    return out
+
+
+def fields_fwd(T, B, device, ids=None, dense_in=None, cross=False, bi=False, pairs=False, concat=False, stash=False,
+               dot2=False, had2=False):
+    """Fused lookup + interaction forward.  Returns a dict of the requested outputs."""
+    F, D = T.num_fields, T.width
+    io = _lib.rs_fields_io()
+    keep = []
+    if ids is not None:
+        ids = _i64(ids)
+        _need_cuda(ids)
+        io.ids = ids.data_ptr()
+    else:
+        dense_in = _f32(dense_in)
+        _need_cuda(dense_in)
+        io.dense_in = dense_in.data_ptr()
+    out = {}
+
+    def alloc(name, *shape):
+        t = torch.empty(*shape, dtype=torch.float32, device=device)
+        out[name] = t
+        setattr(io, name, t.data_ptr())
+
+    if cross:
+        alloc("cross", B)
+    if bi:
+        alloc("bi", B, D)
+    if pairs:
+        alloc("pairs", B, F * (F - 1) // 2)
+    if concat:
+        alloc("concat", B, F * D)
+    if stash:
+        alloc("stash", B, F, D)
+    if dot2:
+        alloc("dot2", B)
+    if had2:
+        alloc("had2", B, D)
+    _lib.check(_lib.load().rs_fields_fwd(C.byref(T), C.byref(io), B, status_word(device).data_ptr(), _stream()), "rs_fields_fwd")
+    _count()
+    del keep
+    return out
+
+
+def fields_bwd(T, B, device, ids=None, dense_in=None, g_cross=None, g_bi=None, g_pairs=None, g_concat=None, g_dot2=None,
+               g_had2=None):
+    """dE (B, F, D): gradient of the interaction outputs w.r.t. the field embeddings."""
+    F, D = T.num_fields, T.width
+    g = _lib.rs_fields_grad()
+    if ids is not None:
+        ids = _i64(ids)
+        g.ids = ids.data_ptr()
+    else:
+        dense_in = _f32(dense_in)
+        g.dense_in = dense_in.data_ptr()
+    ups = dict(g_cross=_f32(g_cross), g_bi=_f32(g_bi), g_pairs=_f32(g_pairs), g_concat=_f32(g_concat), g_dot2=_f32(g_dot2),
+               g_had2=_f32(g_had2))
+    for k, t in ups.items():
+        _need_cuda(t)
+        setattr(g, k, _p(t))
+    dE = torch.empty(B, F, D, dtype=torch.float32, device=device)
+    g.dE = dE.data_ptr()
+    _lib.check(_lib.load().rs_fields_bwd(C.byref(T), C.byref(g), B, _stream()), "rs_fields_bwd")
+    _count()
+    return dE
+
+
+def ffm_fwd(T, ids, D, want_stash=True):
+    """cross (B,), stash (B, F, F*D) | None for an F-field FFM whose table rows are (F, D)."""
+    ids = _i64(ids)
+    _need_cuda(ids)
+    F = T.num_fields
+    B = ids.numel() // F
+    cross = torch.empty(B, dtype=torch.float32, device=ids.device)
+    stash = torch.empty(B, F, F * D, dtype=torch.float32, device=ids.device) if want_stash else None
+    _lib.check(_lib.load().rs_ffm_fwd(C.byref(T), ids.data_ptr(), B, D, cross.data_ptr(), _p(stash),
+                                      status_word(ids.device).data_ptr(), _stream()), "rs_ffm_fwd")
+    _count()
+    return cross, stash
+
+
+def _field_of(field_of):
+    return (C.c_int32 * len(field_of))(*field_of)
+
+
+def ffm_dense_fwd(Tin, field_of):
+    Tin = _f32(Tin)
+    _need_cuda(Tin)
+    B, F, NF, D = Tin.shape
+    cross = torch.empty(B, dtype=torch.float32, device=Tin.device)
+    _lib.check(_lib.load().rs_ffm_dense_fwd(Tin.data_ptr(), B, F, NF, D, _field_of(field_of), cross.data_ptr(), _stream()),
+               "rs_ffm_dense_fwd")
+    _count()
+    return cross
+
+
+def ffm_dense_bwd(Tin, g_cross, field_of):
+    Tin, g_cross = _f32(Tin), _f32(g_cross)
+    B, F, NF, D = Tin.shape
+    dT = torch.empty_like(Tin)
+    _lib.check(_lib.load().rs_ffm_dense_bwd(Tin.data_ptr(), g_cross.data_ptr(), B, F, NF, D, _field_of(field_of), dT.data_ptr(),
+                                            _stream()), "rs_ffm_dense_bwd")
+    _count()
+    return dT
+
+
+class Segments:
+    """Result of dedup_sort: device arrays carved out of one workspace tensor (kept alive here)."""
+
+    def __init__(self, ws, seg, n, device):
+        self.ws, self.seg, self.n, self.device = ws, seg, n, device
+
+    def _view(self, ptr, count, dtype):
+        off = ptr - self.ws.data_ptr()
+        size = torch.empty(0, dtype=dtype).element_size()
+        return self.ws[off:off + count * size].view(dtype)
+
+    @property
+    def n_uniq(self):
+        return int(self._view(self.seg.n_uniq, 1, torch.int32).item())
+
+    def uniq(self):
+        return self._view(self.seg.uniq, self.n, torch.int64)[: self.n_uniq]
+
+    def inverse(self):
+        return self._view(self.seg.inverse, self.n, torch.int32)
+
+    def counts(self):
+        return self._view(self.seg.counts, self.n, torch.int32)[: self.n_uniq]
+
+    def sorted_pos(self):
+        return self._view(self.seg.sorted_pos, self.n, torch.int32)
+
+
+_ws_cache = {}
+
+
+def dedup_sort(ids, F=1, row_offset=None, total_rows=None, max_width=1, reuse_workspace=True):
+    """Stable sort of the lookups by global table row + segment/chunk boundaries (no host sync)."""
+    ids = _i64(ids)
+    _need_cuda(ids)
+    n = ids.numel()
+    lib = _lib.load()
+    nbytes = C.c_size_t(0)
+    _lib.check(lib.rs_dedup_workspace_bytes(n, int(max_width), C.byref(nbytes)), "rs_dedup_workspace_bytes")
+    key = (ids.device, n, int(max_width)) if reuse_workspace else None
+    ws = _ws_cache.get(key) if key is not None else None
+    if ws is None:
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=ids.device)
+        if key is not None:
+            _ws_cache[key] = ws
+    seg = _lib.rs_segments()
+    offs = None
+    if row_offset is not None:
+        offs = (C.c_int64 * F)(*[int(o) for o in row_offset])
+    _lib.check(lib.rs_dedup_sort(ids.data_ptr(), n, F, offs, int(total_rows), ws.data_ptr(), nbytes.value, C.byref(seg),
+                                 status_word(ids.device).data_ptr(), _stream()), "rs_dedup_sort")
+    _count(8)
+    return Segments(ws, seg, n, ids.device)
+
+
+def segment_update(segs, mode, width, F, stash=None, scale=None, dense=None, table=None, m=None, v=None, dense_grad=None,
+                   lr=0.0, wd=0.0, betas=(0.9, 0.999), eps=1e-8, step=1):
+    """Segment-reduce the per-lookup row gradients (scale*stash + dense) and apply `mode` to the touched rows."""
+    u = _lib.rs_update()
+    u.mode, u.width, u.F = mode, width, F
+    stash, scale, dense = _f32(stash), _f32(scale), _f32(dense)
+    u.scale_width = 1 if (scale is None or scale.numel() * F == segs.n) else width
+    for name, t in (("stash", stash), ("scale", scale), ("dense", dense), ("table", table), ("m", m), ("v", v),
+                    ("dense_grad", dense_grad)):
+        _need_cuda(t)
+        if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
+            raise ValueError(f"{name} must be contiguous float32")
+        setattr(u, name, _p(t))
+    u.lr, u.wd, u.beta1, u.beta2, u.eps, u.step = lr, wd, betas[0], betas[1], eps, step
+    _lib.check(_lib.load().rs_segment_update(C.byref(segs.seg), segs.n, C.byref(u), _stream()), "rs_segment_update")
+    _count(2)
+
+
+def adam_dense(p, g, m, v, step, lr=1e-3, wd=0.0, betas=(0.9, 0.999), eps=1e-8):
+    _need_cuda(p, g, m, v)
+    _lib.check(_lib.load().rs_adam_dense(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, wd, betas[0],
+                                         betas[1], eps, step, _stream()), "rs_adam_dense")
+    _count()
+
+
+def make_xslots(slots, width, xcols):
+    """slots: list of (col, ncols, kind, table|None)."""
+    S = _lib.rs_xslots()
+    S.num_slots, S.width, S.xcols = len(slots), width, xcols
+    for t, (col, ncols, kind, table) in enumerate(slots):
+        S.col[t], S.ncols[t], S.kind[t] = col, ncols, kind
+        if table is not None:
+            _need_cuda(table)
+            S.table[t] = table.data_ptr()
+            S.rows[t] = table.shape[0]
+    return S
+
+
+def xembed_fwd(S, x):
+    x = _f32(x)
+    _need_cuda(x)
+    B = x.shape[0]
+    E = torch.empty(B, S.num_slots, S.width, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().rs_xembed_fwd(C.byref(S), x.data_ptr(), B, E.data_ptr(), status_word(x.device).data_ptr(), _stream()),
+               "rs_xembed_fwd")
+    _count()
+    return E
+
+
+def xembed_bag_bwd(S, x, dE, slots):
+    """-> list (per slot) of dW (ncols, W) for bag slots, None otherwise.  Fixed-order two-pass reduction."""
+    x, dE = _f32(x), _f32(dE)
+    B = x.shape[0]
+    lib = _lib.load()
+    nbytes = C.c_size_t(0)
+    _lib.check(lib.rs_xembed_bag_ws_bytes(C.byref(S), B, C.byref(nbytes)), "rs_xembed_bag_ws_bytes")
+    ws = torch.empty(nbytes.value // 4 + 1, dtype=torch.float32, device=x.device)
+    outs, ptrs = [], (C.c_void_p * S.num_slots)()
+    for t, (col, ncols, kind, table) in enumerate(slots):
+        if kind == 1:
+            w = torch.empty(ncols, S.width, dtype=torch.float32, device=x.device)
+            outs.append(w)
+            ptrs[t] = w.data_ptr()
+        else:
+            outs.append(None)
+    _lib.check(lib.rs_xembed_bag_bwd(C.byref(S), x.data_ptr(), dE.data_ptr(), B, ptrs, ws.data_ptr(), nbytes.value, _stream()),
+               "rs_xembed_bag_bwd")
+    _count(2)
+    return outs
+
+
+def xcol_to_ids(x, col):
+    x = _f32(x)
+    _need_cuda(x)
+    ids = torch.empty(x.shape[0], dtype=torch.int64, device=x.device)
+    _lib.check(_lib.load().rs_xcol_to_ids(x.data_ptr(), x.shape[0], x.shape[1], col, ids.data_ptr(), _stream()), "rs_xcol_to_ids")
+    _count()
+    return ids
+
+
+def sigmoid_bce(logit, y, want_grad=True):
+    """pred, mean BCE loss (0-d tensor), d loss / d logit -- one fused pass + fixed-order reduction."""
+    logit, y = _f32(logit).view(-1), _f32(y).view(-1)
+    _need_cuda(logit, y)
+    B = logit.numel()
+    pred = torch.empty_like(logit)
+    g = torch.empty_like(logit) if want_grad else None
+    loss = torch.empty((), dtype=torch.float32, device=logit.device)
+    ws = torch.empty(1024, dtype=torch.float32, device=logit.device)
+    _lib.check(_lib.load().rs_sigmoid_bce(logit.data_ptr(), y.data_ptr(), B, pred.data_ptr(), _p(g), loss.data_ptr(), ws.data_ptr(),
+                                          _stream()), "rs_sigmoid_bce")
+    _count(2)
+    return pred, loss, g

@@ -1,0 +1,111 @@
+"""Train / validate / test step protocol -- mirror of reference trainer/trainer.py:8-146.
+
+Same public surface: ``Trainer(model, loss_fn, optimizer)``; ``train_loop(*args, train_rating=)``,
+``valid_loop``, ``test_loop`` dispatch on the number of positional inputs (1 -> ``model(x)``, 2 -> ``model(a, b)``,
+anything else -> ValueError); the ``*_loop2(matrix, mask)`` AutoRec variants; results are left on the instance in
+``predictions_*``, ``*_loss`` and ``*_rating``.  ``optimizer`` only needs ``zero_grad()`` and ``step()``, so a
+``FusedRowOptimizer`` drops in.  ``model_eval`` computes the reference Evaluator's five metrics
+(evaluator/evaluator.py:13-20: predictions thresholded at 0.5 *before* AUC) on the device, one host read per split.
+"""
+import torch
+
+
+def _binary_metrics(y_true, y_pred):
+    """[accuracy, precision, recall, f1, auc] with sklearn's conventions for hard 0/1 predictions."""
+    t = (y_true.detach().reshape(-1) > 0.5)
+    p = (y_pred.detach().reshape(-1) > 0.5)
+    tp = (t & p).sum().double()
+    tn = (~t & ~p).sum().double()
+    fp = (~t & p).sum().double()
+    fn = (t & ~p).sum().double()
+    n = tp + tn + fp + fn
+    zero = torch.zeros((), dtype=torch.float64, device=tp.device)
+    acc = (tp + tn) / n
+    prec = torch.where(tp + fp > 0, tp / (tp + fp).clamp(min=1), zero)
+    rec = torch.where(tp + fn > 0, tp / (tp + fn).clamp(min=1), zero)
+    f1 = torch.where(prec + rec > 0, 2 * prec * rec / (prec + rec).clamp(min=1e-300), zero)
+    tpr = torch.where(tp + fn > 0, tp / (tp + fn).clamp(min=1), zero)
+    fpr = torch.where(fp + tn > 0, fp / (fp + tn).clamp(min=1), zero)
+    auc = 0.5 * (1.0 + tpr - fpr)          # ROC of a hard classifier has a single interior point
+    return [float(v) for v in torch.stack([acc, prec, rec, f1, auc]).cpu()]
+
+
+class Trainer:
+    def __init__(self, model, loss_fn, optimizer):
+        self.model, self.loss_fn, self.optimizer = model, loss_fn, optimizer
+        self.train_loss = self.valid_loss = self.test_loss = None
+        self.predictions_train = self.predictions_valid = self.predictions_test = None
+        self.train_rating = self.valid_rating = self.test_rating = None
+
+    def _forward(self, args, who):
+        if len(args) not in (1, 2):
+            raise ValueError(f"Invalid number of arguments provided to {who}")
+        return self.model(*args)
+
+    def train_loop(self, *args, train_rating):
+        self.model.train()
+        self.optimizer.zero_grad()
+        self.predictions_train = self._forward(args, "train_loop")
+        self.train_loss = self.loss_fn(self.predictions_train, train_rating)
+        self.train_loss.backward()
+        self.optimizer.step()
+        self.train_rating = train_rating
+
+    def _eval(self, args, rating, who):
+        self.model.eval()
+        with torch.no_grad():
+            pred = self._forward(args, who)
+            loss = self.loss_fn(pred, rating)
+        return pred, loss
+
+    def valid_loop(self, *args, valid_rating):
+        self.predictions_valid, self.valid_loss = self._eval(args, valid_rating, "valid_loop")
+        self.valid_rating = valid_rating
+
+    def test_loop(self, *args, test_rating):
+        self.predictions_test, self.test_loss = self._eval(args, test_rating, "test_loop")
+        self.test_rating = test_rating
+
+    # masked single-input variants (AutoRec scripts)
+    def train_loop2(self, train_matrix, mask):
+        self.model.train()
+        self.optimizer.zero_grad()
+        self.predictions_train = self.model(train_matrix)[mask]
+        self.train_rating = train_matrix[mask]
+        self.train_loss = self.loss_fn(self.predictions_train, self.train_rating)
+        self.train_loss.backward()
+        self.optimizer.step()
+
+    def _eval2(self, matrix, mask):
+        self.model.eval()
+        with torch.no_grad():
+            pred = self.model(matrix)[mask]
+            rating = matrix[mask]
+            return pred, rating, self.loss_fn(pred, rating)
+
+    def valid_loop2(self, valid_matrix, mask):
+        self.predictions_valid, self.valid_rating, self.valid_loss = self._eval2(valid_matrix, mask)
+
+    def test_loop2(self, test_matrix, mask):
+        self.predictions_test, self.test_rating, self.test_loss = self._eval2(test_matrix, mask)
+
+    def metrics(self):
+        """{'train'|'valid'|'test': [acc, precision, recall, f1, auc]} for the splits that have run."""
+        out = {}
+        for split in ("train", "valid", "test"):
+            pred, rating = getattr(self, f"predictions_{split}"), getattr(self, f"{split}_rating")
+            if pred is not None:
+                out[split] = _binary_metrics(rating, pred)
+        return out
+
+    def model_eval(self, epoch):
+        m = self.metrics()
+        names = ["Accuracy", "Precision", "Recall", "F1 Score", "ROC AUC Score"]
+        title = {"train": "Training", "valid": "Valid", "test": "Test"}
+        lines = [f"Epoch {epoch + 1}:"]
+        for split in m:
+            lines.append(f"  - {title[split]} Loss: {getattr(self, split + '_loss').item()}")
+        for k, name in enumerate(names):
+            for split in m:
+                lines.append(f"  - {title[split]} {name}: {m[split][k]}")
+        print("\n".join(lines))

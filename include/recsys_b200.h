@@ -1,0 +1,183 @@
+/*
+ * recsys_b200.h -- C ABI of the B200 (sm_100a) embedding -> interaction -> sparse-update hot path.
+ *
+ * The reference (WardellZc/DeepLearningRecommendationSystem) is pure Python and has NO FFI layer; its
+ * "plugin interface" for this path is the nn.Module / optimizer protocol used by trainer/trainer.py:23-40.
+ * Each entry point below cites the reference call it replaces.  The Python host mirror
+ * (deeplearningrecommendationsystem_b200/) binds these symbols with ctypes; INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every data pointer is a DEVICE pointer owned by the caller (no allocation, no ownership transfer);
+ *     structs themselves (rs_tables, rs_fields_io, ...) are HOST memory, read during the call;
+ *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return value: 0 on success, RS_E_* (< 0) on a bad argument, a positive cudaError_t on a launch
+ *     failure; rs_last_error() gives a message; nothing throws across the boundary;
+ *   - arithmetic is fp32, ids are int64, exactly as the reference's CPU path;
+ *   - out-of-range ids never fault: the lookup is clamped and bit 0 of the optional device word
+ *     `status` is set (the host mirror turns that into the reference's IndexError).
+ */
+#ifndef RECSYS_B200_H
+#define RECSYS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RS_MAX_FIELDS 64
+#define RS_CHUNK 64 /* sorted lookups summed sequentially by one lane group (segment-reduce granularity) */
+
+enum { RS_OK = 0, RS_E_ARG = -1, RS_E_SHAPE = -2, RS_E_WORKSPACE = -3, RS_E_UNSUPPORTED = -4 };
+
+/* F embedding tables read by one lookup call; field f's table is base[f], shape (rows[f], width) fp32,
+ * row-major.  A single concatenated table is the special case base[f] = weight + row_offset[f]*width. */
+typedef struct rs_tables {
+  int32_t num_fields;
+  int32_t width;
+  const float *base[RS_MAX_FIELDS];
+  int64_t rows[RS_MAX_FIELDS];
+} rs_tables;
+
+int rs_version(void);
+const char *rs_last_error(void);
+
+/* ---- gather: replaces nn.Embedding.forward (model/deepfm.py:45-46, model/mf.py:24-25, model/din.py:35-36).
+ * out[b, f, :] = T.base[f][ids[b, f], :]   -- a pure copy, bit-exact.  ids (B, F) int64, out (B, F, width). */
+int rs_gather_rows(const rs_tables *T, const int64_t *ids, int64_t B, float *out, int32_t *status, void *stream);
+
+/* ---- fused multi-field lookup + interaction forward.
+ * Replaces the per-model python between the embedding calls and the MLP:
+ *   FM sum-square second order          model/deepfm.py:71-77
+ *   NFM bi-interaction pooling          model/nfm.py:58-62
+ *   PNN inner products                  model/pnn.py:61-66
+ *   field concat for the deep tower     model/deepfm.py:54, model/pnn.py:55, model/neuralcf.py:46
+ *   MF dot / GMF Hadamard (F == 2)      model/mf.py:26, model/neuralcf.py:39
+ * Source of the (B, F, D) field embeddings: `ids` (gather from T) or, when ids == NULL, the dense tensor
+ * `dense_in` (already-materialised embeddings, used by the MovieLens feature-vector front end).
+ * Any subset of the outputs may be requested (NULL = not wanted). */
+typedef struct rs_fields_io {
+  const int64_t *ids;     /* (B, F) or NULL */
+  const float *dense_in;  /* (B, F, D) when ids == NULL */
+  float *cross;           /* (B)      0.5 * sum_d[(sum_f e)^2 - sum_f e^2]                       */
+  float *bi;              /* (B, D)   0.5 * [(sum_f e)^2 - sum_f e^2]  == sum_{i<j} e_i * e_j   */
+  float *pairs;           /* (B, F(F-1)/2)  <e_i, e_j>, i<j in nested-loop order                 */
+  float *concat;          /* (B, F*D) the gathered rows                                           */
+  float *stash;           /* (B, F, D) S_b - e_bf : d cross / d e_bf, consumed by rs_segment_update */
+  float *dot2;            /* (B)      <e_0, e_1>            (F == 2 only)                         */
+  float *had2;            /* (B, D)   e_0 * e_1             (F == 2 only)                         */
+} rs_fields_io;
+int rs_fields_fwd(const rs_tables *T, const rs_fields_io *io, int64_t B, int32_t *status, void *stream);
+
+/* Backward of the same interactions w.r.t. the field embeddings (autograd of the python listed above):
+ *   dE[b,f,:] = g_cross[b]*(S_b - e_bf) + g_bi[b,:]*(S_b - e_bf) + sum_{j!=f} g_pairs[b,(f,j)]*e_bj
+ *             + g_concat[b,f,:] + (F==2) g_dot2[b]*e_other + g_had2[b,:]*e_other
+ * Any upstream gradient may be NULL.  dE (B, F, D) is the per-lookup row gradient that rs_segment_update
+ * reduces over duplicate ids. */
+typedef struct rs_fields_grad {
+  const int64_t *ids;
+  const float *dense_in;
+  const float *g_cross, *g_bi, *g_pairs, *g_concat, *g_dot2, *g_had2;
+  float *dE;
+} rs_fields_grad;
+int rs_fields_bwd(const rs_tables *T, const rs_fields_grad *g, int64_t B, void *stream);
+
+/* ---- FFM: field-aware lookup + pairwise interaction  (model/ffm.py:46-82, generalised to F fields).
+ * Table row of feature i = (F, D): slot j is v_{i,j}, feature i's vector toward field j.
+ *   cross[b] = sum_{i<j} <v_{i,j}(b), v_{j,i}(b)>
+ *   stash[b, i, j, :] = v_{j,i}(b) (0 on the diagonal) = d cross[b] / d v_{i,j}(b), the Jacobian row that
+ *   rs_segment_update scales by dL/dcross[b]; pass NULL for inference.
+ * Rows travel global->shared with cp.async.bulk (TMA bulk copy) through an mbarrier ring. */
+int rs_ffm_fwd(const rs_tables *T /* width = F*D */, const int64_t *ids, int64_t B, int32_t D, float *cross,
+               float *stash, int32_t *status, void *stream);
+/* Dense small-F variant used by the MovieLens FFM module: Tin (B, F, NF, D), field_of[F] (host). */
+int rs_ffm_dense_fwd(const float *Tin, int64_t B, int32_t F, int32_t NF, int32_t D, const int32_t *field_of,
+                     float *cross, void *stream);
+int rs_ffm_dense_bwd(const float *Tin, const float *g_cross, int64_t B, int32_t F, int32_t NF, int32_t D,
+                     const int32_t *field_of, float *dT, void *stream);
+
+/* ---- deterministic dedup: stable sort of the lookups by table row + segment boundaries.
+ * Replaces the bookkeeping inside autograd's embedding_dense_backward (implicit at trainer/trainer.py:38).
+ * (uniq, inverse, counts) equal torch.unique(keys, sorted=True, return_inverse=True, return_counts=True)
+ * where keys[p] = row_offset[p % F] + ids[p]. */
+typedef struct rs_segments {
+  uint32_t *sorted_key;      /* [n]   global row of each lookup, ascending                        */
+  int32_t *sorted_pos;       /* [n]   lookup index p = b*F+f; ascending inside a segment (stable) */
+  int64_t *uniq;             /* [n]   first *n_uniq entries valid                                 */
+  int32_t *inverse;          /* [n]   segment index of lookup p                                   */
+  int32_t *counts;           /* [n]                                                               */
+  int32_t *seg_start;        /* [n+1] start of each segment in the sorted order                   */
+  int32_t *seg_first_chunk;  /* [n+1]                                                             */
+  int32_t *chunk_start;      /* [n+1] segments cut into chunks of <= RS_CHUNK lookups             */
+  int32_t *chunk_seg;        /* [n]                                                               */
+  int32_t *n_uniq;           /* [1] device scalar                                                 */
+  int32_t *n_chunks;         /* [1] device scalar                                                 */
+  float *partial;            /* scratch for chunk partial sums, sized by rs_dedup_workspace_bytes */
+  int64_t partial_floats;
+} rs_segments;
+int rs_dedup_workspace_bytes(int64_t n, int32_t max_width, size_t *bytes);
+/* row_offset: HOST array of F int64 (NULL = all zero).  Fills `seg` with pointers carved from ws. */
+int rs_dedup_sort(const int64_t *ids, int64_t n, int32_t F, const int64_t *row_offset, int64_t total_rows,
+                  void *ws, size_t ws_bytes, rs_segments *seg, int32_t *status, void *stream);
+
+/* ---- segment-reduce of duplicate rows fused with the row update.
+ * Replaces embedding_dense_backward + optimizer.step() for embedding tables (trainer/trainer.py:38-39).
+ * Gradient of lookup p (sample b = p / F):  G[p,:] = scale[b]*stash[p,:] + dense[p,:]   (either may be NULL)
+ *   scale_width 1: per-sample scalar (dL/dcross); == width: per-sample vector (dL/dbi), only with F*W stash.
+ * For every unique row r the G[p] of its lookups are summed in ascending p (chunks of RS_CHUNK, then the
+ * chunk partials in order) -- deterministic -- and `mode` is applied to row r of `table` (global row index):
+ *   RS_UPD_GRAD   dense_grad[r] = sum                     (table untouched; feeds stock torch optimisers)
+ *   RS_UPD_SGD    w -= lr * (sum + wd*w)
+ *   RS_UPD_ADAM   lazy row-wise Adam on (w, m[r], v[r]) with torch.optim.Adam's arithmetic */
+enum { RS_UPD_GRAD = 0, RS_UPD_SGD = 1, RS_UPD_ADAM = 2 };
+typedef struct rs_update {
+  int32_t mode;
+  int32_t width;
+  int32_t F;
+  int32_t scale_width;
+  const float *stash, *scale, *dense;
+  float *table;       /* (total_rows, width) */
+  float *m, *v;       /* Adam moments, same shape */
+  float *dense_grad;  /* RS_UPD_GRAD target, same shape, pre-zeroed by the caller */
+  float lr, wd, beta1, beta2, eps;
+  int32_t step;       /* 1-based */
+} rs_update;
+int rs_segment_update(const rs_segments *seg, int64_t n, const rs_update *u, void *stream);
+
+/* Fused DENSE Adam sweep with torch.optim.Adam's exact arithmetic order ("reference-Adam" mode for the
+ * MovieLens-sized tables; scripts/deepfm.py:55). */
+int rs_adam_dense(float *p, const float *g, float *m, float *v, int64_t numel, float lr, float wd, float beta1,
+                  float beta2, float eps, int32_t step, void *stream);
+
+/* ---- MovieLens feature-vector front end (x (B,45) f32, data/reader.py:98-101 column order).
+ * Each output "slot" t is described by (col, ncols, kind): kind 0 = id column -> row gather
+ * (model/deepfm.py:45-46), 1 = one-/multi-hot bag -> sum_k x[b,col+k]*W_t[k,:] (the matmul at
+ * model/deepfm.py:47-51), 2 = scalar broadcast over D (AFM's age, model/afm.py:45,54; no table). */
+typedef struct rs_xslots {
+  int32_t num_slots, width, xcols;
+  int32_t col[RS_MAX_FIELDS], ncols[RS_MAX_FIELDS], kind[RS_MAX_FIELDS];
+  const float *table[RS_MAX_FIELDS];
+  int64_t rows[RS_MAX_FIELDS];
+} rs_xslots;
+int rs_xembed_fwd(const rs_xslots *S, const float *x, int64_t B, float *E /* (B, slots, width) */,
+                  int32_t *status, void *stream);
+/* bag-table gradient: dW_t[k,:] = sum_b x[b,col+k]*dE[b,t,:], two-pass fixed-order reduction.
+ * dW[t] points at a (ncols[t], width) buffer (NULL for non-bag slots); ws holds the block partials. */
+int rs_xembed_bag_bwd(const rs_xslots *S, const float *x, const float *dE, int64_t B, float *const *dW,
+                      float *ws, size_t ws_bytes, void *stream);
+int rs_xembed_bag_ws_bytes(const rs_xslots *S, int64_t B, size_t *bytes);
+/* float-encoded id column -> int64 (x[:,c].long(), model/deepfm.py:45) */
+int rs_xcol_to_ids(const float *x, int64_t B, int32_t xcols, int32_t col, int64_t *ids, void *stream);
+
+/* ---- sigmoid + BCELoss(mean) forward/backward in one pass (model/*: torch.sigmoid; scripts/deepfm.py:54).
+ * pred = sigmoid(logit); loss_sum += sum(-[y*max(log p,-100)+(1-y)*max(log(1-p),-100)]);
+ * g_logit = (pred - y) / B.  loss_sum is a device scalar accumulated with a fixed-order two-pass reduce. */
+int rs_sigmoid_bce(const float *logit, const float *y, int64_t B, float *pred, float *g_logit, float *loss_mean,
+                   float *ws /* >= 1024 floats */, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RECSYS_B200_H */

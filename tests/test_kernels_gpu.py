@@ -1,0 +1,288 @@
+"""Parity of every C-ABI kernel against the CPU oracle on seeded inputs (run on the B200: -m gpu).
+
+Bars (north star): bit-exact for gather / dedup / index work; 1e-5 relative (fp32) for interactions, gradients
+and updated rows.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import index as oidx, interactions as OI, optim as ooptim
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 1e-6
+
+
+def _ops():
+    from deeplearningrecommendationsystem_b200 import ops
+    return ops
+
+
+def close(got, want, rtol=RTOL, atol=ATOL, msg=""):
+    np.testing.assert_allclose(got.detach().cpu().numpy(), want.detach().cpu().numpy(), rtol=rtol, atol=atol, err_msg=msg)
+
+
+def make_fields(F, D, rows, B, seed, zipf=False):
+    g = torch.Generator().manual_seed(seed)
+    tabs = [torch.randn(r, D, generator=g) * 0.3 for r in rows]
+    if zipf:  # heavy duplicates: most lookups hit the first few rows
+        ids = torch.stack([(torch.rand(B, generator=g) ** 4 * r).long().clamp_(max=r - 1) for r in rows], dim=1)
+    else:
+        ids = torch.stack([torch.randint(0, r, (B,), generator=g) for r in rows], dim=1)
+    return tabs, ids
+
+
+# ------------------------------------------------------------------ gather (bit-exact)
+@pytest.mark.parametrize("F,W,B", [(1, 16, 1000), (3, 64, 257), (26, 16, 513), (2, 1, 300), (4, 10, 77), (2, 256, 65)])
+def test_gather_bit_exact(F, W, B):
+    ops = _ops()
+    rows = [7 + 13 * f for f in range(F)]
+    tabs, ids = make_fields(F, W, rows, B, seed=F * 100 + W)
+    T = ops.make_tables([t.cuda() for t in tabs])
+    keep = [t.cuda() for t in tabs]
+    T = ops.make_tables(keep)
+    out = ops.gather_rows(T, ids.cuda())
+    want = np.stack([oidx.gather(tabs[f].numpy(), ids[:, f].numpy()) for f in range(F)], axis=1)
+    assert np.array_equal(out.cpu().numpy(), want)
+    ops.check_status()
+
+
+def test_gather_out_of_range_sets_status():
+    ops = _ops()
+    tab = torch.randn(5, 8).cuda()
+    ids = torch.tensor([[0], [5], [2]]).cuda()
+    ops.gather_rows(ops.make_tables([tab]), ids)
+    with pytest.raises(IndexError):
+        ops.check_status()
+    ops.check_status()  # flag was cleared
+
+
+# ------------------------------------------------------------------ dedup (bit-exact)
+@pytest.mark.parametrize("n,F,card", [(1, 1, 5), (64, 1, 3), (1000, 1, 50), (4096, 4, 17), (26 * 700, 26, 1000), (65 * 129, 1, 1)])
+def test_dedup_matches_unique(n, F, card):
+    ops = _ops()
+    g = torch.Generator().manual_seed(n + F)
+    ids = torch.randint(0, card, (n,), generator=g)
+    offs = [f * card for f in range(F)]
+    segs = ops.dedup_sort(ids.cuda(), F, offs, F * card, reuse_workspace=False)
+    keys = ids.numpy() + np.tile(np.asarray(offs), n // F)
+    u, inv, cnt = oidx.dedup(keys)
+    assert segs.n_uniq == len(u)
+    assert np.array_equal(segs.uniq().cpu().numpy(), u)
+    assert np.array_equal(segs.inverse().cpu().numpy().astype(np.int64), inv)
+    assert np.array_equal(segs.counts().cpu().numpy().astype(np.int64), cnt)
+    assert np.array_equal(segs.sorted_pos().cpu().numpy().astype(np.int64), oidx.stable_order(keys))
+
+
+# ------------------------------------------------------------------ segment reduce + update
+@pytest.mark.parametrize("W", [1, 4, 8, 16, 64, 128, 416, 10, 1248])
+@pytest.mark.parametrize("hot", [False, True])
+def test_segment_grad_and_sgd(W, hot):
+    ops = _ops()
+    g = torch.Generator().manual_seed(W + hot)
+    rows, n = 300, 5000
+    ids = (torch.rand(n, generator=g) ** (6 if hot else 1) * rows).long().clamp_(max=rows - 1)
+    if hot:
+        ids[::3] = 7                      # one segment of > 1600 lookups -> many chunks
+    G = torch.randn(n, W, generator=g)
+    table = torch.randn(rows, W, generator=g)
+    segs = ops.dedup_sort(ids.cuda(), 1, None, rows, max_width=W, reuse_workspace=False)
+    dense = torch.zeros(rows, W).cuda()
+    ops.segment_update(segs, ops.RS_UPD_GRAD, W, 1, dense=G.cuda(), dense_grad=dense)
+    want = torch.zeros(rows, W).index_add_(0, ids, G)
+    close(dense, want, rtol=1e-5, atol=2e-5 if hot else 1e-6)
+    # determinism: bitwise identical on a second run
+    dense2 = torch.zeros(rows, W).cuda()
+    ops.segment_update(segs, ops.RS_UPD_GRAD, W, 1, dense=G.cuda(), dense_grad=dense2)
+    assert torch.equal(dense, dense2)
+    tc = table.clone().cuda()
+    ops.segment_update(segs, ops.RS_UPD_SGD, W, 1, dense=G.cuda(), table=tc, lr=0.05)
+    close(tc, ooptim.sgd_rows(table.clone(), ids, G, 0.05), rtol=1e-5, atol=2e-5 if hot else 1e-6)
+
+
+def test_segment_short_segments_bit_exact_vs_sequential():
+    """segments <= RS_CHUNK are summed in ascending position, the CPU index_add order -> bit-identical."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    rows, n, W = 2000, 6000, 16
+    ids = torch.randint(0, rows, (n,), generator=g)
+    G = torch.randn(n, W, generator=g)
+    segs = ops.dedup_sort(ids.cuda(), 1, None, rows, max_width=W, reuse_workspace=False)
+    dense = torch.zeros(rows, W).cuda()
+    ops.segment_update(segs, ops.RS_UPD_GRAD, W, 1, dense=G.cuda(), dense_grad=dense)
+    want = torch.zeros(rows, W)
+    for p in range(n):                         # strictly sequential fp32 adds
+        want[ids[p]] += G[p]
+    assert torch.equal(dense.cpu(), want)
+
+
+def test_segment_scaled_stash_and_adam():
+    ops = _ops()
+    g = torch.Generator().manual_seed(11)
+    F, B, W, card = 3, 400, 8, 40
+    ids = torch.randint(0, card, (B, F), generator=g)
+    offs = [0, card, 2 * card]
+    stash = torch.randn(B, F, W, generator=g)
+    scale = torch.randn(B, generator=g)
+    vscale = torch.randn(B, W, generator=g)
+    extra = torch.randn(B, F, W, generator=g)
+    keys = (ids + torch.tensor(offs)).reshape(-1)
+    table = torch.randn(F * card, W, generator=g)
+    segs = ops.dedup_sort(ids.cuda(), F, offs, F * card, max_width=W, reuse_workspace=False)
+    # scalar scale + dense term, SGD with weight decay
+    G = (scale[:, None, None] * stash + extra).reshape(-1, W)
+    tc = table.clone().cuda()
+    ops.segment_update(segs, ops.RS_UPD_SGD, W, F, stash=stash.cuda(), scale=scale.cuda(), dense=extra.cuda(), table=tc, lr=0.1, wd=0.01)
+    uniq, gs = ooptim.segment_sum_rows(keys, G)
+    want = table.clone()
+    want[uniq] -= 0.1 * (gs + 0.01 * want[uniq])
+    close(tc, want)
+    # vector scale, lazy Adam, two steps
+    G2 = (vscale[:, None, :] * stash).reshape(-1, W)
+    tc, m, v = table.clone().cuda(), torch.zeros_like(table).cuda(), torch.zeros_like(table).cuda()
+    wt, wm, wv = table.clone(), torch.zeros_like(table), torch.zeros_like(table)
+    for step in (1, 2):
+        ops.segment_update(segs, ops.RS_UPD_ADAM, W, F, stash=stash.cuda(), scale=vscale.cuda(), table=tc, m=m, v=v, lr=1e-2, step=step)
+        ooptim.adam_rows(wt, wm, wv, keys, G2, step, lr=1e-2)
+    close(tc, wt, rtol=1e-5, atol=1e-6)
+    close(m, wm)
+    close(v, wv)
+
+
+def test_adam_dense_matches_torch_adam():
+    ops = _ops()
+    torch.manual_seed(0)
+    p0, grads = torch.randn(1000), [torch.randn(1000) for _ in range(3)]
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=1e-3, weight_decay=1e-5)
+    p, m, v = p0.clone().cuda(), torch.zeros(1000).cuda(), torch.zeros(1000).cuda()
+    for s, g in enumerate(grads, 1):
+        ref.grad = g.clone()
+        opt.step()
+        ops.adam_dense(p, g.cuda(), m, v, s, lr=1e-3, wd=1e-5)
+    close(p, ref.data, rtol=1e-6, atol=1e-7)
+
+
+# ------------------------------------------------------------------ fused lookup + interaction
+@pytest.mark.parametrize("F,D,B", [(26, 16, 1000), (6, 128, 300), (39, 32, 257), (2, 64, 500), (2, 256, 130), (6, 8, 96), (5, 4, 64)])
+@pytest.mark.parametrize("src", ["ids", "dense"])
+def test_fields_fwd(F, D, B, src):
+    ops = _ops()
+    rows = [11 + 7 * f for f in range(F)]
+    tabs, ids = make_fields(F, D, rows, B, seed=F * D)
+    E = torch.stack([tabs[f][ids[:, f]] for f in range(F)], dim=1)
+    keep = [t.cuda() for t in tabs]
+    two = F == 2
+    if src == "ids":
+        out = ops.fields_fwd(ops.make_tables(keep), B, "cuda", ids=ids.cuda(), cross=True, bi=True, pairs=True, concat=True,
+                             stash=True, dot2=two, had2=two)
+    else:
+        out = ops.fields_fwd(ops.dummy_tables(F, D), B, "cuda", dense_in=E.cuda(), cross=True, bi=True, pairs=True, concat=True,
+                             stash=True, dot2=two, had2=two)
+    assert torch.equal(out["concat"].cpu(), E.flatten(1))                   # gather part is a pure copy
+    close(out["cross"], OI.fm_second_order(E), rtol=1e-5, atol=2e-5)
+    close(out["bi"], OI.bi_interaction(E), rtol=1e-5, atol=1e-5)
+    close(out["pairs"], OI.inner_products(E), rtol=1e-5, atol=2e-6)
+    close(out["stash"], E.sum(1, keepdim=True) - E, rtol=1e-5, atol=2e-6)
+    if two:
+        close(out["dot2"], (E[:, 0] * E[:, 1]).sum(1), rtol=1e-5, atol=2e-6)
+        assert torch.equal(out["had2"].cpu(), E[:, 0] * E[:, 1])
+    ops.check_status()
+
+
+@pytest.mark.parametrize("F,D,B", [(26, 16, 300), (6, 128, 100), (39, 32, 65), (2, 64, 200), (6, 8, 96)])
+def test_fields_bwd(F, D, B):
+    ops = _ops()
+    rows = [11 + 7 * f for f in range(F)]
+    tabs, ids = make_fields(F, D, rows, B, seed=F + D)
+    g = torch.Generator().manual_seed(5)
+    E = torch.stack([tabs[f][ids[:, f]] for f in range(F)], dim=1).requires_grad_(True)
+    P = F * (F - 1) // 2
+    gc, gb, gp, gcat = torch.randn(B, generator=g), torch.randn(B, D, generator=g), torch.randn(B, P, generator=g), torch.randn(B, F * D, generator=g)
+    loss = (OI.fm_second_order(E) * gc).sum() + (OI.bi_interaction(E) * gb).sum() + (OI.inner_products(E) * gp).sum() + (E.flatten(1) * gcat).sum()
+    two = F == 2
+    if two:
+        gd, gh = torch.randn(B, generator=g), torch.randn(B, D, generator=g)
+        loss = loss + ((E[:, 0] * E[:, 1]).sum(1) * gd).sum() + (E[:, 0] * E[:, 1] * gh).sum()
+    (want,) = torch.autograd.grad(loss, E)
+    kw = dict(g_cross=gc.cuda(), g_bi=gb.cuda(), g_pairs=gp.cuda(), g_concat=gcat.cuda())
+    if two:
+        kw.update(g_dot2=gd.cuda(), g_had2=gh.cuda())
+    keep = [t.cuda() for t in tabs]
+    dE1 = ops.fields_bwd(ops.make_tables(keep), B, "cuda", ids=ids.cuda(), **kw)
+    dE2 = ops.fields_bwd(ops.dummy_tables(F, D), B, "cuda", dense_in=E.detach().cuda(), **kw)
+    close(dE1, want, rtol=1e-5, atol=2e-5)
+    assert torch.equal(dE1, dE2)
+
+
+# ------------------------------------------------------------------ FFM
+@pytest.mark.parametrize("F,D,B", [(26, 16, 300), (4, 8, 1000), (39, 32, 20), (3, 4, 129), (8, 64, 50), (6, 128, 40)])
+def test_ffm_fwd_and_stash(F, D, B):
+    ops = _ops()
+    rows = [5 + 3 * f for f in range(F)]
+    tabs, ids = make_fields(F, F * D, rows, B, seed=F * 3 + D)
+    T = torch.stack([tabs[f][ids[:, f]] for f in range(F)], dim=1).view(B, F, F, D).requires_grad_(True)
+    want = OI.ffm_cross(T)
+    (jac,) = torch.autograd.grad(want.sum(), T)
+    keep = [t.cuda() for t in tabs]
+    cross, stash = ops.ffm_fwd(ops.make_tables(keep), ids.cuda(), D, want_stash=True)
+    close(cross, want.detach(), rtol=1e-5, atol=2e-5)
+    assert torch.equal(stash.cpu().view(B, F, F, D), jac)                  # transposed copy with zero diagonal
+    cross2, none = ops.ffm_fwd(ops.make_tables(keep), ids.cuda(), D, want_stash=False)
+    assert none is None and torch.equal(cross, cross2)
+    ops.check_status()
+
+
+def test_ffm_dense():
+    ops = _ops()
+    g = torch.Generator().manual_seed(9)
+    B, F, NF, D = 70, 6, 2, 8
+    fo = [0, 0, 0, 1, 0, 1]
+    T = torch.randn(B, F, NF, D, generator=g, requires_grad=True)
+    gc = torch.randn(B, generator=g)
+    want = OI.ffm_cross(T, fo)
+    (dT,) = torch.autograd.grad((want * gc).sum(), T)
+    close(ops.ffm_dense_fwd(T.detach().cuda(), fo), want.detach(), rtol=1e-5, atol=2e-6)
+    close(ops.ffm_dense_bwd(T.detach().cuda(), gc.cuda(), fo), dT, rtol=1e-5, atol=2e-6)
+
+
+# ------------------------------------------------------------------ MovieLens feature-vector front end
+def test_xembed_fwd_bwd():
+    ops = _ops()
+    from helpers import feature_matrix
+    g = torch.Generator().manual_seed(4)
+    B, D = 300, 16
+    x = feature_matrix(g, B, 50, 60)
+    tabs = [torch.randn(r, D, generator=g) for r in (50, 60, 1, 2, 21, 19)]
+    slots = [(0, 1, 0, tabs[0].cuda()), (1, 1, 0, tabs[1].cuda()), (2, 1, 1, tabs[2].cuda()), (3, 2, 1, tabs[3].cuda()),
+             (5, 21, 1, tabs[4].cuda()), (26, 19, 1, tabs[5].cuda()), (2, 1, 2, None)]
+    S = ops.make_xslots(slots, D, 45)
+    E = ops.xembed_fwd(S, x.cuda())
+    want = torch.stack([tabs[0][x[:, 0].long()], tabs[1][x[:, 1].long()], x[:, 2:3] @ tabs[2], x[:, 3:5] @ tabs[3],
+                        x[:, 5:26] @ tabs[4], x[:, 26:45] @ tabs[5], x[:, 2:3].expand(-1, D)], dim=1)
+    close(E, want, rtol=1e-6, atol=1e-6)
+    dE = torch.randn(B, 7, D, generator=g)
+    dW = ops.xembed_bag_bwd(S, x.cuda(), dE.cuda(), slots)
+    for t, (c0, nc) in {2: (2, 1), 3: (3, 2), 4: (5, 21), 5: (26, 19)}.items():
+        close(dW[t], x[:, c0:c0 + nc].t() @ dE[:, t], rtol=1e-5, atol=1e-5)
+    assert dW[0] is None and dW[6] is None
+    assert torch.equal(ops.xcol_to_ids(x.cuda(), 1).cpu(), x[:, 1].long())
+
+
+def test_sigmoid_bce():
+    ops = _ops()
+    g = torch.Generator().manual_seed(2)
+    z = (torch.randn(5000, generator=g) * 3).requires_grad_(True)
+    z.data[0], z.data[1] = 200.0, -200.0              # exercise the -100 clamp
+    y = (torch.rand(5000, generator=g) < 0.3).float()
+    p = torch.sigmoid(z)
+    loss = torch.nn.BCELoss()(p, y)
+    pred, l, gz = ops.sigmoid_bce(z.detach().cuda(), y.cuda())
+    close(pred, p.detach(), rtol=1e-6, atol=1e-7)
+    close(l, OI.bce(p.detach(), y), rtol=1e-5)
+    close(l, loss.detach(), rtol=1e-5)
+    z.data[0], z.data[1] = 20.0, -20.0                # away from the clamp the analytic gradient is (p-y)/B
+    pred, l, gz = ops.sigmoid_bce(z.detach().cuda(), y.cuda())
+    (want,) = torch.autograd.grad(torch.nn.BCELoss()(torch.sigmoid(z), y), z)
+    close(gz, want, rtol=1e-4, atol=1e-9)

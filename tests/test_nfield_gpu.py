@@ -1,0 +1,95 @@
+"""N-field FM / FFM train steps (the BASELINE.json configs[1] path) against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nfield as onf
+
+pytestmark = pytest.mark.gpu
+
+CARDS = [3, 50, 7, 1000, 24, 12, 301, 5]
+
+
+def _setup(kind, D, B, seed, zipf):
+    from deeplearningrecommendationsystem_b200.nfield import FieldFFM, FieldFM
+    g = torch.Generator().manual_seed(seed)
+    model = (FieldFM if kind == "fm" else FieldFFM)(CARDS, D, fused=True, seed=seed, device="cuda")
+    if zipf:
+        ids = torch.stack([(torch.rand(B, generator=g) ** 3 * c).long().clamp_(max=c - 1) for c in CARDS], dim=1)
+    else:
+        ids = torch.stack([torch.randint(0, c, (B,), generator=g) for c in CARDS], dim=1)
+    y = (torch.rand(B, 1, generator=g) < 0.3).float()
+    return model, ids, y
+
+
+@pytest.mark.parametrize("kind,D", [("fm", 16), ("ffm", 4), ("ffm", 16), ("fm", 64)])
+@pytest.mark.parametrize("zipf", [False, True])
+def test_fused_sgd_steps_match_oracle(kind, D, zipf):
+    from deeplearningrecommendationsystem_b200.optim import FusedRowOptimizer
+    from deeplearningrecommendationsystem_b200.trainer import Trainer
+    B, lr = 700, 0.5
+    model, ids, y = _setup(kind, D, B, 21, zipf)
+    table = model.weight.detach().cpu().clone()
+    bias = model.bias.detach().cpu().clone()
+    offsets = torch.tensor(model.offsets_host)
+    opt = FusedRowOptimizer(model, torch.optim.SGD([model.bias], lr=lr), lr=lr, kind="sgd")
+    tr = Trainer(model, torch.nn.BCELoss(), opt)
+    for step in range(3):
+        tr.train_loop(ids.cuda(), train_rating=y.cuda())
+        pred, loss = onf.train_step(kind, table, bias, ids, offsets, y[:, 0], lr)
+        np.testing.assert_allclose(tr.predictions_train.detach().cpu().numpy()[:, 0], pred.numpy(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(tr.train_loss.item(), loss.item(), rtol=1e-5)
+        np.testing.assert_allclose(model.weight.detach().cpu().numpy(), table.numpy(), rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(model.bias.detach().cpu().numpy(), bias.numpy(), rtol=1e-5, atol=1e-6)
+    from deeplearningrecommendationsystem_b200 import ops
+    ops.check_status()
+
+
+@pytest.mark.parametrize("kind,D", [("fm", 16), ("ffm", 8)])
+def test_dense_grad_mode_matches_autograd(kind, D):
+    """fused=False: the table is an ordinary dense-gradient Parameter (reference semantics, any torch optimizer)."""
+    from deeplearningrecommendationsystem_b200.nfield import FieldFFM, FieldFM
+    g = torch.Generator().manual_seed(5)
+    B = 300
+    model = (FieldFM if kind == "fm" else FieldFFM)(CARDS, D, fused=False, seed=3, device="cuda")
+    ids = torch.stack([torch.randint(0, c, (B,), generator=g) for c in CARDS], dim=1)
+    y = (torch.rand(B, 1, generator=g) < 0.3).float()
+    loss = torch.nn.BCELoss()(model(ids.cuda()), y.cuda())
+    loss.backward()
+    table = model.weight.detach().cpu().clone().requires_grad_(True)
+    bias = model.bias.detach().cpu().clone().requires_grad_(True)
+    offsets = torch.tensor(model.offsets_host)
+    logit = (onf.fm_logit if kind == "fm" else onf.ffm_logit)(table, ids, offsets, bias)
+    want = torch.nn.BCELoss()(torch.sigmoid(logit), y[:, 0])
+    want.backward()
+    np.testing.assert_allclose(loss.item(), want.item(), rtol=1e-5)
+    np.testing.assert_allclose(model.weight.grad.cpu().numpy(), table.grad.numpy(), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(model.bias.grad.cpu().numpy(), bias.grad.numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_inference_path_needs_no_stash():
+    model, ids, y = _setup("ffm", 8, 100, 2, False)
+    with torch.no_grad():
+        p1 = model(ids.cuda())
+    p2 = model(ids.cuda())
+    assert torch.equal(p1, p2.detach()) and p1.shape == (100, 1)
+
+
+def test_fused_adam_matches_row_oracle():
+    from deeplearningrecommendationsystem_b200.optim import FusedRowOptimizer
+    from oracle import optim as oo, interactions as OI
+    model, ids, y = _setup("fm", 16, 500, 8, True)
+    table = model.weight.detach().cpu().clone()
+    m, v = torch.zeros_like(table), torch.zeros_like(table)
+    offsets = torch.tensor(model.offsets_host)
+    opt = FusedRowOptimizer(model, None, lr=1e-2, kind="adam")
+    for step in (1, 2, 3):
+        opt.zero_grad()
+        loss = torch.nn.BCELoss()(model(ids.cuda()), y.cuda())
+        loss.backward()
+        opt.step()
+        E = onf.gather_fields(table, ids, offsets).requires_grad_(True)
+        l = OI.bce(torch.sigmoid(OI.fm_second_order(E) + model.bias.detach().cpu()), y[:, 0])
+        (G,) = torch.autograd.grad(l, E)
+        oo.adam_rows(table, m, v, (ids + offsets).reshape(-1), G.reshape(-1, 16), step, lr=1e-2)
+        np.testing.assert_allclose(model.weight.detach().cpu().numpy(), table.numpy(), rtol=2e-5, atol=2e-6)
