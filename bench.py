@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""Headline benchmark: train samples/sec (fwd + bwd + update) of the embedding hot path on B200.
+
+Workload (BASELINE.json configs[1], the config the metric is quoted on): FFM + FM second-order on synthetic
+Criteo-shaped data -- 26 sparse fields, D = 16, batch 65536 per GPU, the public Criteo-Kaggle cardinalities
+(33.76 M rows; FFM table 56.2 GB, FM table 2.2 GB), uniform ids, Bernoulli(0.3) labels, plain SGD.
+One "step" = one FM train step + one FFM train step over the same batch through the public API
+(model -> BCELoss -> backward -> FusedRowOptimizer.step(), driven by Trainer.train_loop).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--dist uniform|zipf] [--light]
+
+Prints ONE JSON line (contract in the task brief): value = whole-job samples/s with inputs resident in HBM;
+e2e = same metric with the ids/labels copied from pinned host memory and the loss read back every step;
+roofline = algorithmic bytes of the dominant kernel / its CUDA-event duration vs MEASURED_PEAKS.json;
+cpu_baseline = the oracle port timed on this box's host cores on a bounded sample.
+`--impl reference` times the reference's CPU implementation of the path (the oracle port: torch CPU fp32,
+nn.Embedding-style dense gradient + dense SGD) on the host cores.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CRITEO = [1460, 583, 10131227, 2202608, 305, 24, 12517, 633, 3, 93145, 5683, 8351593, 3194, 27, 14992, 5461306, 10, 5652,
+          2173, 4, 7046547, 18, 15, 286181, 105, 142572]
+F, D, BATCH = 26, 16, 65536
+LR = 0.05
+# algorithmic bytes per sample (fp32 rows, int64 ids, no duplicate reuse)
+BYTES = {
+    "fm_fwd": 26 * 64 + 208 + 4, "fm_bwd_upd": 1664 + 2 * 1664 + 208,
+    "ffm_fwd": 26 * 26 * 64 + 208, "ffm_bwd_upd": 43264 + 2 * 43264,
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+def make_ids(cards, B, seed, dist, device):
+    g = torch.Generator(device=device).manual_seed(seed)
+    cols = []
+    for c in cards:
+        if dist == "zipf":  # inverse-CDF of a continuous power law with exponent 1.05, truncated to [1, c]
+            u = torch.rand(B, generator=g, device=device, dtype=torch.float64)
+            a = 1.05
+            x = ((c ** (1 - a) - 1) * u + 1) ** (1 / (1 - a))
+            cols.append((x.floor().long() - 1).clamp_(0, c - 1))
+        else:
+            cols.append(torch.randint(0, c, (B,), generator=g, device=device))
+    ids = torch.stack(cols, dim=1).contiguous()
+    y = (torch.rand(B, 1, generator=g, device=device) < 0.3).float()
+    return ids, y
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML every few ms on a background thread while the timed
+    region runs (the same counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index, period_s=0.004):
+        import threading
+        self.sm, self.mask, self.max_mhz, self.ok = [], 0, None, False
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            return
+        self.period = period_s
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        if not self.ok:
+            return out
+        self._stop.set()
+        self.t.join(timeout=2)
+        if self.sm:
+            v = sorted(self.sm)
+            out.update(sm_mhz=v[len(v) // 2], samples=len(v), reasons=sorted(n for bit, n in self.REASONS.items() if self.mask & bit))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_step_factory(B, cap, threads):
+    """Oracle port of the C2 step on a bounded sample: B samples, cardinalities capped at `cap` rows per field."""
+    from oracle import nfield as onf
+    torch.set_num_threads(threads)
+    cards = [min(c, cap) for c in CRITEO]
+    offsets = torch.tensor([sum(cards[:i]) for i in range(F)])
+    g = torch.Generator().manual_seed(0)
+    total = sum(cards)
+    fm_t = torch.randn(total, D, generator=g) * 0.01
+    ffm_t = torch.randn(total, F * D, generator=g) * 0.01
+    fm_b, ffm_b = torch.zeros(1), torch.zeros(1)
+    ids = torch.stack([torch.randint(0, c, (B,), generator=g) for c in cards], dim=1)
+    y = (torch.rand(B, generator=g) < 0.3).float()
+
+    def step():
+        onf.train_step("fm", fm_t, fm_b, ids, offsets, y, LR)
+        _, loss = onf.train_step("ffm", ffm_t, ffm_b, ids, offsets, y, LR, fast=True)
+        return float(loss)
+
+    return step, f"B={B} of {BATCH}, cardinalities capped at {cap} rows/field ({total} rows), dense-gradient SGD as nn.Embedding+optim.SGD"
+
+
+def time_cpu(steps, warmup, B=4096, cap=20000):
+    threads = os.cpu_count() or 1
+    step, sample = cpu_step_factory(B, cap, threads)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return B / dt, dt * 1e3, threads, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    val, ms, threads, sample = time_cpu(max(1, args.steps), max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": "train samples/sec (fwd+bwd+update)", "value": val, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2: FM second-order + FFM, 26 Criteo-shaped fields, D=16, SGD (CPU oracle port on a bounded sample)",
+                   "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch.distributed as dist
+    from deeplearningrecommendationsystem_b200 import ops
+    from deeplearningrecommendationsystem_b200.nfield import FieldFFM, FieldFM
+    from deeplearningrecommendationsystem_b200.optim import FusedRowOptimizer
+    from deeplearningrecommendationsystem_b200.trainer import Trainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cards = [min(c, 1 << 17) for c in CRITEO] if args.light else CRITEO
+    B = args.batch
+
+    fm = FieldFM(cards, D, fused=True, seed=1, device=dev)
+    ffm = FieldFFM(cards, D, fused=True, seed=2, device=dev)
+    loss_fn = torch.nn.BCELoss()
+    trainers = []
+    for m in (fm, ffm):
+        opt = FusedRowOptimizer(m, torch.optim.SGD([m.bias], lr=LR), lr=LR, kind="sgd")
+        trainers.append(Trainer(m, loss_fn, opt))
+
+    # a pool of distinct batches so no step re-reads the previous step's rows from L2
+    pool = [make_ids(cards, B, 1234 + rank * 100 + k, args.dist, dev) for k in range(4)]
+    host_pool = [(i.cpu().pin_memory(), y.cpu().pin_memory()) for i, y in pool]
+
+    def step(ids, y):
+        for tr in trainers:
+            tr.train_loop(ids, train_rating=y)
+        return trainers[1].train_loss
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(args.warmup):
+        step(*pool[k % len(pool)])
+    ops.check_status(dev)
+
+    # ---- timed: device-resident inputs
+    ops.PROFILE = []
+    clocks = ClockSampler(local)
+    sync()
+    launches0 = ops.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        step(*pool[k % len(pool)])
+    e1.record()
+    sync()
+    ms_total = e0.elapsed_time(e1)
+    gpu_launches = ops.launches() - launches0
+    prof, ops.PROFILE = ops.PROFILE, None
+
+    # ---- timed: end to end from pinned host memory, loss read back every step
+    sync()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for k in range(args.steps):
+        hi, hy = host_pool[k % len(host_pool)]
+        ids = hi.to(dev, non_blocking=True)
+        y = hy.to(dev, non_blocking=True)
+        loss_val = step(ids, y).item()
+    t1.record()
+    sync()
+    ms_e2e = t0.elapsed_time(t1)
+    clk = clocks.stop()
+
+    times = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = times.tolist()
+    value = world * B * args.steps / (ms_total / 1e3)
+    e2e = world * B * args.steps / (ms_e2e / 1e3)
+
+    if rank == 0:
+        # per-kernel durations recorded around the C-ABI calls (CUDA events on the launching stream)
+        agg = {}
+        for name, a, b in prof:
+            agg.setdefault(name, []).append(a.elapsed_time(b))
+        kern = {k: sum(v) / len(v) for k, v in agg.items()}
+        peak, which = peaks()
+        dom = "segment_update[w416]"
+        roof = None
+        if dom in kern:
+            achieved = BYTES["ffm_bwd_upd"] * B / (kern[dom] / 1e3) / 1e9
+            roof = {"bound": "hbm", "kernel": "seg_chunk_kernel<FFM row 416 floats, SGD> (rs_segment_update)", "achieved": achieved,
+                    "peak": peak, "peak_source": which, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "algorithmic_bytes_per_launch": BYTES["ffm_bwd_upd"] * B, "ms_per_launch": kern[dom]}
+        extra = {}
+        for name, key in (("ffm_fwd", "ffm_fwd"), ("fields_fwd", "fm_fwd"), ("segment_update[w16]", "fm_bwd_upd")):
+            if name in kern:
+                extra[name] = {"ms": kern[name], "algorithmic_GBps": BYTES[key] * B / (kern[name] / 1e3) / 1e9}
+        if "dedup_sort" in kern:
+            extra["dedup_sort"] = {"ms": kern["dedup_sort"]}
+        line = {
+            "metric": "train samples/sec (fwd+bwd+update)", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C2: FM second-order + FFM train step, 26 Criteo-shaped sparse fields, D=16, SGD",
+                       "batch_per_gpu": B, "fields": F, "dim": D, "rows": sum(cards), "ids": args.dist, "light": bool(args.light),
+                       "l2": "4 distinct id batches cycled; per-step traffic (>8 GB) far exceeds the 126 MB L2",
+                       "parallelism": f"dp{world}"},
+            "roofline": roof, "kernels": extra,
+            "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": B * F * 8 + B * 4, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps, "last_loss": loss_val},
+            "gpu_launches": gpu_launches, "clocks": clk,
+        }
+        if world == 1 and not args.no_cpu:
+            val, ms, threads, sample = time_cpu(2, 1)
+            line["cpu_baseline"] = {"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--dist", default="uniform", choices=["uniform", "zipf"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--light", action="store_true", help="cap every cardinality at 2^17 rows (fits any GPU)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -124,7 +124,9 @@ __global__ void __launch_bounds__(256) sigmoid_bce_kernel(const float *__restric
     float l1p = fmaxf(logf(1.0f - p), -100.f);
     acc -= t * lp + (1.0f - t) * l1p;
     if (pred) pred[b] = p;
-    if (g_logit) g_logit[b] = (p - t) * invB;
+    // autograd's exact sequence (binary_cross_entropy_backward then sigmoid_backward), so that saturated
+    // probabilities (p == 0 or 1 in fp32) give the same gradient as the reference, not the analytic (p-t)/B
+    if (g_logit) g_logit[b] = (invB * (p - t) / fmaxf((1.0f - p) * p, 1e-12f)) * ((1.0f - p) * p);
   }
   acc = rs::warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;

@@ -11,7 +11,7 @@
 
 namespace {
 
-constexpr int NCW = 4;                 // consumer warps
+constexpr int NCW = 8;                 // consumer warps
 constexpr int NTHREADS = (NCW + 1) * 32;
 constexpr int MAX_STAGES = 8;
 
@@ -80,12 +80,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) ffm_fwd_kernel(const __grid_const
       float acc = 0.f;
       for (int i = cw; i < P.F; i += NCW) {
         const float4 *Ti = T + (size_t)i * P.pitchv;
-        for (int w = lane; w < P.rowv; w += 32) {
-          const int j = w >> P.dvs, d4 = w & (P.dv - 1);
-          float4 tr = T[(size_t)j * P.pitchv + i * P.dv + d4];  // v_{j,i}
-          if (j == i) tr = rs::f4_zero();
-          if (j > i) acc += rs::f4_dot(Ti[w], tr);
-          if (st_out) rs::stg_cs_f4(reinterpret_cast<float *>(st_out + (size_t)i * P.rowv + w), tr);
+        const float4 *Tcol = T + i * P.dv;  // + j*pitchv + d4 -> v_{j,i}
+        float4 *out_i = st_out ? st_out + (size_t)i * P.rowv : nullptr;
+        for (int w0 = lane; w0 < P.rowv; w0 += 128) {
+          float4 tr[4], own[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {  // four independent shared-memory reads per lane before any use
+            const int w = w0 + 32 * u;
+            const int j = w >> P.dvs, d4 = w & (P.dv - 1);
+            const bool live = w < P.rowv;
+            tr[u] = (live && j != i) ? Tcol[(size_t)j * P.pitchv + d4] : rs::f4_zero();
+            own[u] = (live && j > i) ? Ti[w] : rs::f4_zero();
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int w = w0 + 32 * u;
+            acc += rs::f4_dot(own[u], tr[u]);
+            if (out_i && w < P.rowv) rs::stg_cs_f4(reinterpret_cast<float *>(out_i + w), tr[u]);
+          }
         }
       }
       acc = rs::warp_sum(acc);
@@ -193,8 +205,8 @@ RS_API int rs_ffm_fwd(const rs_tables *T, const int64_t *ids, int64_t B, int32_t
   if (P.dv < 8) pad = (((P.dv * 16 - row_bytes) % 128) + 128) % 128;  // rows of consecutive j land 16*dv bytes apart mod 128
   P.pitchv = (row_bytes + pad) / 16;
   const size_t stage_bytes = (size_t)F * P.pitchv * 16;
-  int nst = (int)((200 * 1024) / stage_bytes);
-  RS_CHECK_ARG(nst >= 2, RS_E_UNSUPPORTED, "rs_ffm_fwd: F*F*D tile (%zu B) too large for a 2-stage ring", stage_bytes);
+  int nst = (int)((220 * 1024) / stage_bytes);  // 227 KB per CTA minus the static barriers/pointer tables
+  RS_CHECK_ARG(nst >= 1, RS_E_UNSUPPORTED, "rs_ffm_fwd: F*F*D tile (%zu B) does not fit in shared memory", stage_bytes);
   if (nst > MAX_STAGES) nst = MAX_STAGES;
   P.nst = nst;
   P.status = status;

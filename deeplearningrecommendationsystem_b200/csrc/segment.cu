@@ -282,7 +282,7 @@ __device__ __forceinline__ void apply_row(const UpdParams &P, int64_t row, int e
 // sorted (= ascending position) order; loads for UNR lookups are issued before their adds so the dependent FADD
 // chain does not serialise the memory latency.
 template <int VEC, int GS, int NA, int MODE>
-__global__ void __launch_bounds__(256) seg_chunk_kernel(const __grid_constant__ UpdParams P, int64_t n) {
+__global__ void __launch_bounds__(256, (NA <= 4) ? 4 : 1) seg_chunk_kernel(const __grid_constant__ UpdParams P, int64_t n) {
   using V = Vec<VEC>;
   constexpr int GPB = 256 / GS;
   const int lane = threadIdx.x % GS;
@@ -291,6 +291,9 @@ __global__ void __launch_bounds__(256) seg_chunk_kernel(const __grid_constant__ 
   for (int64_t c = (int64_t)blockIdx.x * GPB + threadIdx.x / GS; c < nchunks; c += (int64_t)gridDim.x * GPB) {
     const int s0 = P.chunk_start[c], s1 = P.chunk_start[c + 1];
     const int g = P.chunk_seg[c];
+    // everything that depends only on g is requested now, so it is in flight together with the gradient rows
+    const bool single = (P.seg_first_chunk[g + 1] - P.seg_first_chunk[g]) == 1;
+    const int64_t row = P.uniq[g];
     typename V::T acc[NA];
 #pragma unroll
     for (int a = 0; a < NA; ++a) acc[a] = V::zero();
@@ -326,9 +329,7 @@ __global__ void __launch_bounds__(256) seg_chunk_kernel(const __grid_constant__ 
 #pragma unroll
         for (int a = 0; a < NA; ++a) acc[a] = V::add(acc[a], val[u][a]);
     }
-    const bool single = (P.seg_first_chunk[g + 1] - P.seg_first_chunk[g]) == 1;
     if (single) {
-      const int64_t row = P.uniq[g];
 #pragma unroll
       for (int a = 0; a < NA; ++a) {
         const int e = lane + a * GS;

@@ -1,0 +1,192 @@
+"""autograd building blocks shared by the drop-in modules.
+
+Every Function's forward and backward is one or two calls into the C ABI (ops.*); torch.autograd only carries
+the tensors between them.  Embedding-table gradients are produced by the deterministic sort / segment-reduce
+(rs_dedup_sort + rs_segment_update in RS_UPD_GRAD mode) as ordinary dense ``.grad`` tensors, so the reference's
+``optim.Adam(model.parameters(), lr, weight_decay=1e-5)`` (scripts/deepfm.py:55) runs unchanged on top.
+"""
+import torch
+
+from .. import ops
+
+# x (B,45) column layout, data/reader.py:98-101: [uid, iid, age, gender(2), occupation(21), genre(19)]
+COL_USER, COL_ITEM = 0, 1
+AGE, GENDER, OCC, GENRE = (2, 1), (3, 2), (5, 21), (26, 19)
+KIND_ID, KIND_BAG, KIND_SCALAR = 0, 1, 2
+
+
+def table_grads(ids, dE, rows):
+    """Dense gradients of F tables from per-lookup row gradients.
+
+    ids (N, F) int64, dE (N, F, W) fp32, rows[f] = number of rows of table f.  One stable sort over all F fields
+    (keys = row offset of the field + id), one fixed-order segment-reduce; the F gradients are views of one buffer.
+    """
+    F, W = len(rows), dE.shape[-1]
+    offs, total = [], 0
+    for r in rows:
+        offs.append(total)
+        total += r
+    ids = ids.reshape(-1, F)
+    segs = ops.dedup_sort(ids, F, offs, total, max_width=W)
+    buf = torch.zeros(total, W, dtype=torch.float32, device=dE.device)
+    ops.segment_update(segs, ops.RS_UPD_GRAD, W, F, dense=dE.reshape(-1, W), dense_grad=buf)
+    return [buf[o:o + r] for o, r in zip(offs, rows)]
+
+
+class EmbeddingLookup(torch.autograd.Function):
+    """weight[ids] for one table -- nn.Embedding.forward / embedding_dense_backward
+    (reference model/mf.py:24-25, model/din.py:35-36; backward implicit at trainer/trainer.py:38)."""
+
+    @staticmethod
+    def forward(ctx, weight, ids):
+        ctx.save_for_backward(ids)
+        ctx.rows = weight.shape[0]
+        out = ops.gather_rows(ops.make_tables([weight.detach()]), ids.reshape(-1, 1))
+        return out.view(*ids.shape, weight.shape[1])
+
+    @staticmethod
+    def backward(ctx, g):
+        (ids,) = ctx.saved_tensors
+        (gw,) = table_grads(ids.reshape(-1, 1), g.contiguous().view(-1, 1, g.shape[-1]), [ctx.rows])
+        return gw, None
+
+
+def lookup(weight, ids):
+    return EmbeddingLookup.apply(weight, ids)
+
+
+class XEmbed(torch.autograd.Function):
+    """Feature-vector front end: x (B,45) -> E (B, slots, D)  (reference model/deepfm.py:45-51 and siblings).
+
+    slots: tuple of (col, ncols, kind); tables: one tensor per non-scalar slot, in slot order.
+    Backward: id slots -> table_grads (sort/segment-reduce); bag slots -> rs_xembed_bag_bwd (two-pass fixed order).
+    """
+
+    @staticmethod
+    def forward(ctx, x, slots, *tables):
+        it = iter(tables)
+        full = [(c, n, k, None if k == KIND_SCALAR else next(it).detach()) for c, n, k in slots]
+        S = ops.make_xslots(full, tables[0].shape[1], x.shape[1])
+        E = ops.xembed_fwd(S, x)
+        ctx.slots = slots
+        ctx.save_for_backward(x, *tables)
+        return E
+
+    @staticmethod
+    def backward(ctx, dE):
+        x, *tables = ctx.saved_tensors
+        slots = ctx.slots
+        dE = dE.contiguous()
+        it = iter(tables)
+        full = [(c, n, k, None if k == KIND_SCALAR else next(it).detach()) for c, n, k in slots]
+        S = ops.make_xslots(full, tables[0].shape[1], x.shape[1])
+        bag = ops.xembed_bag_bwd(S, x, dE, full) if any(k == KIND_BAG for _, _, k in slots) else [None] * len(slots)
+        id_slots = [t for t, (_, _, k) in enumerate(slots) if k == KIND_ID]
+        id_grads = {}
+        if id_slots:
+            ids = torch.stack([ops.xcol_to_ids(x, slots[t][0]) for t in id_slots], dim=1)
+            g = dE[:, id_slots, :].contiguous() if len(id_slots) != len(slots) else dE
+            for t, gw in zip(id_slots, table_grads(ids, g, [full[t][3].shape[0] for t in id_slots])):
+                id_grads[t] = gw
+        grads = []
+        for t, (_, _, k) in enumerate(slots):
+            if k == KIND_ID:
+                grads.append(id_grads[t])
+            elif k == KIND_BAG:
+                grads.append(bag[t])
+        return (None, None, *grads)
+
+
+def six_slots():
+    """[user, item, age, gender, occupation, movie] as the reference orders them (model/deepfm.py:54)."""
+    return ((COL_USER, 1, KIND_ID), (COL_ITEM, 1, KIND_ID), (AGE[0], AGE[1], KIND_BAG), (GENDER[0], GENDER[1], KIND_BAG),
+            (OCC[0], OCC[1], KIND_BAG), (GENRE[0], GENRE[1], KIND_BAG))
+
+
+class _Interact(torch.autograd.Function):
+    """Interaction over dense field embeddings E (B, F, D); `what` picks the output (rs_fields_fwd / rs_fields_bwd)."""
+
+    @staticmethod
+    def forward(ctx, E, what):
+        E = E.contiguous()
+        B, F, D = E.shape
+        ctx.what = what
+        ctx.save_for_backward(E)
+        return ops.fields_fwd(ops.dummy_tables(F, D), B, E.device, dense_in=E, **{what: True})[what]
+
+    @staticmethod
+    def backward(ctx, g):
+        (E,) = ctx.saved_tensors
+        B, F, D = E.shape
+        return ops.fields_bwd(ops.dummy_tables(F, D), B, E.device, dense_in=E, **{"g_" + ctx.what: g.contiguous()}), None
+
+
+def fm_cross(E):
+    """0.5*sum_d[(sum_f e)^2 - sum_f e^2] -> (B,)             model/deepfm.py:71-76"""
+    return _Interact.apply(E, "cross")
+
+
+def bi_interaction(E):
+    """sum_{i<j} e_i*e_j -> (B, D)                             model/nfm.py:58-62"""
+    return _Interact.apply(E, "bi")
+
+
+def inner_products(E):
+    """[<e_i,e_j>]_{i<j} -> (B, F(F-1)/2)                      model/pnn.py:61-66"""
+    return _Interact.apply(E, "pairs")
+
+
+class PairLookup(torch.autograd.Function):
+    """Two id columns into two tables in one fused pass: MF dot (model/mf.py:24-26), GMF Hadamard
+    (model/neuralcf.py:37-39) or the MLP-tower concat (model/neuralcf.py:43-46)."""
+
+    @staticmethod
+    def forward(ctx, wu, wi, u, i, what):
+        ids = torch.stack([u, i], dim=1).contiguous()
+        T = ops.make_tables([wu.detach(), wi.detach()])
+        ctx.what, ctx.rows = what, (wu.shape[0], wi.shape[0])
+        ctx.save_for_backward(ids, wu, wi)
+        return ops.fields_fwd(T, ids.shape[0], ids.device, ids=ids, **{what: True})[what]
+
+    @staticmethod
+    def backward(ctx, g):
+        ids, wu, wi = ctx.saved_tensors
+        T = ops.make_tables([wu.detach(), wi.detach()])
+        dE = ops.fields_bwd(T, ids.shape[0], ids.device, ids=ids, **{"g_" + ctx.what: g.contiguous()})
+        gu, gi = table_grads(ids, dE, list(ctx.rows))
+        return gu, gi, None, None, None
+
+
+class FFMDense(torch.autograd.Function):
+    """sum_{i<j} <T[i, field(j)], T[j, field(i)]> over dense T (B, F, NF, D)     model/ffm.py:61-82"""
+
+    @staticmethod
+    def forward(ctx, T, field_of):
+        T = T.contiguous()
+        ctx.field_of = field_of
+        ctx.save_for_backward(T)
+        return ops.ffm_dense_fwd(T, field_of)
+
+    @staticmethod
+    def backward(ctx, g):
+        (T,) = ctx.saved_tensors
+        return ops.ffm_dense_bwd(T, g.contiguous(), ctx.field_of), None
+
+
+def first_order(module_user, module_item, linear, x):
+    """user(1)[uid] + item(1)[iid] + Linear(43,1)(x[:,2:])     model/lr.py:24-25 and the wide terms of the others."""
+    uid, iid = ops.xcol_to_ids(x, COL_USER), ops.xcol_to_ids(x, COL_ITEM)
+    return lookup(module_user.weight, uid) + lookup(module_item.weight, iid) + linear(x[:, 2:])
+
+
+def topk_per_user(model, num_users, user_item, k):
+    """recommendation(): per-user forward over that user's rows + top-k (reference model/deepfm.py:85-95)."""
+    import numpy as np
+    device = next(model.parameters()).device
+    out = []
+    with torch.no_grad():
+        for u in range(num_users):
+            rows = torch.tensor(user_item[user_item["user_id"] == u].values, dtype=torch.float32, device=device)
+            scores = model(rows)
+            out.append(torch.topk(scores, k, dim=0).indices.view(-1).tolist())
+    return np.array(out)

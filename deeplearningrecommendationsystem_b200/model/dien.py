@@ -1,0 +1,51 @@
+"""DIEN as the reference defines it (model/dien.py:8-81): a DIN-style attention with a smaller unit (3D->64->32->1)
+that SCALES the history instead of pooling it, an nn.GRU(D, D) over the scaled sequence (h0 = 0), and
+fc 2D->128->64->1->Sigmoid on [h_L, target].  This is a plain GRU on attention-scaled inputs, not the paper's AUGRU.
+state_dict keys: din.item_embedding.weight, din.attention.{0,2,4}.*, interest_evolution.*_l0, fc.{0,2,4}.*"""
+import numpy as np
+import torch
+from torch import nn
+from torch.nn.init import xavier_normal_
+
+from . import _blocks as K
+from .. import attention
+
+
+class DIN(nn.Module):
+    """Attention front half of DIEN: returns (history * attention weight (B, L, D), target embedding (B, D))."""
+
+    def __init__(self, num_items, embed_size):
+        super().__init__()
+        self.item_embedding = nn.Embedding(num_items, embed_size)
+        self.attention = nn.Sequential(nn.Linear(embed_size * 3, 64), nn.ReLU(), nn.Linear(64, 32), nn.ReLU(), nn.Linear(32, 1))
+        xavier_normal_(self.item_embedding.weight.data)
+
+    def forward(self, hist, target_item):
+        rows = K.lookup(self.item_embedding.weight, torch.cat([hist, target_item.unsqueeze(1)], dim=1))
+        hist_embed, target_embed = rows[:, :-1], rows[:, -1]
+        return attention.din_attention(hist_embed, target_embed, self.attention, pool=False), target_embed
+
+
+class DIEN(nn.Module):
+    def __init__(self, num_items, embed_size):
+        super().__init__()
+        self.din = DIN(num_items, embed_size)
+        self.interest_evolution = nn.GRU(embed_size, embed_size, batch_first=True)
+        self.fc = nn.Sequential(nn.Linear(embed_size * 2, 128), nn.ReLU(), nn.Linear(128, 64), nn.ReLU(), nn.Linear(64, 1),
+                                nn.Sigmoid())
+
+    def forward(self, hist, target_item):
+        att_hist, target_embed = self.din(hist, target_item)
+        final_interest = attention.gru_last_hidden(att_hist, self.interest_evolution)                  # (B, D)
+        return self.fc(torch.cat([final_interest, target_embed], dim=-1))
+
+    def recommendation(self, num_users, num_items, hist_list, k):
+        device = next(self.parameters()).device
+        out = []
+        with torch.no_grad():
+            target = torch.arange(0, num_items, device=device)
+            for u in range(num_users):
+                hist = torch.tensor(hist_list[u]).repeat(num_items, 1).to(device)
+                scores = self.forward(hist, target)
+                out.append(torch.topk(scores, k, dim=0).indices.view(1, -1).tolist()[0])
+        return np.array(out)

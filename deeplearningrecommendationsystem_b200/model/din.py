@@ -1,0 +1,39 @@
+"""Deep Interest Network -- drop-in for reference model/din.py:9-66.
+
+One item table, looked up for the target and for the L history slots in ONE gather (so the backward needs one sort
+/ segment-reduce); attention unit MLP 3D->128->64->1 over [h, h-t, t]; softmax over L with no padding mask and no
+scaling (padded slots hold the real item id 0, scripts/din.py:31); weighted sum; fc 2D->256->128->1->Sigmoid."""
+import numpy as np
+import torch
+from torch import nn
+from torch.nn.init import xavier_normal_
+
+from . import _blocks as K
+from .. import attention
+
+
+class DIN(nn.Module):
+    def __init__(self, num_items, embed_size):
+        super().__init__()
+        self.item_embedding = nn.Embedding(num_items, embed_size)
+        self.attention = nn.Sequential(nn.Linear(embed_size * 3, 128), nn.ReLU(), nn.Linear(128, 64), nn.ReLU(), nn.Linear(64, 1))
+        self.fc = nn.Sequential(nn.Linear(embed_size * 2, 256), nn.ReLU(), nn.Linear(256, 128), nn.ReLU(), nn.Linear(128, 1),
+                                nn.Sigmoid())
+        xavier_normal_(self.item_embedding.weight.data)
+
+    def forward(self, hist, target_item):
+        rows = K.lookup(self.item_embedding.weight, torch.cat([hist, target_item.unsqueeze(1)], dim=1))   # (B, L+1, D)
+        hist_embed, target_embed = rows[:, :-1], rows[:, -1]
+        pooled = attention.din_attention(hist_embed, target_embed, self.attention, pool=True)           # (B, D)
+        return self.fc(torch.cat([pooled, target_embed], dim=1))
+
+    def recommendation(self, num_users, num_items, hist_list, k):
+        device = next(self.parameters()).device
+        out = []
+        with torch.no_grad():
+            target = torch.arange(0, num_items, device=device)
+            for u in range(num_users):
+                hist = torch.tensor(hist_list[u]).repeat(num_items, 1).to(device)
+                scores = self.forward(hist, target)
+                out.append(torch.topk(scores, k, dim=0).indices.view(1, -1).tolist()[0])
+        return np.array(out)

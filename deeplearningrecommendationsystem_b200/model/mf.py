@@ -1,0 +1,24 @@
+"""Matrix factorisation sigmoid(<U[u], V[i]>) -- drop-in for reference model/mf.py:11-35 (note the 1-D output)."""
+import torch
+from torch import nn
+from torch.nn.init import xavier_normal_
+
+from . import _blocks as K
+
+
+class MatrixFactorization(nn.Module):
+    def __init__(self, num_users: int, num_items: int, embedding_size: int):
+        super().__init__()
+        self.user_embeddings = nn.Embedding(num_users, embedding_size)
+        self.item_embeddings = nn.Embedding(num_items, embedding_size)
+        xavier_normal_(self.user_embeddings.weight.data)
+        xavier_normal_(self.item_embeddings.weight.data)
+
+    def forward(self, user_indices: torch.Tensor, item_indices: torch.Tensor) -> torch.Tensor:
+        dot = K.PairLookup.apply(self.user_embeddings.weight, self.item_embeddings.weight, user_indices, item_indices, "dot2")
+        return torch.sigmoid(dot)                                   # (B,)
+
+    def recommendation(self, num_users, num_items):
+        with torch.no_grad():
+            scores = self.user_embeddings.weight[:num_users] @ self.item_embeddings.weight[:num_items].T
+            return torch.topk(scores, num_items, dim=1).indices.cpu().numpy()

@@ -9,6 +9,23 @@ from ._lib import RS_MAX_FIELDS, RS_UPD_ADAM, RS_UPD_GRAD, RS_UPD_SGD  # noqa: F
 
 _status = {}
 _launches = 0
+PROFILE = None   # bench.py sets this to a list; ops then bracket their C-ABI call with CUDA events on the launching stream
+
+
+class _timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            PROFILE.append((self.name, self.a, b))
 
 
 def launches():
@@ -146,7 +163,8 @@ def fields_fwd(T, B, device, ids=None, dense_in=None, cross=False, bi=False, pai
         alloc("dot2", B)
     if had2:
         alloc("had2", B, D)
-    _lib.check(_lib.load().rs_fields_fwd(C.byref(T), C.byref(io), B, status_word(device).data_ptr(), _stream()), "rs_fields_fwd")
+    with _timed("fields_fwd"):
+        _lib.check(_lib.load().rs_fields_fwd(C.byref(T), C.byref(io), B, status_word(device).data_ptr(), _stream()), "rs_fields_fwd")
     _count()
     del keep
     return out
@@ -183,8 +201,9 @@ def ffm_fwd(T, ids, D, want_stash=True):
     B = ids.numel() // F
     cross = torch.empty(B, dtype=torch.float32, device=ids.device)
     stash = torch.empty(B, F, F * D, dtype=torch.float32, device=ids.device) if want_stash else None
-    _lib.check(_lib.load().rs_ffm_fwd(C.byref(T), ids.data_ptr(), B, D, cross.data_ptr(), _p(stash),
-                                      status_word(ids.device).data_ptr(), _stream()), "rs_ffm_fwd")
+    with _timed("ffm_fwd"):
+        _lib.check(_lib.load().rs_ffm_fwd(C.byref(T), ids.data_ptr(), B, D, cross.data_ptr(), _p(stash),
+                                          status_word(ids.device).data_ptr(), _stream()), "rs_ffm_fwd")
     _count()
     return cross, stash
 
@@ -263,8 +282,9 @@ def dedup_sort(ids, F=1, row_offset=None, total_rows=None, max_width=1, reuse_wo
     offs = None
     if row_offset is not None:
         offs = (C.c_int64 * F)(*[int(o) for o in row_offset])
-    _lib.check(lib.rs_dedup_sort(ids.data_ptr(), n, F, offs, int(total_rows), ws.data_ptr(), nbytes.value, C.byref(seg),
-                                 status_word(ids.device).data_ptr(), _stream()), "rs_dedup_sort")
+    with _timed("dedup_sort"):
+        _lib.check(lib.rs_dedup_sort(ids.data_ptr(), n, F, offs, int(total_rows), ws.data_ptr(), nbytes.value, C.byref(seg),
+                                     status_word(ids.device).data_ptr(), _stream()), "rs_dedup_sort")
     _count(8)
     return Segments(ws, seg, n, ids.device)
 
@@ -283,7 +303,8 @@ def segment_update(segs, mode, width, F, stash=None, scale=None, dense=None, tab
             raise ValueError(f"{name} must be contiguous float32")
         setattr(u, name, _p(t))
     u.lr, u.wd, u.beta1, u.beta2, u.eps, u.step = lr, wd, betas[0], betas[1], eps, step
-    _lib.check(_lib.load().rs_segment_update(C.byref(segs.seg), segs.n, C.byref(u), _stream()), "rs_segment_update")
+    with _timed(f"segment_update[w{width}]"):
+        _lib.check(_lib.load().rs_segment_update(C.byref(segs.seg), segs.n, C.byref(u), _stream()), "rs_segment_update")
     _count(2)
 
 

@@ -173,7 +173,8 @@ int rs_xcol_to_ids(const float *x, int64_t B, int32_t xcols, int32_t col, int64_
 
 /* ---- sigmoid + BCELoss(mean) forward/backward in one pass (model/*: torch.sigmoid; scripts/deepfm.py:54).
  * pred = sigmoid(logit); loss_sum += sum(-[y*max(log p,-100)+(1-y)*max(log(1-p),-100)]);
- * g_logit = (pred - y) / B.  loss_sum is a device scalar accumulated with a fixed-order two-pass reduce. */
+ * g_logit follows autograd's op sequence ((p-y)/max(p(1-p),1e-12)/B * p(1-p)), i.e. (p-y)/B except where p
+ * saturates.  loss_mean is a device scalar produced by a fixed-order two-pass reduce. */
 int rs_sigmoid_bce(const float *logit, const float *y, int64_t B, float *pred, float *g_logit, float *loss_mean,
                    float *ws /* >= 1024 floats */, void *stream);
 

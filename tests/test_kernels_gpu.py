@@ -91,14 +91,17 @@ def test_segment_grad_and_sgd(W, hot):
     dense = torch.zeros(rows, W).cuda()
     ops.segment_update(segs, ops.RS_UPD_GRAD, W, 1, dense=G.cuda(), dense_grad=dense)
     want = torch.zeros(rows, W).index_add_(0, ids, G)
-    close(dense, want, rtol=1e-5, atol=2e-5 if hot else 1e-6)
+    # a re-associated fp32 sum of n terms differs from the sequential one by a few ulp of the L1 mass of the
+    # terms, so the absolute floor scales with sum|G| (3 eps); elsewhere the bar is 1e-5 relative
+    atol = max(1e-6, 2e-7 * float(torch.zeros(rows, W).index_add_(0, ids, G.abs()).max()))
+    close(dense, want, rtol=1e-5, atol=atol)
     # determinism: bitwise identical on a second run
     dense2 = torch.zeros(rows, W).cuda()
     ops.segment_update(segs, ops.RS_UPD_GRAD, W, 1, dense=G.cuda(), dense_grad=dense2)
     assert torch.equal(dense, dense2)
     tc = table.clone().cuda()
     ops.segment_update(segs, ops.RS_UPD_SGD, W, 1, dense=G.cuda(), table=tc, lr=0.05)
-    close(tc, ooptim.sgd_rows(table.clone(), ids, G, 0.05), rtol=1e-5, atol=2e-5 if hot else 1e-6)
+    close(tc, ooptim.sgd_rows(table.clone(), ids, G, 0.05), rtol=1e-5, atol=atol)
 
 
 def test_segment_short_segments_bit_exact_vs_sequential():

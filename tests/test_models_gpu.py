@@ -1,0 +1,163 @@
+"""Drop-in modules on the B200 against (a) the golden vectors recorded from the unmodified reference and (b) the
+CPU oracle on fresh seeded inputs.  Bar: 1e-5 relative (fp32) on predictions, loss, every gradient and the
+parameters after two Trainer.train_loop steps with the scripts' Adam(lr=1e-3, weight_decay=1e-5)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from helpers import feature_matrix
+from oracle import ml100k
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def build(name):
+    from deeplearningrecommendationsystem_b200 import model as M
+    return {
+        "lr": lambda: M.LogisticRegression(50, 60, 43),
+        "mf": lambda: M.MatrixFactorization(50, 60, 16),
+        "deepfm": lambda: M.DeepFM(50, 60, [32, 16, 8, 1], 16),
+        "nfm": lambda: M.NFM(50, 60, [32, 16, 8, 1], 16),
+        "afm": lambda: M.AFM(50, 60, 16, 8),
+        "ffm": lambda: M.FFM(43, 8),
+        "pnn_in": lambda: M.PNN(8, [32, 16, 8, 4], "in"),
+        "pnn_out": lambda: M.PNN(16, [32, 16, 8, 4], "out"),
+        "din": lambda: M.DIN(60, 16),
+        "dien": lambda: M.DIEN(60, 16),
+        "neuralcf": lambda: M.NeuralCF(50, 60, 8, [32, 16, 8]),
+    }[name]()
+
+
+NAMES = ["lr", "mf", "deepfm", "nfm", "afm", "ffm", "pnn_in", "pnn_out", "din", "dien", "neuralcf"]
+
+
+def close(got, want, atol, msg=""):
+    np.testing.assert_allclose(got.detach().cpu().numpy(), np.asarray(want), rtol=RTOL, atol=atol, err_msg=msg)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_state_dict_is_reference_compatible(name):
+    _, _, sd0, _ = load_golden(name)
+    m = build(name)
+    own = m.state_dict()
+    assert list(own.keys()) == list(sd0.keys())
+    for k in sd0:
+        assert tuple(own[k].shape) == tuple(sd0[k].shape), k
+    m.load_state_dict(sd0, strict=True)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_forward_loss_grads_match_reference(name):
+    ins, y, sd0, z = load_golden(name)
+    m = build(name)
+    m.load_state_dict(sd0)
+    m = m.cuda()
+    pred = m(*[t.cuda() for t in ins])
+    assert tuple(pred.shape) == tuple(z["pred"].shape)
+    loss = torch.nn.BCELoss()(pred, y.cuda())
+    loss.backward()
+    close(pred, z["pred"], 1e-6)
+    np.testing.assert_allclose(loss.item(), z["loss"], rtol=RTOL)
+    for k, p in m.named_parameters():
+        assert p.grad is not None, k
+        close(p.grad, z[f"grad/{k}"], 1e-7, k)
+    from deeplearningrecommendationsystem_b200 import ops
+    ops.check_status()
+
+
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("optim_kind", ["torch", "fused_dense"])
+def test_two_trainer_steps_match_reference(name, optim_kind):
+    from deeplearningrecommendationsystem_b200.optim import DenseAdam
+    from deeplearningrecommendationsystem_b200.trainer import Trainer
+    ins, y, sd0, z = load_golden(name)
+    m = build(name)
+    m.load_state_dict(sd0)
+    m = m.cuda()
+    opt = (torch.optim.Adam if optim_kind == "torch" else DenseAdam)(m.parameters(), lr=1e-3, weight_decay=1e-5)
+    tr = Trainer(m, torch.nn.BCELoss(), opt)
+    cin, cy = [t.cuda() for t in ins], y.cuda()
+    losses = []
+    for _ in range(2):
+        tr.train_loop(*cin, train_rating=cy)
+        losses.append(tr.train_loss.item())
+    np.testing.assert_allclose(losses, z["losses"], rtol=RTOL)
+    for k, v in m.state_dict().items():
+        close(v, z[f"sd2/{k}"], 2e-6, k)
+    tr.valid_loop(*cin, valid_rating=cy)
+    np.testing.assert_allclose(tr.predictions_valid.cpu().numpy(), z["pred_after"], rtol=1e-4, atol=1e-6)
+
+
+def test_pnn_out_raises_when_batch_differs_from_dim():
+    ins, _, sd0, _ = load_golden("pnn_out")
+    m = build("pnn_out")
+    m.load_state_dict(sd0)
+    with pytest.raises(RuntimeError):
+        m.cuda()(ins[0][:7].cuda())
+
+
+@pytest.mark.parametrize("name", ["lr", "deepfm", "nfm", "afm", "ffm", "pnn_in"])
+def test_against_oracle_on_fresh_inputs(name):
+    """larger batch, more duplicates, different seed than the golden fixtures; also run twice for determinism."""
+    _, _, sd0, _ = load_golden(name)
+    g = torch.Generator().manual_seed(99)
+    nu, ni = (943, 1682) if name in ("ffm", "pnn_in") else (50, 60)
+    B = 1500
+    x = feature_matrix(g, B, nu, ni)
+    x[:, 0] = (torch.rand(B, generator=g) ** 3 * nu).floor()        # skewed users -> long duplicate segments
+    y = (torch.rand(B, 1, generator=g) < 0.4).float()
+    pred, loss, grads = ml100k.loss_and_grads(name, sd0, [x], y)
+    runs = []
+    for _ in range(2):
+        m = build(name)
+        m.load_state_dict(sd0)
+        m = m.cuda()
+        p = m(x.cuda())
+        l = torch.nn.BCELoss()(p, y.cuda())
+        l.backward()
+        runs.append({k: v.grad.clone() for k, v in m.named_parameters()})
+        close(p, pred.numpy(), 1e-6)
+        np.testing.assert_allclose(l.item(), loss.item(), rtol=RTOL)
+        for k, v in m.named_parameters():
+            close(v.grad, grads[k].numpy(), 2e-7, k)
+    for k in runs[0]:
+        if "embed" in k or k in ("user.weight", "item.weight") or k.endswith(("_user.weight", "_item.weight")):
+            assert torch.equal(runs[0][k], runs[1][k]), f"{k}: embedding gradient not bitwise reproducible"
+
+
+@pytest.mark.parametrize("name", ["mf", "neuralcf", "din", "dien"])
+def test_id_models_against_oracle_on_fresh_inputs(name):
+    _, _, sd0, _ = load_golden(name)
+    g = torch.Generator().manual_seed(17)
+    B = 1200
+    if name in ("mf", "neuralcf"):
+        ins = [(torch.rand(B, generator=g) ** 2 * 50).long(), torch.randint(0, 60, (B,), generator=g)]
+    else:
+        ins = [torch.randint(0, 60, (B, 23), generator=g), torch.randint(0, 60, (B,), generator=g)]
+    y = (torch.rand(B, generator=g) < 0.4).float()
+    y = y if name == "mf" else y.unsqueeze(1)
+    pred, loss, grads = ml100k.loss_and_grads(name, sd0, ins, y)
+    m = build(name)
+    m.load_state_dict(sd0)
+    m = m.cuda()
+    p = m(*[t.cuda() for t in ins])
+    l = torch.nn.BCELoss()(p, y.cuda())
+    l.backward()
+    close(p, pred.numpy(), 1e-6)
+    np.testing.assert_allclose(l.item(), loss.item(), rtol=RTOL)
+    for k, v in m.named_parameters():
+        close(v.grad, grads[k].numpy(), 2e-7, k)
+
+
+def test_eval_mode_and_no_grad():
+    ins, y, sd0, z = load_golden("deepfm")
+    m = build("deepfm")
+    m.load_state_dict(sd0)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        p = m(ins[0].cuda())
+    assert not p.requires_grad
+    close(p, z["pred"], 1e-6)
+    assert next(m.parameters()).device.type == "cuda"
