@@ -177,8 +177,10 @@ def run_gpu(args):
     cards = [min(c, 1 << 17) for c in CRITEO] if args.light else CRITEO
     B = args.batch
 
-    fm = FieldFM(cards, D, fused=True, seed=1, device=dev)
-    ffm = FieldFFM(cards, D, fused=True, seed=2, device=dev)
+    # N > 1: tables are row-sharded over the ranks (global row r on rank r % N); every step exchanges the
+    # deduplicated ids / rows / row-gradients with three all-to-alls (dist.RowExchange)
+    fm = FieldFM(cards, D, fused=True, seed=1, device=dev, sharded=world > 1)
+    ffm = FieldFFM(cards, D, fused=True, seed=2, device=dev, sharded=world > 1)
     loss_fn = torch.nn.BCELoss()
     trainers = []
     for m in (fm, ffm):
@@ -266,7 +268,7 @@ def run_gpu(args):
             "config": {"workload": "C2: FM second-order + FFM train step, 26 Criteo-shaped sparse fields, D=16, SGD",
                        "batch_per_gpu": B, "fields": F, "dim": D, "rows": sum(cards), "ids": args.dist, "light": bool(args.light),
                        "l2": "4 distinct id batches cycled; per-step traffic (>8 GB) far exceeds the 126 MB L2",
-                       "parallelism": f"dp{world}"},
+                       "parallelism": f"dp{world}" + ("" if world == 1 else ": batch split, tables row-sharded, dedup all-to-all of ids/rows/grads")},
             "roofline": roof, "kernels": extra,
             "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": B * F * 8 + B * 4, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps, "last_loss": loss_val},

@@ -85,10 +85,18 @@ __global__ void __launch_bounds__(256) chunk_scatter_kernel(const int32_t *__res
   }
 }
 
+// segments cut into more than one chunk need a second pass; list them (order is irrelevant to the numerics)
+__global__ void __launch_bounds__(256) multi_list_kernel(const int32_t *__restrict__ seg_first_chunk, const int32_t *__restrict__ n_uniq,
+                                                        int32_t *__restrict__ multi_seg, int32_t *__restrict__ n_multi) {
+  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= *n_uniq) return;
+  if (seg_first_chunk[g + 1] - seg_first_chunk[g] > 1) multi_seg[atomicAdd(n_multi, 1)] = (int32_t)g;
+}
+
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t sorted_key, sorted_pos, uniq, inverse, counts, seg_start, seg_first_chunk, chunk_start, chunk_seg, scalars;
+  size_t sorted_key, sorted_pos, uniq, inverse, counts, seg_start, seg_first_chunk, chunk_start, chunk_seg, multi_seg, scalars;
   size_t keys_in, pos_in, head, segidx1, chead, chunkidx1, cub, partial, total;
   size_t cub_bytes, partial_floats;
 };
@@ -111,6 +119,7 @@ WsLayout layout(int64_t n, int max_width) {
   L.seg_first_chunk = take(n1 * 4);
   L.chunk_start = take(n1 * 4);
   L.chunk_seg = take(n * 4);
+  L.multi_seg = take(n * 4);
   L.scalars = take(64);
   L.keys_in = take(n * 4);
   L.pos_in = take(n * 4);
@@ -161,8 +170,10 @@ RS_API int rs_dedup_sort(const int64_t *ids, int64_t n, int32_t F, const int64_t
   seg->seg_first_chunk = (int32_t *)(w + L.seg_first_chunk);
   seg->chunk_start = (int32_t *)(w + L.chunk_start);
   seg->chunk_seg = (int32_t *)(w + L.chunk_seg);
+  seg->multi_seg = (int32_t *)(w + L.multi_seg);
   seg->n_uniq = (int32_t *)(w + L.scalars);
   seg->n_chunks = seg->n_uniq + 1;
+  seg->n_multi = seg->n_uniq + 2;
   seg->partial = (float *)(w + L.partial);
   seg->partial_floats = (int64_t)((ws_bytes - L.partial) / 4);
   uint32_t *keys_in = (uint32_t *)(w + L.keys_in);
@@ -196,6 +207,9 @@ RS_API int rs_dedup_sort(const int64_t *ids, int64_t n, int32_t F, const int64_t
   chunk_scatter_kernel<<<blocks, 256, 0, st>>>(head, segidx1, chead, chunkidx1, n, seg->chunk_start, seg->chunk_seg,
                                                seg->seg_first_chunk, seg->n_chunks);
   RS_CHECK_LAUNCH();
+  RS_CUDA(cudaMemsetAsync(seg->n_multi, 0, sizeof(int32_t), st));
+  multi_list_kernel<<<blocks, 256, 0, st>>>(seg->seg_first_chunk, seg->n_uniq, seg->multi_seg, seg->n_multi);
+  RS_CHECK_LAUNCH();
   return RS_OK;
 }
 
@@ -203,7 +217,7 @@ RS_API int rs_dedup_sort(const int64_t *ids, int64_t n, int32_t F, const int64_t
 namespace {
 
 struct UpdParams {
-  const int32_t *sorted_pos, *seg_start, *seg_first_chunk, *chunk_start, *chunk_seg, *n_uniq, *n_chunks;
+  const int32_t *sorted_pos, *seg_start, *seg_first_chunk, *chunk_start, *chunk_seg, *n_uniq, *n_chunks, *multi_seg, *n_multi;
   const int64_t *uniq;
   float *partial;
   const float *stash, *scale, *dense;
@@ -353,10 +367,10 @@ __global__ void __launch_bounds__(256) seg_combine_kernel(const __grid_constant_
   constexpr int GPB = 256 / GS;
   const int lane = threadIdx.x % GS;
   const int WV = P.W / VEC;
-  const int nu = *P.n_uniq;
-  for (int64_t g = (int64_t)blockIdx.x * GPB + threadIdx.x / GS; g < nu; g += (int64_t)gridDim.x * GPB) {
+  const int nm = *P.n_multi;
+  for (int64_t k = (int64_t)blockIdx.x * GPB + threadIdx.x / GS; k < nm; k += (int64_t)gridDim.x * GPB) {
+    const int g = P.multi_seg[k];
     const int c0 = P.seg_first_chunk[g], c1 = P.seg_first_chunk[g + 1];
-    if (c1 - c0 <= 1) continue;
     typename V::T acc[NA];
 #pragma unroll
     for (int a = 0; a < NA; ++a) acc[a] = V::zero();
@@ -386,7 +400,10 @@ int launch_update(const UpdParams &P, int64_t n, cudaStream_t st) {
   int blocks = (int)(blocks64 < cap ? blocks64 : cap);
   seg_chunk_kernel<VEC, GS, NA, MODE><<<blocks, 256, 0, st>>>(P, n);
   RS_CHECK_LAUNCH();
-  seg_combine_kernel<VEC, GS, NA, MODE><<<blocks, 256, 0, st>>>(P, n);
+  // a multi-chunk segment has > RS_CHUNK lookups, so there are at most n / RS_CHUNK of them
+  int64_t cblocks64 = (n / RS_CHUNK + GPB) / GPB;
+  int cblocks = (int)(cblocks64 < cap ? cblocks64 : cap);
+  seg_combine_kernel<VEC, GS, NA, MODE><<<cblocks, 256, 0, st>>>(P, n);
   RS_CHECK_LAUNCH();
   return RS_OK;
 }
@@ -425,6 +442,8 @@ RS_API int rs_segment_update(const rs_segments *seg, int64_t n, const rs_update 
   P.chunk_seg = seg->chunk_seg;
   P.n_uniq = seg->n_uniq;
   P.n_chunks = seg->n_chunks;
+  P.multi_seg = seg->multi_seg;
+  P.n_multi = seg->n_multi;
   P.uniq = seg->uniq;
   P.partial = seg->partial;
   P.stash = u->stash;

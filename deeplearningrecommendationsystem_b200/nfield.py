@@ -5,6 +5,10 @@ The reference modules are hard-wired to the six MovieLens features; these keep t
 order model/deepfm.py:71-77, FFM pairs model/ffm.py:61-82, sigmoid head, BCELoss outside) for F id-fields.  All F
 tables live in ONE concatenated (total_rows, W) tensor; ids are int64 (B, F), local to each field.
 
+With ``sharded=True`` (multi-GPU) the concatenated table is ROW-SHARDED over the process group (global row r on rank
+r % N) and every step runs the deduplicated ids / rows / row-gradients all-to-alls of ``dist.RowExchange``; the
+result equals the single-GPU step on the concatenated global batch (gradients are averaged over ranks).
+
 Two update modes:
   fused=True   (default) the table is not an autograd leaf.  forward launches the fused lookup+interaction kernel
                and keeps the Jacobian rows; backward only records dL/dcross; ``FusedRowOptimizer.step()`` runs the
@@ -69,7 +73,7 @@ class _DenseGradFn(torch.autograd.Function):
 
 
 class _FieldModel(nn.Module):
-    def __init__(self, cardinalities, width, row_dim, fused=True, seed=None, device=None):
+    def __init__(self, cardinalities, width, row_dim, fused=True, seed=None, device=None, sharded=False, group=None):
         super().__init__()
         self.cards = [int(c) for c in cardinalities]
         self.F, self.width, self.fused = len(self.cards), width, fused
@@ -77,10 +81,28 @@ class _FieldModel(nn.Module):
         for c in self.cards:
             offs.append(offs[-1] + c)
         self.offsets_host, self.total_rows = offs[:-1], offs[-1]
-        self.weight = nn.Parameter(_xavier_concat(self.cards, width, row_dim, device, seed), requires_grad=not fused)
+        self.sharded, self.exchange = sharded, None
+        if sharded:
+            if not fused:
+                raise ValueError("sharded tables are updated by the fused row optimizer (fused=True)")
+            from . import dist as rsdist
+            self.exchange = rsdist.RowExchange(rsdist.cuda_prims(), group)
+            rows = self.exchange.local_rows(self.total_rows)
+            std = math.sqrt(2.0 / (self.total_rows / self.F + row_dim))
+            w = torch.empty(rows, width, dtype=torch.float32, device=device)
+            g = torch.Generator(device=w.device).manual_seed((seed or 0) * 1000 + self.exchange.rank)
+            self.weight = nn.Parameter(w.normal_(0.0, std, generator=g), requires_grad=False)
+            self.register_buffer("offsets_dev", torch.tensor(self.offsets_host, dtype=torch.int64, device=device), persistent=False)
+        else:
+            self.weight = nn.Parameter(_xavier_concat(self.cards, width, row_dim, device, seed), requires_grad=not fused)
         self.bias = nn.Parameter(torch.zeros(1, device=device))
         self._pending, self._anchor, self._token = {}, None, 0
         self.adam_m = self.adam_v = None
+
+    def load_global(self, global_weight):
+        """sharded mode: take this rank's rows (r % N == rank) of a full (total_rows, W) table."""
+        from . import dist as rsdist
+        self.weight.data.copy_(rsdist.shard_rows(global_weight.to(self.weight.device), self.exchange.rank, self.exchange.world))
 
     def tables(self):
         return ops.tables_from_concat(self.weight.data, self.offsets_host, self.cards)
@@ -93,36 +115,58 @@ class _FieldModel(nn.Module):
     def clear_pending(self):
         self._pending.clear()
 
+    def _row_update(self, opt, segs, F, **src):
+        """Apply the optimizer to the rows of self.weight named by `segs` (gradient source in **src)."""
+        if opt.kind == "sgd":
+            ops.segment_update(segs, ops.RS_UPD_SGD, self.width, F, table=self.weight.data, lr=opt.lr, wd=opt.weight_decay, **src)
+        else:
+            if self.adam_m is None:
+                self.adam_m = torch.zeros_like(self.weight.data)
+                self.adam_v = torch.zeros_like(self.weight.data)
+            ops.segment_update(segs, ops.RS_UPD_ADAM, self.width, F, table=self.weight.data, m=self.adam_m, v=self.adam_v,
+                               lr=opt.lr, wd=opt.weight_decay, betas=opt.betas, eps=opt.eps, step=opt.step_count, **src)
+
     def apply_pending(self, opt):
         for rec in self._pending.values():
             if "g" not in rec:
                 continue
-            segs = ops.dedup_sort(rec["ids"], self.F, self.offsets_host, self.total_rows, max_width=self.width)
-            if opt.kind == "sgd":
-                ops.segment_update(segs, ops.RS_UPD_SGD, self.width, self.F, stash=rec["stash"], scale=rec["g"],
-                                   table=self.weight.data, lr=opt.lr, wd=opt.weight_decay)
-            else:
-                if self.adam_m is None:
-                    self.adam_m = torch.zeros_like(self.weight.data)
-                    self.adam_v = torch.zeros_like(self.weight.data)
-                ops.segment_update(segs, ops.RS_UPD_ADAM, self.width, self.F, stash=rec["stash"], scale=rec["g"],
-                                   table=self.weight.data, m=self.adam_m, v=self.adam_v, lr=opt.lr, wd=opt.weight_decay,
-                                   betas=opt.betas, eps=opt.eps, step=opt.step_count)
+            if not self.sharded:
+                segs = ops.dedup_sort(rec["ids"], self.F, self.offsets_host, self.total_rows, max_width=self.width)
+                self._row_update(opt, segs, self.F, stash=rec["stash"], scale=rec["g"])
+                continue
+            # row-sharded: reduce the batch's gradients per fetched row, send them to the owners, update there
+            plan, ex = rec["plan"], self.exchange
+            segs = ops.dedup_sort(rec["ids"].reshape(-1), 1, None, plan.n_uniq, max_width=self.width)
+            block_grad = torch.zeros(plan.n_uniq, self.width, dtype=torch.float32, device=rec["g"].device)
+            ops.segment_update(segs, ops.RS_UPD_GRAD, self.width, self.F, stash=rec["stash"], scale=rec["g"] * (1.0 / ex.world),
+                               dense_grad=block_grad)
+            recv = ex.push_grads(plan, block_grad)
+            if recv.shape[0]:
+                osegs = ops.dedup_sort(plan.recv_local, 1, None, self.weight.shape[0], max_width=self.width)
+                self._row_update(opt, osegs, 1, dense=recv)
         self._pending.clear()
 
-    def _interact(self, ids, want_stash):
+    def _interact(self, T, ids, want_stash):
         raise NotImplementedError
 
     def logit(self, ids):
         if ids.dim() != 2 or ids.shape[1] != self.F:
             raise ValueError(f"ids must be (B, {self.F})")
         train = torch.is_grad_enabled()
-        cross, stash = self._interact(ids, want_stash=train)
+        rec = {}
+        if self.sharded:
+            plan = self.exchange.plan((ids + self.offsets_dev).reshape(-1), self.total_rows)
+            block = self.exchange.fetch(plan, self.weight.data)
+            ids = plan.local_ids.view(ids.shape)
+            cross, stash = self._interact(ops.make_tables([block] * self.F), ids, want_stash=train)
+            rec = {"plan": plan}
+        else:
+            cross, stash = self._interact(self.tables(), ids, want_stash=train)
         if train and self.fused:
             if self._anchor is None or self._anchor.device != ids.device:
                 self._anchor = torch.zeros(1, device=ids.device, requires_grad=True)
             self._token += 1
-            self._pending[self._token] = {"ids": ids, "stash": stash}
+            self._pending[self._token] = {"ids": ids, "stash": stash, **rec}
             cross = _CrossFn.apply(self._anchor, cross, self, self._token)
         elif train:
             cross = _DenseGradFn.apply(self.weight, cross, self, ids, stash)
@@ -135,21 +179,21 @@ class _FieldModel(nn.Module):
 class FieldFM(_FieldModel):
     """sigmoid(b + 0.5 * sum_d[(sum_f e_f)^2 - sum_f e_f^2]) over F id-fields, D-dim rows."""
 
-    def __init__(self, cardinalities, embedding_dim, fused=True, seed=None, device=None):
-        super().__init__(cardinalities, embedding_dim, embedding_dim, fused, seed, device)
+    def __init__(self, cardinalities, embedding_dim, fused=True, seed=None, device=None, sharded=False, group=None):
+        super().__init__(cardinalities, embedding_dim, embedding_dim, fused, seed, device, sharded, group)
 
-    def _interact(self, ids, want_stash):
-        out = ops.fields_fwd(self.tables(), ids.shape[0], ids.device, ids=ids, cross=True, stash=want_stash)
+    def _interact(self, T, ids, want_stash):
+        out = ops.fields_fwd(T, ids.shape[0], ids.device, ids=ids, cross=True, stash=want_stash)
         return out["cross"], out.get("stash")
 
 
 class FieldFFM(_FieldModel):
     """sigmoid(b + sum_{i<j} <v_{i,j}, v_{j,i}>): feature i's table row is (F, D), slot j aimed at field j."""
 
-    def __init__(self, cardinalities, num_vector, fused=True, seed=None, device=None):
+    def __init__(self, cardinalities, num_vector, fused=True, seed=None, device=None, sharded=False, group=None):
         F = len(cardinalities)
-        super().__init__(cardinalities, F * num_vector, num_vector, fused, seed, device)
+        super().__init__(cardinalities, F * num_vector, num_vector, fused, seed, device, sharded, group)
         self.D = num_vector
 
-    def _interact(self, ids, want_stash):
-        return ops.ffm_fwd(self.tables(), ids, self.D, want_stash=want_stash)
+    def _interact(self, T, ids, want_stash):
+        return ops.ffm_fwd(T, ids, self.D, want_stash=want_stash)

@@ -37,6 +37,8 @@ class FusedRowOptimizer:
         for m in self._sparse_modules():
             m.apply_pending(self)
         if self.dense is not None:
+            from .dist import allreduce_dense_grads
+            allreduce_dense_grads([p for g in self.dense.param_groups for p in g["params"]])
             self.dense.step()
 
 

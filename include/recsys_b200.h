@@ -112,8 +112,10 @@ typedef struct rs_segments {
   int32_t *seg_first_chunk;  /* [n+1]                                                             */
   int32_t *chunk_start;      /* [n+1] segments cut into chunks of <= RS_CHUNK lookups             */
   int32_t *chunk_seg;        /* [n]                                                               */
+  int32_t *multi_seg;        /* [n]   segments that span more than one chunk (any order)          */
   int32_t *n_uniq;           /* [1] device scalar                                                 */
   int32_t *n_chunks;         /* [1] device scalar                                                 */
+  int32_t *n_multi;          /* [1] device scalar                                                 */
   float *partial;            /* scratch for chunk partial sums, sized by rs_dedup_workspace_bytes */
   int64_t partial_floats;
 } rs_segments;
