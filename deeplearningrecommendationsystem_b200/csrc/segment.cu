@@ -5,8 +5,12 @@
 #include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
+#include "segment.cuh"
 
 namespace {
+using rs::UpdParams;
+using rs::upd_sgd;
+using rs::adam1;
 
 struct Offsets {
   int64_t off[RS_MAX_FIELDS];
@@ -93,10 +97,26 @@ __global__ void __launch_bounds__(256) multi_list_kernel(const int32_t *__restri
   if (seg_first_chunk[g + 1] - seg_first_chunk[g] > 1) multi_seg[atomicAdd(n_multi, 1)] = (int32_t)g;
 }
 
+// One 16-byte record per sorted lookup so the streaming update kernel needs a single coalesced read per lookup
+// instead of chasing chunk -> segment -> row through three arrays.
+__global__ void __launch_bounds__(256) lookup_desc_kernel(const int32_t *__restrict__ sorted_pos, const int32_t *__restrict__ chunkidx1,
+                                                         const int32_t *__restrict__ chunk_start, const int32_t *__restrict__ chunk_seg,
+                                                         const int32_t *__restrict__ seg_first_chunk, const int64_t *__restrict__ uniq,
+                                                         int64_t n, int4 *__restrict__ desc) {
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const int c = chunkidx1[s] - 1;
+  const int s0 = chunk_start[c], s1 = chunk_start[c + 1];
+  const int g = chunk_seg[c];
+  const bool single = (seg_first_chunk[g + 1] - seg_first_chunk[g]) == 1;
+  int flags = (s == s0 ? 1 : 0) | (s + 1 == s1 ? 2 : 0) | (single ? 4 : 0);
+  desc[s] = make_int4(sorted_pos[s], flags, (int)(uint32_t)uniq[g], 2 * (s0 / RS_CHUNK) + ((s1 - s0) < RS_CHUNK ? 1 : 0));
+}
+
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t sorted_key, sorted_pos, uniq, inverse, counts, seg_start, seg_first_chunk, chunk_start, chunk_seg, multi_seg, scalars;
+  size_t sorted_key, sorted_pos, uniq, inverse, counts, seg_start, seg_first_chunk, chunk_start, chunk_seg, multi_seg, lookup_desc, scalars;
   size_t keys_in, pos_in, head, segidx1, chead, chunkidx1, cub, partial, total;
   size_t cub_bytes, partial_floats;
 };
@@ -120,6 +140,7 @@ WsLayout layout(int64_t n, int max_width) {
   L.chunk_start = take(n1 * 4);
   L.chunk_seg = take(n * 4);
   L.multi_seg = take(n * 4);
+  L.lookup_desc = take(n * 16);
   L.scalars = take(64);
   L.keys_in = take(n * 4);
   L.pos_in = take(n * 4);
@@ -174,6 +195,8 @@ RS_API int rs_dedup_sort(const int64_t *ids, int64_t n, int32_t F, const int64_t
   seg->n_uniq = (int32_t *)(w + L.scalars);
   seg->n_chunks = seg->n_uniq + 1;
   seg->n_multi = seg->n_uniq + 2;
+  seg->work_counter = seg->n_uniq + 3;
+  seg->lookup_desc = (int32_t *)(w + L.lookup_desc);
   seg->partial = (float *)(w + L.partial);
   seg->partial_floats = (int64_t)((ws_bytes - L.partial) / 4);
   uint32_t *keys_in = (uint32_t *)(w + L.keys_in);
@@ -210,21 +233,14 @@ RS_API int rs_dedup_sort(const int64_t *ids, int64_t n, int32_t F, const int64_t
   RS_CUDA(cudaMemsetAsync(seg->n_multi, 0, sizeof(int32_t), st));
   multi_list_kernel<<<blocks, 256, 0, st>>>(seg->seg_first_chunk, seg->n_uniq, seg->multi_seg, seg->n_multi);
   RS_CHECK_LAUNCH();
+  lookup_desc_kernel<<<blocks, 256, 0, st>>>(seg->sorted_pos, chunkidx1, seg->chunk_start, seg->chunk_seg, seg->seg_first_chunk,
+                                             seg->uniq, n, (int4 *)seg->lookup_desc);
+  RS_CHECK_LAUNCH();
   return RS_OK;
 }
 
 // =================================================================== segment reduce + update
 namespace {
-
-struct UpdParams {
-  const int32_t *sorted_pos, *seg_start, *seg_first_chunk, *chunk_start, *chunk_seg, *n_uniq, *n_chunks, *multi_seg, *n_multi;
-  const int64_t *uniq;
-  float *partial;
-  const float *stash, *scale, *dense;
-  float *table, *m, *v, *dense_grad;
-  int W, F, scale_width;
-  float lr, wd, beta1, beta2, eps, step_size, inv_sqrt_bc2;
-};
 
 // Slot of a chunk's partial sum.  Full chunks are disjoint runs of RS_CHUNK sorted lookups, so start/RS_CHUNK is
 // unique among them; a tail chunk (len < RS_CHUNK) is preceded by at least one full chunk of its own segment, so
@@ -255,19 +271,6 @@ struct Vec<1> {
   static __device__ __forceinline__ T mul(T a, T b) { return a * b; }
   static __device__ __forceinline__ T scale(T a, float s) { return a * s; }
 };
-
-__device__ __forceinline__ float upd_sgd(float w, float g, const UpdParams &P) { return w - P.lr * (g + P.wd * w); }
-__device__ __forceinline__ float4 upd_sgd(float4 w, float4 g, const UpdParams &P) {
-  return make_float4(upd_sgd(w.x, g.x, P), upd_sgd(w.y, g.y, P), upd_sgd(w.z, g.z, P), upd_sgd(w.w, g.w, P));
-}
-// torch.optim.Adam single-tensor arithmetic on one element
-__device__ __forceinline__ void adam1(float &w, float &m, float &v, float g, const UpdParams &P) {
-  g = g + P.wd * w;
-  m = m + (1.0f - P.beta1) * (g - m);               // lerp_(g, 1-beta1)
-  v = P.beta2 * v + (1.0f - P.beta2) * g * g;
-  float denom = sqrtf(v) * P.inv_sqrt_bc2 + P.eps;
-  w = w - P.step_size * (m / denom);
-}
 
 template <int VEC, int MODE>
 __device__ __forceinline__ void apply_row(const UpdParams &P, int64_t row, int e /* element (in VEC units) */, typename Vec<VEC>::T g) {
@@ -398,7 +401,12 @@ int launch_update(const UpdParams &P, int64_t n, cudaStream_t st) {
   int64_t blocks64 = (n + GPB - 1) / GPB;
   int cap = rs::num_sms() * 64;
   int blocks = (int)(blocks64 < cap ? blocks64 : cap);
-  seg_chunk_kernel<VEC, GS, NA, MODE><<<blocks, 256, 0, st>>>(P, n);
+  if (P.use_stream) {
+    int rc = rs::launch_seg_stream(P, n, MODE, st);   // chunk pass as a TMA-fed streaming kernel (segment_stream.cu)
+    if (rc) return rc;
+  } else {
+    seg_chunk_kernel<VEC, GS, NA, MODE><<<blocks, 256, 0, st>>>(P, n);
+  }
   RS_CHECK_LAUNCH();
   // a multi-chunk segment has > RS_CHUNK lookups, so there are at most n / RS_CHUNK of them
   int64_t cblocks64 = (n / RS_CHUNK + GPB) / GPB;
@@ -444,6 +452,8 @@ RS_API int rs_segment_update(const rs_segments *seg, int64_t n, const rs_update 
   P.n_chunks = seg->n_chunks;
   P.multi_seg = seg->multi_seg;
   P.n_multi = seg->n_multi;
+  P.lookup_desc = (const int4 *)seg->lookup_desc;
+  P.work_counter = seg->work_counter;
   P.uniq = seg->uniq;
   P.partial = seg->partial;
   P.stash = u->stash;
@@ -467,6 +477,9 @@ RS_API int rs_segment_update(const rs_segments *seg, int64_t n, const rs_update 
   P.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2 > 0 ? bc2 : 1.0));
   cudaStream_t st = (cudaStream_t)stream;
   const int W = u->width, mode = u->mode;
+  // wide rows (>= 256 B) with one gradient source and at most a per-sample scalar scale take the TMA-fed streaming kernel
+  P.use_stream = (W % 4 == 0 && W >= 64 && W <= 640 && !(u->stash && u->dense) && (!u->scale || u->scale_width == 1) &&
+                  !getenv("RS_NO_STREAM")) ? 1 : 0;
   if (W % 4 == 0) {
     const int wv = W / 4;
     if (wv <= 1) return launch_mode<4, 1, 1>(P, mode, n, st);

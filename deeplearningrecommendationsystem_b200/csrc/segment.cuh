@@ -1,0 +1,34 @@
+// Shared between segment.cu (generic lane-group kernels) and segment_stream.cu (TMA-fed streaming kernel).
+#pragma once
+#include "common.cuh"
+
+namespace rs {
+
+struct UpdParams {
+  const int32_t *sorted_pos, *seg_start, *seg_first_chunk, *chunk_start, *chunk_seg, *n_uniq, *n_chunks, *multi_seg, *n_multi;
+  const int64_t *uniq;
+  const int4 *lookup_desc;
+  int32_t *work_counter;
+  float *partial;
+  const float *stash, *scale, *dense;
+  float *table, *m, *v, *dense_grad;
+  int W, F, scale_width, use_stream;
+  float lr, wd, beta1, beta2, eps, step_size, inv_sqrt_bc2;
+};
+
+__device__ __forceinline__ float upd_sgd(float w, float g, const UpdParams &P) { return w - P.lr * (g + P.wd * w); }
+__device__ __forceinline__ float4 upd_sgd(float4 w, float4 g, const UpdParams &P) {
+  return make_float4(upd_sgd(w.x, g.x, P), upd_sgd(w.y, g.y, P), upd_sgd(w.z, g.z, P), upd_sgd(w.w, g.w, P));
+}
+// torch.optim.Adam single-tensor arithmetic on one element
+__device__ __forceinline__ void adam1(float &w, float &m, float &v, float g, const UpdParams &P) {
+  g = g + P.wd * w;
+  m = m + (1.0f - P.beta1) * (g - m);  // lerp_(g, 1-beta1)
+  v = P.beta2 * v + (1.0f - P.beta2) * g * g;
+  float denom = sqrtf(v) * P.inv_sqrt_bc2 + P.eps;
+  w = w - P.step_size * (m / denom);
+}
+
+int launch_seg_stream(const UpdParams &P, int64_t n, int mode, cudaStream_t st);
+
+}  // namespace rs

@@ -1,0 +1,265 @@
+// Streaming segment-reduce + row update for wide rows (FFM: 416 floats = 1664 B per row).
+//
+// The generic lane-group kernel in segment.cu is latency bound on wide rows: each warp walks
+// metadata -> position -> gradient row -> table row with one or two rows in flight.  Here a persistent CTA per SM
+// decouples memory from arithmetic: a producer warp reads one 16-byte record per sorted lookup (lookup_desc, built by
+// rs_dedup_sort) and issues cp.async.bulk (TMA bulk copy, SASS UBLKCP) of the 1.6 KB gradient row -- and, for a
+// segment that fits one chunk, of the table row it will update -- into a ring of shared-memory stages guarded by
+// full/empty mbarriers; four consumer warps own one float4 column each, add the rows of a chunk in sorted
+// (= ascending position) order, and at the chunk end write the updated table row (SGD), the dense gradient row,
+// or the chunk partial.  Work is handed out in units of ~256 sorted lookups through an atomic counter; units start
+// at chunk boundaries, so the summation order -- and therefore every bit of the result -- does not depend on the
+// schedule.
+#include <cstddef>
+
+#include "segment.cuh"
+
+namespace rs {
+namespace {
+
+constexpr int SR = 8;          // gradient rows per stage (and table-row slots per stage)
+constexpr int BATCH = 4;       // stages the producer fills per iteration (32 lanes = 4 x 8 lookups)
+constexpr int NCW = 4;         // consumer warps
+constexpr int NCT = NCW * 32;  // consumer threads: thread t owns float4 columns t, t+128, ...
+constexpr int NTHREADS = NCT + 32;
+constexpr int UNIT = 256;      // sorted lookups per work unit
+constexpr int MAX_ST = 12;
+
+struct __align__(16) StageHdr {
+  int flags[SR];      // 1 first | 2 last lookup of its chunk | 4 segment is a single chunk
+  float scale[SR];
+  uint32_t row[SR];   // global table row
+  int pslot[SR];      // chunk-partial slot (multi-chunk segments)
+  int tslot[SR];      // table-row slot inside the stage (single-chunk segments, SGD)
+  int count, done, pad0, pad1;
+};
+
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ int4 lds_i4(uint32_t addr) {
+  int4 v;
+  asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
+template <int NA, int MODE>
+__global__ void __launch_bounds__(NTHREADS, 1) seg_stream_kernel(const __grid_constant__ UpdParams P, int n, int nst) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint64_t full_bar[MAX_ST], empty_bar[MAX_ST];
+  __shared__ StageHdr hdr[MAX_ST];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int WV = P.W >> 2;
+  const uint32_t row_bytes = (uint32_t)P.W * 4u;
+  const size_t stage_floats = (size_t)2 * SR * P.W;  // SR gradient rows then SR table rows
+  float *ring = reinterpret_cast<float *>(smem_raw);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nst; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], NCW);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const float *src = P.stash ? P.stash : P.dense;
+
+  if (warp == NCW) {
+    // ===================== producer =====================
+    int k = 0;  // running stage counter
+    for (;;) {
+      int u = 0;
+      if (lane == 0) u = atomicAdd(P.work_counter, 1);
+      u = __shfl_sync(0xffffffffu, u, 0);
+      const int64_t lo = (int64_t)u * UNIT;
+      if (lo >= n) break;
+      // unit = chunks whose first lookup lies in [lo, lo+UNIT): find the first chunk start >= lo and >= lo+UNIT
+      int sA = n, sB = n;
+      for (int base = (int)lo; base < n && sA == n; base += 32) {
+        const int s = base + lane;
+        const bool first = s < n && (P.lookup_desc[s].y & 1);
+        const unsigned m = __ballot_sync(0xffffffffu, first);
+        if (m) sA = base + __ffs(m) - 1;
+        if (base - (int)lo >= RS_CHUNK) break;
+      }
+      if (sA >= lo + UNIT || sA >= n) continue;  // no chunk starts inside this unit
+      for (int base = (int)lo + UNIT; base < n && sB == n; base += 32) {
+        const int s = base + lane;
+        const bool first = s < n && (P.lookup_desc[s].y & 1);
+        const unsigned m = __ballot_sync(0xffffffffu, first);
+        if (m) sB = base + __ffs(m) - 1;
+      }
+      for (int s0 = sA; s0 < sB; s0 += SR * BATCH) {
+        const int s = s0 + lane;
+        const bool valid = s < sB;
+        int4 d = make_int4(0, 0, 0, 0);
+        float sc = 1.0f;
+        if (valid) {
+          d = P.lookup_desc[s];
+          if (P.scale) sc = __ldg(P.scale + d.x / P.F);
+        }
+        const bool want_table = valid && MODE == RS_UPD_SGD && (d.y & 6) == 6;  // last lookup of a single-chunk segment
+        const int sub = lane >> 3, e = lane & 7;                                 // stage within the batch, entry within the stage
+        const unsigned tmask = __ballot_sync(0xffffffffu, want_table);
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        const unsigned grp = 0xffu << (sub * 8);
+        const int tslot = __popc(tmask & grp & ((1u << lane) - 1u));
+        const int ntab = __popc(tmask & grp), nval = __popc(vmask & grp);
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) {
+          // every lane walks the four stages in order so the empty-waits are warp-uniform
+          const int st = (k + b) % nst;
+          const uint32_t ph = (uint32_t)((k + b) / nst) & 1u;
+          mbar_wait(&empty_bar[st], ph ^ 1u);
+          if (sub == b) {
+            if (valid) {
+              hdr[st].flags[e] = d.y;
+              hdr[st].scale[e] = sc;
+              hdr[st].row[e] = (uint32_t)d.z;
+              hdr[st].pslot[e] = d.w;
+              hdr[st].tslot[e] = tslot;
+            }
+            if (e == 0) {
+              hdr[st].count = nval;
+              hdr[st].done = 0;
+            }
+          }
+          __syncwarp();
+          if (sub == b && e == 0) mbar_arrive_expect_tx(&full_bar[st], row_bytes * (uint32_t)(nval + ntab));
+          __syncwarp();
+          if (sub == b && valid) {
+            float *dst = ring + (size_t)st * stage_floats;
+            bulk_g2s(dst + (size_t)e * P.W, src + (int64_t)d.x * P.W, row_bytes, &full_bar[st]);
+            if (want_table) bulk_g2s(dst + (size_t)(SR + tslot) * P.W, P.table + (int64_t)(uint32_t)d.z * P.W, row_bytes, &full_bar[st]);
+          }
+        }
+        k += BATCH;
+      }
+    }
+    // terminator stage
+    const int st = k % nst;
+    const uint32_t ph = (uint32_t)(k / nst) & 1u;
+    mbar_wait(&empty_bar[st], ph ^ 1u);
+    if (lane == 0) {
+      hdr[st].count = 0;
+      hdr[st].done = 1;
+      mbar_arrive(&full_bar[st]);
+    }
+  } else {
+    // ===================== consumers =====================
+    // Everything of a stage that does not depend on the running sums is read first (flags, scales, the eight
+    // gradient values of this thread's column): 4 + 8 independent LDS.128, then a short FMUL/FADD chain per entry.
+    const int t = threadIdx.x;
+    const uint32_t ring_s = smem_u32(ring), hdr_s = smem_u32(&hdr[0]);
+    const uint32_t stage_bytes = (uint32_t)stage_floats * 4u;
+    float4 acc[NA];
+#pragma unroll
+    for (int a = 0; a < NA; ++a) acc[a] = f4_zero();
+    for (int k = 0;; ++k) {
+      const int st = k % nst;
+      const uint32_t ph = (uint32_t)(k / nst) & 1u;
+      mbar_wait(&full_bar[st], ph);
+      const uint32_t h = hdr_s + (uint32_t)st * (uint32_t)sizeof(StageHdr);
+      const int4 tail = lds_i4(h + offsetof(StageHdr, count));
+      if (tail.y) break;
+      const int count = tail.x;
+      int fl[SR];
+      float sc[SR];
+      *reinterpret_cast<int4 *>(&fl[0]) = lds_i4(h + offsetof(StageHdr, flags));
+      *reinterpret_cast<int4 *>(&fl[4]) = lds_i4(h + offsetof(StageHdr, flags) + 16);
+      *reinterpret_cast<float4 *>(&sc[0]) = lds_f4(h + offsetof(StageHdr, scale));
+      *reinterpret_cast<float4 *>(&sc[4]) = lds_f4(h + offsetof(StageHdr, scale) + 16);
+      const uint32_t rows_s = ring_s + (uint32_t)st * stage_bytes;
+#pragma unroll
+      for (int a = 0; a < NA; ++a) {
+        const int col = t + a * NCT;
+        if (col >= WV) continue;
+        const uint32_t col_s = rows_s + (uint32_t)col * 16u;
+        float4 v[SR];
+#pragma unroll
+        for (int e = 0; e < SR; ++e) v[e] = (e < count) ? lds_f4(col_s + (uint32_t)e * row_bytes) : f4_zero();
+#pragma unroll
+        for (int e = 0; e < SR; ++e) {
+          if (e < count) {
+            // explicit mul then add (no fma contraction): same bits as scale*stash summed sequentially
+            acc[a].x = __fadd_rn(acc[a].x, __fmul_rn(v[e].x, sc[e]));
+            acc[a].y = __fadd_rn(acc[a].y, __fmul_rn(v[e].y, sc[e]));
+            acc[a].z = __fadd_rn(acc[a].z, __fmul_rn(v[e].z, sc[e]));
+            acc[a].w = __fadd_rn(acc[a].w, __fmul_rn(v[e].w, sc[e]));
+            if (fl[e] & 2) {  // chunk ends here
+              if (fl[e] & 4) {
+                uint32_t row;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(row) : "r"(h + (uint32_t)offsetof(StageHdr, row) + 4u * e));
+                float *dst = (MODE == RS_UPD_GRAD ? P.dense_grad : P.table) + (int64_t)row * P.W + col * 4;
+                if (MODE == RS_UPD_SGD) {
+                  int ts;
+                  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(ts) : "r"(h + (uint32_t)offsetof(StageHdr, tslot) + 4u * e));
+                  const float4 w = lds_f4(col_s + (uint32_t)(SR + ts) * row_bytes);
+                  stg_f4(dst, upd_sgd(w, acc[a], P));
+                } else if (MODE == RS_UPD_GRAD) {
+                  stg_f4(dst, acc[a]);
+                } else {
+                  float wv[4], mv[4], vv[4], gv[4];
+                  *reinterpret_cast<float4 *>(wv) = ldg_f4(dst);
+                  *reinterpret_cast<float4 *>(mv) = ldg_f4(P.m + (int64_t)row * P.W + col * 4);
+                  *reinterpret_cast<float4 *>(vv) = ldg_f4(P.v + (int64_t)row * P.W + col * 4);
+                  *reinterpret_cast<float4 *>(gv) = acc[a];
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) adam1(wv[i], mv[i], vv[i], gv[i], P);
+                  stg_f4(dst, *reinterpret_cast<float4 *>(wv));
+                  stg_f4(P.m + (int64_t)row * P.W + col * 4, *reinterpret_cast<float4 *>(mv));
+                  stg_f4(P.v + (int64_t)row * P.W + col * 4, *reinterpret_cast<float4 *>(vv));
+                }
+              } else {
+                int ps;
+                asm volatile("ld.shared.s32 %0, [%1];" : "=r"(ps) : "r"(h + (uint32_t)offsetof(StageHdr, pslot) + 4u * e));
+                stg_f4(P.partial + (int64_t)ps * P.W + col * 4, acc[a]);
+              }
+              acc[a] = f4_zero();
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[st]);
+    }
+  }
+}
+
+template <int NA>
+int launch_na(const UpdParams &P, int n, int mode, cudaStream_t st) {
+  const size_t stage_bytes = (size_t)2 * SR * P.W * 4;
+  int nst = (int)((200 * 1024) / stage_bytes);
+  if (nst > MAX_ST) nst = MAX_ST;
+  if (nst < BATCH + 1) {
+    set_error("rs_segment_update: row of %d floats too wide for the streaming kernel", P.W);
+    return RS_E_UNSUPPORTED;
+  }
+  const size_t smem = stage_bytes * nst;
+  RS_CUDA(cudaMemsetAsync(P.work_counter, 0, sizeof(int32_t), st));
+  const int grid = num_sms();
+#define RS_LAUNCH_STREAM(M)                                                                                        \
+  do {                                                                                                             \
+    RS_CUDA(cudaFuncSetAttribute(seg_stream_kernel<NA, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    seg_stream_kernel<NA, M><<<grid, NTHREADS, smem, st>>>(P, n, nst);                                             \
+  } while (0)
+  switch (mode) {
+    case RS_UPD_GRAD: RS_LAUNCH_STREAM(RS_UPD_GRAD); break;
+    case RS_UPD_SGD: RS_LAUNCH_STREAM(RS_UPD_SGD); break;
+    default: RS_LAUNCH_STREAM(RS_UPD_ADAM); break;
+  }
+#undef RS_LAUNCH_STREAM
+  return RS_OK;
+}
+
+}  // namespace
+
+int launch_seg_stream(const UpdParams &P, int64_t n, int mode, cudaStream_t st) {
+  const int wv = P.W / 4;
+  if (wv <= NCT) return launch_na<1>(P, (int)n, mode, st);
+  if (wv <= 2 * NCT) return launch_na<2>(P, (int)n, mode, st);
+  return launch_na<4>(P, (int)n, mode, st);
+}
+
+}  // namespace rs

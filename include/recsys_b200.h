@@ -113,6 +113,9 @@ typedef struct rs_segments {
   int32_t *chunk_start;      /* [n+1] segments cut into chunks of <= RS_CHUNK lookups             */
   int32_t *chunk_seg;        /* [n]                                                               */
   int32_t *multi_seg;        /* [n]   segments that span more than one chunk (any order)          */
+  int32_t *lookup_desc;      /* [n*4] per sorted lookup: {pos, flags(1 first|2 last|4 single-chunk segment),
+                                 global row, partial slot} -- the record the streaming update kernel reads */
+  int32_t *work_counter;     /* [1]   dynamic work-unit counter of the streaming update kernel     */
   int32_t *n_uniq;           /* [1] device scalar                                                 */
   int32_t *n_chunks;         /* [1] device scalar                                                 */
   int32_t *n_multi;          /* [1] device scalar                                                 */

@@ -120,10 +120,11 @@ def test_segment_short_segments_bit_exact_vs_sequential():
     assert torch.equal(dense.cpu(), want)
 
 
-def test_segment_scaled_stash_and_adam():
+@pytest.mark.parametrize("W", [8, 128])          # 8: lane-group kernel, 128: TMA streaming kernel
+def test_segment_scaled_stash_and_adam(W):
     ops = _ops()
     g = torch.Generator().manual_seed(11)
-    F, B, W, card = 3, 400, 8, 40
+    F, B, card = 3, 400, 40
     ids = torch.randint(0, card, (B, F), generator=g)
     offs = [0, card, 2 * card]
     stash = torch.randn(B, F, W, generator=g)
@@ -148,9 +149,11 @@ def test_segment_scaled_stash_and_adam():
     for step in (1, 2):
         ops.segment_update(segs, ops.RS_UPD_ADAM, W, F, stash=stash.cuda(), scale=vscale.cuda(), table=tc, m=m, v=v, lr=1e-2, step=step)
         ooptim.adam_rows(wt, wm, wv, keys, G2, step, lr=1e-2)
-    close(tc, wt, rtol=1e-5, atol=1e-6)
-    close(m, wm)
-    close(v, wv)
+    # Adam's step is lr*m/(sqrt(v)+eps): rows whose summed gradient nearly cancels move in a direction set by
+    # rounding noise, so the table gets the same 2%-of-lr absolute floor as the model tests
+    close(tc, wt, rtol=1e-5, atol=2e-4)
+    close(m, wm, rtol=1e-5, atol=2e-6)
+    close(v, wv, rtol=1e-5, atol=2e-6)
 
 
 def test_adam_dense_matches_torch_adam():
