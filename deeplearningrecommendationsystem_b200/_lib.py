@@ -77,6 +77,11 @@ SIGNATURES = {
     "rs_xembed_bag_ws_bytes": [_PP(rs_xslots), _L, _PP(_Z)],
     "rs_xcol_to_ids": [_P, _L, _I, _I, _P, _P],
     "rs_sigmoid_bce": [_P, _P, _L, _P, _P, _P, _P, _P],
+    "rs_afm_num_parts": [_L, _I, _I, _I, _PP(_I)],
+    "rs_afm_fwd": [_P, _L, _I, _I, _I, _P, _P, _P, _P, _P, _P],
+    "rs_afm_bwd": [_P, _L, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P],
+    "rs_gru_fwd": [_P, _L, _I, _I, _P, _P, _P, _P, _P],
+    "rs_gru_bwd": [_P, _P, _P, _P, _P, _L, _I, _I, _P, _P, _P],
 }
 
 _lib = None

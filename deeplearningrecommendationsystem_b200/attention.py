@@ -2,14 +2,29 @@
 import torch
 
 
+class _AFMPool(torch.autograd.Function):
+    """rs_afm_fwd / rs_afm_bwd: the pair tensor stays in shared memory, parameter gradients are fixed-order sums."""
+
+    @staticmethod
+    def forward(ctx, E, W, b, h):
+        from . import ops
+        need = any(t.requires_grad for t in (E, W, b, h))
+        pooled, attw = ops.afm_fwd(E, W.detach(), b.detach(), h.detach(), want_attw=need)
+        if need:
+            ctx.save_for_backward(E, W, b, h, attw)
+        return pooled
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import ops
+        E, W, b, h, attw = ctx.saved_tensors
+        dE, dW, db, dh = ops.afm_bwd(E, W.detach(), b.detach(), h.detach(), attw, g.contiguous())
+        return dE, dW, db, dh.view_as(h)
+
+
 def afm_pool(E, W, b, h):
-    """Attention pooling over the pairwise Hadamard products of E (B, F, D)            reference model/afm.py:55-65."""
-    F = E.shape[1]
-    iu = torch.triu_indices(F, F, offset=1, device=E.device)
-    P = E[:, iu[0]] * E[:, iu[1]]
-    a = torch.relu(torch.matmul(P, W) + b)
-    w = torch.softmax(torch.matmul(a, h), dim=1)
-    return (w * P).sum(dim=1)
+    """Attention pooling over the pairwise Hadamard products of E (B, F, D) -> (B, D)   reference model/afm.py:55-65."""
+    return _AFMPool.apply(E.contiguous(), W, b, h)
 
 
 def din_attention(hist_embed, target_embed, unit, pool):
@@ -21,7 +36,34 @@ def din_attention(hist_embed, target_embed, unit, pool):
     return scaled.sum(dim=1) if pool else scaled
 
 
+class _GRURecurrence(torch.autograd.Function):
+    """L sequential GRU steps on precomputed input projections (rs_gru_fwd / rs_gru_bwd).  Returns h_L (B, H)."""
+
+    @staticmethod
+    def forward(ctx, gi, w_hh, b_hh):
+        from . import ops
+        need = gi.requires_grad or w_hh.requires_grad or b_hh.requires_grad
+        h_all, gates = ops.gru_fwd(gi, w_hh.detach(), b_hh.detach(), want_gates=need)
+        if need:
+            ctx.save_for_backward(w_hh, h_all, gates)
+        return h_all[:, -1].clone()
+
+    @staticmethod
+    def backward(ctx, g_last):
+        from . import ops
+        w_hh, h_all, gates = ctx.saved_tensors
+        B, L, H = h_all.shape
+        d_gi, d_gh = ops.gru_bwd(w_hh.detach(), h_all, gates, g_h_last=g_last.contiguous())
+        h_prev = torch.cat([torch.zeros(B, 1, H, device=h_all.device), h_all[:, :-1]], dim=1)
+        flat = d_gh.view(B * L, 3 * H)
+        return d_gi, flat.t() @ h_prev.reshape(B * L, H), flat.sum(dim=0)
+
+
 def gru_last_hidden(x, gru):
-    """hidden[-1] of a single-layer batch_first GRU started from zeros                  reference model/dien.py:61-64."""
-    _, hidden = gru(x)
-    return hidden[-1]
+    """hidden[-1] of a single-layer batch_first GRU started from zeros                  reference model/dien.py:61-64.
+    Input projection = one library GEMM; the recurrence and its BPTT run in the hand-written kernels."""
+    H = gru.hidden_size
+    if gru.num_layers != 1 or gru.bidirectional or not gru.batch_first or H not in (8, 16, 32, 64):
+        raise NotImplementedError("gru_last_hidden: single-layer batch_first GRU with hidden size in {8,16,32,64}")
+    gi = torch.nn.functional.linear(x, gru.weight_ih_l0, gru.bias_ih_l0)
+    return _GRURecurrence.apply(gi, gru.weight_hh_l0, gru.bias_hh_l0)

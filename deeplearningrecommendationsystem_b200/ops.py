@@ -383,3 +383,67 @@ def sigmoid_bce(logit, y, want_grad=True):
                                           _stream()), "rs_sigmoid_bce")
     _count(2)
     return pred, loss, g
+
+
+def gru_fwd(gi, w_hh, b_hh, want_gates=True):
+    """gi (B, L, 3H) = x.W_ih^T + b_ih  ->  h_all (B, L, H), gates (B, L, 4H) | None."""
+    gi, w_hh, b_hh = _f32(gi), _f32(w_hh), _f32(b_hh)
+    _need_cuda(gi, w_hh, b_hh)
+    B, L, H3 = gi.shape
+    H = H3 // 3
+    h_all = torch.empty(B, L, H, dtype=torch.float32, device=gi.device)
+    gates = torch.empty(B, L, 4 * H, dtype=torch.float32, device=gi.device) if want_gates else None
+    with _timed("gru_fwd"):
+        _lib.check(_lib.load().rs_gru_fwd(gi.data_ptr(), B, L, H, w_hh.data_ptr(), b_hh.data_ptr(), h_all.data_ptr(), _p(gates),
+                                          _stream()), "rs_gru_fwd")
+    _count()
+    return h_all, gates
+
+
+def gru_bwd(w_hh, h_all, gates, g_h_all=None, g_h_last=None):
+    """-> d_gi, d_gh (B, L, 3H)."""
+    B, L, H = h_all.shape
+    g_h_all, g_h_last = _f32(g_h_all), _f32(g_h_last)
+    d_gi = torch.empty(B, L, 3 * H, dtype=torch.float32, device=h_all.device)
+    d_gh = torch.empty_like(d_gi)
+    with _timed("gru_bwd"):
+        _lib.check(_lib.load().rs_gru_bwd(_f32(w_hh).data_ptr(), h_all.data_ptr(), gates.data_ptr(), _p(g_h_all), _p(g_h_last), B, L, H,
+                                          d_gi.data_ptr(), d_gh.data_ptr(), _stream()), "rs_gru_bwd")
+    _count()
+    return d_gi, d_gh
+
+
+def afm_fwd(E, W, b, h, want_attw=True):
+    """pooled (B, D), attw (B, P) | None."""
+    E, W, b, h = _f32(E), _f32(W), _f32(b), _f32(h).reshape(-1)
+    _need_cuda(E, W, b, h)
+    B, F, D = E.shape
+    A = W.shape[1]
+    pooled = torch.empty(B, D, dtype=torch.float32, device=E.device)
+    attw = torch.empty(B, F * (F - 1) // 2, dtype=torch.float32, device=E.device) if want_attw else None
+    with _timed("afm_fwd"):
+        _lib.check(_lib.load().rs_afm_fwd(E.data_ptr(), B, F, D, A, W.data_ptr(), b.data_ptr(), h.data_ptr(), pooled.data_ptr(),
+                                          _p(attw), _stream()), "rs_afm_fwd")
+    _count()
+    return pooled, attw
+
+
+def afm_bwd(E, W, b, h, attw, g_pooled):
+    """-> dE (B,F,D), dW (D,A), db (A), dh (A)  (per-warp partials added in warp order)."""
+    E, W, b, h, g_pooled = _f32(E), _f32(W), _f32(b), _f32(h).reshape(-1), _f32(g_pooled)
+    B, F, D = E.shape
+    A = W.shape[1]
+    lib = _lib.load()
+    parts = C.c_int32(0)
+    _lib.check(lib.rs_afm_num_parts(B, F, D, A, C.byref(parts)), "rs_afm_num_parts")
+    n = parts.value
+    dE = torch.empty_like(E)
+    dWp = torch.empty(n, D, A, dtype=torch.float32, device=E.device)
+    dbp = torch.empty(n, A, dtype=torch.float32, device=E.device)
+    dhp = torch.empty(n, A, dtype=torch.float32, device=E.device)
+    with _timed("afm_bwd"):
+        _lib.check(lib.rs_afm_bwd(E.data_ptr(), B, F, D, A, W.data_ptr(), b.data_ptr(), h.data_ptr(), attw.data_ptr(),
+                                  g_pooled.data_ptr(), dE.data_ptr(), dWp.data_ptr(), dbp.data_ptr(), dhp.data_ptr(), n, _stream()),
+                   "rs_afm_bwd")
+    _count()
+    return dE, dWp.sum(dim=0), dbp.sum(dim=0), dhp.sum(dim=0)

@@ -176,6 +176,29 @@ int rs_xembed_bag_ws_bytes(const rs_xslots *S, int64_t B, size_t *bytes);
 /* float-encoded id column -> int64 (x[:,c].long(), model/deepfm.py:45) */
 int rs_xcol_to_ids(const float *x, int64_t B, int32_t xcols, int32_t col, int64_t *ids, void *stream);
 
+/* ---- AFM attention pooling over the pairwise Hadamard products (model/afm.py:55-65).
+ *   P_p = e_i*e_j (i<j), s_p = h.relu(P_p W + b), w = softmax_p(s), pooled = sum_p w_p P_p
+ * E (B, F, D) dense field embeddings, W (D, A), b (A), h (A).  The (B, P, D) pair tensor is never materialised.
+ * Forward saves the softmax weights attw (B, P) for the backward.  Backward returns dE and PER-WARP partial sums of
+ * dW (parts, D, A), db (parts, A), dh (parts, A) -- add them over `parts` (= rs_afm_num_parts) in index order. */
+int rs_afm_num_parts(int64_t B, int32_t F, int32_t D, int32_t A, int32_t *parts);
+int rs_afm_fwd(const float *E, int64_t B, int32_t F, int32_t D, int32_t A, const float *W, const float *bvec,
+               const float *h, float *pooled /* (B,D) */, float *attw /* (B,P) or NULL */, void *stream);
+int rs_afm_bwd(const float *E, int64_t B, int32_t F, int32_t D, int32_t A, const float *W, const float *bvec,
+               const float *h, const float *attw, const float *g_pooled, float *dE, float *dW_part, float *db_part,
+               float *dh_part, int32_t num_parts, void *stream);
+
+/* ---- GRU recurrence (nn.GRU(D, H, batch_first=True), one layer, h0 = 0, gate order r,z,n; model/dien.py:47,61).
+ * The input projection gi = x.W_ih^T + b_ih (B, L, 3H) is a plain library GEMM done by the caller; rs_gru_fwd runs
+ * the L sequential steps (W_hh register-resident, BT batch rows per CTA): h_all (B, L, H) and, for BPTT,
+ * gates (B, L, 4H) = r | z | n | (W_hn.h + b_hn)  (NULL for inference).  H in {8,16,32,64}.
+ * rs_gru_bwd walks t = L-1..0 from g_h_all (B, L, H) and/or g_h_last (B, H) and emits d_gi and d_gh (B, L, 3H);
+ * dW_ih = d_gi^T.x, dW_hh = d_gh^T.h_prev, dx = d_gi.W_ih and the bias sums are plain GEMMs/reductions on them. */
+int rs_gru_fwd(const float *gi, int64_t B, int32_t L, int32_t H, const float *w_hh, const float *b_hh, float *h_all,
+               float *gates, void *stream);
+int rs_gru_bwd(const float *w_hh, const float *h_all, const float *gates, const float *g_h_all, const float *g_h_last,
+               int64_t B, int32_t L, int32_t H, float *d_gi, float *d_gh, void *stream);
+
 /* ---- sigmoid + BCELoss(mean) forward/backward in one pass (model/*: torch.sigmoid; scripts/deepfm.py:54).
  * pred = sigmoid(logit); loss_sum += sum(-[y*max(log p,-100)+(1-y)*max(log(1-p),-100)]);
  * g_logit follows autograd's op sequence ((p-y)/max(p(1-p),1e-12)/B * p(1-p)), i.e. (p-y)/B except where p

@@ -292,3 +292,60 @@ def test_sigmoid_bce():
     pred, l, gz = ops.sigmoid_bce(z.detach().cuda(), y.cuda())
     (want,) = torch.autograd.grad(torch.nn.BCELoss()(torch.sigmoid(z), y), z)
     close(gz, want, rtol=1e-4, atol=1e-9)
+
+
+# ------------------------------------------------------------------ AFM attention pooling
+@pytest.mark.parametrize("F,D,A,B", [(6, 16, 8, 200), (6, 128, 64, 70), (39, 32, 64, 24), (5, 8, 40, 64), (3, 4, 1, 33)])
+def test_afm_pool_fwd_bwd(F, D, A, B):
+    ops = _ops()
+    g = torch.Generator().manual_seed(F * D + A)
+    E = (torch.randn(B, F, D, generator=g) * 0.5).requires_grad_(True)
+    W = (torch.randn(D, A, generator=g) * 0.3).requires_grad_(True)
+    b = torch.randn(A, generator=g).requires_grad_(True)
+    h = torch.randn(A, 1, generator=g).requires_grad_(True)
+    gp = torch.randn(B, D, generator=g)
+    want = OI.afm_pool(E, W, b, h)
+    gE, gW, gb, gh = torch.autograd.grad((want * gp).sum(), [E, W, b, h])
+    pooled, attw = ops.afm_fwd(E.detach().cuda(), W.detach().cuda(), b.detach().cuda(), h.detach().cuda())
+    # every output is a softmax-weighted sum of D- or A-term dot products: 1e-5 relative, with the absolute floor
+    # tied to the tensor's own scale (elements far below the scale carry the rounding of the large terms)
+    def scaled(got, ref):
+        close(got, ref, rtol=1e-5, atol=1e-5 * max(1e-3, float(ref.abs().max())))
+    scaled(pooled, want.detach())
+    dE, dW, db, dh = ops.afm_bwd(E.detach().cuda(), W.detach().cuda(), b.detach().cuda(), h.detach().cuda(), attw, gp.cuda())
+    scaled(dE, gE)
+    scaled(dW, gW)
+    scaled(db, gb)
+    scaled(dh, gh.view(-1))
+    dE2, dW2, _, _ = ops.afm_bwd(E.detach().cuda(), W.detach().cuda(), b.detach().cuda(), h.detach().cuda(), attw, gp.cuda())
+    assert torch.equal(dE, dE2) and torch.equal(dW, dW2)            # deterministic
+
+
+# ------------------------------------------------------------------ GRU recurrence
+@pytest.mark.parametrize("H,B,L", [(16, 50, 7), (64, 33, 100), (8, 17, 3), (32, 16, 20)])
+def test_gru_recurrence_fwd_bwd(H, B, L):
+    ops = _ops()
+    g = torch.Generator().manual_seed(H + L)
+    D = H
+    x = (torch.randn(B, L, D, generator=g) * 0.5).requires_grad_(True)
+    k = 1.0 / H ** 0.5
+    w_ih, w_hh = [((torch.rand(3 * H, n, generator=g) * 2 - 1) * k).requires_grad_(True) for n in (D, H)]
+    b_ih, b_hh = [((torch.rand(3 * H, generator=g) * 2 - 1) * k).requires_grad_(True) for _ in range(2)]
+    gl = torch.randn(B, H, generator=g)
+    want = OI.gru(x, w_ih, w_hh, b_ih, b_hh)
+    grads = torch.autograd.grad((want * gl).sum(), [x, w_ih, w_hh, b_ih, b_hh])
+    # the oracle restatement itself equals torch.nn.GRU
+    ref = torch.nn.GRU(D, H, batch_first=True)
+    with torch.no_grad():
+        ref.weight_ih_l0.copy_(w_ih), ref.weight_hh_l0.copy_(w_hh), ref.bias_ih_l0.copy_(b_ih), ref.bias_hh_l0.copy_(b_hh)
+    np.testing.assert_allclose(ref(x)[1][-1].detach().numpy(), want.detach().numpy(), rtol=1e-5, atol=1e-6)
+    gi = (x.detach() @ w_ih.detach().t() + b_ih.detach()).cuda()
+    h_all, gates = ops.gru_fwd(gi, w_hh.detach().cuda(), b_hh.detach().cuda())
+    close(h_all[:, -1], want.detach(), rtol=1e-5, atol=1e-6)
+    d_gi, d_gh = ops.gru_bwd(w_hh.detach().cuda(), h_all, gates, g_h_last=gl.cuda())
+    d_gi, d_gh = d_gi.cpu(), d_gh.cpu()
+    h_prev = torch.cat([torch.zeros(B, 1, H), h_all.cpu()[:, :-1]], dim=1)
+    got = [d_gi @ w_ih.detach(), d_gi.reshape(-1, 3 * H).t() @ x.detach().reshape(-1, D),
+           d_gh.reshape(-1, 3 * H).t() @ h_prev.reshape(-1, H), d_gi.sum((0, 1)), d_gh.sum((0, 1))]
+    for a, w_, name in zip(got, grads, ["dx", "dW_ih", "dW_hh", "db_ih", "db_hh"]):
+        np.testing.assert_allclose(a.numpy(), w_.numpy(), rtol=1e-5, atol=2e-6 * max(1.0, float(w_.abs().max())), err_msg=name)
