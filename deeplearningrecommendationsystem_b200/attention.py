@@ -27,13 +27,32 @@ def afm_pool(E, W, b, h):
     return _AFMPool.apply(E.contiguous(), W, b, h)
 
 
-def din_attention(hist_embed, target_embed, unit, pool):
+class _DINAttention(torch.autograd.Function):
+    """rs_din_fwd / rs_din_bwd on rows (B, L+1, D) = [history | target]."""
+
+    @staticmethod
+    def forward(ctx, rows, pool, W0, b0, W1, b1, W2, b2):
+        from . import ops
+        ws = (W0, b0, W1, b1, W2, b2)
+        out, _ = ops.din_fwd(rows, [t.detach() for t in ws], pool)
+        ctx.pool = pool
+        ctx.save_for_backward(rows, *ws)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import ops
+        rows, *ws = ctx.saved_tensors
+        d_rows, dws = ops.din_bwd(rows, [t.detach() for t in ws], ctx.pool, g.contiguous())
+        return (d_rows, None, *dws)
+
+
+def din_attention(rows, unit, pool):
     """softmax_L(MLP([h, h-t, t])) applied to the history                               reference model/din.py:39-47.
-    pool=True -> (B, D) weighted sum; pool=False -> (B, L, D) scaled history (model/dien.py:33-37)."""
-    t = target_embed.unsqueeze(1).expand_as(hist_embed)
-    w = torch.softmax(unit(torch.cat([hist_embed, hist_embed - t, t], dim=-1)).squeeze(-1), dim=-1)
-    scaled = hist_embed * w.unsqueeze(-1)
-    return scaled.sum(dim=1) if pool else scaled
+    rows (B, L+1, D): gathered history rows followed by the target row; unit = Sequential(Linear, ReLU, Linear, ReLU,
+    Linear).  pool=True -> (B, D) weighted sum; pool=False -> (B, L, D) scaled history (model/dien.py:33-37)."""
+    l0, l1, l2 = unit[0], unit[2], unit[4]
+    return _DINAttention.apply(rows.contiguous(), pool, l0.weight, l0.bias, l1.weight, l1.bias, l2.weight, l2.bias)
 
 
 class _GRURecurrence(torch.autograd.Function):

@@ -22,8 +22,7 @@ class DIN(nn.Module):
 
     def forward(self, hist, target_item):
         rows = K.lookup(self.item_embedding.weight, torch.cat([hist, target_item.unsqueeze(1)], dim=1))
-        hist_embed, target_embed = rows[:, :-1], rows[:, -1]
-        return attention.din_attention(hist_embed, target_embed, self.attention, pool=False), target_embed
+        return attention.din_attention(rows, self.attention, pool=False), rows[:, -1]
 
 
 class DIEN(nn.Module):

@@ -23,9 +23,8 @@ class DIN(nn.Module):
 
     def forward(self, hist, target_item):
         rows = K.lookup(self.item_embedding.weight, torch.cat([hist, target_item.unsqueeze(1)], dim=1))   # (B, L+1, D)
-        hist_embed, target_embed = rows[:, :-1], rows[:, -1]
-        pooled = attention.din_attention(hist_embed, target_embed, self.attention, pool=True)           # (B, D)
-        return self.fc(torch.cat([pooled, target_embed], dim=1))
+        pooled = attention.din_attention(rows, self.attention, pool=True)                                # (B, D)
+        return self.fc(torch.cat([pooled, rows[:, -1]], dim=1))
 
     def recommendation(self, num_users, num_items, hist_list, k):
         device = next(self.parameters()).device

@@ -447,3 +447,52 @@ def afm_bwd(E, W, b, h, attw, g_pooled):
                    "rs_afm_bwd")
     _count()
     return dE, dWp.sum(dim=0), dbp.sum(dim=0), dhp.sum(dim=0)
+
+
+def _din_weights(ws):
+    W0, b0, W1, b1, W2, b2 = [_f32(t) for t in ws]
+    _need_cuda(W0, b0, W1, b1, W2, b2)
+    w = _lib.rs_din_weights()
+    w.W0, w.b0, w.W1, w.b1, w.W2, w.b2 = (t.data_ptr() for t in (W0, b0, W1, b1, W2, b2))
+    w.H1, w.H2 = W0.shape[0], W1.shape[0]
+    return w, (W0, b0, W1, b1, W2, b2)
+
+
+def din_fwd(rows, ws, pool, want_attw=False):
+    """rows (B, L+1, D) = [history | target]; ws = (W0, b0, W1, b1, W2, b2) -> out (B,D) | (B,L,D), attw (B,L) | None."""
+    rows = _f32(rows)
+    _need_cuda(rows)
+    B, L1, D = rows.shape
+    L = L1 - 1
+    w, keep = _din_weights(ws)
+    out = torch.empty((B, D) if pool else (B, L, D), dtype=torch.float32, device=rows.device)
+    attw = torch.empty(B, L, dtype=torch.float32, device=rows.device) if want_attw else None
+    with _timed("din_fwd"):
+        _lib.check(_lib.load().rs_din_fwd(rows.data_ptr(), B, L, D, C.byref(w), int(bool(pool)), out.data_ptr(), _p(attw), _stream()),
+                   "rs_din_fwd")
+    _count()
+    return out, attw
+
+
+def din_bwd(rows, ws, pool, g_out):
+    """-> d_rows (B, L+1, D), (dW0, db0, dW1, db1, dW2, db2)."""
+    rows, g_out = _f32(rows), _f32(g_out)
+    B, L1, D = rows.shape
+    L = L1 - 1
+    w, keep = _din_weights(ws)
+    H1, H2 = w.H1, w.H2
+    lib = _lib.load()
+    parts = C.c_int32(0)
+    _lib.check(lib.rs_din_num_parts(B, C.byref(parts)), "rs_din_num_parts")
+    n, dev = parts.value, rows.device
+    d_rows = torch.empty_like(rows)
+    mk = lambda *shape: torch.empty(n, *shape, dtype=torch.float32, device=dev)   # noqa: E731
+    dWab, dWt, dW1, db0, db1, dW2, db2 = mk(H1, D), mk(H1, D), mk(H2, H1), mk(H1), mk(H2), mk(H2), mk()
+    with _timed("din_bwd"):
+        _lib.check(lib.rs_din_bwd(rows.data_ptr(), B, L, D, C.byref(w), int(bool(pool)), g_out.data_ptr(), d_rows.data_ptr(),
+                                  dWab.data_ptr(), dWt.data_ptr(), dW1.data_ptr(), db0.data_ptr(), db1.data_ptr(), dW2.data_ptr(),
+                                  db2.data_ptr(), n, _stream()), "rs_din_bwd")
+    _count()
+    dWab, dWt = dWab.sum(0), dWt.sum(0)
+    dW0 = torch.cat([dWab, dWab - dWt, dWt], dim=1)
+    return d_rows, (dW0, db0.sum(0), dW1.sum(0), db1.sum(0), dW2.sum(0).view(1, H2), db2.sum(0).view(1))

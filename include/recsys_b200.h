@@ -188,6 +188,27 @@ int rs_afm_bwd(const float *E, int64_t B, int32_t F, int32_t D, int32_t A, const
                const float *h, const float *attw, const float *g_pooled, float *dE, float *dW_part, float *db_part,
                float *dh_part, int32_t num_parts, void *stream);
 
+/* ---- DIN target attention (model/din.py:39-47; model/dien.py:27-37 with pool == 0), forward and backward.
+ * rows (B, L+1, D): the L gathered history rows followed by the target row (the layout rs_gather_rows produces for
+ * ids = [hist | target]).  Attention unit 3D -> H1 -> H2 -> 1 with ReLU (torch Linear layout (out, in)), softmax over
+ * L without mask or scaling.  pool != 0: out (B, D) = sum_l w_l h_l;  pool == 0: out (B, L, D) = w_l h_l.
+ * The concat [h, h-t, t] is never built: W0 z = (Wa+Wb) h + (Wc-Wb) t.  Built for D in {16,32,64} and
+ * (H1,H2) in {(128,64),(64,32)}.
+ * Backward recomputes the activations; d_rows (B, L+1, D) is the gradient THROUGH the attention (add the direct uses
+ * of the rows outside).  Weight gradients come back as per-CTA partials (num_parts = rs_din_num_parts(B)), to be
+ * added in index order:  dW0 = [dWab | dWab - dWt | dWt]  with dWab, dWt (parts, H1, D);  dW1 (parts, H2, H1);
+ * db0 (parts, H1); db1 (parts, H2); dW2 (parts, H2); db2 (parts). */
+typedef struct rs_din_weights {
+  const float *W0, *b0, *W1, *b1, *W2, *b2;
+  int32_t H1, H2;
+} rs_din_weights;
+int rs_din_num_parts(int64_t B, int32_t *parts);
+int rs_din_fwd(const float *rows, int64_t B, int32_t L, int32_t D, const rs_din_weights *w, int32_t pool, float *out,
+               float *attw /* (B, L) or NULL */, void *stream);
+int rs_din_bwd(const float *rows, int64_t B, int32_t L, int32_t D, const rs_din_weights *w, int32_t pool,
+               const float *g_out, float *d_rows, float *dWab_part, float *dWt_part, float *dW1_part, float *db0_part,
+               float *db1_part, float *dW2_part, float *db2_part, int32_t num_parts, void *stream);
+
 /* ---- GRU recurrence (nn.GRU(D, H, batch_first=True), one layer, h0 = 0, gate order r,z,n; model/dien.py:47,61).
  * The input projection gi = x.W_ih^T + b_ih (B, L, 3H) is a plain library GEMM done by the caller; rs_gru_fwd runs
  * the L sequential steps (W_hh register-resident, BT batch rows per CTA): h_all (B, L, H) and, for BPTT,

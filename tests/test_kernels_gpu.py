@@ -310,7 +310,7 @@ def test_afm_pool_fwd_bwd(F, D, A, B):
     # every output is a softmax-weighted sum of D- or A-term dot products: 1e-5 relative, with the absolute floor
     # tied to the tensor's own scale (elements far below the scale carry the rounding of the large terms)
     def scaled(got, ref):
-        close(got, ref, rtol=1e-5, atol=1e-5 * max(1e-3, float(ref.abs().max())))
+        close(got, ref, rtol=1e-5, atol=max(1e-6, 1e-5 * float(ref.abs().max())))
     scaled(pooled, want.detach())
     dE, dW, db, dh = ops.afm_bwd(E.detach().cuda(), W.detach().cuda(), b.detach().cuda(), h.detach().cuda(), attw, gp.cuda())
     scaled(dE, gE)
@@ -349,3 +349,35 @@ def test_gru_recurrence_fwd_bwd(H, B, L):
            d_gh.reshape(-1, 3 * H).t() @ h_prev.reshape(-1, H), d_gi.sum((0, 1)), d_gh.sum((0, 1))]
     for a, w_, name in zip(got, grads, ["dx", "dW_ih", "dW_hh", "db_ih", "db_hh"]):
         np.testing.assert_allclose(a.numpy(), w_.numpy(), rtol=1e-5, atol=2e-6 * max(1.0, float(w_.abs().max())), err_msg=name)
+
+
+# ------------------------------------------------------------------ DIN target attention
+@pytest.mark.parametrize("D,H1,H2,L,B,pool", [(16, 128, 64, 7, 90, True), (64, 128, 64, 100, 20, True), (16, 64, 32, 7, 90, False),
+                                             (64, 64, 32, 100, 11, False), (32, 128, 64, 33, 40, True), (16, 128, 64, 1, 5, True)])
+def test_din_attention_fwd_bwd(D, H1, H2, L, B, pool):
+    ops = _ops()
+    g = torch.Generator().manual_seed(D + L + H1)
+    rows = (torch.randn(B, L + 1, D, generator=g) * 0.5).requires_grad_(True)
+    lin = lambda o, i: ((torch.rand(o, i, generator=g) * 2 - 1) / i ** 0.5).requires_grad_(True)   # noqa: E731
+    vec = lambda o, i: ((torch.rand(o, generator=g) * 2 - 1) / i ** 0.5).requires_grad_(True)      # noqa: E731
+    ws = [lin(H1, 3 * D), vec(H1, 3 * D), lin(H2, H1), vec(H2, H1), lin(1, H2), vec(1, H2)]
+    h, t = rows[:, :-1], rows[:, -1]
+    w = OI.din_attention(h, t, [(ws[0], ws[1]), (ws[2], ws[3]), (ws[4], ws[5])])
+    want = (h * w.unsqueeze(-1)).sum(1) if pool else h * w.unsqueeze(-1)
+    gup = torch.randn(*want.shape, generator=g)
+    grads = torch.autograd.grad((want * gup).sum(), [rows] + ws)
+    cw = [t_.detach().cuda() for t_ in ws]
+    out, attw = ops.din_fwd(rows.detach().cuda(), cw, pool, want_attw=True)
+
+    def scaled(got, ref, name=""):
+        close(got, ref, rtol=1e-5, atol=1e-5 * max(1e-3, float(ref.abs().max())), msg=name)
+    scaled(attw, w.detach(), "attw")
+    scaled(out, want.detach(), "out")
+    d_rows, dws = ops.din_bwd(rows.detach().cuda(), cw, pool, gup.cuda())
+    scaled(d_rows, grads[0], "d_rows")
+    for got, ref, name in zip(dws[:5], grads[1:6], ["dW0", "db0", "dW1", "db1", "dW2"]):
+        scaled(got, ref, name)
+    # softmax is shift invariant, so d loss / d b2 == 0 analytically: both sides are pure rounding noise
+    assert float(dws[5].abs().max()) <= 1e-5 * max(1e-3, float(grads[5].abs().max()), float(grads[4].abs().max()))
+    d2, dws2 = ops.din_bwd(rows.detach().cuda(), cw, pool, gup.cuda())
+    assert torch.equal(d_rows, d2) and all(torch.equal(a, b_) for a, b_ in zip(dws, dws2))   # deterministic
