@@ -51,10 +51,23 @@ class Plan:
 
 
 class RowExchange:
+    _memo = {}    # (device, group) -> (key tensor, version, total_rows, Plan): the plan depends only on the keys
+
     def __init__(self, prims, group=None):
         self.prims, self.group = prims, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def plan_for(self, ids, offsets, total_rows):
+        """plan() on keys = ids + offsets, memoised on the identity of `ids`: two tables indexed by the same id
+        tensor with the same row offsets (the FM and the FFM model of one batch) exchange the same rows."""
+        slot = (ids.device, id(self.group))
+        hit = RowExchange._memo.get(slot)
+        if hit is not None and hit[0] is ids and hit[1] == ids._version and hit[2] == total_rows and hit[3] is offsets:
+            return hit[4]
+        plan = self.plan((ids + offsets).reshape(-1), total_rows)
+        RowExchange._memo[slot] = (ids, ids._version, total_rows, offsets, plan)
+        return plan
 
     def local_rows(self, total_rows):
         return (total_rows - self.rank + self.world - 1) // self.world

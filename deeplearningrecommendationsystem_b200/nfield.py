@@ -99,6 +99,17 @@ class _FieldModel(nn.Module):
         self._pending, self._anchor, self._token = {}, None, 0
         self.adam_m = self.adam_v = None
 
+    _offset_cache = {}
+
+    def _offsets_key(self):
+        """one shared device tensor per (device, offsets): models with equal field layouts share exchange plans"""
+        key = (self.weight.device, tuple(self.offsets_host))
+        t = _FieldModel._offset_cache.get(key)
+        if t is None:
+            t = torch.tensor(self.offsets_host, dtype=torch.int64, device=self.weight.device)
+            _FieldModel._offset_cache[key] = t
+        return t
+
     def load_global(self, global_weight):
         """sharded mode: take this rank's rows (r % N == rank) of a full (total_rows, W) table."""
         from . import dist as rsdist
@@ -137,7 +148,8 @@ class _FieldModel(nn.Module):
             # row-sharded: reduce the batch's gradients per fetched row, send them to the owners, update there
             plan, ex = rec["plan"], self.exchange
             segs = ops.dedup_sort(rec["ids"].reshape(-1), 1, None, plan.n_uniq, max_width=self.width)
-            block_grad = torch.zeros(plan.n_uniq, self.width, dtype=torch.float32, device=rec["g"].device)
+            # every fetched row has at least one lookup in this batch, so RS_UPD_GRAD writes every row of the block
+            block_grad = torch.empty(plan.n_uniq, self.width, dtype=torch.float32, device=rec["g"].device)
             ops.segment_update(segs, ops.RS_UPD_GRAD, self.width, self.F, stash=rec["stash"], scale=rec["g"] * (1.0 / ex.world),
                                dense_grad=block_grad)
             recv = ex.push_grads(plan, block_grad)
@@ -155,7 +167,7 @@ class _FieldModel(nn.Module):
         train = torch.is_grad_enabled()
         rec = {}
         if self.sharded:
-            plan = self.exchange.plan((ids + self.offsets_dev).reshape(-1), self.total_rows)
+            plan = self.exchange.plan_for(ids, self._offsets_key(), self.total_rows)
             block = self.exchange.fetch(plan, self.weight.data)
             ids = plan.local_ids.view(ids.shape)
             cross, stash = self._interact(ops.make_tables([block] * self.F), ids, want_stash=train)
