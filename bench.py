@@ -276,8 +276,9 @@ def run_gpu(args):
         for name, key in (("ffm_fwd", "ffm_fwd"), ("fields_fwd", "fm_fwd"), ("segment_update[w16]", "fm_bwd_upd")):
             if name in kern:
                 extra[name] = {"ms": kern[name], "algorithmic_GBps": BYTES[key] * B / (kern[name] / 1e3) / 1e9}
-        if "dedup_sort" in kern:
-            extra["dedup_sort"] = {"ms": kern["dedup_sort"]}
+        for name in kern:
+            if name not in extra and name != dom:
+                extra[name] = {"ms": kern[name], "calls_per_step": len(agg[name]) / args.steps}
         line = {
             "metric": "train samples/sec (fwd+bwd+update)", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

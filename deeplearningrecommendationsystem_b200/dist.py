@@ -21,6 +21,18 @@ import torch
 import torch.distributed as dist
 
 
+def _phase(name):
+    """CUDA-event bracket used by bench.py's per-phase timing (no-op unless ops.PROFILE is set, or on CPU)."""
+    import contextlib
+    try:
+        from . import ops
+        if ops.PROFILE is not None and torch.cuda.is_available():
+            return ops._timed(name)
+    except Exception:
+        pass
+    return contextlib.nullcontext()
+
+
 @dataclass
 class Prims:
     unique: callable      # (keys (n,) int64, total_rows) -> (uniq ascending (nu,), inverse (n,) int64)
@@ -74,6 +86,10 @@ class RowExchange:
 
     def plan(self, keys, total_rows):
         """keys: (n,) int64 GLOBAL row of every lookup of the local batch."""
+        with _phase("exchange_plan"):
+            return self._plan(keys, total_rows)
+
+    def _plan(self, keys, total_rows):
         N = self.world
         uniq, inverse = self.prims.unique(keys, total_rows)
         owner = uniq % N
@@ -101,19 +117,21 @@ class RowExchange:
         """-> (n_uniq, W) block holding the rows this rank's batch needs, in the order `local_ids` indexes."""
         mine = self.prims.gather(local_table, plan.recv_local)
         out = torch.empty(plan.n_uniq, local_table.shape[1], dtype=local_table.dtype, device=local_table.device)
-        if self.world > 1:
-            dist.all_to_all_single(out, mine, plan.send_counts, plan.recv_counts, group=self.group)
-        else:
-            out.copy_(mine)
+        with _phase("exchange_rows"):
+            if self.world > 1:
+                dist.all_to_all_single(out, mine, plan.send_counts, plan.recv_counts, group=self.group)
+            else:
+                out.copy_(mine)
         return out
 
     def push_grads(self, plan, grads):
         """grads (n_uniq, W) in fetched-block order -> (m, W) aligned with plan.recv_local on the owners."""
         out = torch.empty(plan.recv_local.numel(), grads.shape[1], dtype=grads.dtype, device=grads.device)
-        if self.world > 1:
-            dist.all_to_all_single(out, grads.contiguous(), plan.recv_counts, plan.send_counts, group=self.group)
-        else:
-            out.copy_(grads)
+        with _phase("exchange_grads"):
+            if self.world > 1:
+                dist.all_to_all_single(out, grads.contiguous(), plan.recv_counts, plan.send_counts, group=self.group)
+            else:
+                out.copy_(grads)
         return out
 
 

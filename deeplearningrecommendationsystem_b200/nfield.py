@@ -147,7 +147,7 @@ class _FieldModel(nn.Module):
                 continue
             # row-sharded: reduce the batch's gradients per fetched row, send them to the owners, update there
             plan, ex = rec["plan"], self.exchange
-            segs = ops.dedup_sort(rec["ids"].reshape(-1), 1, None, plan.n_uniq, max_width=self.width)
+            segs = ops.dedup_sort(plan.local_ids, 1, None, plan.n_uniq, max_width=self.width)   # memoised per plan
             # every fetched row has at least one lookup in this batch, so RS_UPD_GRAD writes every row of the block
             block_grad = torch.empty(plan.n_uniq, self.width, dtype=torch.float32, device=rec["g"].device)
             ops.segment_update(segs, ops.RS_UPD_GRAD, self.width, self.F, stash=rec["stash"], scale=rec["g"] * (1.0 / ex.world),
@@ -182,7 +182,9 @@ class _FieldModel(nn.Module):
             cross = _CrossFn.apply(self._anchor, cross, self, self._token)
         elif train:
             cross = _DenseGradFn.apply(self.weight, cross, self, ids, stash)
-        return cross + self.bias
+        return cross + self.bias if self.use_bias else cross
+
+    use_bias = True
 
     def forward(self, ids):
         return torch.sigmoid(self.logit(ids)).unsqueeze(1)
@@ -209,3 +211,24 @@ class FieldFFM(_FieldModel):
 
     def _interact(self, T, ids, want_stash):
         return ops.ffm_fwd(T, ids, self.D, want_stash=want_stash)
+
+
+class FieldMF(_FieldModel):
+    """sigmoid(<U[u], V[i]>) with the user and item tables in one concatenated (optionally row-sharded) buffer --
+    the large-table form of reference model/mf.py:11-26 (same forward signature and 1-D output) for the synthetic
+    100 M-row configs.  d dot / d U[u] = V[i] is exactly the FM Jacobian S - e for two fields, so the fused lookup
+    kernel's stash and the segment-reduce/update path are shared with FieldFM."""
+
+    use_bias = False
+
+    def __init__(self, num_users, num_items, embedding_size, fused=True, seed=None, device=None, sharded=False, group=None):
+        super().__init__([num_users, num_items], embedding_size, embedding_size, fused, seed, device, sharded, group)
+        self.bias.requires_grad_(False)
+
+    def _interact(self, T, ids, want_stash):
+        out = ops.fields_fwd(T, ids.shape[0], ids.device, ids=ids, dot2=True, stash=want_stash)
+        return out["dot2"], out.get("stash")
+
+    def forward(self, user_indices, item_indices):
+        ids = torch.stack([user_indices, item_indices], dim=1)
+        return torch.sigmoid(self.logit(ids))                       # (B,)

@@ -122,8 +122,9 @@ def gather_rows(T, ids):
     _need_cuda(ids)
     B = ids.numel() // T.num_fields
     out = torch.empty(B, T.num_fields, T.width, dtype=torch.float32, device=ids.device)
-    _lib.check(_lib.load().rs_gather_rows(C.byref(T), ids.data_ptr(), B, out.data_ptr(), status_word(ids.device).data_ptr(), _stream()),
-               "rs_gather_rows")
+    with _timed(f"gather_rows[w{T.width}]"):
+        _lib.check(_lib.load().rs_gather_rows(C.byref(T), ids.data_ptr(), B, out.data_ptr(), status_word(ids.device).data_ptr(),
+                                              _stream()), "rs_gather_rows")
     _count()
     return out
 
@@ -261,9 +262,9 @@ class Segments:
         return self._view(self.seg.sorted_pos, self.n, torch.int32)
 
 
-_ws_cache = {}
 _partial_cache = {}
 _seg_memo = {}
+_MEMO_SLOTS = 4      # memoised dedup results per device (each owns its workspace)
 
 
 def _partial_buffer(device, n, width):
@@ -288,31 +289,37 @@ def dedup_sort(ids, F=1, row_offset=None, total_rows=None, max_width=1, reuse_wo
     _need_cuda(ids)
     n = ids.numel()
     lib = _lib.load()
-    memo_key = (ids.device, ids.data_ptr(), ids._version, n, F, tuple(int(o) for o in row_offset) if row_offset is not None else None,
+    memo_key = (ids.data_ptr(), ids._version, n, F, tuple(int(o) for o in row_offset) if row_offset is not None else None,
                 int(total_rows)) if reuse_workspace else None
-    hit = _seg_memo.get(ids.device) if reuse_workspace else None
-    if hit is not None and hit[0] == memo_key and hit[2] is ids:
-        segs = hit[1]
-    else:
+    slots = _seg_memo.setdefault(ids.device, []) if reuse_workspace else None
+    segs = None
+    if reuse_workspace:
+        for i, (k, sg, ref) in enumerate(slots):
+            if k == memo_key and ref is ids:
+                segs = sg
+                slots.append(slots.pop(i))          # most recently used last
+                break
+    if segs is None:
         nbytes = C.c_size_t(0)
         _lib.check(lib.rs_dedup_workspace_bytes(n, 1, C.byref(nbytes)), "rs_dedup_workspace_bytes")
-        key = (ids.device, n) if reuse_workspace else None
-        ws = _ws_cache.get(key) if key is not None else None
+        ws = None
+        if reuse_workspace and len(slots) >= _MEMO_SLOTS:     # recycle the least recently used slot's workspace
+            _, old, _ = slots.pop(0)
+            if old.ws.numel() >= nbytes.value:
+                ws = old.ws
         if ws is None:
             ws = torch.empty(nbytes.value, dtype=torch.uint8, device=ids.device)
-            if key is not None:
-                _ws_cache[key] = ws
         seg = _lib.rs_segments()
         offs = None
         if row_offset is not None:
             offs = (C.c_int64 * F)(*[int(o) for o in row_offset])
         with _timed("dedup_sort"):
-            _lib.check(lib.rs_dedup_sort(ids.data_ptr(), n, F, offs, int(total_rows), ws.data_ptr(), nbytes.value, C.byref(seg),
+            _lib.check(lib.rs_dedup_sort(ids.data_ptr(), n, F, offs, int(total_rows), ws.data_ptr(), ws.numel(), C.byref(seg),
                                          status_word(ids.device).data_ptr(), _stream()), "rs_dedup_sort")
         _count(10)
         segs = Segments(ws, seg, n, ids.device)
         if reuse_workspace:
-            _seg_memo[ids.device] = (memo_key, segs, ids)      # one live memo per device: the workspace is shared
+            slots.append((memo_key, segs, ids))
     part = _partial_buffer(ids.device, n, int(max_width)) if reuse_workspace else \
         torch.empty(2 * (n // _lib.RS_CHUNK + 2) * int(max_width), dtype=torch.float32, device=ids.device)
     segs.partial = part

@@ -93,3 +93,43 @@ def test_fused_adam_matches_row_oracle():
         (G,) = torch.autograd.grad(l, E)
         oo.adam_rows(table, m, v, (ids + offsets).reshape(-1), G.reshape(-1, 16), step, lr=1e-2)
         np.testing.assert_allclose(model.weight.detach().cpu().numpy(), table.numpy(), rtol=2e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("kind", ["sgd", "adam"])
+def test_field_mf_matches_mf_oracle(kind):
+    """FieldMF (one concatenated table, fused row update) == the reference MF arithmetic (oracle.ml100k.mf)."""
+    from deeplearningrecommendationsystem_b200.nfield import FieldMF
+    from deeplearningrecommendationsystem_b200.optim import FusedRowOptimizer
+    from oracle import ml100k, optim as oo, interactions as OI
+    nu, ni, D, B = 300, 500, 64, 2000
+    g = torch.Generator().manual_seed(3)
+    u = (torch.rand(B, generator=g) ** 2 * nu).long()
+    i = torch.randint(0, ni, (B,), generator=g)
+    y = (torch.rand(B, generator=g) < 0.3).float()
+    m = FieldMF(nu, ni, D, fused=True, seed=5, device="cuda")
+    U, V = m.weight.detach().cpu()[:nu].clone(), m.weight.detach().cpu()[nu:].clone()
+    opt = FusedRowOptimizer(m, None, lr=0.05, kind=kind)
+    state = {k: (torch.zeros_like(t), torch.zeros_like(t)) for k, t in (("U", U), ("V", V))}
+    for step in (1, 2, 3):
+        opt.zero_grad()
+        pred = m(u.cuda(), i.cuda())
+        assert pred.shape == (B,)
+        loss = torch.nn.BCELoss()(pred, y.cuda())
+        loss.backward()
+        opt.step()
+        sd = {"user_embeddings.weight": U.clone().requires_grad_(True), "item_embeddings.weight": V.clone().requires_grad_(True)}
+        p = ml100k.mf(sd, u, i)
+        l = OI.bce(p, y)
+        gU, gV = torch.autograd.grad(l, list(sd.values()))
+        np.testing.assert_allclose(pred.detach().cpu().numpy(), p.detach().numpy(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(loss.item(), l.item(), rtol=1e-5)
+        if kind == "sgd":
+            U -= 0.05 * gU
+            V -= 0.05 * gV
+        else:
+            for name, tab, gr, ids in (("U", U, gU, u), ("V", V, gV, i)):
+                touched = torch.unique(ids)
+                oo.adam_rows(tab, state[name][0], state[name][1], touched, gr[touched], step, lr=0.05)
+        got = m.weight.detach().cpu()
+        np.testing.assert_allclose(got[:nu].numpy(), U.numpy(), rtol=2e-5, atol=2e-4 if kind == "adam" else 2e-6)
+        np.testing.assert_allclose(got[nu:].numpy(), V.numpy(), rtol=2e-5, atol=2e-4 if kind == "adam" else 2e-6)
