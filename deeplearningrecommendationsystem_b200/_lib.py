@@ -34,7 +34,7 @@ class rs_fields_grad(C.Structure):
 class rs_segments(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
                 ("sorted_key", "sorted_pos", "uniq", "inverse", "counts", "seg_start", "seg_first_chunk",
-                 "chunk_start", "chunk_seg", "multi_seg", "lookup_desc", "work_counter", "n_uniq", "n_chunks", "n_multi", "partial")] + [("partial_floats", C.c_int64)]
+                 "chunk_start", "chunk_seg", "multi_seg", "lookup_desc", "work_counter", "unit_start", "scale_sorted", "n_uniq", "n_chunks", "n_multi", "partial")] + [("partial_floats", C.c_int64)]
 
 
 class rs_update(C.Structure):

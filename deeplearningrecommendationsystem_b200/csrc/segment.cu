@@ -113,10 +113,20 @@ __global__ void __launch_bounds__(256) lookup_desc_kernel(const int32_t *__restr
   desc[s] = make_int4(sorted_pos[s], flags, (int)(uint32_t)uniq[g], 2 * (s0 / RS_CHUNK) + ((s1 - s0) < RS_CHUNK ? 1 : 0));
 }
 
+// Work units of the streaming kernel start on chunk boundaries: unit u = chunks whose first lookup is in
+// [u*RS_UNIT, (u+1)*RS_UNIT).  unit_start[u] = first chunk start >= u*RS_UNIT (n past the end).
+__global__ void __launch_bounds__(256) unit_start_kernel(const int4 *__restrict__ desc, int64_t n, int nunits, int32_t *__restrict__ unit_start) {
+  int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u > nunits) return;
+  int64_t s = (int64_t)u * RS_UNIT;
+  while (s < n && !(desc[s].y & 1)) ++s;  // a chunk has at most RS_CHUNK lookups, so this stops within RS_CHUNK steps
+  unit_start[u] = (int32_t)(s < n ? s : n);
+}
+
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t sorted_key, sorted_pos, uniq, inverse, counts, seg_start, seg_first_chunk, chunk_start, chunk_seg, multi_seg, lookup_desc, scalars;
+  size_t sorted_key, sorted_pos, uniq, inverse, counts, seg_start, seg_first_chunk, chunk_start, chunk_seg, multi_seg, lookup_desc, unit_start, scale_sorted, scalars;
   size_t keys_in, pos_in, head, segidx1, chead, chunkidx1, cub, partial, total;
   size_t cub_bytes, partial_floats;
 };
@@ -141,6 +151,8 @@ WsLayout layout(int64_t n, int max_width) {
   L.chunk_seg = take(n * 4);
   L.multi_seg = take(n * 4);
   L.lookup_desc = take(n * 16);
+  L.unit_start = take((n / RS_UNIT + 2) * 4);
+  L.scale_sorted = take(n * 4);
   L.scalars = take(64);
   L.keys_in = take(n * 4);
   L.pos_in = take(n * 4);
@@ -197,6 +209,8 @@ RS_API int rs_dedup_sort(const int64_t *ids, int64_t n, int32_t F, const int64_t
   seg->n_multi = seg->n_uniq + 2;
   seg->work_counter = seg->n_uniq + 3;
   seg->lookup_desc = (int32_t *)(w + L.lookup_desc);
+  seg->unit_start = (int32_t *)(w + L.unit_start);
+  seg->scale_sorted = (float *)(w + L.scale_sorted);
   seg->partial = (float *)(w + L.partial);
   seg->partial_floats = (int64_t)((ws_bytes - L.partial) / 4);
   uint32_t *keys_in = (uint32_t *)(w + L.keys_in);
@@ -235,6 +249,9 @@ RS_API int rs_dedup_sort(const int64_t *ids, int64_t n, int32_t F, const int64_t
   RS_CHECK_LAUNCH();
   lookup_desc_kernel<<<blocks, 256, 0, st>>>(seg->sorted_pos, chunkidx1, seg->chunk_start, seg->chunk_seg, seg->seg_first_chunk,
                                              seg->uniq, n, (int4 *)seg->lookup_desc);
+  RS_CHECK_LAUNCH();
+  const int nunits = (int)(n / RS_UNIT + 1);
+  unit_start_kernel<<<(nunits + 256) / 256, 256, 0, st>>>((const int4 *)seg->lookup_desc, n, nunits, seg->unit_start);
   RS_CHECK_LAUNCH();
   return RS_OK;
 }
@@ -454,6 +471,8 @@ RS_API int rs_segment_update(const rs_segments *seg, int64_t n, const rs_update 
   P.n_multi = seg->n_multi;
   P.lookup_desc = (const int4 *)seg->lookup_desc;
   P.work_counter = seg->work_counter;
+  P.unit_start = seg->unit_start;
+  P.scale_sorted = seg->scale_sorted;
   P.uniq = seg->uniq;
   P.partial = seg->partial;
   P.stash = u->stash;

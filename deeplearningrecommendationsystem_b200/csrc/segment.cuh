@@ -9,6 +9,8 @@ struct UpdParams {
   const int64_t *uniq;
   const int4 *lookup_desc;
   int32_t *work_counter;
+  const int32_t *unit_start;
+  float *scale_sorted;
   float *partial;
   const float *stash, *scale, *dense;
   float *table, *m, *v, *dense_grad;

@@ -22,7 +22,7 @@ constexpr int BATCH = 4;       // stages the producer fills per iteration (32 la
 constexpr int NCW = 4;         // consumer warps
 constexpr int NCT = NCW * 32;  // consumer threads: thread t owns float4 columns t, t+128, ...
 constexpr int NTHREADS = NCT + 32;
-constexpr int UNIT = 256;      // sorted lookups per work unit
+constexpr int UNIT = RS_UNIT;   // sorted lookups per work unit
 constexpr int MAX_ST = 12;
 
 struct __align__(16) StageHdr {
@@ -67,37 +67,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) seg_stream_kernel(const __grid_co
 
   if (warp == NCW) {
     // ===================== producer =====================
+    // The producer is latency bound on its own metadata reads, so they are software pipelined: the record (and
+    // the pre-permuted scale) of batch i+1 and the boundaries of the next work unit are requested before batch i
+    // is issued.
     int k = 0;  // running stage counter
-    for (;;) {
-      int u = 0;
-      if (lane == 0) u = atomicAdd(P.work_counter, 1);
-      u = __shfl_sync(0xffffffffu, u, 0);
-      const int64_t lo = (int64_t)u * UNIT;
-      if (lo >= n) break;
-      // unit = chunks whose first lookup lies in [lo, lo+UNIT): find the first chunk start >= lo and >= lo+UNIT
-      int sA = n, sB = n;
-      for (int base = (int)lo; base < n && sA == n; base += 32) {
-        const int s = base + lane;
-        const bool first = s < n && (P.lookup_desc[s].y & 1);
-        const unsigned m = __ballot_sync(0xffffffffu, first);
-        if (m) sA = base + __ffs(m) - 1;
-        if (base - (int)lo >= RS_CHUNK) break;
-      }
-      if (sA >= lo + UNIT || sA >= n) continue;  // no chunk starts inside this unit
-      for (int base = (int)lo + UNIT; base < n && sB == n; base += 32) {
-        const int s = base + lane;
-        const bool first = s < n && (P.lookup_desc[s].y & 1);
-        const unsigned m = __ballot_sync(0xffffffffu, first);
-        if (m) sB = base + __ffs(m) - 1;
+    int u = 0;
+    if (lane == 0) u = atomicAdd(P.work_counter, 1);
+    u = __shfl_sync(0xffffffffu, u, 0);
+    const int nunits = n / UNIT + 1;
+    while (u < nunits) {
+      const int sA = P.unit_start[u], sB = P.unit_start[u + 1];
+      int un = 0;                                    // claim the next unit now; its latency hides behind this one
+      if (lane == 0) un = atomicAdd(P.work_counter, 1);
+      int4 d_nxt = make_int4(0, 0, 0, 0);
+      float sc_nxt = 1.0f;
+      if (sA + lane < sB) {
+        d_nxt = P.lookup_desc[sA + lane];
+        if (P.scale) sc_nxt = P.scale_sorted[sA + lane];
       }
       for (int s0 = sA; s0 < sB; s0 += SR * BATCH) {
         const int s = s0 + lane;
         const bool valid = s < sB;
-        int4 d = make_int4(0, 0, 0, 0);
-        float sc = 1.0f;
-        if (valid) {
-          d = P.lookup_desc[s];
-          if (P.scale) sc = __ldg(P.scale + d.x / P.F);
+        const int4 d = d_nxt;
+        const float sc = sc_nxt;
+        const int sn = s + SR * BATCH;               // prefetch the next batch of this unit
+        if (sn < sB) {
+          d_nxt = P.lookup_desc[sn];
+          if (P.scale) sc_nxt = P.scale_sorted[sn];
         }
         const bool want_table = valid && MODE == RS_UPD_SGD && (d.y & 6) == 6;  // last lookup of a single-chunk segment
         const int sub = lane >> 3, e = lane & 7;                                 // stage within the batch, entry within the stage
@@ -136,6 +132,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) seg_stream_kernel(const __grid_co
         }
         k += BATCH;
       }
+      u = __shfl_sync(0xffffffffu, un, 0);
     }
     // terminator stage
     const int st = k % nst;
@@ -227,6 +224,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) seg_stream_kernel(const __grid_co
   }
 }
 
+__global__ void __launch_bounds__(256) scale_sorted_kernel(const int4 *__restrict__ desc, const float *__restrict__ scale, int F, int n,
+                                                          float *__restrict__ out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n) out[s] = __ldg(scale + desc[s].x / F);
+}
+
 template <int NA>
 int launch_na(const UpdParams &P, int n, int mode, cudaStream_t st) {
   const size_t stage_bytes = (size_t)2 * SR * P.W * 4;
@@ -238,6 +241,10 @@ int launch_na(const UpdParams &P, int n, int mode, cudaStream_t st) {
   }
   const size_t smem = stage_bytes * nst;
   RS_CUDA(cudaMemsetAsync(P.work_counter, 0, sizeof(int32_t), st));
+  if (P.scale) {  // per-sample scale gathered into sorted-lookup order: the producer then reads it coalesced
+    scale_sorted_kernel<<<(n + 255) / 256, 256, 0, st>>>(P.lookup_desc, P.scale, P.F, n, P.scale_sorted);
+    RS_CHECK_LAUNCH();
+  }
   const int grid = num_sms();
 #define RS_LAUNCH_STREAM(M)                                                                                        \
   do {                                                                                                             \

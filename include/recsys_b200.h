@@ -29,6 +29,7 @@ extern "C" {
 
 #define RS_MAX_FIELDS 64
 #define RS_CHUNK 64 /* sorted lookups summed sequentially by one lane group (segment-reduce granularity) */
+#define RS_UNIT 512 /* sorted lookups per dynamically scheduled work unit of the streaming update kernel */
 
 enum { RS_OK = 0, RS_E_ARG = -1, RS_E_SHAPE = -2, RS_E_WORKSPACE = -3, RS_E_UNSUPPORTED = -4 };
 
@@ -116,6 +117,8 @@ typedef struct rs_segments {
   int32_t *lookup_desc;      /* [n*4] per sorted lookup: {pos, flags(1 first|2 last|4 single-chunk segment),
                                  global row, partial slot} -- the record the streaming update kernel reads */
   int32_t *work_counter;     /* [1]   dynamic work-unit counter of the streaming update kernel     */
+  int32_t *unit_start;       /* [n/RS_UNIT + 2] first chunk start at or after u*RS_UNIT (work-unit boundaries) */
+  float *scale_sorted;       /* [n]   scratch: per-sample scale permuted into sorted-lookup order   */
   int32_t *n_uniq;           /* [1] device scalar                                                 */
   int32_t *n_chunks;         /* [1] device scalar                                                 */
   int32_t *n_multi;          /* [1] device scalar                                                 */
