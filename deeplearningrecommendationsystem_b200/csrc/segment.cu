@@ -380,35 +380,65 @@ __global__ void __launch_bounds__(256, (NA <= 4) ? 4 : 1) seg_chunk_kernel(const
   }
 }
 
-// One lane group per segment that has more than one chunk: add the chunk partials in chunk order, apply.
+// One CTA per segment that has more than one chunk.  Its 256/GS lane groups each add a contiguous run of the chunk
+// partials in chunk order (loads of four partials issued before their adds); group 0 then adds the group sums in
+// group order and applies the update.  The association is a fixed function of the segment length -> deterministic,
+// and the hottest row (tens of thousands of lookups) no longer serialises ~hundreds of dependent memory latencies.
 template <int VEC, int GS, int NA, int MODE>
 __global__ void __launch_bounds__(256) seg_combine_kernel(const __grid_constant__ UpdParams P, int64_t n) {
   using V = Vec<VEC>;
   constexpr int GPB = 256 / GS;
-  const int lane = threadIdx.x % GS;
+  extern __shared__ __align__(16) float s_grp[];  // [GPB][W]
+  const int lane = threadIdx.x % GS, grp = threadIdx.x / GS;
   const int WV = P.W / VEC;
   const int nm = *P.n_multi;
-  for (int64_t k = (int64_t)blockIdx.x * GPB + threadIdx.x / GS; k < nm; k += (int64_t)gridDim.x * GPB) {
+  for (int64_t k = blockIdx.x; k < nm; k += gridDim.x) {
     const int g = P.multi_seg[k];
     const int c0 = P.seg_first_chunk[g], c1 = P.seg_first_chunk[g + 1];
+    const int per = (c1 - c0 + GPB - 1) / GPB;
+    const int lo = c0 + grp * per, hi = (lo + per < c1) ? lo + per : c1;
     typename V::T acc[NA];
 #pragma unroll
     for (int a = 0; a < NA; ++a) acc[a] = V::zero();
-    for (int c = c0; c < c1; ++c) {
-      const int s0 = P.chunk_start[c], s1 = P.chunk_start[c + 1];
-      const float *src = P.partial + (int64_t)partial_slot(s0, s1 - s0) * P.W;
+    constexpr int UNR = (NA <= 2) ? 4 : (NA <= 4 ? 2 : 1);
+    for (int c = lo; c < hi; c += UNR) {
+      typename V::T val[UNR][NA];
 #pragma unroll
-      for (int a = 0; a < NA; ++a) {
-        const int e = lane + a * GS;
-        if (e < WV) acc[a] = V::add(acc[a], V::ld(src + e * VEC));
+      for (int u = 0; u < UNR; ++u) {
+        const bool live = c + u < hi;
+        const int s0 = live ? P.chunk_start[c + u] : 0, s1 = live ? P.chunk_start[c + u + 1] : 0;
+        const float *src = P.partial + (int64_t)partial_slot(s0, s1 - s0) * P.W;
+#pragma unroll
+        for (int a = 0; a < NA; ++a) {
+          const int e = lane + a * GS;
+          val[u][a] = (live && e < WV) ? V::ld(src + e * VEC) : V::zero();
+        }
       }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u)
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+          if (c + u < hi) acc[a] = V::add(acc[a], val[u][a]);
     }
-    const int64_t row = P.uniq[g];
 #pragma unroll
     for (int a = 0; a < NA; ++a) {
       const int e = lane + a * GS;
-      if (e < WV) apply_row<VEC, MODE>(P, row, e, acc[a]);
+      if (e < WV) V::st(s_grp + (size_t)grp * P.W + e * VEC, acc[a]);
     }
+    __syncthreads();
+    if (grp == 0) {
+      const int used = (c1 - c0 + per - 1) / per;  // groups that had at least one chunk
+#pragma unroll
+      for (int a = 0; a < NA; ++a) {
+        const int e = lane + a * GS;
+        if (e < WV) {
+          typename V::T t = V::ld(s_grp + e * VEC);
+          for (int q = 1; q < used; ++q) t = V::add(t, V::ld(s_grp + (size_t)q * P.W + e * VEC));
+          apply_row<VEC, MODE>(P, P.uniq[g], e, t);
+        }
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -426,9 +456,12 @@ int launch_update(const UpdParams &P, int64_t n, cudaStream_t st) {
   }
   RS_CHECK_LAUNCH();
   // a multi-chunk segment has > RS_CHUNK lookups, so there are at most n / RS_CHUNK of them
-  int64_t cblocks64 = (n / RS_CHUNK + GPB) / GPB;
-  int cblocks = (int)(cblocks64 < cap ? cblocks64 : cap);
-  seg_combine_kernel<VEC, GS, NA, MODE><<<cblocks, 256, 0, st>>>(P, n);
+  int64_t cblocks64 = n / RS_CHUNK + 1;
+  int cblocks = (int)(cblocks64 < rs::num_sms() * 8 ? cblocks64 : rs::num_sms() * 8);
+  const size_t csmem = (size_t)GPB * P.W * 4;
+  if (csmem > 48 * 1024)
+    RS_CUDA(cudaFuncSetAttribute(seg_combine_kernel<VEC, GS, NA, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+  seg_combine_kernel<VEC, GS, NA, MODE><<<cblocks, 256, csmem, st>>>(P, n);
   RS_CHECK_LAUNCH();
   return RS_OK;
 }
