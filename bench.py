@@ -301,6 +301,99 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------ other configs
+def run_other(args):
+    """Non-headline BASELINE.json configs (one JSON line per model): c3 PNN-inner + AFM (F=39, D=32, B=32768),
+    c4 DIN + DIEN (L=100, D=64, B=8192, 1 M items), c5 MF with two 100 M-row tables (row-sharded when N > 1)."""
+    import torch.distributed as dist
+    from deeplearningrecommendationsystem_b200 import ops
+    from deeplearningrecommendationsystem_b200.model import DIEN, DIN
+    from deeplearningrecommendationsystem_b200.nfield import FieldAFM, FieldMF, FieldPNN
+    from deeplearningrecommendationsystem_b200.optim import FusedRowOptimizer
+    from deeplearningrecommendationsystem_b200.trainer import Trainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    g = torch.Generator(device=dev).manual_seed(77 + rank)
+    loss_fn = torch.nn.BCELoss()
+    jobs = []
+    if args.workload == "c3":
+        cards, B = CRITEO + [64] * 13, 32768
+
+        def batches(k):
+            return [make_ids(cards, B, 900 + rank * 100 + i, args.dist, dev) for i in range(k)]
+        for name, m in (("PNN-inner", FieldPNN(cards, 32, [256, 128, 64, 32], seed=1, device=dev, sharded=world > 1)),
+                        ("AFM", FieldAFM(cards, 32, 64, seed=2, device=dev, sharded=world > 1))):
+            dense = [p for p in m.parameters() if p.requires_grad]
+            opt = FusedRowOptimizer(m, torch.optim.SGD(dense, lr=LR), lr=LR)
+            pool = batches(4)
+            jobs.append((name, m, opt, [((i,), y) for i, y in pool], B, "F=39, D=32, fused sparse SGD on 33.8 M rows"))
+    elif args.workload == "c4":
+        B, L, items = 8192, 100, 1_000_000
+        for name, cls in (("DIN", DIN), ("DIEN", DIEN)):
+            m = cls(items, 64).to(dev)
+            opt = torch.optim.SGD(m.parameters(), lr=0.01)
+            pool = []
+            for _ in range(4):
+                u = torch.rand(B, L, generator=g, device=dev, dtype=torch.float64)
+                hist = ((((items ** (1 - 1.05) - 1) * u + 1) ** (1 / (1 - 1.05))).floor().long() - 1).clamp_(0, items - 1)
+                tgt = torch.randint(0, items, (B,), generator=g, device=dev)
+                pool.append(((hist, tgt), (torch.rand(B, 1, generator=g, device=dev) < 0.3).float()))
+            jobs.append((name, m, opt, pool, B, "L=100, D=64, 1 M-row item table, dense-gradient SGD (reference semantics)"))
+    else:
+        rows, B = (100_000_000 if not args.light else 1_000_000), 65536
+        m = FieldMF(rows, rows, 64, seed=3, device=dev, sharded=world > 1)
+        opt = FusedRowOptimizer(m, None, lr=LR)
+        pool = []
+        for _ in range(8):
+            u = torch.randint(0, rows, (B,), generator=g, device=dev)
+            i = torch.randint(0, rows, (B,), generator=g, device=dev)
+            pool.append(((u, i), (torch.rand(B, generator=g, device=dev) < 0.3).float()))
+        jobs.append(("MF", m, opt, pool, B, f"2 x {rows} rows, D=64, fused sparse SGD" + (", row-sharded all-to-all" if world > 1 else "")))
+
+    for name, m, opt, pool, B, note in jobs:
+        tr = Trainer(m, loss_fn, opt)
+        for k in range(args.warmup):
+            tr.train_loop(*pool[k % len(pool)][0], train_rating=pool[k % len(pool)][1])
+        ops.check_status(dev)
+        ops.PROFILE = []
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(args.steps):
+            tr.train_loop(*pool[k % len(pool)][0], train_rating=pool[k % len(pool)][1])
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        prof, ops.PROFILE = ops.PROFILE, None
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = ms.item() / args.steps
+        if rank == 0:
+            agg = {}
+            for kn, a, b in prof:
+                agg.setdefault(kn, []).append(a.elapsed_time(b))
+            print(json.dumps({"metric": "train samples/sec (fwd+bwd+update)", "value": world * B / (ms / 1e3), "unit": "samples/s",
+                              "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                              "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                              "config": {"workload": f"{args.workload}: {name}", "batch_per_gpu": B, "note": note, "ids": args.dist},
+                              "kernels": {kn: {"ms": sum(v) / len(v), "calls_per_step": len(v) / args.steps} for kn, v in agg.items()},
+                              "last_loss": tr.train_loss.item()}))
+        del tr, m, opt, pool
+        torch.cuda.empty_cache()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -311,11 +404,15 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--light", action="store_true", help="cap every cardinality at 2^17 rows (fits any GPU)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
+                    help="c2 = headline (BASELINE.json configs[1]); c3/c4/c5 = the other synthetic configs, one line per model")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    else:
+    elif args.workload == "c2":
         run_gpu(args)
+    else:
+        run_other(args)
 
 
 if __name__ == "__main__":

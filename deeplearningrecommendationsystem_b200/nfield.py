@@ -72,6 +72,31 @@ class _DenseGradFn(torch.autograd.Function):
         return grad, None, None, None, None
 
 
+class _EmbedFn(torch.autograd.Function):
+    """Fused lookup that hands the field embeddings (and optionally their pairwise inner products) to dense layers:
+    forward = rs_fields_fwd(concat[, pairs]); backward = rs_fields_bwd -> per-lookup row gradients (B, F, D), recorded
+    for the fused row optimizer instead of being scattered into a dense table gradient."""
+
+    @staticmethod
+    def forward(ctx, anchor, owner, token, T, ids, want_pairs):
+        out = ops.fields_fwd(T, ids.shape[0], ids.device, ids=ids, concat=True, pairs=want_pairs)
+        ctx.owner, ctx.token, ctx.T, ctx.want_pairs = owner, token, T, want_pairs
+        ctx.save_for_backward(ids)
+        if want_pairs:
+            return out["concat"], out["pairs"]
+        dummy = out["concat"].new_empty(0)
+        ctx.mark_non_differentiable(dummy)
+        return out["concat"], dummy
+
+    @staticmethod
+    def backward(ctx, g_concat, g_pairs):
+        (ids,) = ctx.saved_tensors
+        dE = ops.fields_bwd(ctx.T, ids.shape[0], ids.device, ids=ids, g_concat=g_concat.contiguous(),
+                            g_pairs=g_pairs.contiguous() if ctx.want_pairs else None)
+        ctx.owner._record(ctx.token, dE)
+        return torch.zeros(1, device=dE.device), None, None, None, None, None
+
+
 class _FieldModel(nn.Module):
     def __init__(self, cardinalities, width, row_dim, fused=True, seed=None, device=None, sharded=False, group=None):
         super().__init__()
@@ -141,17 +166,21 @@ class _FieldModel(nn.Module):
         for rec in self._pending.values():
             if "g" not in rec:
                 continue
+            src = {"dense": rec["g"]} if rec.get("stash") is None else {"stash": rec["stash"], "scale": rec["g"]}
             if not self.sharded:
                 segs = ops.dedup_sort(rec["ids"], self.F, self.offsets_host, self.total_rows, max_width=self.width)
-                self._row_update(opt, segs, self.F, stash=rec["stash"], scale=rec["g"])
+                self._row_update(opt, segs, self.F, **src)
                 continue
             # row-sharded: reduce the batch's gradients per fetched row, send them to the owners, update there
             plan, ex = rec["plan"], self.exchange
             segs = ops.dedup_sort(plan.local_ids, 1, None, plan.n_uniq, max_width=self.width)   # memoised per plan
             # every fetched row has at least one lookup in this batch, so RS_UPD_GRAD writes every row of the block
             block_grad = torch.empty(plan.n_uniq, self.width, dtype=torch.float32, device=rec["g"].device)
-            ops.segment_update(segs, ops.RS_UPD_GRAD, self.width, self.F, stash=rec["stash"], scale=rec["g"] * (1.0 / ex.world),
-                               dense_grad=block_grad)
+            if "scale" in src:
+                src["scale"] = src["scale"] * (1.0 / ex.world)          # gradients are averaged over the ranks
+            else:
+                src["dense"] = src["dense"] * (1.0 / ex.world)
+            ops.segment_update(segs, ops.RS_UPD_GRAD, self.width, self.F, dense_grad=block_grad, **src)
             recv = ex.push_grads(plan, block_grad)
             if recv.shape[0]:
                 osegs = ops.dedup_sort(plan.recv_local, 1, None, self.weight.shape[0], max_width=self.width)
@@ -160,6 +189,30 @@ class _FieldModel(nn.Module):
 
     def _interact(self, T, ids, want_stash):
         raise NotImplementedError
+
+    def embed(self, ids, want_pairs=False):
+        """(B, F*D) concat of the field embeddings [and (B, P) inner products], differentiable for the layers above;
+        the table update goes through the fused row optimizer (fused=True only)."""
+        if not self.fused:
+            raise NotImplementedError("embed() is implemented for fused tables")
+        if ids.dim() != 2 or ids.shape[1] != self.F:
+            raise ValueError(f"ids must be (B, {self.F})")
+        rec = {}
+        if self.sharded:
+            plan = self.exchange.plan_for(ids, self._offsets_key(), self.total_rows)
+            block = self.exchange.fetch(plan, self.weight.data)
+            ids, T, rec = plan.local_ids.view(ids.shape), ops.make_tables([block] * self.F), {"plan": plan, "block": block}
+        else:
+            T = self.tables()
+        if not torch.is_grad_enabled():
+            out = ops.fields_fwd(T, ids.shape[0], ids.device, ids=ids, concat=True, pairs=want_pairs)
+            return out["concat"], out.get("pairs")
+        if self._anchor is None or self._anchor.device != ids.device:
+            self._anchor = torch.zeros(1, device=ids.device, requires_grad=True)
+        self._token += 1
+        self._pending[self._token] = {"ids": ids, "stash": None, **rec}
+        concat, pairs = _EmbedFn.apply(self._anchor, self, self._token, T, ids, want_pairs)
+        return concat, (pairs if want_pairs else None)
 
     def logit(self, ids):
         if ids.dim() != 2 or ids.shape[1] != self.F:
@@ -232,3 +285,48 @@ class FieldMF(_FieldModel):
     def forward(self, user_indices, item_indices):
         ids = torch.stack([user_indices, item_indices], dim=1)
         return torch.sigmoid(self.logit(ids))                       # (B,)
+
+
+class FieldPNN(_FieldModel):
+    """Inner-product PNN over F id-fields (reference model/pnn.py:55-77,111-131 generalised from six features):
+    lz = Linear(F*D, H0)(concat), lp = Linear(F(F-1)/2, H0)(inner products), ReLU tower, Linear(H[-1], 1), sigmoid."""
+
+    use_bias = False
+
+    def __init__(self, cardinalities, embed_dim, hidden_units, fused=True, seed=None, device=None, sharded=False, group=None):
+        super().__init__(cardinalities, embed_dim, embed_dim, fused, seed, device, sharded, group)
+        F = self.F
+        self.bias.requires_grad_(False)
+        self.linear1 = nn.Linear(F * embed_dim, hidden_units[0], device=device)
+        self.linear2 = nn.Linear(F * (F - 1) // 2, hidden_units[0], device=device)
+        self.dnn_network = nn.ModuleList([nn.Linear(a, b, device=device) for a, b in zip(hidden_units[:-1], hidden_units[1:])])
+        self.output = nn.Linear(hidden_units[-1], 1, device=device)
+
+    def forward(self, ids):
+        concat, pairs = self.embed(ids, want_pairs=True)
+        h = self.linear1(concat) + self.linear2(pairs)
+        for layer in self.dnn_network:
+            h = torch.relu(layer(h))
+        return torch.sigmoid(self.output(h)).view(-1, 1)
+
+
+class FieldAFM(_FieldModel):
+    """Attentional pooling over the F(F-1)/2 pairwise products of F id-fields (reference model/afm.py:55-66):
+    sigmoid(Linear(D,1)(sum_p softmax_p(h.relu(P_p W + b)) P_p))."""
+
+    use_bias = False
+
+    def __init__(self, cardinalities, embed_dim, attention_dim, fused=True, seed=None, device=None, sharded=False, group=None):
+        super().__init__(cardinalities, embed_dim, embed_dim, fused, seed, device, sharded, group)
+        self.bias.requires_grad_(False)
+        g = torch.Generator(device="cpu").manual_seed(seed or 0)
+        self.attention_W = nn.Parameter((torch.randn(embed_dim, attention_dim, generator=g) * 0.1).to(device))
+        self.attention_b = nn.Parameter(torch.zeros(attention_dim, device=device))
+        self.attention_h = nn.Parameter((torch.randn(attention_dim, 1, generator=g) * 0.1).to(device))
+        self.output_layer = nn.Linear(embed_dim, 1, device=device)
+
+    def forward(self, ids):
+        from . import attention
+        concat, _ = self.embed(ids)
+        pooled = attention.afm_pool(concat.view(ids.shape[0], self.F, self.width), self.attention_W, self.attention_b, self.attention_h)
+        return torch.sigmoid(self.output_layer(pooled))

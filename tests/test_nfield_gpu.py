@@ -133,3 +133,46 @@ def test_field_mf_matches_mf_oracle(kind):
         got = m.weight.detach().cpu()
         np.testing.assert_allclose(got[:nu].numpy(), U.numpy(), rtol=2e-5, atol=2e-4 if kind == "adam" else 2e-6)
         np.testing.assert_allclose(got[nu:].numpy(), V.numpy(), rtol=2e-5, atol=2e-4 if kind == "adam" else 2e-6)
+
+
+@pytest.mark.parametrize("kind", ["pnn", "afm"])
+def test_field_pnn_afm_train_steps(kind):
+    """N-field PNN (inner product) / AFM: fused sparse SGD on the tables + torch SGD on the dense layers == the CPU
+    restatement with dense embedding gradients (oracle.interactions) -- predictions, loss and every parameter."""
+    from deeplearningrecommendationsystem_b200.nfield import FieldAFM, FieldPNN
+    from deeplearningrecommendationsystem_b200.optim import FusedRowOptimizer
+    from deeplearningrecommendationsystem_b200.trainer import Trainer
+    from oracle import interactions as OI
+    cards, D, B, lr = [7, 300, 40, 1000, 5, 64, 12], 16, 600, 0.2
+    g = torch.Generator().manual_seed(4)
+    ids = torch.stack([(torch.rand(B, generator=g) ** 2 * c).long().clamp_(max=c - 1) for c in cards], dim=1)
+    y = (torch.rand(B, 1, generator=g) < 0.4).float()
+    torch.manual_seed(0)
+    m = (FieldPNN(cards, D, [32, 16, 8], seed=2, device="cuda") if kind == "pnn" else FieldAFM(cards, D, 8, seed=2, device="cuda"))
+    dense = [p for n, p in m.named_parameters() if p.requires_grad]
+    ref = {n: p.detach().cpu().clone().requires_grad_(True) for n, p in m.named_parameters() if n != "bias"}
+    offs = torch.tensor(m.offsets_host)
+    tr = Trainer(m, torch.nn.BCELoss(), FusedRowOptimizer(m, torch.optim.SGD(dense, lr=lr), lr=lr))
+    for _ in range(3):
+        tr.train_loop(ids.cuda(), train_rating=y.cuda())
+        E = ref["weight"][ids + offs]
+        if kind == "pnn":
+            h = E.flatten(1) @ ref["linear1.weight"].t() + ref["linear1.bias"] + OI.inner_products(E) @ ref["linear2.weight"].t() + ref["linear2.bias"]
+            k = 0
+            while f"dnn_network.{k}.weight" in ref:
+                h = torch.relu(h @ ref[f"dnn_network.{k}.weight"].t() + ref[f"dnn_network.{k}.bias"])
+                k += 1
+            pred = torch.sigmoid(h @ ref["output.weight"].t() + ref["output.bias"])
+        else:
+            pooled = OI.afm_pool(E, ref["attention_W"], ref["attention_b"], ref["attention_h"])
+            pred = torch.sigmoid(pooled @ ref["output_layer.weight"].t() + ref["output_layer.bias"])
+        loss = OI.bce(pred, y)
+        grads = torch.autograd.grad(loss, list(ref.values()))
+        np.testing.assert_allclose(tr.predictions_train.detach().cpu().numpy(), pred.detach().numpy(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(tr.train_loss.item(), loss.item(), rtol=1e-5)
+        with torch.no_grad():
+            for (n, p), gr in zip(ref.items(), grads):
+                p -= lr * gr
+        for n, p in m.named_parameters():
+            if n != "bias":
+                np.testing.assert_allclose(p.detach().cpu().numpy(), ref[n].detach().numpy(), rtol=1e-5, atol=2e-6, err_msg=n)
