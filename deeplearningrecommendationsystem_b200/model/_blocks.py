@@ -157,6 +157,22 @@ class PairLookup(torch.autograd.Function):
         return gu, gi, None, None, None
 
 
+class OuterPooled(torch.autograd.Function):
+    """p = S^T S (D, D), the batch-collapsed outer product of PNN's "out" mode (reference model/pnn.py:69-72), on the
+    tcgen05 tensor cores with a 3xTF32 split (rs_gemm_tn_3xtf32).  d loss / dS = S (G + G^T)."""
+
+    @staticmethod
+    def forward(ctx, S):
+        S = S.contiguous()
+        ctx.save_for_backward(S)
+        return ops.gemm_tn(S, S)
+
+    @staticmethod
+    def backward(ctx, G):
+        (S,) = ctx.saved_tensors
+        return S @ (G + G.t())
+
+
 class FFMDense(torch.autograd.Function):
     """sum_{i<j} <T[i, field(j)], T[j, field(i)]> over dense T (B, F, NF, D)     model/ffm.py:61-82"""
 

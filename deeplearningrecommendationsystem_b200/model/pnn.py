@@ -41,7 +41,7 @@ class ProductLayers(nn.Module):
             p = K.inner_products(E)
         elif self.model == "out":
             s = E.sum(dim=1)
-            p = torch.matmul(s.T, s)
+            p = K.OuterPooled.apply(s) if s.is_cuda and s.shape[1] <= 128 else torch.matmul(s.T, s)
         return self.linear1(z) + self.linear2(p)
 
 

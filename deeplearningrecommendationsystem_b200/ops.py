@@ -535,3 +535,21 @@ def din_bwd(rows, ws, pool, g_out):
     dWab, dWt = dWab.sum(0), dWt.sum(0)
     dW0 = torch.cat([dWab, dWab - dWt, dWt], dim=1)
     return d_rows, (dW0, db0.sum(0), dW1.sum(0), db1.sum(0), dW2.sum(0).view(1, H2), db2.sum(0).view(1))
+
+
+def gemm_tn(A, B):
+    """A^T B for row-major A (K, M), B (K, N) on tcgen05 (3xTF32, fp32 accumulate in TMEM).  M <= 128, N <= 256."""
+    A, B = _f32(A), _f32(B)
+    _need_cuda(A, B)
+    K, M = A.shape
+    N = B.shape[1]
+    lib = _lib.load()
+    nbytes = C.c_size_t(0)
+    _lib.check(lib.rs_gemm_tn_ws_bytes(K, M, N, C.byref(nbytes)), "rs_gemm_tn_ws_bytes")
+    ws = torch.empty(nbytes.value // 4 + 1, dtype=torch.float32, device=A.device)
+    out = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    with _timed("gemm_tn_3xtf32"):
+        _lib.check(lib.rs_gemm_tn_3xtf32(A.data_ptr(), B.data_ptr(), K, M, N, out.data_ptr(), ws.data_ptr(), nbytes.value, _stream()),
+                   "rs_gemm_tn_3xtf32")
+    _count(2)
+    return out

@@ -381,3 +381,17 @@ def test_din_attention_fwd_bwd(D, H1, H2, L, B, pool):
     assert float(dws[5].abs().max()) <= 1e-5 * max(1e-3, float(grads[5].abs().max()), float(grads[4].abs().max()))
     d2, dws2 = ops.din_bwd(rows.detach().cuda(), cw, pool, gup.cuda())
     assert torch.equal(d_rows, d2) and all(torch.equal(a, b_) for a, b_ in zip(dws, dws2))   # deterministic
+
+
+# ------------------------------------------------------------------ tcgen05 3xTF32 A^T B (PNN "out")
+@pytest.mark.parametrize("K,M,N", [(1000, 32, 32), (4096, 128, 256), (33, 8, 16), (70000, 16, 16), (257, 100, 72)])
+def test_gemm_tn_3xtf32(K, M, N):
+    ops = _ops()
+    g = torch.Generator().manual_seed(K + M)
+    A, B = torch.randn(K, M, generator=g), torch.randn(K, N, generator=g)
+    want = (A.double().t() @ B.double())
+    got = ops.gemm_tn(A.cuda(), B.cuda()).cpu().double()
+    # 1e-5 relative to the scale of the sums (|a||b| mass), the bar a plain fp32 matmul meets as well
+    tol = 1e-5 * float((A.abs().double().t() @ B.abs().double()).max())
+    assert float((got - want).abs().max()) <= tol, (float((got - want).abs().max()), tol)
+    # a single-pass TF32 product would miss this bar by two orders of magnitude (~1e-3 relative)
