@@ -192,7 +192,17 @@ def run_gpu(args):
     pool = [make_ids(cards, B, 1234 + rank * 100 + k, args.dist, dev) for k in range(8)]
     host_pool = [(i.cpu().pin_memory(), y.cpu().pin_memory()) for i, y in pool]
 
+    graphed = None
+    if args.graph and world == 1:
+        from deeplearningrecommendationsystem_b200.graph import GraphedTrainStep
+        graphed = [GraphedTrainStep(tr.model, loss_fn, tr.optimizer) for tr in trainers]
+
     def step(ids, y):
+        if graphed is not None:
+            loss = None
+            for gs in graphed:
+                _, loss = gs(ids, rating=y)
+            return loss
         for tr in trainers:
             tr.train_loop(ids, train_rating=y)
         return trainers[1].train_loss
@@ -358,7 +368,18 @@ def run_other(args):
 
     for name, m, opt, pool, B, note in jobs:
         tr = Trainer(m, loss_fn, opt)
-        for k in range(args.warmup):
+        if args.graph and world == 1:
+            from deeplearningrecommendationsystem_b200.graph import GraphedTrainStep
+            gs = GraphedTrainStep(m, loss_fn, opt)
+
+            class _G:                                   # same surface as Trainer for the loop below
+                train_loss = None
+
+                def train_loop(self, *a, train_rating):
+                    _, self.train_loss = gs(*a, rating=train_rating)
+            tr = _G()
+            note += ", CUDA-graph replay"
+        for k in range(max(args.warmup, 4)):
             tr.train_loop(*pool[k % len(pool)][0], train_rating=pool[k % len(pool)][1])
         ops.check_status(dev)
         ops.PROFILE = []
@@ -404,6 +425,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--light", action="store_true", help="cap every cardinality at 2^17 rows (fits any GPU)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--graph", action="store_true", help="replay the train step as a CUDA graph (single GPU)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
                     help="c2 = headline (BASELINE.json configs[1]); c3/c4/c5 = the other synthetic configs, one line per model")
     args = ap.parse_args()

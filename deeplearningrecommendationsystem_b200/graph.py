@@ -1,0 +1,64 @@
+"""CUDA-graph capture of a whole train step (forward -> loss -> backward -> fused row update -> dense optimizer).
+
+The step of the small-row configs is launch bound (C5 MF: ~0.3 ms of kernels inside a ~1.1 ms step), so the launch
+sequence -- our C-ABI kernels and torch's elementwise/optimizer kernels alike -- is recorded once and replayed.
+Everything in the step must be shape-static and free of host synchronisation, which holds for the single-GPU fused
+path (`FusedRowOptimizer` + `nfield` models, drop-in modules with torch optimizers).  The row-sharded multi-GPU path
+syncs for its all-to-all split sizes and is not captured.
+"""
+import torch
+
+
+class GraphedTrainStep:
+    """step(*inputs, rating) -> (predictions, loss) with identical semantics to Trainer.train_loop.
+
+    The first `warmup` calls run eagerly (they are real train steps on their own inputs and also let every library
+    and cache initialise); the next call captures the step on static input buffers and replays it.  From then on
+    inputs are copied into the static buffers, the graph is replayed, and the static outputs are returned (valid
+    until the next call).
+    """
+
+    def __init__(self, model, loss_fn, optimizer, warmup=2):
+        self.model, self.loss_fn, self.optimizer, self.warmup = model, loss_fn, optimizer, warmup
+        self.graph, self.calls, self.side = None, 0, None
+        self.static_in = self.static_rating = self.pred = self.loss = None
+
+    def _eager(self, inputs, rating):
+        self.model.train()
+        self.optimizer.zero_grad()
+        pred = self.model(*inputs)
+        loss = self.loss_fn(pred, rating)
+        loss.backward()
+        self.optimizer.step()
+        return pred, loss
+
+    def _capture(self, inputs, rating):
+        self.static_in = [t.clone() for t in inputs]
+        self.static_rating = rating.clone()
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            pred, loss = self._eager(self.static_in, self.static_rating)
+        self.pred, self.loss = pred, loss
+
+    def __call__(self, *inputs, rating):
+        self.calls += 1
+        if self.graph is None and self.calls <= self.warmup:
+            # eager steps run on a side stream: autograd remembers the stream a parameter's AccumulateGrad node was
+            # created on, and a node created on the legacy default stream cannot be used while capturing
+            if self.side is None:
+                self.side = torch.cuda.Stream()
+            cur = torch.cuda.current_stream()
+            self.side.wait_stream(cur)
+            with torch.cuda.stream(self.side):
+                out = self._eager(inputs, rating)
+            cur.wait_stream(self.side)
+            return out
+        if self.graph is None:
+            self._capture(inputs, rating)
+            # the capture itself does not execute the step; fall through to one replay on these inputs
+        for dst, src in zip(self.static_in, inputs):
+            dst.copy_(src, non_blocking=True)
+        self.static_rating.copy_(rating, non_blocking=True)
+        self.graph.replay()
+        return self.pred, self.loss

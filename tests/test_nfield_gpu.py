@@ -176,3 +176,40 @@ def test_field_pnn_afm_train_steps(kind):
         for n, p in m.named_parameters():
             if n != "bias":
                 np.testing.assert_allclose(p.detach().cpu().numpy(), ref[n].detach().numpy(), rtol=1e-5, atol=2e-6, err_msg=n)
+
+
+@pytest.mark.parametrize("kind", ["fm", "ffm", "mf"])
+def test_graphed_step_equals_eager(kind):
+    """CUDA-graph replay of the whole train step gives bit-identical tables to the eager Trainer loop."""
+    from deeplearningrecommendationsystem_b200.graph import GraphedTrainStep
+    from deeplearningrecommendationsystem_b200.nfield import FieldFFM, FieldFM, FieldMF
+    from deeplearningrecommendationsystem_b200.optim import FusedRowOptimizer
+    from deeplearningrecommendationsystem_b200.trainer import Trainer
+    B, lr = 512, 0.3
+
+    def build():
+        if kind == "mf":
+            return FieldMF(200, 300, 16, seed=1, device="cuda")
+        return (FieldFM if kind == "fm" else FieldFFM)(CARDS, 8, seed=1, device="cuda")
+
+    def batch(k):
+        g = torch.Generator().manual_seed(40 + k)
+        if kind == "mf":
+            return (torch.randint(0, 200, (B,), generator=g).cuda(), torch.randint(0, 300, (B,), generator=g).cuda()), \
+                (torch.rand(B, generator=g) < 0.3).float().cuda()
+        ids = torch.stack([torch.randint(0, c, (B,), generator=g) for c in CARDS], dim=1).cuda()
+        return (ids,), (torch.rand(B, 1, generator=g) < 0.3).float().cuda()
+
+    def opt_for(m):
+        dense = torch.optim.SGD([m.bias], lr=lr) if m.bias.requires_grad else None
+        return FusedRowOptimizer(m, dense, lr=lr)
+
+    m1, m2 = build(), build()
+    tr = Trainer(m1, torch.nn.BCELoss(), opt_for(m1))
+    gs = GraphedTrainStep(m2, torch.nn.BCELoss(), opt_for(m2), warmup=1)
+    for k in range(5):
+        ins, y = batch(k)
+        tr.train_loop(*ins, train_rating=y)
+        pred, loss = gs(*ins, rating=y)
+        assert torch.equal(pred, tr.predictions_train) and torch.equal(loss, tr.train_loss)
+    assert torch.equal(m1.weight, m2.weight) and torch.equal(m1.bias, m2.bias)
