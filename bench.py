@@ -212,6 +212,9 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if world > 1:                      # NCCL sets its peer connections up lazily: prime them outside the W warm-up steps
+        for k in range(3):
+            step(*pool[k % len(pool)])
     for k in range(args.warmup):
         step(*pool[k % len(pool)])
     ops.check_status(dev)
@@ -379,7 +382,7 @@ def run_other(args):
                     _, self.train_loss = gs(*a, rating=train_rating)
             tr = _G()
             note += ", CUDA-graph replay"
-        for k in range(max(args.warmup, 4)):
+        for k in range(max(args.warmup, 4) + (5 if world > 1 else 0)):
             tr.train_loop(*pool[k % len(pool)][0], train_rating=pool[k % len(pool)][1])
         ops.check_status(dev)
         ops.PROFILE = []

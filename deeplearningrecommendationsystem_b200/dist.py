@@ -56,7 +56,7 @@ def cuda_prims():
 class Plan:
     n_uniq: int
     local_ids: torch.Tensor      # (n,) index of each lookup's row inside the fetched block (owner-grouped order)
-    send_rows: torch.Tensor      # (nu,) global rows requested, grouped by owner rank
+    send_rows: torch.Tensor      # (nu,) owner-local row indices requested, grouped by owner rank
     send_counts: list
     recv_counts: list
     recv_local: torch.Tensor     # (m,) local row indices other ranks asked this rank for (grouped by requester)
@@ -91,27 +91,26 @@ class RowExchange:
 
     def _plan(self, keys, total_rows):
         N = self.world
-        uniq, inverse = self.prims.unique(keys, total_rows)
-        owner = uniq % N
-        order = torch.sort(owner, stable=True).indices            # unique rows grouped by owner, ascending inside
-        send_rows = uniq[order]
-        pos = torch.empty_like(order)
-        pos[order] = torch.arange(order.numel(), device=order.device)
-        local_ids = pos[inverse]
-        send_counts_t = torch.bincount(owner, minlength=N)
+        R = (total_rows + N - 1) // N                       # local rows per rank (upper bound)
+        # Sort key = owner * R + local index: ONE dedup then yields the unique rows already grouped by owner and
+        # ascending inside each group, so `inverse` is directly the position inside the fetched block.
+        okeys = (keys % N) * R + keys // N if N > 1 else keys
+        uniq, inverse = self.prims.unique(okeys, N * R)
+        bounds = torch.arange(N + 1, device=keys.device, dtype=uniq.dtype) * R
+        send_counts_t = torch.diff(torch.searchsorted(uniq, bounds))
         recv_counts_t = torch.empty_like(send_counts_t)
         if N > 1:
             dist.all_to_all_single(recv_counts_t, send_counts_t, group=self.group)
         else:
             recv_counts_t.copy_(send_counts_t)
-        both = torch.stack([send_counts_t, recv_counts_t]).tolist()   # the one host sync of the plan
-        send_counts, recv_counts = both
-        recv_rows = torch.empty(sum(recv_counts), dtype=torch.int64, device=keys.device)
+        send_counts, recv_counts = torch.stack([send_counts_t, recv_counts_t]).tolist()   # the one host sync of the plan
+        send_local = uniq % R if N > 1 else uniq              # local index at the owner
+        recv_local = torch.empty(sum(recv_counts), dtype=torch.int64, device=keys.device)
         if N > 1:
-            dist.all_to_all_single(recv_rows, send_rows, recv_counts, send_counts, group=self.group)
+            dist.all_to_all_single(recv_local, send_local, recv_counts, send_counts, group=self.group)
         else:
-            recv_rows.copy_(send_rows)
-        return Plan(int(uniq.numel()), local_ids, send_rows, send_counts, recv_counts, recv_rows // N)
+            recv_local.copy_(send_local)
+        return Plan(int(uniq.numel()), inverse, send_local, send_counts, recv_counts, recv_local)
 
     def fetch(self, plan, local_table):
         """-> (n_uniq, W) block holding the rows this rank's batch needs, in the order `local_ids` indexes."""
