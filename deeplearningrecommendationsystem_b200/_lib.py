@@ -52,6 +52,12 @@ class rs_xslots(C.Structure):
                 ("rows", C.c_int64 * RS_MAX_FIELDS)]
 
 
+class rs_gemm_nt(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("A", "B", "bias", "rowbias", "mask", "C")] + \
+               [(n, C.c_int64) for n in ("M", "lda", "a_group", "a_group_stride", "ldb", "rb_group", "ldm", "ldc")] + \
+               [(n, C.c_int32) for n in ("K", "N", "relu")]
+
+
 class rs_din_weights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("W0", "b0", "W1", "b1", "W2", "b2")] + [("H1", C.c_int32), ("H2", C.c_int32)]
 
@@ -85,6 +91,7 @@ SIGNATURES = {
     "rs_din_bwd": [_P, _L, _I, _I, _PP(rs_din_weights), _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P],
     "rs_gemm_tn_ws_bytes": [_L, _I, _I, _PP(_Z)],
     "rs_gemm_tn_3xtf32": [_P, _P, _L, _I, _I, _P, _P, _Z, _P],
+    "rs_gemm_nt_3xtf32": [_PP(rs_gemm_nt), _P],
     "rs_gru_fwd": [_P, _L, _I, _I, _P, _P, _P, _P, _P],
     "rs_gru_bwd": [_P, _P, _P, _P, _P, _L, _I, _I, _P, _P, _P],
 }

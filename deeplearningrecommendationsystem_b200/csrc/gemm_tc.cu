@@ -144,6 +144,152 @@ __global__ void slab_reduce_kernel(const float *__restrict__ partial, int nslabs
   C[e] = acc;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// C (M x N) = epilogue(A B^T): A (M x K) rows K-contiguous, B (N x K) in torch Linear layout (out, in) -- the DIN /
+// DIEN attention-unit layers (reference model/din.py:14-20,43) over all B*L (sample, position) rows at once.
+// Persistent CTA per SM.  B is split into hi/lo and kept resident in shared memory in the canonical K-major core
+// matrix layout; A streams through a double-buffered 128 x 32 chunk (thread r copies 128 contiguous bytes of row r
+// -> conflict-free 16-byte stores); one thread issues the 3xTF32 MMAs of a chunk and commits them to that buffer's
+// mbarrier, so the next chunk is repacked while the tensor core works.  Epilogue (warp w <-> TMEM lanes 32w..):
+// + bias[n] + rowbias[r / rb_group][n], ReLU, multiply by (mask[r][n] > 0), store.
+struct NtParams {
+  const float *A, *B, *bias, *rowbias, *mask;
+  float *C;
+  int64_t M, lda, a_group, a_group_stride, ldb, rb_group, ldm, ldc;
+  int K, N, NP, KP, relu, tmem_cols;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_nt_3xtf32_kernel(const __grid_constant__ NtParams P) {
+  extern __shared__ __align__(128) uint32_t sm[];
+  __shared__ uint64_t bar[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nchunk = P.KP / KC;
+  uint32_t *b_hi = sm, *b_lo = b_hi + (size_t)P.KP * P.NP;
+  uint32_t *a_buf = b_lo + (size_t)P.KP * P.NP;  // [2][hi|lo][KC*MT]
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(rs::smem_u32(&tmem_base_s)), "r"(P.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    rs::mbar_init(&bar[0], 1);
+    rs::mbar_init(&bar[1], 1);
+    rs::mbar_fence_init();
+  }
+  // resident B: element (n, k) -> chunk k/4, row n
+  for (int e = tid; e < P.KP * P.NP; e += NTHREADS) {
+    const int k = e / P.NP, n = e - k * P.NP;
+    const float x = (n < P.N && k < P.K) ? P.B[(int64_t)n * P.ldb + k] : 0.f;
+    const uint32_t h = to_tf32(x);
+    b_hi[tile_off(P.NP, n, k)] = h;
+    b_lo[tile_off(P.NP, n, k)] = to_tf32(x - __uint_as_float(h));
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.NP >> 3) << 17) | ((uint32_t)(MT >> 4) << 24);
+  const uint32_t lbo_a = MT * 16, lbo_b = (uint32_t)P.NP * 16, sbo = 128;
+  uint32_t uses[2] = {0, 0};  // how many times each A buffer has been committed (-> mbarrier parity)
+  const int64_t ntiles = (P.M + MT - 1) / MT;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t r = tile * MT + tid;  // this thread's row (A repack and epilogue use different row mappings)
+    const float *arow = nullptr;
+    if (r < P.M) arow = P.A + (P.a_group ? (r / P.a_group) * P.a_group_stride + (r % P.a_group) * P.lda : r * P.lda);
+    for (int c = 0; c < nchunk; ++c) {
+      const int bi = c & 1;
+      uint32_t *ah = a_buf + (size_t)bi * 2 * KC * MT, *al = ah + KC * MT;
+      if (uses[bi] > 0) rs::mbar_wait(&bar[bi], (uses[bi] - 1) & 1u);  // MMAs that read this buffer are done
+#pragma unroll
+      for (int q = 0; q < KC / 4; ++q) {
+        const int k = c * KC + q * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (arow && k < P.K) v = rs::ldg_nc_f4(arow + k);
+        uint4 h, l;
+        h.x = to_tf32(v.x), h.y = to_tf32(v.y), h.z = to_tf32(v.z), h.w = to_tf32(v.w);
+        l.x = to_tf32(v.x - __uint_as_float(h.x)), l.y = to_tf32(v.y - __uint_as_float(h.y));
+        l.z = to_tf32(v.z - __uint_as_float(h.z)), l.w = to_tf32(v.w - __uint_as_float(h.w));
+        *reinterpret_cast<uint4 *>(ah + (q * MT + tid) * 4) = h;
+        *reinterpret_cast<uint4 *>(al + (q * MT + tid) * 4) = l;
+      }
+      rs::fence_proxy_async();
+      __syncthreads();
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int s = 0; s < KC / 8; ++s) {
+          const uint32_t kb = (uint32_t)(c * (KC / 4) + s * 2);  // 16-byte K chunk index inside resident B
+          const uint64_t dah = smem_desc(rs::smem_u32(ah) + s * 2 * lbo_a, lbo_a, sbo);
+          const uint64_t dal = smem_desc(rs::smem_u32(al) + s * 2 * lbo_a, lbo_a, sbo);
+          const uint64_t dbh = smem_desc(rs::smem_u32(b_hi) + kb * lbo_b, lbo_b, sbo);
+          const uint64_t dbl = smem_desc(rs::smem_u32(b_lo) + kb * lbo_b, lbo_b, sbo);
+          mma_tf32(tmem, dal, dbh, idesc, (c == 0 && s == 0) ? 0u : 1u);
+          mma_tf32(tmem, dah, dbl, idesc, 1u);
+          mma_tf32(tmem, dah, dbh, idesc, 1u);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(rs::smem_u32(&bar[bi])) : "memory");
+      }
+      uses[bi]++;
+    }
+    // all MMAs of this tile done?  the last commit covers every earlier MMA
+    const int lb = (nchunk - 1) & 1;
+    rs::mbar_wait(&bar[lb], (uses[lb] - 1) & 1u);
+    if (nchunk > 1) rs::mbar_wait(&bar[lb ^ 1], (uses[lb ^ 1] - 1) & 1u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // Epilogue.  tcgen05.ld hands lane l the 32 columns [c0, c0+32) of row 32w+l; the warp transposes that 32x32
+    // block through shared memory so that each store instruction writes 128 contiguous bytes of ONE row, and the
+    // bias / per-group row bias / ReLU mask are applied with lane <-> column (coalesced reads of rowbias and mask).
+    float *stg = reinterpret_cast<float *>(a_buf + (size_t)4 * KC * MT) + warp * 32 * 33;
+    const int64_t row0 = tile * MT + warp * 32;
+    for (int c0 = 0; c0 < P.NP; c0 += 32) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+      if (c0 + 32 <= P.NP) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
+            "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+              "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+              "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+              "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+      } else {  // NP is a multiple of 16: a 16-column tail
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+              "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(taddr));
+#pragma unroll
+        for (int j = 16; j < 32; ++j) v[j] = 0u;
+      }
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);
+      __syncwarp();
+      const int n = c0 + lane;
+      const float bn = (P.bias && n < P.N) ? P.bias[n] : 0.f;
+      for (int rr = 0; rr < 32; ++rr) {
+        const int64_t row = row0 + rr;
+        if (row >= P.M) break;
+        if (n < P.N) {
+          float x = stg[rr * 33 + lane] + bn;
+          if (P.rowbias) x += P.rowbias[(row / P.rb_group) * P.N + n];
+          if (P.relu) x = fmaxf(x, 0.f);
+          if (P.mask && !(P.mask[row * P.ldm + n] > 0.f)) x = 0.f;
+          P.C[row * P.ldc + n] = x;
+        }
+      }
+      __syncwarp();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();  // every warp has drained the accumulator before the next tile overwrites it
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(P.tmem_cols) : "memory");
+}
+
 int plan_slabs(int64_t K, int64_t *slab) {
   int64_t chunks = (K + KC - 1) / KC;
   int64_t n = rs::num_sms();
@@ -180,6 +326,33 @@ RS_API int rs_gemm_tn_3xtf32(const float *A, const float *B, int64_t K, int32_t 
   RS_CHECK_LAUNCH();
   const int64_t mn = (int64_t)M * N;
   slab_reduce_kernel<<<(int)((mn + 255) / 256), 256, 0, st>>>(ws, nslabs, mn, C);
+  RS_CHECK_LAUNCH();
+  return RS_OK;
+}
+
+RS_API int rs_gemm_nt_3xtf32(const rs_gemm_nt *g, void *stream) {
+  RS_CHECK_ARG(g && g->A && g->B && g->C && g->M >= 0 && g->K >= 1 && g->N >= 1, RS_E_ARG, "rs_gemm_nt_3xtf32: bad argument");
+  RS_CHECK_ARG(g->K % 4 == 0 && g->lda % 4 == 0 && (g->a_group == 0 || g->a_group_stride % 4 == 0), RS_E_UNSUPPORTED,
+               "rs_gemm_nt_3xtf32: K, lda and a_group_stride must be multiples of 4 (16-byte row chunks)");
+  RS_CHECK_ARG(g->N <= 256, RS_E_UNSUPPORTED, "rs_gemm_nt_3xtf32: N=%d > 256", g->N);
+  RS_CHECK_ARG(!g->rowbias || g->rb_group >= 1, RS_E_ARG, "rs_gemm_nt_3xtf32: rowbias needs rb_group >= 1");
+  if (g->M == 0) return RS_OK;
+  NtParams P = {};
+  P.A = g->A, P.B = g->B, P.bias = g->bias, P.rowbias = g->rowbias, P.mask = g->mask, P.C = g->C;
+  P.M = g->M, P.lda = g->lda, P.a_group = g->a_group, P.a_group_stride = g->a_group_stride, P.ldb = g->ldb;
+  P.rb_group = g->rb_group, P.ldm = g->ldm, P.ldc = g->ldc;
+  P.K = g->K, P.N = g->N, P.relu = g->relu;
+  P.NP = (g->N + 15) / 16 * 16;
+  P.KP = (g->K + KC - 1) / KC * KC;
+  P.tmem_cols = 32;
+  while (P.tmem_cols < P.NP) P.tmem_cols <<= 1;
+  const size_t smem = ((size_t)2 * P.KP * P.NP + (size_t)4 * KC * MT + 4 * 32 * 33) * 4;
+  RS_CHECK_ARG(smem <= 220 * 1024, RS_E_UNSUPPORTED, "rs_gemm_nt_3xtf32: N=%d, K=%d need %zu B of shared memory for the resident B", g->N,
+               g->K, smem);
+  RS_CUDA(cudaFuncSetAttribute(gemm_nt_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t ntiles = (g->M + MT - 1) / MT;
+  int grid = (int)(ntiles < rs::num_sms() ? ntiles : rs::num_sms());
+  gemm_nt_3xtf32_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(P);
   RS_CHECK_LAUNCH();
   return RS_OK;
 }

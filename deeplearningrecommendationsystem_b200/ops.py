@@ -553,3 +553,29 @@ def gemm_tn(A, B):
                    "rs_gemm_tn_3xtf32")
     _count(2)
     return out
+
+
+def gemm_nt(A, W, bias=None, rowbias=None, rb_group=1, relu=False, mask=None, M=None, a_rows=None):
+    """epilogue(A W^T) on tcgen05 (3xTF32).  A (M, K) contiguous, or -- with a_rows=(group, group_stride, lda) -- a
+    strided view whose row r lives at A.data_ptr + (r // group)*group_stride + (r % group)*lda floats.
+    W (N, K) torch Linear layout.  Epilogue: + bias[n] + rowbias[r // rb_group][n], ReLU, zero where mask <= 0."""
+    W = _f32(W)
+    _need_cuda(A, W)
+    g = _lib.rs_gemm_nt()
+    N, K = W.shape
+    if a_rows is None:
+        A = _f32(A)
+        M = A.shape[0]
+        g.lda, g.a_group, g.a_group_stride = A.shape[1], 0, 0
+    else:
+        g.a_group, g.a_group_stride, g.lda = a_rows
+    out = torch.empty(M, N, dtype=torch.float32, device=W.device)
+    g.A, g.B, g.C = A.data_ptr(), W.data_ptr(), out.data_ptr()
+    bias, rowbias, mask = _f32(bias), _f32(rowbias), _f32(mask)
+    g.bias, g.rowbias, g.mask = _p(bias), _p(rowbias), _p(mask)
+    g.M, g.ldb, g.rb_group, g.ldm, g.ldc = M, K, rb_group, N, N
+    g.K, g.N, g.relu = K, N, int(bool(relu))
+    with _timed(f"gemm_nt[{N}x{K}]"):
+        _lib.check(_lib.load().rs_gemm_nt_3xtf32(C.byref(g), _stream()), "rs_gemm_nt_3xtf32")
+    _count()
+    return out

@@ -230,6 +230,19 @@ int rs_gemm_tn_ws_bytes(int64_t K, int32_t M, int32_t N, size_t *bytes);
 int rs_gemm_tn_3xtf32(const float *A, const float *B, int64_t K, int32_t M, int32_t N, float *C, float *ws,
                       size_t ws_bytes, void *stream);
 
+/* C (M, N) = epilogue(A B^T) on tcgen05 (3xTF32): the DIN / DIEN attention-unit layers over all B*L rows
+ * (model/din.py:14-20,43).  A (M, K): row r at A + (r / a_group)*a_group_stride + (r % a_group)*lda when a_group > 0
+ * (rows of a (B, L+1, D) gather viewed as B*L history rows), else A + r*lda.  B (N, K) in torch Linear layout, kept
+ * resident in shared memory (N <= 256, N*K bounded by shared memory).  Epilogue, in order: + bias[n],
+ * + rowbias[r / rb_group][n], ReLU, zero where mask[r*ldm + n] <= 0. */
+typedef struct rs_gemm_nt {
+  const float *A, *B, *bias, *rowbias, *mask;
+  float *C;
+  int64_t M, lda, a_group, a_group_stride, ldb, rb_group, ldm, ldc;
+  int32_t K, N, relu;
+} rs_gemm_nt;
+int rs_gemm_nt_3xtf32(const rs_gemm_nt *g, void *stream);
+
 /* ---- sigmoid + BCELoss(mean) forward/backward in one pass (model/*: torch.sigmoid; scripts/deepfm.py:54).
  * pred = sigmoid(logit); loss_sum += sum(-[y*max(log p,-100)+(1-y)*max(log(1-p),-100)]);
  * g_logit follows autograd's op sequence ((p-y)/max(p(1-p),1e-12)/B * p(1-p)), i.e. (p-y)/B except where p

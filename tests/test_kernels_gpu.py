@@ -395,3 +395,38 @@ def test_gemm_tn_3xtf32(K, M, N):
     tol = 1e-5 * float((A.abs().double().t() @ B.abs().double()).max())
     assert float((got - want).abs().max()) <= tol, (float((got - want).abs().max()), tol)
     # a single-pass TF32 product would miss this bar by two orders of magnitude (~1e-3 relative)
+
+
+@pytest.mark.parametrize("M,K,N", [(1000, 64, 128), (128, 128, 64), (4097, 16, 128), (333, 128, 128), (50, 32, 1), (700, 64, 256)])
+def test_gemm_nt_3xtf32_with_epilogue(M, K, N):
+    ops = _ops()
+    g = torch.Generator().manual_seed(M + K + N)
+    A, W = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5
+    bias, group = torch.randn(N, generator=g), 7
+    rowbias = torch.randn((M + group - 1) // group, N, generator=g)
+    mask = torch.randn(M, N, generator=g)
+    z = A.double() @ W.double().t() + bias.double() + rowbias.double().repeat_interleave(group, 0)[:M]
+    want = torch.where(mask > 0, torch.relu(z), torch.zeros_like(z))
+    got = ops.gemm_nt(A.cuda(), W.cuda(), bias=bias.cuda(), rowbias=rowbias.cuda(), rb_group=group, relu=True, mask=mask.cuda()).cpu().double()
+    tol = 1e-5 * float((A.abs().double() @ W.abs().double().t()).max())
+    assert float((got - want).abs().max()) <= tol
+    plain = ops.gemm_nt(A.cuda(), W.cuda()).cpu().double()
+    assert float((plain - A.double() @ W.double().t()).abs().max()) <= tol
+
+
+def test_gemm_nt_rejects_weights_that_do_not_fit():
+    ops = _ops()
+    with pytest.raises(RuntimeError, match="shared memory"):
+        ops.gemm_nt(torch.zeros(10, 192).cuda(), torch.zeros(128, 192).cuda())
+
+
+def test_gemm_nt_grouped_rows():
+    """A given as the first L rows of each (L+1)-row group of a (B, L+1, D) tensor -- the DIN history view."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(1)
+    B, L, D, N = 37, 9, 64, 128
+    rows = torch.randn(B, L + 1, D, generator=g).cuda()
+    W = (torch.randn(N, D, generator=g) / 8).cuda()
+    got = ops.gemm_nt(rows, W, M=B * L, a_rows=(L, (L + 1) * D, D))
+    want = (rows[:, :L].reshape(B * L, D).double() @ W.double().t())
+    assert float((got.double() - want).abs().max()) <= 1e-5 * float((rows.abs().max() * W.abs().sum(1).max()))

@@ -168,3 +168,25 @@ def test_eval_mode_and_no_grad():
     assert not p.requires_grad
     close(p, z["pred"], 1e-6)
     assert next(m.parameters()).device.type == "cuda"
+
+
+@pytest.mark.parametrize("pool", [True, False])
+def test_din_attention_tc_equals_fused(pool):
+    """tensor-core (GEMM) and fused CUDA-core implementations of the attention unit agree on outputs and gradients."""
+    from deeplearningrecommendationsystem_b200 import attention
+    g = torch.Generator().manual_seed(0)
+    B, L, D = 70, 100, 64
+    unit = torch.nn.Sequential(torch.nn.Linear(3 * D, 128), torch.nn.ReLU(), torch.nn.Linear(128, 64), torch.nn.ReLU(),
+                               torch.nn.Linear(64, 1)).cuda()
+    rows = (torch.randn(B, L + 1, D, generator=g) * 0.5).cuda()
+    gup = torch.randn((B, D) if pool else (B, L, D), generator=g).cuda()
+    res = {}
+    for impl in ("tc", "fused"):
+        r = rows.clone().requires_grad_(True)
+        unit.zero_grad()
+        out = attention.din_attention(r, unit, pool, impl=impl)
+        (out * gup).sum().backward()
+        res[impl] = [out.detach(), r.grad] + [p.grad.clone() for p in unit.parameters()]
+    for a, b in list(zip(res["tc"], res["fused"]))[:-1]:          # the last entry is d/d b2, analytically zero (softmax shift)
+        np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-5, atol=1e-5 * max(1e-3, float(b.abs().max())))
+    assert float(res["tc"][-1].abs().max()) < 1e-4 and float(res["fused"][-1].abs().max()) < 1e-4
