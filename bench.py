@@ -31,6 +31,10 @@ CRITEO = [1460, 583, 10131227, 2202608, 305, 24, 12517, 633, 3, 93145, 5683, 835
           2173, 4, 7046547, 18, 15, 286181, 105, 142572]
 F, D, BATCH = 26, 16, 65536
 LR = 0.05
+WORKLOAD = "C2: FM second-order + FFM train step, 26 Criteo-shaped sparse fields, D=16, batch 65536, SGD"
+# dram__bytes_read.sum + dram__bytes_write.sum of one seg_stream_kernel launch on the full uniform-id config
+# (ncu --set full, profiles/r1_ncu_full_c2.md): 2.84 GB Jacobian stash + the ~0.53 M unique table rows read and written
+NCU_TRAFFIC_SEG_STREAM = 4.616e9
 # algorithmic bytes per sample (fp32 rows, int64 ids, no duplicate reuse)
 BYTES = {
     "fm_fwd": 26 * 64 + 208 + 4, "fm_bwd_upd": 1664 + 2 * 1664 + 208,
@@ -150,8 +154,7 @@ def run_reference(args):
         "impl": "reference", "metric": "train samples/sec (fwd+bwd+update)", "value": val, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2: FM second-order + FFM, 26 Criteo-shaped fields, D=16, SGD (CPU oracle port on a bounded sample)",
-                   "sample": sample},
+        "config": {"workload": WORKLOAD, "sample": sample, "impl": "CPU oracle port (torch CPU fp32, all host threads)"},
         "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -284,8 +287,11 @@ def run_gpu(args):
         if dom in kern:
             achieved = BYTES["ffm_bwd_upd"] * B / (kern[dom] / 1e3) / 1e9
             roof = {"bound": "hbm", "kernel": "rs_segment_update on FFM rows (416 floats): seg_stream_kernel<SGD> + scale gather + combine", "achieved": achieved,
-                    "peak": peak, "peak_source": which, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                    "algorithmic_bytes_per_launch": BYTES["ffm_bwd_upd"] * B, "ms_per_launch": kern[dom]}
+                    "peak": peak, "peak_source": which, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": NCU_TRAFFIC_SEG_STREAM if (not args.light and args.dist == "uniform" and B == BATCH) else None,
+                    "algorithmic_bytes_per_launch": BYTES["ffm_bwd_upd"] * B, "ms_per_launch": kern[dom],
+                    "note": "algorithmic bytes charge a table-row read+write per LOOKUP (no duplicate reuse, SURVEY 8d); "
+                            "DRAM traffic is per UNIQUE row, hence frac > 1 while traffic/time stays below the peak"}
         extra = {}
         for name, key in (("ffm_fwd", "ffm_fwd"), ("fields_fwd", "fm_fwd"), ("segment_update[w16]", "fm_bwd_upd")):
             if name in kern:
@@ -297,7 +303,7 @@ def run_gpu(args):
             "metric": "train samples/sec (fwd+bwd+update)", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2: FM second-order + FFM train step, 26 Criteo-shaped sparse fields, D=16, SGD",
+            "config": {"workload": WORKLOAD,
                        "batch_per_gpu": B, "fields": F, "dim": D, "rows": sum(cards), "ids": args.dist, "light": bool(args.light),
                        "l2": "8 distinct id batches cycled; per-step traffic (>8 GB) far exceeds the 126 MB L2",
                        "parallelism": f"dp{world}" + ("" if world == 1 else ": batch split, tables row-sharded, dedup all-to-all of ids/rows/grads")},

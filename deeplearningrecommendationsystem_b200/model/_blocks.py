@@ -27,8 +27,10 @@ def table_grads(ids, dE, rows):
         offs.append(total)
         total += r
     ids = ids.reshape(-1, F)
-    segs = ops.dedup_sort(ids, F, offs, total, max_width=W)
     buf = torch.zeros(total, W, dtype=torch.float32, device=dE.device)
+    if ids.numel() == 0:
+        return [buf[o:o + r] for o, r in zip(offs, rows)]
+    segs = ops.dedup_sort(ids, F, offs, total, max_width=W)
     ops.segment_update(segs, ops.RS_UPD_GRAD, W, F, dense=dE.reshape(-1, W), dense_grad=buf)
     return [buf[o:o + r] for o, r in zip(offs, rows)]
 

@@ -122,6 +122,8 @@ def gather_rows(T, ids):
     _need_cuda(ids)
     B = ids.numel() // T.num_fields
     out = torch.empty(B, T.num_fields, T.width, dtype=torch.float32, device=ids.device)
+    if B == 0:
+        return out
     with _timed(f"gather_rows[w{T.width}]"):
         _lib.check(_lib.load().rs_gather_rows(C.byref(T), ids.data_ptr(), B, out.data_ptr(), status_word(ids.device).data_ptr(),
                                               _stream()), "rs_gather_rows")
@@ -164,6 +166,8 @@ def fields_fwd(T, B, device, ids=None, dense_in=None, cross=False, bi=False, pai
         alloc("dot2", B)
     if had2:
         alloc("had2", B, D)
+    if B == 0:
+        return out
     with _timed("fields_fwd"):
         _lib.check(_lib.load().rs_fields_fwd(C.byref(T), C.byref(io), B, status_word(device).data_ptr(), _stream()), "rs_fields_fwd")
     _count()
@@ -189,6 +193,8 @@ def fields_bwd(T, B, device, ids=None, dense_in=None, g_cross=None, g_bi=None, g
         setattr(g, k, _p(t))
     dE = torch.empty(B, F, D, dtype=torch.float32, device=device)
     g.dE = dE.data_ptr()
+    if B == 0:
+        return dE
     _lib.check(_lib.load().rs_fields_bwd(C.byref(T), C.byref(g), B, _stream()), "rs_fields_bwd")
     _count()
     return dE
@@ -202,6 +208,8 @@ def ffm_fwd(T, ids, D, want_stash=True):
     B = ids.numel() // F
     cross = torch.empty(B, dtype=torch.float32, device=ids.device)
     stash = torch.empty(B, F, F * D, dtype=torch.float32, device=ids.device) if want_stash else None
+    if B == 0:
+        return cross, stash
     with _timed("ffm_fwd"):
         _lib.check(_lib.load().rs_ffm_fwd(C.byref(T), ids.data_ptr(), B, D, cross.data_ptr(), _p(stash),
                                           status_word(ids.device).data_ptr(), _stream()), "rs_ffm_fwd")
@@ -218,6 +226,8 @@ def ffm_dense_fwd(Tin, field_of):
     _need_cuda(Tin)
     B, F, NF, D = Tin.shape
     cross = torch.empty(B, dtype=torch.float32, device=Tin.device)
+    if B == 0:
+        return cross
     _lib.check(_lib.load().rs_ffm_dense_fwd(Tin.data_ptr(), B, F, NF, D, _field_of(field_of), cross.data_ptr(), _stream()),
                "rs_ffm_dense_fwd")
     _count()
@@ -228,6 +238,8 @@ def ffm_dense_bwd(Tin, g_cross, field_of):
     Tin, g_cross = _f32(Tin), _f32(g_cross)
     B, F, NF, D = Tin.shape
     dT = torch.empty_like(Tin)
+    if B == 0:
+        return dT
     _lib.check(_lib.load().rs_ffm_dense_bwd(Tin.data_ptr(), g_cross.data_ptr(), B, F, NF, D, _field_of(field_of), dT.data_ptr(),
                                             _stream()), "rs_ffm_dense_bwd")
     _count()
@@ -372,6 +384,8 @@ def xembed_fwd(S, x):
     _need_cuda(x)
     B = x.shape[0]
     E = torch.empty(B, S.num_slots, S.width, dtype=torch.float32, device=x.device)
+    if B == 0:
+        return E
     _lib.check(_lib.load().rs_xembed_fwd(C.byref(S), x.data_ptr(), B, E.data_ptr(), status_word(x.device).data_ptr(), _stream()),
                "rs_xembed_fwd")
     _count()
@@ -382,6 +396,8 @@ def xembed_bag_bwd(S, x, dE, slots):
     """-> list (per slot) of dW (ncols, W) for bag slots, None otherwise.  Fixed-order two-pass reduction."""
     x, dE = _f32(x), _f32(dE)
     B = x.shape[0]
+    if B == 0:
+        return [torch.zeros(nc, S.width, dtype=torch.float32, device=x.device) if kind == 1 else None for _, nc, kind, _ in slots]
     lib = _lib.load()
     nbytes = C.c_size_t(0)
     _lib.check(lib.rs_xembed_bag_ws_bytes(C.byref(S), B, C.byref(nbytes)), "rs_xembed_bag_ws_bytes")
@@ -404,6 +420,8 @@ def xcol_to_ids(x, col):
     x = _f32(x)
     _need_cuda(x)
     ids = torch.empty(x.shape[0], dtype=torch.int64, device=x.device)
+    if x.shape[0] == 0:
+        return ids
     _lib.check(_lib.load().rs_xcol_to_ids(x.data_ptr(), x.shape[0], x.shape[1], col, ids.data_ptr(), _stream()), "rs_xcol_to_ids")
     _count()
     return ids
@@ -432,6 +450,8 @@ def gru_fwd(gi, w_hh, b_hh, want_gates=True):
     H = H3 // 3
     h_all = torch.empty(B, L, H, dtype=torch.float32, device=gi.device)
     gates = torch.empty(B, L, 4 * H, dtype=torch.float32, device=gi.device) if want_gates else None
+    if B == 0:
+        return h_all, gates
     with _timed("gru_fwd"):
         _lib.check(_lib.load().rs_gru_fwd(gi.data_ptr(), B, L, H, w_hh.data_ptr(), b_hh.data_ptr(), h_all.data_ptr(), _p(gates),
                                           _stream()), "rs_gru_fwd")
@@ -460,6 +480,8 @@ def afm_fwd(E, W, b, h, want_attw=True):
     A = W.shape[1]
     pooled = torch.empty(B, D, dtype=torch.float32, device=E.device)
     attw = torch.empty(B, F * (F - 1) // 2, dtype=torch.float32, device=E.device) if want_attw else None
+    if B == 0:
+        return pooled, attw
     with _timed("afm_fwd"):
         _lib.check(_lib.load().rs_afm_fwd(E.data_ptr(), B, F, D, A, W.data_ptr(), b.data_ptr(), h.data_ptr(), pooled.data_ptr(),
                                           _p(attw), _stream()), "rs_afm_fwd")
@@ -506,6 +528,8 @@ def din_fwd(rows, ws, pool, want_attw=False):
     w, keep = _din_weights(ws)
     out = torch.empty((B, D) if pool else (B, L, D), dtype=torch.float32, device=rows.device)
     attw = torch.empty(B, L, dtype=torch.float32, device=rows.device) if want_attw else None
+    if B == 0:
+        return out, attw
     with _timed("din_fwd"):
         _lib.check(_lib.load().rs_din_fwd(rows.data_ptr(), B, L, D, C.byref(w), int(bool(pool)), out.data_ptr(), _p(attw), _stream()),
                    "rs_din_fwd")
