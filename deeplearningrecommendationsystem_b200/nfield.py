@@ -226,6 +226,8 @@ class _FieldModel(nn.Module):
             cross, stash = self._interact(ops.make_tables([block] * self.F), ids, want_stash=train)
             rec = {"plan": plan}
         else:
+            if train and self.fused:      # the sort depends only on the ids: overlap it with the forward kernels
+                ops.prefetch_dedup(ids, self.F, self.offsets_host, self.total_rows)
             cross, stash = self._interact(self.tables(), ids, want_stash=train)
         if train and self.fused:
             if self._anchor is None or self._anchor.device != ids.device:

@@ -251,6 +251,7 @@ class Segments:
 
     def __init__(self, ws, seg, n, device):
         self.ws, self.seg, self.n, self.device = ws, seg, n, device
+        self.ready = None
 
     def _view(self, ptr, count, dtype):
         off = ptr - self.ws.data_ptr()
@@ -310,6 +311,8 @@ def dedup_sort(ids, F=1, row_offset=None, total_rows=None, max_width=1, reuse_wo
             if k == memo_key and ref is ids:
                 segs = sg
                 slots.append(slots.pop(i))          # most recently used last
+                if segs.ready is not None:          # produced on another stream (prefetch_dedup): order after it
+                    torch.cuda.current_stream().wait_event(segs.ready)
                 break
     if segs is None:
         nbytes = C.c_size_t(0)
@@ -332,12 +335,36 @@ def dedup_sort(ids, F=1, row_offset=None, total_rows=None, max_width=1, reuse_wo
         segs = Segments(ws, seg, n, ids.device)
         if reuse_workspace:
             slots.append((memo_key, segs, ids))
+        if _prefetching:
+            segs.ready = torch.cuda.Event()
+            segs.ready.record()
     part = _partial_buffer(ids.device, n, int(max_width)) if reuse_workspace else \
         torch.empty(2 * (n // _lib.RS_CHUNK + 2) * int(max_width), dtype=torch.float32, device=ids.device)
     segs.partial = part
     segs.seg.partial = part.data_ptr()
     segs.seg.partial_floats = part.numel()
     return segs
+
+
+_prefetching = False
+_side_streams = {}
+
+
+def prefetch_dedup(ids, F=1, row_offset=None, total_rows=None):
+    """Run rs_dedup_sort for `ids` on a side stream NOW (it depends only on the ids), so the sort overlaps the forward
+    kernels; the later dedup_sort() call on the main stream finds the memoised result and waits on its event."""
+    global _prefetching
+    dev = ids.device
+    side = _side_streams.get(dev)
+    if side is None:
+        side = _side_streams[dev] = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))      # ids may have just been produced on the main stream
+    _prefetching = True
+    try:
+        with torch.cuda.stream(side):
+            dedup_sort(ids, F, row_offset, total_rows, max_width=1)
+    finally:
+        _prefetching = False
 
 
 def segment_update(segs, mode, width, F, stash=None, scale=None, dense=None, table=None, m=None, v=None, dense_grad=None,
