@@ -313,6 +313,279 @@ __global__ void __launch_bounds__(AW * 32) afm_bwd_kernel(const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Fast path for the shapes the configs use (D in {16,32,64}, A = 32*NC, D*NC <= 64): every lane keeps its NC columns
+// of W (and, in the backward, of dW) in registers, so the projection is 8 broadcast LDS.128 per 64 FMAs and the
+// weight-gradient accumulation never touches shared memory.  Eight pairs are processed together.
+constexpr int PT8 = 8;
+
+template <int D, int NC>
+__device__ __forceinline__ void project_reg(const float (&Wr)[D][NC], const float (&br)[NC], const float *prod, float (&z)[PT8][NC]) {
+#pragma unroll
+  for (int pt = 0; pt < PT8; ++pt)
+#pragma unroll
+    for (int c = 0; c < NC; ++c) z[pt][c] = br[c];
+#pragma unroll
+  for (int d = 0; d < D; d += 4) {
+    float4 pv[PT8];
+#pragma unroll
+    for (int pt = 0; pt < PT8; ++pt) pv[pt] = *reinterpret_cast<const float4 *>(prod + pt * D + d);
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int pt = 0; pt < PT8; ++pt) {
+        z[pt][c] = fmaf(pv[pt].x, Wr[d][c], z[pt][c]);
+        z[pt][c] = fmaf(pv[pt].y, Wr[d + 1][c], z[pt][c]);
+        z[pt][c] = fmaf(pv[pt].z, Wr[d + 2][c], z[pt][c]);
+        z[pt][c] = fmaf(pv[pt].w, Wr[d + 3][c], z[pt][c]);
+      }
+  }
+}
+
+// same projection with W read from shared memory (W[d][a], lanes over a: conflict free) -- used by the backward,
+// whose registers are taken by the dW accumulators
+template <int D, int NC>
+__device__ __forceinline__ void project_smem(const float *Ws, const float (&br)[NC], const float *prod, int lane, float (&z)[PT8][NC]) {
+  constexpr int A = 32 * NC;
+#pragma unroll
+  for (int pt = 0; pt < PT8; ++pt)
+#pragma unroll
+    for (int c = 0; c < NC; ++c) z[pt][c] = br[c];
+#pragma unroll 2
+  for (int d = 0; d < D; d += 4) {
+    float4 pv[PT8];
+#pragma unroll
+    for (int pt = 0; pt < PT8; ++pt) pv[pt] = *reinterpret_cast<const float4 *>(prod + pt * D + d);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const float w0 = Ws[(d + 0) * A + lane + 32 * c], w1 = Ws[(d + 1) * A + lane + 32 * c];
+      const float w2 = Ws[(d + 2) * A + lane + 32 * c], w3 = Ws[(d + 3) * A + lane + 32 * c];
+#pragma unroll
+      for (int pt = 0; pt < PT8; ++pt) {
+        z[pt][c] = fmaf(pv[pt].x, w0, z[pt][c]);
+        z[pt][c] = fmaf(pv[pt].y, w1, z[pt][c]);
+        z[pt][c] = fmaf(pv[pt].z, w2, z[pt][c]);
+        z[pt][c] = fmaf(pv[pt].w, w3, z[pt][c]);
+      }
+    }
+  }
+}
+
+template <int D, int NC, bool BWD>
+__global__ void __launch_bounds__(AW * 32) afm_reg_kernel(const __grid_constant__ AfmParams P) {
+  constexpr int A = 32 * NC;
+  extern __shared__ __align__(16) float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // CTA-wide: Wt [A][D] and W [D][A] (backward), pair table; per warp: E, score, prod[8][D], dz[8][A], dEt
+  float *Wt = smem;
+  float *Ws = Wt + (BWD ? A * D : 0);
+  uint16_t *pair = reinterpret_cast<uint16_t *>(Ws + (BWD ? A * D : 0));
+  float *wbase = reinterpret_cast<float *>(pair) + r4((P.NP + 1) / 2);
+  const int per_warp = r4(P.F * D) + r4(P.NP) + PT8 * D + (BWD ? PT8 * A + r4(P.F * D) : 0);
+  float *sE = wbase + (size_t)warp * per_warp, *score = sE + r4(P.F * D), *prod = score + r4(P.NP);
+  float *dz = prod + PT8 * D, *dEt = dz + (BWD ? PT8 * A : 0);
+  if (BWD)
+    for (int e = threadIdx.x; e < D * A; e += blockDim.x) {
+      Wt[(e % A) * D + e / A] = P.W[e];
+      Ws[e] = P.W[e];
+    }
+  for (int p = threadIdx.x; p < P.NP; p += blockDim.x) {
+    int i, j;
+    pair_of(P.F, p, i, j);
+    pair[p] = (uint16_t)((i << 8) | j);
+  }
+  float Wr[BWD ? 1 : D][NC], br[NC], hr[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    br[c] = P.bvec[lane + 32 * c];
+    hr[c] = P.h[lane + 32 * c];
+#pragma unroll
+    for (int d = 0; d < (BWD ? 1 : D); ++d) Wr[d][c] = P.W[d * A + lane + 32 * c];
+  }
+  float dWr[BWD ? D : 1][NC], acc_db[NC], acc_dh[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    acc_db[c] = acc_dh[c] = 0.f;
+#pragma unroll
+    for (int d = 0; d < (BWD ? D : 1); ++d) dWr[d][c] = 0.f;
+  }
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * P.aw;
+  for (int64_t b = (int64_t)blockIdx.x * P.aw + warp; b < P.B; b += stride) {
+    const float *Eg = P.E + b * (int64_t)P.F * D;
+    for (int e = lane; e < P.F * D; e += 32) {
+      sE[e] = Eg[e];
+      if (BWD) dEt[e] = 0.f;
+    }
+    __syncwarp();
+    const float *g = BWD ? P.g_pooled + b * D : nullptr;
+    if (BWD) {  // ds_p = w_p (<g, P_p> - sum_q w_q <g, P_q>), kept in score[]
+      float tsum = 0.f;
+      for (int p = 0; p < P.NP; ++p) {
+        const int ij = pair[p];
+        float part = 0.f;
+        for (int d = lane; d < D; d += 32) part = fmaf(g[d], sE[(ij >> 8) * D + d] * sE[(ij & 255) * D + d], part);
+        part = rs::warp_sum(part);
+        if (lane == 0) score[p] = part;
+        tsum = fmaf(P.attw_in[b * P.NP + p], part, tsum);
+      }
+      __syncwarp();
+      for (int p = lane; p < P.NP; p += 32) score[p] = P.attw_in[b * P.NP + p] * (score[p] - tsum);
+      __syncwarp();
+    }
+    for (int p0 = 0; p0 < P.NP; p0 += PT8) {
+      const int npt = P.NP - p0 < PT8 ? P.NP - p0 : PT8;
+      for (int e = lane; e < PT8 * D; e += 32) {
+        const int pt = e / D, d = e - pt * D;
+        const int ij = pt < npt ? pair[p0 + pt] : 0;
+        prod[e] = pt < npt ? sE[(ij >> 8) * D + d] * sE[(ij & 255) * D + d] : 0.f;
+      }
+      __syncwarp();
+      float z[PT8][NC];
+      if constexpr (BWD)
+        project_smem<D, NC>(Ws, br, prod, lane, z);
+      else
+        project_reg<D, NC>(Wr, br, prod, z);
+      if (!BWD) {
+#pragma unroll
+        for (int pt = 0; pt < PT8; ++pt) {
+          float part = 0.f;
+#pragma unroll
+          for (int c = 0; c < NC; ++c) part = fmaf(hr[c], fmaxf(z[pt][c], 0.f), part);
+          part = rs::warp_sum(part);
+          if (lane == 0 && pt < npt) score[p0 + pt] = part;
+        }
+      } else {
+#pragma unroll
+        for (int pt = 0; pt < PT8; ++pt) {
+          const float ds = pt < npt ? score[p0 + pt] : 0.f;
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            acc_dh[c] = fmaf(ds, fmaxf(z[pt][c], 0.f), acc_dh[c]);
+            const float dzv = z[pt][c] > 0.f ? ds * hr[c] : 0.f;
+            acc_db[c] += dzv;
+            z[pt][c] = dzv;  // reuse the registers for dz
+            dz[pt * A + lane + 32 * c] = dzv;
+          }
+        }
+        // dW[d][a] += sum_pt P[pt][d] dz[pt][a]: registers only
+#pragma unroll
+        for (int d = 0; d < D; d += 4) {
+          float4 pv[PT8];
+#pragma unroll
+          for (int pt = 0; pt < PT8; ++pt) pv[pt] = *reinterpret_cast<const float4 *>(prod + pt * D + d);
+#pragma unroll
+          for (int c = 0; c < NC; ++c)
+#pragma unroll
+            for (int pt = 0; pt < PT8; ++pt) {
+              dWr[BWD ? d : 0][c] = fmaf(pv[pt].x, z[pt][c], dWr[BWD ? d : 0][c]);
+              dWr[BWD ? d + 1 : 0][c] = fmaf(pv[pt].y, z[pt][c], dWr[BWD ? d + 1 : 0][c]);
+              dWr[BWD ? d + 2 : 0][c] = fmaf(pv[pt].z, z[pt][c], dWr[BWD ? d + 2 : 0][c]);
+              dWr[BWD ? d + 3 : 0][c] = fmaf(pv[pt].w, z[pt][c], dWr[BWD ? d + 3 : 0][c]);
+            }
+        }
+        __syncwarp();
+        // dP[pt][d] = w_p g[d] + sum_a W[d][a] dz[pt][a]  (lane owns columns d); dE_i += dP e_j, dE_j += dP e_i
+        for (int d = lane; d < D; d += 32) {
+          float dp[PT8];
+#pragma unroll
+          for (int pt = 0; pt < PT8; ++pt) dp[pt] = pt < npt ? P.attw_in[b * P.NP + p0 + pt] * g[d] : 0.f;
+          for (int a = 0; a < A; ++a) {
+            const float wt = Wt[a * D + d];
+#pragma unroll
+            for (int pt = 0; pt < PT8; ++pt) dp[pt] = fmaf(wt, dz[pt * A + a], dp[pt]);
+          }
+#pragma unroll
+          for (int pt = 0; pt < PT8; ++pt)
+            if (pt < npt) {
+              const int ij = pair[p0 + pt];
+              const int i = ij >> 8, j = ij & 255;
+              dEt[i * D + d] = fmaf(dp[pt], sE[j * D + d], dEt[i * D + d]);
+              dEt[j * D + d] = fmaf(dp[pt], sE[i * D + d], dEt[j * D + d]);
+            }
+        }
+      }
+      __syncwarp();
+    }
+    if (!BWD) {
+      float mx = -INFINITY;
+      for (int p = lane; p < P.NP; p += 32) mx = fmaxf(mx, score[p]);
+      mx = rs::warp_max(mx);
+      float sum = 0.f;
+      for (int p = lane; p < P.NP; p += 32) {
+        const float e = expf(score[p] - mx);
+        score[p] = e;
+        sum += e;
+      }
+      sum = rs::warp_sum(sum);
+      const float inv = 1.0f / sum;
+      for (int p = lane; p < P.NP; p += 32) {
+        const float w = score[p] * inv;
+        score[p] = w;
+        if (P.attw_out) P.attw_out[b * P.NP + p] = w;
+      }
+      __syncwarp();
+      for (int d = lane; d < D; d += 32) {
+        float acc = 0.f;
+        for (int p = 0; p < P.NP; ++p) {
+          const int ij = pair[p];
+          acc = fmaf(score[p], sE[(ij >> 8) * D + d] * sE[(ij & 255) * D + d], acc);
+        }
+        P.pooled[b * D + d] = acc;
+      }
+    } else {
+      float *dEg = P.dE + b * (int64_t)P.F * D;
+      for (int e = lane; e < P.F * D; e += 32) dEg[e] = dEt[e];
+    }
+    __syncwarp();
+  }
+  if (BWD) {
+    const int64_t part = (int64_t)blockIdx.x * P.aw + warp;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int a = lane + 32 * c;
+#pragma unroll
+      for (int d = 0; d < D; ++d) P.dW_part[(part * D + d) * A + a] = dWr[BWD ? d : 0][c];
+      P.db_part[part * A + a] = acc_db[c];
+      P.dh_part[part * A + a] = acc_dh[c];
+    }
+  }
+}
+
+size_t reg_smem_bytes(const AfmParams &P, bool bwd, int aw) {
+  size_t f = (bwd ? (size_t)2 * P.A * P.D : 0) + r4((P.NP + 1) / 2);
+  f += (size_t)aw * (r4(P.F * P.D) + r4(P.NP) + PT8 * P.D + (bwd ? PT8 * P.A + r4(P.F * P.D) : 0));
+  return f * 4;
+}
+
+template <int D, int NC>
+int launch_reg(const AfmParams &P, bool bwd, int grid, cudaStream_t st) {
+  const size_t smem = reg_smem_bytes(P, bwd, P.aw);
+  if (bwd) {
+    RS_CUDA(cudaFuncSetAttribute(afm_reg_kernel<D, NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    afm_reg_kernel<D, NC, true><<<grid, P.aw * 32, smem, st>>>(P);
+  } else {
+    RS_CUDA(cudaFuncSetAttribute(afm_reg_kernel<D, NC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    afm_reg_kernel<D, NC, false><<<grid, P.aw * 32, smem, st>>>(P);
+  }
+  RS_CHECK_LAUNCH();
+  return RS_OK;
+}
+
+// returns RS_OK if the register-resident fast path handled the launch, 1 if the shape is not covered
+int try_reg(const AfmParams &P, bool bwd, int grid, cudaStream_t st) {
+  if (reg_smem_bytes(P, true, P.aw) > 200 * 1024) return 1;
+#define RS_AFM_CASE(d, nc) \
+  if (P.D == d && P.A == 32 * nc) return launch_reg<d, nc>(P, bwd, grid, st);
+  RS_AFM_CASE(32, 2)
+  RS_AFM_CASE(32, 1)
+  RS_AFM_CASE(16, 1)
+  RS_AFM_CASE(16, 2)
+  RS_AFM_CASE(64, 1)
+#undef RS_AFM_CASE
+  return 1;
+}
+
 int check(const AfmParams &P, const char *who) {
   RS_CHECK_ARG(P.F >= 2 && P.F <= 255, RS_E_SHAPE, "%s: F=%d out of range", who, P.F);
   RS_CHECK_ARG(P.D >= 4 && P.D % 4 == 0 && P.D <= 32 * MAXQ, RS_E_UNSUPPORTED, "%s: D=%d must be a multiple of 4, <= 256", who, P.D);
@@ -368,6 +641,10 @@ RS_API int rs_afm_fwd(const float *E, int64_t B, int32_t F, int32_t D, int32_t A
   RS_CHECK_ARG(P.aw >= 1, RS_E_UNSUPPORTED, "rs_afm_fwd: F=%d D=%d A=%d do not fit in shared memory", F, D, A);
   const size_t smem = smem_bytes(P, false, P.aw);
   RS_CUDA(cudaFuncSetAttribute(afm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    int rc2 = try_reg(P, false, grid_for(P, P.aw), (cudaStream_t)stream);
+    if (rc2 != 1) return rc2;
+  }
   afm_fwd_kernel<<<grid_for(P, P.aw), P.aw * 32, smem, (cudaStream_t)stream>>>(P);
   RS_CHECK_LAUNCH();
   return RS_OK;
@@ -401,6 +678,10 @@ RS_API int rs_afm_bwd(const float *E, int64_t B, int32_t F, int32_t D, int32_t A
   RS_CHECK_ARG(num_parts == grid * P.aw, RS_E_ARG, "rs_afm_bwd: num_parts %d != rs_afm_num_parts() = %d", num_parts, grid * P.aw);
   const size_t smem = smem_bytes(P, true, P.aw);
   RS_CUDA(cudaFuncSetAttribute(afm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    int rc2 = try_reg(P, true, grid, (cudaStream_t)stream);
+    if (rc2 != 1) return rc2;
+  }
   afm_bwd_kernel<<<grid, P.aw * 32, smem, (cudaStream_t)stream>>>(P);
   RS_CHECK_LAUNCH();
   return RS_OK;

@@ -295,7 +295,8 @@ def test_sigmoid_bce():
 
 
 # ------------------------------------------------------------------ AFM attention pooling
-@pytest.mark.parametrize("F,D,A,B", [(6, 16, 8, 200), (6, 128, 64, 70), (39, 32, 64, 24), (5, 8, 40, 64), (3, 4, 1, 33)])
+@pytest.mark.parametrize("F,D,A,B", [(6, 16, 8, 200), (6, 128, 64, 70), (39, 32, 64, 24), (5, 8, 40, 64), (3, 4, 1, 33),
+                                     (7, 16, 32, 150), (4, 64, 32, 60), (6, 32, 32, 77), (9, 16, 64, 600)])
 def test_afm_pool_fwd_bwd(F, D, A, B):
     ops = _ops()
     g = torch.Generator().manual_seed(F * D + A)
