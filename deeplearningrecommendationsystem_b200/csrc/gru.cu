@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(3 * H) gru_fwd_kernel(const float *__restrict_
                                                        float *__restrict__ gates) {
   __shared__ __align__(16) float s_h[BT][H];
   __shared__ float s_gh[BT][3 * H];
+  __shared__ __align__(16) float s_gi[2][BT][3 * H];  // input projections of step t / t+1 (cp.async double buffer)
   const int j = threadIdx.x;  // gate column 0..3H-1
   float w[H];
 #pragma unroll
@@ -29,8 +30,18 @@ __global__ void __launch_bounds__(3 * H) gru_fwd_kernel(const float *__restrict_
   const int64_t b0 = (int64_t)blockIdx.x * BT;
   const int nb = (int)((B - b0) < BT ? (B - b0) : BT);
   for (int e = j; e < BT * H; e += 3 * H) (&s_h[0][0])[e] = 0.f;
+  // the global reads of gi sit on the critical path of every step: fetch step t+1 while step t's mat-vec runs
+  auto prefetch = [&](int t, int buf) {
+    for (int e = j; e < nb * (3 * H / 4); e += 3 * H) {
+      const int b = e / (3 * H / 4), q = e - b * (3 * H / 4);
+      rs::cp_async16(&s_gi[buf][b][q * 4], gi + ((b0 + b) * L + t) * 3 * H + q * 4);
+    }
+    rs::cp_async_commit();
+  };
+  prefetch(0, 0);
   __syncthreads();
   for (int t = 0; t < L; ++t) {
+    if (t + 1 < L) prefetch(t + 1, (t + 1) & 1);
     float acc[BT];
 #pragma unroll
     for (int b = 0; b < BT; ++b) acc[b] = bj;
@@ -47,11 +58,15 @@ __global__ void __launch_bounds__(3 * H) gru_fwd_kernel(const float *__restrict_
     }
 #pragma unroll
     for (int b = 0; b < BT; ++b) s_gh[b][j] = acc[b];
+    if (t + 1 < L)
+      rs::cp_async_wait<1>();  // step t's projections have landed (step t+1's may still be in flight)
+    else
+      rs::cp_async_wait<0>();
     __syncthreads();
     for (int e = j; e < nb * H; e += 3 * H) {
       const int b = e / H, i = e - b * H;
       const int64_t row = (b0 + b) * L + t;
-      const float *g = gi + row * 3 * H;
+      const float *g = &s_gi[t & 1][b][0];
       const float hr = s_gh[b][i], hz = s_gh[b][H + i], hn = s_gh[b][2 * H + i];
       const float r = sigmoidf_(g[i] + hr);
       const float z = sigmoidf_(g[H + i] + hz);
