@@ -21,6 +21,14 @@ class rs_tables(C.Structure):
                 ("base", C.c_void_p * RS_MAX_FIELDS), ("rows", C.c_int64 * RS_MAX_FIELDS)]
 
 
+RS_MAX_RANKS = 64
+
+
+class rs_routes(C.Structure):
+    _fields_ = [("n", C.c_int32), ("start", C.c_int64 * (RS_MAX_RANKS + 1)), ("base", C.c_void_p * RS_MAX_RANKS),
+                ("row0", C.c_int64 * RS_MAX_RANKS)]
+
+
 class rs_fields_io(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
                 ("ids", "dense_in", "cross", "bi", "pairs", "concat", "stash", "dot2", "had2")]
@@ -42,7 +50,7 @@ class rs_update(C.Structure):
                 ("stash", C.c_void_p), ("scale", C.c_void_p), ("dense", C.c_void_p),
                 ("table", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("dense_grad", C.c_void_p),
                 ("lr", C.c_float), ("wd", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
-                ("step", C.c_int32)]
+                ("step", C.c_int32), ("grad_routes", C.POINTER(rs_routes))]
 
 
 class rs_xslots(C.Structure):
@@ -69,6 +77,7 @@ _PP = C.POINTER
 SIGNATURES = {
     "rs_version": [],
     "rs_gather_rows": [_PP(rs_tables), _P, _L, _P, _P, _P],
+    "rs_gather_rows_peer": [_P, _L, _I, _P, _L, _PP(rs_routes), _P, _P],
     "rs_fields_fwd": [_PP(rs_tables), _PP(rs_fields_io), _L, _P, _P],
     "rs_fields_bwd": [_PP(rs_tables), _PP(rs_fields_grad), _L, _P],
     "rs_ffm_fwd": [_PP(rs_tables), _P, _L, _I, _P, _P, _P, _P],

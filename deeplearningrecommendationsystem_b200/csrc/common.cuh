@@ -140,6 +140,20 @@ __device__ __forceinline__ void bulk_wait_read() {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// by-value copy of rs_routes for kernel parameters
+struct Routes {
+  int n;
+  int64_t start[RS_MAX_RANKS + 1];
+  float *base[RS_MAX_RANKS];
+  int64_t row0[RS_MAX_RANKS];
+};
+// destination of logical row r (floats): linear scan over at most n <= 64 ranges
+__device__ __forceinline__ float *route_row(const Routes &R, int64_t r, int W) {
+  int k = 0;
+  while (k + 1 < R.n && r >= R.start[k + 1]) ++k;
+  return R.base[k] + (R.row0[k] + (r - R.start[k])) * W;
+}
+
 __device__ __forceinline__ int64_t clamp_id(int64_t id, int64_t rows, int32_t *status) {
   if ((uint64_t)id >= (uint64_t)rows) {
     if (status) atomicOr(status, 1);

@@ -95,6 +95,52 @@ RS_API int rs_gather_rows(const rs_tables *T, const int64_t *ids, int64_t B, flo
   return RS_OK;
 }
 
+// ------------------------------------------------------------------ gather fused with the row all-to-all
+namespace rs {
+int fill_routes(Routes &R, const rs_routes *r, const char *who) {
+  RS_CHECK_ARG(r && r->n >= 1 && r->n <= RS_MAX_RANKS, RS_E_ARG, "%s: bad routes", who);
+  R.n = r->n;
+  for (int k = 0; k < r->n; ++k) {
+    R.start[k] = r->start[k];
+    R.base[k] = r->base[k];
+    R.row0[k] = r->row0[k];
+  }
+  R.start[r->n] = r->start[r->n];
+  return RS_OK;
+}
+}  // namespace rs
+
+// Thread e copies one 16-byte piece of one requested row into the requester's block through its peer-mapped
+// pointer: coalesced 128-bit loads from the local shard, coalesced 128-bit stores over NVLink.
+__global__ void __launch_bounds__(256) gather_rows_peer_kernel(const float *__restrict__ table, int64_t rows, int wv,
+                                                              const int64_t *__restrict__ idx, int64_t m,
+                                                              const __grid_constant__ rs::Routes R, int32_t *status) {
+  const int64_t total = m * wv;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = e / wv;
+    const int v = (int)(e - i * wv);
+    const int64_t id = rs::clamp_id(idx[i], rows, status);
+    const float4 val = rs::ldg_nc_f4(table + (id * wv + v) * 4);
+    rs::stg_f4(rs::route_row(R, i, wv * 4) + v * 4, val);
+  }
+}
+
+RS_API int rs_gather_rows_peer(const float *table, int64_t rows, int32_t width, const int64_t *idx, int64_t m, const rs_routes *routes,
+                               int32_t *status, void *stream) {
+  RS_CHECK_ARG(table && rows > 0 && width >= 4 && width % 4 == 0, RS_E_ARG, "rs_gather_rows_peer: bad table/width");
+  rs::Routes R;
+  int rc = rs::fill_routes(R, routes, "rs_gather_rows_peer");
+  if (rc) return rc;
+  if (m == 0) return RS_OK;
+  RS_CHECK_ARG(idx, RS_E_ARG, "rs_gather_rows_peer: null idx");
+  const int wv = width / 4;
+  int64_t blocks64 = (m * wv + 255) / 256;
+  int cap = rs::num_sms() * 16;
+  gather_rows_peer_kernel<<<(int)(blocks64 < cap ? blocks64 : cap), 256, 0, (cudaStream_t)stream>>>(table, rows, wv, idx, m, R, status);
+  RS_CHECK_LAUNCH();
+  return RS_OK;
+}
+
 // ------------------------------------------------------------------ x[:, col].long()
 __global__ void xcol_to_ids_kernel(const float *__restrict__ x, int64_t B, int xcols, int col, int64_t *__restrict__ ids) {
   int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

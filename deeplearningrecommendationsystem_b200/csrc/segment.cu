@@ -294,7 +294,10 @@ __device__ __forceinline__ void apply_row(const UpdParams &P, int64_t row, int e
   using V = Vec<VEC>;
   int64_t off = (row * P.W) + (int64_t)e * VEC;
   if (MODE == RS_UPD_GRAD) {
-    V::st(P.dense_grad + off, g);
+    if (P.routes.n > 0)
+      V::st(rs::route_row(P.routes, row, P.W) + (int64_t)e * VEC, g);
+    else
+      V::st(P.dense_grad + off, g);
   } else if (MODE == RS_UPD_SGD) {
     typename V::T w = V::ld(P.table + off);
     V::st(P.table + off, upd_sgd(w, g, P));
@@ -486,7 +489,7 @@ RS_API int rs_segment_update(const rs_segments *seg, int64_t n, const rs_update 
   RS_CHECK_ARG(u->stash || u->dense, RS_E_ARG, "rs_segment_update: need stash and/or dense gradient source");
   RS_CHECK_ARG(!u->scale || (u->stash && (u->scale_width == 1 || u->scale_width == u->width)), RS_E_ARG,
                "rs_segment_update: scale needs stash and scale_width in {1,width}");
-  if (u->mode == RS_UPD_GRAD) RS_CHECK_ARG(u->dense_grad, RS_E_ARG, "rs_segment_update: dense_grad is NULL");
+  if (u->mode == RS_UPD_GRAD) RS_CHECK_ARG(u->dense_grad || u->grad_routes, RS_E_ARG, "rs_segment_update: dense_grad is NULL");
   if (u->mode != RS_UPD_GRAD) RS_CHECK_ARG(u->table, RS_E_ARG, "rs_segment_update: table is NULL");
   if (u->mode == RS_UPD_ADAM) RS_CHECK_ARG(u->m && u->v && u->step >= 1, RS_E_ARG, "rs_segment_update: Adam needs m, v, step>=1");
   RS_CHECK_ARG((int64_t)(2 * (n / RS_CHUNK + 2)) * u->width <= seg->partial_floats, RS_E_WORKSPACE,
@@ -515,6 +518,11 @@ RS_API int rs_segment_update(const rs_segments *seg, int64_t n, const rs_update 
   P.m = u->m;
   P.v = u->v;
   P.dense_grad = u->dense_grad;
+  P.routes.n = 0;
+  if (u->mode == RS_UPD_GRAD && u->grad_routes) {
+    int rc = rs::fill_routes(P.routes, u->grad_routes, "rs_segment_update");
+    if (rc) return rc;
+  }
   P.W = u->width;
   P.F = u->F;
   P.scale_width = u->scale_width;

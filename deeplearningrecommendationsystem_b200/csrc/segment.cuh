@@ -15,6 +15,7 @@ struct UpdParams {
   const float *stash, *scale, *dense;
   float *table, *m, *v, *dense_grad;
   int W, F, scale_width, use_stream;
+  Routes routes;  // routes.n > 0: RS_UPD_GRAD writes row r to a peer instead of dense_grad[r]
   float lr, wd, beta1, beta2, eps, step_size, inv_sqrt_bc2;
 };
 
@@ -31,6 +32,7 @@ __device__ __forceinline__ void adam1(float &w, float &m, float &v, float g, con
   w = w - P.step_size * (m / denom);
 }
 
+int fill_routes(Routes &R, const rs_routes *r, const char *who);
 int launch_seg_stream(const UpdParams &P, int64_t n, int mode, cudaStream_t st);
 
 }  // namespace rs

@@ -188,7 +188,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) seg_stream_kernel(const __grid_co
               if (fl[e] & 4) {
                 uint32_t row;
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(row) : "r"(h + (uint32_t)offsetof(StageHdr, row) + 4u * e));
-                float *dst = (MODE == RS_UPD_GRAD ? P.dense_grad : P.table) + (int64_t)row * P.W + col * 4;
+                float *dst = (MODE == RS_UPD_GRAD ? (P.routes.n > 0 ? route_row(P.routes, row, P.W) : P.dense_grad + (int64_t)row * P.W)
+                                                  : P.table + (int64_t)row * P.W) + col * 4;
                 if (MODE == RS_UPD_SGD) {
                   int ts;
                   asm volatile("ld.shared.s32 %0, [%1];" : "=r"(ts) : "r"(h + (uint32_t)offsetof(StageHdr, tslot) + 4u * e));

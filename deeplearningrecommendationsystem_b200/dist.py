@@ -134,6 +134,99 @@ class RowExchange:
         return out
 
 
+class PeerRowExchange(RowExchange):
+    """RowExchange whose two heavy all-to-alls are fused into the kernels over NVLink peer memory.
+
+    Every rank owns two symmetric (peer-mapped) buffers per row width: `block` (the rows its batch needs) and `grads`
+    (the per-row gradients other ranks push to it).  Forward: the OWNER's gather kernel stores each requested row
+    straight into the requester's `block` (rs_gather_rows_peer) -- no staging buffer, no NCCL copy.  Backward: the
+    requester's segment-reduce kernel stores each reduced row gradient straight into the owner's `grads`
+    (RS_UPD_GRAD with grad_routes).  A device-side barrier on the symmetric-memory signal pads orders the phases.
+    Only the small id/count messages still go through NCCL.
+    """
+
+    def __init__(self, prims, group=None, grads_slack=2.0):
+        super().__init__(prims, group)
+        self.grads_slack = grads_slack
+        self._bufs = {}
+
+    def _buffers(self, width, cap_rows, device):
+        import torch.distributed._symmetric_memory as symm
+        key = (width, device)
+        ent = self._bufs.get(key)
+        if ent is None or ent["cap"] < cap_rows:
+            group = self.group if self.group is not None else dist.group.WORLD
+            gcap = int(cap_rows * self.grads_slack)
+            block = symm.empty((cap_rows, width), dtype=torch.float32, device=device)
+            grads = symm.empty((gcap, width), dtype=torch.float32, device=device)
+            hb = symm.rendezvous(block, group.group_name)
+            hg = symm.rendezvous(grads, group.group_name)
+            ent = {"cap": cap_rows, "gcap": gcap, "block": block, "grads": grads, "hb": hb, "hg": hg}
+            self._bufs[key] = ent
+        return ent
+
+    def _plan(self, keys, total_rows):
+        N = self.world
+        R = (total_rows + N - 1) // N
+        okeys = (keys % N) * R + keys // N
+        uniq, inverse = self.prims.unique(okeys, N * R)
+        bounds = torch.arange(N + 1, device=keys.device, dtype=uniq.dtype) * R
+        send_counts_t = torch.diff(torch.searchsorted(uniq, bounds))
+        # every rank learns the whole (requester, owner) count matrix in ONE all-gather: that fixes all split sizes
+        # and all destination offsets of both fused exchanges
+        allc = torch.empty(N, N, dtype=send_counts_t.dtype, device=keys.device)
+        dist.all_gather_into_tensor(allc, send_counts_t, group=self.group)
+        counts = allc.tolist()                                        # the one host sync of the plan
+        send_counts = counts[self.rank]
+        recv_counts = [counts[r][self.rank] for r in range(N)]
+        send_local = uniq % R
+        recv_local = torch.empty(sum(recv_counts), dtype=torch.int64, device=keys.device)
+        dist.all_to_all_single(recv_local, send_local, recv_counts, send_counts, group=self.group)
+        plan = Plan(int(uniq.numel()), inverse, send_local, send_counts, recv_counts, recv_local)
+        plan.counts = counts
+        return plan
+
+    def fetch(self, plan, local_table):
+        from . import ops
+        N, me, W = self.world, self.rank, local_table.shape[1]
+        cap = plan.local_ids.numel()                                  # a batch cannot need more distinct rows than lookups
+        ent = self._buffers(W, cap, local_table.device)
+        counts = plan.counts
+        # rows requested by rank r start at sum(recv_counts[:r]) in my request list and belong at
+        # sum(counts[r][:me]) in r's block
+        starts, row0s = [0], []
+        for r in range(N):
+            starts.append(starts[-1] + counts[r][me])
+            row0s.append(sum(counts[r][:me]))
+        routes = ops.make_routes(starts, [ent["hb"].buffer_ptrs[r] for r in range(N)], row0s)
+        ops.gather_rows_peer(local_table, plan.recv_local, routes)
+        with _phase("exchange_barrier"):
+            ent["hb"].barrier()
+        return ent["block"][: plan.n_uniq]
+
+    def grad_routes(self, plan, width, device):
+        """Routes for the reduced row gradients of the fetched block: block rows of owner o go to o's `grads` buffer at
+        the offset where this rank's rows start in o's request list."""
+        from . import ops
+        N, me = self.world, self.rank
+        ent = self._bufs[(width, device)]
+        counts = plan.counts
+        need = max(sum(counts[r][o] for r in range(N)) for o in range(N))
+        if need > ent["gcap"]:
+            raise RuntimeError(f"PeerRowExchange: an owner receives {need} rows > capacity {ent['gcap']}; raise grads_slack")
+        starts, row0s = [0], []
+        for o in range(N):
+            starts.append(starts[-1] + counts[me][o])
+            row0s.append(sum(counts[r][o] for r in range(me)))
+        return ops.make_routes(starts, [ent["hg"].buffer_ptrs[o] for o in range(N)], row0s), ent
+
+    def finish_push(self, plan, ent):
+        """After the routed segment-reduce: barrier, then this rank's received gradients (aligned with recv_local)."""
+        with _phase("exchange_barrier"):
+            ent["hg"].barrier()
+        return ent["grads"][: plan.recv_local.numel()]
+
+
 def shard_rows(global_table, rank, world):
     """The rows of a replicated/global table that `rank` owns (r % world == rank), as a contiguous copy."""
     return global_table[rank::world].contiguous()

@@ -111,7 +111,11 @@ class _FieldModel(nn.Module):
             if not fused:
                 raise ValueError("sharded tables are updated by the fused row optimizer (fused=True)")
             from . import dist as rsdist
-            self.exchange = rsdist.RowExchange(rsdist.cuda_prims(), group)
+            # fused peer-memory exchange over NVLink when symmetric memory is available, NCCL all-to-alls otherwise
+            import os
+            peer = os.environ.get("RS_PEER_EXCHANGE", "1") == "1" and torch.distributed.is_initialized() and \
+                torch.distributed.get_world_size(group) > 1
+            self.exchange = (rsdist.PeerRowExchange if peer else rsdist.RowExchange)(rsdist.cuda_prims(), group)
             rows = self.exchange.local_rows(self.total_rows)
             std = math.sqrt(2.0 / (self.total_rows / self.F + row_dim))
             w = torch.empty(rows, width, dtype=torch.float32, device=device)
@@ -174,14 +178,20 @@ class _FieldModel(nn.Module):
             # row-sharded: reduce the batch's gradients per fetched row, send them to the owners, update there
             plan, ex = rec["plan"], self.exchange
             segs = ops.dedup_sort(plan.local_ids, 1, None, plan.n_uniq, max_width=self.width)   # memoised per plan
-            # every fetched row has at least one lookup in this batch, so RS_UPD_GRAD writes every row of the block
-            block_grad = torch.empty(plan.n_uniq, self.width, dtype=torch.float32, device=rec["g"].device)
             if "scale" in src:
                 src["scale"] = src["scale"] * (1.0 / ex.world)          # gradients are averaged over the ranks
             else:
                 src["dense"] = src["dense"] * (1.0 / ex.world)
-            ops.segment_update(segs, ops.RS_UPD_GRAD, self.width, self.F, dense_grad=block_grad, **src)
-            recv = ex.push_grads(plan, block_grad)
+            if hasattr(ex, "grad_routes"):
+                # segment-reduce fused with the push: reduced rows are stored straight into the owners' buffers
+                routes, ent = ex.grad_routes(plan, self.width, rec["g"].device)
+                ops.segment_update(segs, ops.RS_UPD_GRAD, self.width, self.F, grad_routes=routes, **src)
+                recv = ex.finish_push(plan, ent)
+            else:
+                # every fetched row has at least one lookup in this batch, so RS_UPD_GRAD writes every row of the block
+                block_grad = torch.empty(plan.n_uniq, self.width, dtype=torch.float32, device=rec["g"].device)
+                ops.segment_update(segs, ops.RS_UPD_GRAD, self.width, self.F, dense_grad=block_grad, **src)
+                recv = ex.push_grads(plan, block_grad)
             if recv.shape[0]:
                 osegs = ops.dedup_sort(plan.recv_local, 1, None, self.weight.shape[0], max_width=self.width)
                 self._row_update(opt, osegs, 1, dense=recv)

@@ -367,8 +367,33 @@ def prefetch_dedup(ids, F=1, row_offset=None, total_rows=None):
         _prefetching = False
 
 
+def make_routes(starts, bases, row0s):
+    """rs_routes: logical rows [starts[k], starts[k+1]) go to bases[k] (device pointer, peer-mapped or local) at row
+    offset row0s[k].  len(starts) == len(bases) + 1."""
+    R = _lib.rs_routes()
+    R.n = len(bases)
+    for k, (s0, b, r0) in enumerate(zip(starts, bases, row0s)):
+        R.start[k], R.base[k], R.row0[k] = int(s0), int(b), int(r0)
+    R.start[R.n] = int(starts[-1])
+    return R
+
+
+def gather_rows_peer(table, idx, routes):
+    """Owner side of the fused gather + all-to-all: table[idx[i]] is stored straight into the requesting rank's block
+    through its peer-mapped pointer (routes).  Follow with a cross-rank barrier."""
+    _need_cuda(table, idx)
+    idx = _i64(idx)
+    if idx.numel() == 0:
+        return
+    with _timed(f"gather_rows_peer[w{table.shape[1]}]"):
+        _lib.check(_lib.load().rs_gather_rows_peer(table.data_ptr(), table.shape[0], table.shape[1], idx.data_ptr(), idx.numel(),
+                                                   C.byref(routes), status_word(table.device).data_ptr(), _stream()),
+                   "rs_gather_rows_peer")
+    _count()
+
+
 def segment_update(segs, mode, width, F, stash=None, scale=None, dense=None, table=None, m=None, v=None, dense_grad=None,
-                   lr=0.0, wd=0.0, betas=(0.9, 0.999), eps=1e-8, step=1):
+                   lr=0.0, wd=0.0, betas=(0.9, 0.999), eps=1e-8, step=1, grad_routes=None):
     """Segment-reduce the per-lookup row gradients (scale*stash + dense) and apply `mode` to the touched rows."""
     u = _lib.rs_update()
     u.mode, u.width, u.F = mode, width, F
@@ -381,6 +406,8 @@ def segment_update(segs, mode, width, F, stash=None, scale=None, dense=None, tab
             raise ValueError(f"{name} must be contiguous float32")
         setattr(u, name, _p(t))
     u.lr, u.wd, u.beta1, u.beta2, u.eps, u.step = lr, wd, betas[0], betas[1], eps, step
+    if grad_routes is not None:
+        u.grad_routes = C.pointer(grad_routes)
     with _timed(f"segment_update[w{width}]"):
         _lib.check(_lib.load().rs_segment_update(C.byref(segs.seg), segs.n, C.byref(u), _stream()), "rs_segment_update")
     _count(2)

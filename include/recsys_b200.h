@@ -42,12 +42,28 @@ typedef struct rs_tables {
   int64_t rows[RS_MAX_FIELDS];
 } rs_tables;
 
+/* Destination routing for rows that leave this GPU over NVLink peer memory: rows [start[k], start[k+1]) of the
+ * logical output go to base[k] + (row0[k] + (r - start[k])) * width floats.  base[k] is a device pointer into rank k's
+ * symmetric (peer-mapped) buffer, or into local memory for k == own rank.  n == 0 means "no routing". */
+#define RS_MAX_RANKS 64
+typedef struct rs_routes {
+  int32_t n;
+  int64_t start[RS_MAX_RANKS + 1];
+  float *base[RS_MAX_RANKS];
+  int64_t row0[RS_MAX_RANKS];
+} rs_routes;
+
 int rs_version(void);
 const char *rs_last_error(void);
 
 /* ---- gather: replaces nn.Embedding.forward (model/deepfm.py:45-46, model/mf.py:24-25, model/din.py:35-36).
  * out[b, f, :] = T.base[f][ids[b, f], :]   -- a pure copy, bit-exact.  ids (B, F) int64, out (B, F, width). */
 int rs_gather_rows(const rs_tables *T, const int64_t *ids, int64_t B, float *out, int32_t *status, void *stream);
+/* Fused gather + all-to-all for row-sharded tables: row i of the request list (local indices `idx`, grouped by
+ * requesting rank) is copied from `table` straight into the requester's receive block through its peer-mapped
+ * pointer (routes), i.e. the owner's gather kernel IS the "rows" all-to-all.  A cross-rank barrier must follow. */
+int rs_gather_rows_peer(const float *table, int64_t rows, int32_t width, const int64_t *idx, int64_t m,
+                        const rs_routes *routes, int32_t *status, void *stream);
 
 /* ---- fused multi-field lookup + interaction forward.
  * Replaces the per-model python between the embedding calls and the MLP:
@@ -151,6 +167,8 @@ typedef struct rs_update {
   float *dense_grad;  /* RS_UPD_GRAD target, same shape, pre-zeroed by the caller */
   float lr, wd, beta1, beta2, eps;
   int32_t step;       /* 1-based */
+  const rs_routes *grad_routes; /* RS_UPD_GRAD only, optional: write row r of the reduced gradient to a peer
+                                   (routes) instead of dense_grad[r] -- segment-reduce fused with the gradient push */
 } rs_update;
 int rs_segment_update(const rs_segments *seg, int64_t n, const rs_update *u, void *stream);
 
