@@ -115,13 +115,28 @@ int fill_routes(Routes &R, const rs_routes *r, const char *who) {
 __global__ void __launch_bounds__(256) gather_rows_peer_kernel(const float *__restrict__ table, int64_t rows, int wv,
                                                               const int64_t *__restrict__ idx, int64_t m,
                                                               const __grid_constant__ rs::Routes R, int32_t *status) {
+  // Remote stores are latency bound, so every thread keeps four independent 16-byte pieces in flight: the four
+  // loads are issued before the four stores.
   const int64_t total = m * wv;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = e / wv;
-    const int v = (int)(e - i * wv);
-    const int64_t id = rs::clamp_id(idx[i], rows, status);
-    const float4 val = rs::ldg_nc_f4(table + (id * wv + v) * 4);
-    rs::stg_f4(rs::route_row(R, i, wv * 4) + v * 4, val);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e0 < total; e0 += 4 * stride) {
+    float4 val[4];
+    float *dst[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t e = e0 + u * stride;
+      dst[u] = nullptr;
+      if (e < total) {
+        const int64_t i = e / wv;
+        const int v = (int)(e - i * wv);
+        const int64_t id = rs::clamp_id(idx[i], rows, status);
+        val[u] = rs::ldg_nc_f4(table + (id * wv + v) * 4);
+        dst[u] = rs::route_row(R, i, wv * 4) + v * 4;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (dst[u]) rs::stg_f4(dst[u], val[u]);
   }
 }
 
@@ -135,7 +150,7 @@ RS_API int rs_gather_rows_peer(const float *table, int64_t rows, int32_t width, 
   RS_CHECK_ARG(idx, RS_E_ARG, "rs_gather_rows_peer: null idx");
   const int wv = width / 4;
   int64_t blocks64 = (m * wv + 255) / 256;
-  int cap = rs::num_sms() * 16;
+  int cap = rs::num_sms() * 8;
   gather_rows_peer_kernel<<<(int)(blocks64 < cap ? blocks64 : cap), 256, 0, (cudaStream_t)stream>>>(table, rows, wv, idx, m, R, status);
   RS_CHECK_LAUNCH();
   return RS_OK;
