@@ -53,18 +53,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) ffm_fwd_kernel(const __grid_const
 
   if (warp == 0) {
     // ===== producer: one bulk copy per table row =====
+    // The id reads sit on the producer's critical path (one dependent global load per sample), so the ids of sample
+    // k+1 are requested before the copies of sample k are issued.
     int k = 0;
-    for (int64_t b = blockIdx.x; b < P.B; b += gridDim.x, ++k) {
+    int64_t b = blockIdx.x;
+    int64_t id_cur[2] = {0, 0}, id_nxt[2] = {0, 0};  // lane f holds the ids of fields f and f+32
+    if (b < P.B) {
+      if (lane < P.F) id_cur[0] = P.ids[b * P.F + lane];
+      if (lane + 32 < P.F) id_cur[1] = P.ids[b * P.F + lane + 32];
+    }
+    for (; b < P.B; b += gridDim.x, ++k) {
+      const int64_t bn = b + gridDim.x;
+      if (bn < P.B) {
+        if (lane < P.F) id_nxt[0] = P.ids[bn * P.F + lane];
+        if (lane + 32 < P.F) id_nxt[1] = P.ids[bn * P.F + lane + 32];
+      }
       const int s = k % P.nst;
       const uint32_t ph = (uint32_t)(k / P.nst) & 1u;
       rs::mbar_wait(&empty_bar[s], ph ^ 1u);
       if (lane == 0) rs::mbar_arrive_expect_tx(&full_bar[s], row_bytes * (uint32_t)P.F);
       __syncwarp();
       float4 *dst = tiles + (size_t)s * stage_v;
-      for (int f = lane; f < P.F; f += 32) {
-        const int64_t id = rs::clamp_id(P.ids[b * P.F + f], s_rows[f], P.status);
-        rs::bulk_g2s(dst + (size_t)f * P.pitchv, s_base[f] + id * (int64_t)P.rowv * 4, row_bytes, &full_bar[s]);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int f = lane + 32 * h;
+        if (f < P.F) {
+          const int64_t id = rs::clamp_id(id_cur[h], s_rows[f], P.status);
+          rs::bulk_g2s(dst + (size_t)f * P.pitchv, s_base[f] + id * (int64_t)P.rowv * 4, row_bytes, &full_bar[s]);
+        }
       }
+      id_cur[0] = id_nxt[0];
+      id_cur[1] = id_nxt[1];
     }
   } else {
     // ===== consumers =====
