@@ -71,7 +71,7 @@ class ClockSampler:
     region runs (the same counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints)."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, index, period_s=0.004):
+    def __init__(self, index, period_s=float(os.environ.get("RS_BENCH_CLOCK_PERIOD", "0.004"))):
         import threading
         self.sm, self.mask, self.max_mhz, self.ok = [], 0, None, False
         self._stop = threading.Event()
@@ -246,15 +246,22 @@ def run_gpu(args):
     copied = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
 
+    h2d_events = []
+
     def fetch(k):
         hi, hy = host_pool[k % len(host_pool)]
         b = k & 1
         with torch.cuda.stream(copy_stream):
             if k >= 2:
                 copy_stream.wait_event(consumed[b])        # the step that read this slot has finished
+            c0 = torch.cuda.Event(enable_timing=True)
+            c0.record(copy_stream)
             slots[b][0].copy_(hi, non_blocking=True)
             slots[b][1].copy_(hy, non_blocking=True)
+            c1 = torch.cuda.Event(enable_timing=True)
+            c1.record(copy_stream)
             copied[b].record(copy_stream)
+            h2d_events.append((c0, c1))
 
     # every step's loss is copied back into pinned host memory (non-blocking, one slot per step) and read after the
     # final synchronise, so the host keeps enqueueing work instead of stalling on a 4-byte read each step
@@ -273,6 +280,7 @@ def run_gpu(args):
     t1.record()
     sync()
     loss_val = float(loss_host[-1])
+    h2d_ms = sorted(a.elapsed_time(b) for a, b in h2d_events)
     ms_e2e = t0.elapsed_time(t1)
     clk = clocks.stop()
 
@@ -317,7 +325,8 @@ def run_gpu(args):
                        "parallelism": f"dp{world}" + ("" if world == 1 else ": batch split, tables row-sharded, dedup all-to-all of ids/rows/grads")},
             "roofline": roof, "kernels": extra,
             "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": B * F * 8 + B * 4, "d2h_bytes_per_step": 4,
-                    "ms_per_step": ms_e2e / args.steps, "last_loss": loss_val},
+                    "ms_per_step": ms_e2e / args.steps, "last_loss": loss_val,
+                    "h2d_copy_ms": {"median": h2d_ms[len(h2d_ms) // 2], "max": h2d_ms[-1]}},
             "gpu_launches": gpu_launches, "clocks": clk,
         }
         if world == 1 and not args.no_cpu:
