@@ -12,6 +12,10 @@ import torch
 class GraphedTrainStep:
     """step(*inputs, rating) -> (predictions, loss) with identical semantics to Trainer.train_loop.
 
+    If the model has already been trained eagerly, drop every tensor that still references that autograd graph (e.g.
+    `trainer.train_loss`, `trainer.predictions_train`) first: autograd binds a parameter's AccumulateGrad node to the
+    stream it was created on, and a node from the legacy default stream cannot be reused during capture.
+
     The first `warmup` calls run eagerly (they are real train steps on their own inputs and also let every library
     and cache initialise); the next call captures the step on static input buffers and replays it.  From then on
     inputs are copied into the static buffers, the graph is replayed, and the static outputs are returned (valid
