@@ -1,4 +1,4 @@
-"""Drop-in replacements for reference model/{lr,mf,ffm,deepfm,afm,nfm,pnn,din,dien,neuralcf}.py.
+"""Drop-in replacements for reference model/{lr,mf,ffm,deepfm,afm,nfm,pnn,din,dien,neuralcf,widedeep,deepcross,deepcrossing}.py.
 
 Same constructor signatures, forward signatures, output shapes, state_dict keys/shapes and quirks as the reference
 modules, so the reference's scripts/*.py run with only the import line changed.  Embedding lookups, feature
@@ -15,3 +15,6 @@ from .pnn import PNN, DNN, ProductLayers  # noqa: F401
 from .din import DIN  # noqa: F401
 from .dien import DIEN  # noqa: F401
 from .neuralcf import NeuralCF  # noqa: F401
+from .widedeep import WideDeep  # noqa: F401
+from .deepcross import DeepCross, CrossNetwork, DeepNetwork  # noqa: F401
+from .deepcrossing import DeepCrossing, ResidualBlock  # noqa: F401

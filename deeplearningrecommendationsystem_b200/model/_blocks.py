@@ -105,6 +105,19 @@ def six_slots():
             (OCC[0], OCC[1], KIND_BAG), (GENRE[0], GENRE[1], KIND_BAG))
 
 
+def five_slots():
+    """[user, item, gender, occupation, movie]: the models that feed age as a raw scalar (model/widedeep.py:44-49)."""
+    return ((COL_USER, 1, KIND_ID), (COL_ITEM, 1, KIND_ID), (GENDER[0], GENDER[1], KIND_BAG), (OCC[0], OCC[1], KIND_BAG),
+            (GENRE[0], GENRE[1], KIND_BAG))
+
+
+def stacked_features(x, user_w, item_w, gender_w, occupation_w, movie_w):
+    """[e_user, e_item, age, e_gender, e_occupation, e_movie] -> (B, 5D+1): the stacking layer shared by
+    model/widedeep.py:44-50, model/deepcross.py:60-66 and model/deepcrossing.py:56-63 (one fused lookup, one cat)."""
+    E = XEmbed.apply(x, five_slots(), user_w, item_w, gender_w, occupation_w, movie_w)
+    return torch.cat((E[:, :2].flatten(1), x[:, AGE[0]:AGE[0] + 1], E[:, 2:].flatten(1)), dim=1)
+
+
 class _Interact(torch.autograd.Function):
     """Interaction over dense field embeddings E (B, F, D); `what` picks the output (rs_fields_fwd / rs_fields_bwd)."""
 
@@ -197,14 +210,75 @@ def first_order(module_user, module_item, linear, x):
     return lookup(module_user.weight, uid) + lookup(module_item.weight, iid) + linear(x[:, 2:])
 
 
-def topk_per_user(model, num_users, user_item, k):
-    """recommendation(): per-user forward over that user's rows + top-k (reference model/deepfm.py:85-95)."""
+RANK_CHUNK_ROWS = 1 << 18     # rows scored per forward while ranking the catalogue
+
+
+def rank_catalogue(score_fn, num_users, num_items, k):
+    """All users x all items -> (num_users, k) ranked item positions, as a numpy int64 array.
+
+    ``score_fn(u0, u1)`` returns the scores of users [u0, u1) against items 0..num_items-1, user-major.  Users are
+    scored a chunk at a time (one forward per ~RANK_CHUNK_ROWS rows instead of one per user) and every user's
+    ``torch.topk(scores, k, dim=0)`` (reference model/din.py:63, model/neuralcf.py:69) is one CTA of rs_rank_segments."""
     import numpy as np
-    device = next(model.parameters()).device
+    if num_users == 0:
+        return np.array([])
+    step = max(1, RANK_CHUNK_ROWS // max(num_items, 1))
     out = []
     with torch.no_grad():
-        for u in range(num_users):
-            rows = torch.tensor(user_item[user_item["user_id"] == u].values, dtype=torch.float32, device=device)
-            scores = model(rows)
-            out.append(torch.topk(scores, k, dim=0).indices.view(-1).tolist())
-    return np.array(out)
+        for u0 in range(0, num_users, step):
+            u1 = min(num_users, u0 + step)
+            scores = score_fn(u0, u1).reshape(-1)
+            out.append(ops.rank_segments(scores, k, seg_len=num_items))
+    return torch.cat(out).cpu().numpy()
+
+
+def history_scores(model, hist_list, num_items, device):
+    """score_fn for DIN / DIEN: user u's history against every target item (reference model/din.py:58-62)."""
+    try:
+        hist_all = torch.tensor(hist_list)
+        ragged = hist_all.dim() != 2
+    except (ValueError, TypeError):
+        ragged = True
+    target = torch.arange(0, num_items, device=device)
+
+    def score(u0, u1):
+        if ragged:
+            return torch.cat([model(torch.tensor(hist_list[u]).repeat(num_items, 1).to(device), target).reshape(-1)
+                              for u in range(u0, u1)])
+        hist = hist_all[u0:u1].to(device).repeat_interleave(num_items, dim=0)
+        return model(hist, target.repeat(u1 - u0))
+    return score
+
+
+def topk_per_user(model, num_users, user_item, k, batched=True):
+    """recommendation(): each user's rows of ``user_item`` scored and ranked (reference model/deepfm.py:85-95).
+
+    The reference filters the frame once per user and runs one forward + topk per user.  Here the rows are grouped by
+    user once (stable, so every user keeps the frame's row order -- the returned positions index that order), scored
+    in large chunks, and ranked for all users by one rs_rank_segments launch.  ``batched=False`` keeps one forward per
+    user for models whose output depends on the batch composition (PNN "out", model/pnn.py:72)."""
+    import numpy as np
+    device = next(model.parameters()).device
+    uid = np.asarray(user_item["user_id"].values).astype(np.int64)
+    keep = (uid >= 0) & (uid < num_users)
+    order = np.flatnonzero(keep)
+    order = order[np.argsort(uid[order], kind="stable")]
+    counts = np.bincount(uid[order], minlength=num_users)
+    values = np.asarray(user_item.values, dtype=np.float32)
+    seg = np.zeros(num_users + 1, dtype=np.int64)
+    np.cumsum(counts, out=seg[1:])
+    if num_users == 0:
+        return np.array([])
+    scores = []
+    with torch.no_grad():
+        if batched:
+            for r0 in range(0, len(order), RANK_CHUNK_ROWS):
+                rows = torch.from_numpy(values[order[r0:r0 + RANK_CHUNK_ROWS]]).to(device)
+                scores.append(model(rows).reshape(-1))
+        else:
+            for u in range(num_users):
+                rows = torch.from_numpy(values[order[seg[u]:seg[u + 1]]]).to(device)
+                scores.append(model(rows).reshape(-1))
+        scores = torch.cat(scores) if scores else torch.empty(0, device=device)
+        idx = ops.rank_segments(scores, k, seg_start=torch.from_numpy(seg).to(device), max_len=int(counts.max()))
+    return idx.cpu().numpy()

@@ -2,7 +2,6 @@
 that SCALES the history instead of pooling it, an nn.GRU(D, D) over the scaled sequence (h0 = 0), and
 fc 2D->128->64->1->Sigmoid on [h_L, target].  This is a plain GRU on attention-scaled inputs, not the paper's AUGRU.
 state_dict keys: din.item_embedding.weight, din.attention.{0,2,4}.*, interest_evolution.*_l0, fc.{0,2,4}.*"""
-import numpy as np
 import torch
 from torch import nn
 from torch.nn.init import xavier_normal_
@@ -40,11 +39,4 @@ class DIEN(nn.Module):
 
     def recommendation(self, num_users, num_items, hist_list, k):
         device = next(self.parameters()).device
-        out = []
-        with torch.no_grad():
-            target = torch.arange(0, num_items, device=device)
-            for u in range(num_users):
-                hist = torch.tensor(hist_list[u]).repeat(num_items, 1).to(device)
-                scores = self.forward(hist, target)
-                out.append(torch.topk(scores, k, dim=0).indices.view(1, -1).tolist()[0])
-        return np.array(out)
+        return K.rank_catalogue(K.history_scores(self, hist_list, num_items, device), num_users, num_items, k)

@@ -3,7 +3,6 @@
 One item table, looked up for the target and for the L history slots in ONE gather (so the backward needs one sort
 / segment-reduce); attention unit MLP 3D->128->64->1 over [h, h-t, t]; softmax over L with no padding mask and no
 scaling (padded slots hold the real item id 0, scripts/din.py:31); weighted sum; fc 2D->256->128->1->Sigmoid."""
-import numpy as np
 import torch
 from torch import nn
 from torch.nn.init import xavier_normal_
@@ -28,11 +27,4 @@ class DIN(nn.Module):
 
     def recommendation(self, num_users, num_items, hist_list, k):
         device = next(self.parameters()).device
-        out = []
-        with torch.no_grad():
-            target = torch.arange(0, num_items, device=device)
-            for u in range(num_users):
-                hist = torch.tensor(hist_list[u]).repeat(num_items, 1).to(device)
-                scores = self.forward(hist, target)
-                out.append(torch.topk(scores, k, dim=0).indices.view(1, -1).tolist()[0])
-        return np.array(out)
+        return K.rank_catalogue(K.history_scores(self, hist_list, num_items, device), num_users, num_items, k)

@@ -4,6 +4,7 @@ from torch import nn
 from torch.nn.init import xavier_normal_
 
 from . import _blocks as K
+from .. import ops
 
 
 class MatrixFactorization(nn.Module):
@@ -19,6 +20,6 @@ class MatrixFactorization(nn.Module):
         return torch.sigmoid(dot)                                   # (B,)
 
     def recommendation(self, num_users, num_items):
+        # U @ V^T + topk (reference model/mf.py:28-35) fused: one CTA per user scores and ranks the catalogue in shared memory
         with torch.no_grad():
-            scores = self.user_embeddings.weight[:num_users] @ self.item_embeddings.weight[:num_items].T
-            return torch.topk(scores, num_items, dim=1).indices.cpu().numpy()
+            return ops.mf_rank(self.user_embeddings.weight[:num_users], self.item_embeddings.weight[:num_items], num_items).cpu().numpy()

@@ -1,5 +1,4 @@
 """NeuralCF (GMF * MLP tower) -- drop-in for reference model/neuralcf.py:7-73."""
-import numpy as np
 import torch
 from torch import nn
 from torch.nn.init import xavier_normal_
@@ -32,10 +31,9 @@ class NeuralCF(nn.Module):
 
     def recommendation(self, num_users, num_items):
         device = next(self.parameters()).device
-        out = []
-        with torch.no_grad():
-            items = torch.arange(num_items, device=device)
-            for u in range(num_users):
-                scores = self.forward(torch.full((num_items,), u, device=device), items)
-                out.append(torch.topk(scores, num_items, dim=0).indices.view(-1).tolist())
-        return np.array(out)
+        items = torch.arange(num_items, device=device)
+
+        def score(u0, u1):
+            users = torch.arange(u0, u1, device=device).repeat_interleave(num_items)
+            return self.forward(users, items.repeat(u1 - u0))
+        return K.rank_catalogue(score, num_users, num_items, num_items)

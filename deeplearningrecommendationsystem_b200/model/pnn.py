@@ -67,4 +67,6 @@ class PNN(nn.Module):
         return torch.sigmoid(self.output(h)).view(-1, 1)
 
     def recommendation(self, num_users, user_item, k):
-        return K.topk_per_user(self, num_users, user_item, k)
+        # "out" pools the outer product over the batch (model/pnn.py:72), so a user's scores depend on exactly which
+        # rows share the forward: keep one forward per user there
+        return K.topk_per_user(self, num_users, user_item, k, batched=self.product.model == "in")

@@ -657,3 +657,63 @@ def gemm_nt(A, W, bias=None, rowbias=None, rb_group=1, relu=False, mask=None, M=
         _lib.check(_lib.load().rs_gemm_nt_3xtf32(C.byref(g), _stream()), "rs_gemm_nt_3xtf32")
     _count()
     return out
+
+
+def _rank_status(st, k, who):
+    v = int(st.item())
+    if v & 2:
+        raise RuntimeError(f"{who}: selected index k={k} out of range (a segment is shorter than k)")
+    if v & 4:
+        raise RuntimeError(f"{who}: a segment is longer than the max_len it was launched with")
+
+
+def rank_segments(scores, k, seg_start=None, seg_len=None, max_len=None, values=False, check=True):
+    """Per-segment descending top-k positions (k == segment length: the full ranking) -- one launch for all users.
+
+    scores: flat fp32; segments either uniform (``seg_len``) or given by ``seg_start`` (int64, S+1 offsets; pass
+    ``max_len`` = an upper bound of the segment lengths).  Returns idx (S, k) int64 positions inside each segment
+    [, val (S, k)].  Ties rank the lower position first.  ``check`` reads the status word (one sync)."""
+    scores = _f32(scores).view(-1)
+    _need_cuda(scores, seg_start)
+    if seg_start is None:
+        if seg_len is None or seg_len <= 0 or scores.numel() % seg_len:
+            raise ValueError("rank_segments: uniform segments need seg_len dividing scores.numel()")
+        S, max_len, ss = scores.numel() // seg_len, seg_len, None
+    else:
+        ss = _i64(seg_start)
+        S = ss.numel() - 1
+        if max_len is None:
+            max_len = int((ss[1:] - ss[:-1]).max().item()) if S > 0 else 1
+    idx = torch.empty(S, k, dtype=torch.int64, device=scores.device)
+    val = torch.empty(S, k, dtype=torch.float32, device=scores.device) if values else None
+    if S > 0:
+        st = torch.zeros(1, dtype=torch.int32, device=scores.device)
+        with _timed("rank_segments"):
+            _lib.check(_lib.load().rs_rank_segments(scores.data_ptr(), _p(ss), S, max(int(max_len), 1), k, idx.data_ptr(), _p(val),
+                                                    st.data_ptr(), _stream()), "rs_rank_segments")
+        _count()
+        if check:
+            _rank_status(st, k, "rank_segments")
+    return (idx, val) if values else idx
+
+
+def mf_rank(user_rows, item_rows, k, values=False, check=True):
+    """Fused ``topk(user_rows @ item_rows.T, k, dim=1)``: the (users, items) score matrix never reaches HBM."""
+    U, V = _f32(user_rows), _f32(item_rows)
+    _need_cuda(U, V)
+    if U.dim() != 2 or V.dim() != 2 or U.shape[1] != V.shape[1]:
+        raise ValueError("mf_rank: user_rows (U, W) and item_rows (I, W) must share W")
+    nu, ni = U.shape[0], V.shape[0]
+    if k > ni:
+        raise RuntimeError(f"mf_rank: selected index k={k} out of range ({ni} items)")
+    idx = torch.empty(nu, k, dtype=torch.int64, device=U.device)
+    val = torch.empty(nu, k, dtype=torch.float32, device=U.device) if values else None
+    if nu > 0:
+        st = torch.zeros(1, dtype=torch.int32, device=U.device)
+        with _timed("mf_rank"):
+            _lib.check(_lib.load().rs_mf_rank(U.data_ptr(), V.data_ptr(), nu, ni, U.shape[1], k, idx.data_ptr(),
+                                              _p(val), st.data_ptr(), _stream()), "rs_mf_rank")
+        _count()
+        if check:
+            _rank_status(st, k, "mf_rank")
+    return (idx, val) if values else idx

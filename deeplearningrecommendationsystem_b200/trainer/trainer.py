@@ -5,29 +5,14 @@ Same public surface: ``Trainer(model, loss_fn, optimizer)``; ``train_loop(*args,
 anything else -> ValueError); the ``*_loop2(matrix, mask)`` AutoRec variants; results are left on the instance in
 ``predictions_*``, ``*_loss`` and ``*_rating``.  ``optimizer`` only needs ``zero_grad()`` and ``step()``, so a
 ``FusedRowOptimizer`` drops in.  ``model_eval`` computes the reference Evaluator's five metrics
-(evaluator/evaluator.py:13-20: predictions thresholded at 0.5 *before* AUC) on the device, one host read per split.
+(evaluator/evaluator.py:13-20: predictions thresholded at >= 0.5 *before* AUC) on the device, one host read per split.
 """
 import torch
 
+from ..evaluator.evaluator import binary_metrics
 
-def _binary_metrics(y_true, y_pred):
-    """[accuracy, precision, recall, f1, auc] with sklearn's conventions for hard 0/1 predictions."""
-    t = (y_true.detach().reshape(-1) > 0.5)
-    p = (y_pred.detach().reshape(-1) > 0.5)
-    tp = (t & p).sum().double()
-    tn = (~t & ~p).sum().double()
-    fp = (~t & p).sum().double()
-    fn = (t & ~p).sum().double()
-    n = tp + tn + fp + fn
-    zero = torch.zeros((), dtype=torch.float64, device=tp.device)
-    acc = (tp + tn) / n
-    prec = torch.where(tp + fp > 0, tp / (tp + fp).clamp(min=1), zero)
-    rec = torch.where(tp + fn > 0, tp / (tp + fn).clamp(min=1), zero)
-    f1 = torch.where(prec + rec > 0, 2 * prec * rec / (prec + rec).clamp(min=1e-300), zero)
-    tpr = torch.where(tp + fn > 0, tp / (tp + fn).clamp(min=1), zero)
-    fpr = torch.where(fp + tn > 0, fp / (fp + tn).clamp(min=1), zero)
-    auc = 0.5 * (1.0 + tpr - fpr)          # ROC of a hard classifier has a single interior point
-    return [float(v) for v in torch.stack([acc, prec, rec, f1, auc]).cpu()]
+
+_binary_metrics = binary_metrics
 
 
 class Trainer:

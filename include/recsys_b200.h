@@ -268,6 +268,23 @@ int rs_gemm_nt_3xtf32(const rs_gemm_nt *g, void *stream);
 int rs_sigmoid_bce(const float *logit, const float *y, int64_t B, float *pred, float *g_logit, float *loss_mean,
                    float *ws /* >= 1024 floats */, void *stream);
 
+/* ---- catalogue ranking: the per-user `torch.topk(scores, k, dim=0)` of every recommendation() method
+ * (model/deepfm.py:85-95, model/din.py:55-66, model/neuralcf.py:61-72, model/pnn.py:133-143 ...), all users in one launch.
+ * Segment s covers scores[seg_start[s] .. seg_start[s+1]) (seg_start == NULL: uniform segments of max_len).
+ * out_idx[s*k + r] = position inside segment s of its r-th largest score (descending; ties: lower position first;
+ * NaN ranks highest, as torch.topk); out_val (optional) the scores in that order.  max_len is an upper bound of the
+ * segment lengths (sizes the shared-memory slot buffer; up to 16384 in one pass, longer segments are streamed and then
+ * need k <= 8192).  status |= 2 when a segment is shorter than k (its row is filled with -1), |= 4 when a segment
+ * exceeded max_len and could not be finished. */
+int rs_rank_segments(const float *scores, const int64_t *seg_start, int64_t num_segments, int64_t max_len, int32_t k,
+                     int64_t *out_idx, float *out_val, int32_t *status, void *stream);
+
+/* ---- fused MF scoring + ranking (model/mf.py:28-35: `U @ V^T` then topk over items): scores never reach HBM.
+ * user_rows (num_users, width), item_rows (num_items, width) row-major fp32; out_* as rs_rank_segments with
+ * uniform segments of num_items.  Each score is a fixed-order fp32 dot product. */
+int rs_mf_rank(const float *user_rows, const float *item_rows, int64_t num_users, int64_t num_items, int32_t width, int32_t k,
+               int64_t *out_idx, float *out_val, int32_t *status, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -175,10 +175,46 @@ def neuralcf(sd, u, i):
     return torch.sigmoid(torch.cat([gmf, mlp], dim=1) @ sd["linear2.weight"].t() + sd["linear2.bias"])
 
 
+def _stacked(x, sd):
+    """[e_user, e_item, age, e_gender, e_occupation, e_movie] (B, 5D+1)   model/widedeep.py:44-50."""
+    return torch.cat([sd["user_embedding.weight"][_ids(x, 0)], sd["item_embedding.weight"][_ids(x, 1)], x[:, 2:3],
+                      _bag(x, GENDER, sd["gender_embedding.weight"]), _bag(x, OCC, sd["occupation_embedding.weight"]),
+                      _bag(x, GENRE, sd["movie_embedding.weight"])], dim=1)
+
+
+def widedeep(sd, x):
+    """model/widedeep.py:42-61 -- no ReLU after the first projection."""
+    deep = _stacked(x, sd) @ sd["linear.weight"].t() + sd["linear.bias"]
+    deep = I.relu_tower(deep, _layers(sd, "dnn_network", _count(sd, "dnn_network")))
+    z = torch.cat([_first_order(x, sd, "wide"), deep], dim=1) @ sd["output.weight"].t() + sd["output.bias"]
+    return torch.sigmoid(z)
+
+
+def deepcross(sd, x):
+    """model/deepcross.py:10-18 (x_{l+1} = x_0 * (W_l x_l) + b_l + x_l, full-matrix W) and :58-72."""
+    z0 = _stacked(x, sd)
+    c = z0
+    for l in _count(sd, "cross_network.cross_weights"):
+        c = z0 * (c @ sd[f"cross_network.cross_weights.{l}.weight"].t()) + sd[f"cross_network.cross_biases.{l}"] + c
+    deep = I.relu_tower(z0, _layers(sd, "deep_network.network", _count(sd, "deep_network.network")))
+    both = torch.cat([c, deep], dim=1)
+    return torch.sigmoid(both @ sd["output_layer.weight"].t() + sd["output_layer.bias"])
+
+
+def deepcrossing(sd, x):
+    """model/deepcrossing.py:20-25 residual units and :54-69."""
+    r = _stacked(x, sd)
+    for l in _count(sd, "res_layers"):
+        h = torch.relu(r @ sd[f"res_layers.{l}.linear1.weight"].t() + sd[f"res_layers.{l}.linear1.bias"])
+        r = torch.relu(h @ sd[f"res_layers.{l}.linear2.weight"].t() + sd[f"res_layers.{l}.linear2.bias"] + r)
+    return torch.sigmoid(r @ sd["linear.weight"].t() + sd["linear.bias"])
+
+
 MODELS = {
     "lr": lr, "mf": mf, "deepfm": deepfm, "nfm": nfm, "afm": afm, "ffm": ffm,
     "pnn_in": lambda sd, x: pnn(sd, x, "in"), "pnn_out": lambda sd, x: pnn(sd, x, "out"),
     "din": din, "dien": dien, "neuralcf": neuralcf,
+    "widedeep": widedeep, "deepcross": deepcross, "deepcrossing": deepcrossing,
 }
 
 

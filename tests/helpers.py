@@ -17,3 +17,26 @@ def feature_matrix(g, B, num_users, num_items):
         idx = torch.randperm(19, generator=g)[: int(n_genre[b])]
         x[b, 26 + idx] = 1.0
     return x
+
+
+def catalogue_frame(g, num_users, num_items, shuffle=True):
+    """Every (user, item) pair with that user's and item's side features, as the pandas frame `data.user_item()`
+    builds (data/reader.py:104-112): columns [user_id, item_id, age, gender(2), occupation(21), genre(19)].
+    Rows are shuffled so that grouping by user has real work to do; each user keeps num_items rows."""
+    import numpy as np
+    import pandas as pd
+    fu = feature_matrix(g, num_users, num_users, num_items)      # per-user side features (cols 2..25)
+    fi = feature_matrix(g, num_items, num_users, num_items)      # per-item genres (cols 26..44)
+    u = torch.arange(num_users).repeat_interleave(num_items)
+    i = torch.arange(num_items).repeat(num_users)
+    x = torch.zeros(num_users * num_items, 45)
+    x[:, 0], x[:, 1] = u.float(), i.float()
+    x[:, 2:26] = fu[u, 2:26]
+    x[:, 26:] = fi[i, 26:]
+    if shuffle:
+        x = x[torch.randperm(x.shape[0], generator=g)]
+    cols = ["user_id", "item_id", "age"] + [f"g{k}" for k in range(2)] + [f"o{k}" for k in range(21)] + [f"m{k}" for k in range(19)]
+    df = pd.DataFrame(x.numpy().astype(np.float64), columns=cols)
+    df["user_id"] = df["user_id"].astype(np.int64)
+    df["item_id"] = df["item_id"].astype(np.int64)
+    return df

@@ -91,6 +91,6 @@ def test_trainer_metrics_match_sklearn():
     y = (torch.rand(500, 1, generator=g) < 0.4).float()
     p = torch.rand(500, 1, generator=g)
     got = _binary_metrics(y, p)
-    yt, yp = y.numpy().ravel(), (p.numpy().ravel() > 0.5).astype(int)      # evaluator/evaluator.py:17-19
+    yt, yp = y.numpy().ravel(), (p.numpy().ravel() >= 0.5).astype(int)      # evaluator/evaluator.py:17-19
     want = [accuracy_score(yt, yp), precision_score(yt, yp), recall_score(yt, yp), f1_score(yt, yp), roc_auc_score(yt, yp)]
     np.testing.assert_allclose(got, want, rtol=1e-12)

@@ -27,10 +27,14 @@ def build(name):
         "din": lambda: M.DIN(60, 16),
         "dien": lambda: M.DIEN(60, 16),
         "neuralcf": lambda: M.NeuralCF(50, 60, 8, [32, 16, 8]),
+        "widedeep": lambda: M.WideDeep(50, 60, [32, 16, 8, 1], 16),
+        "deepcross": lambda: M.DeepCross(50, 60, 3, [32, 16], 8),
+        "deepcrossing": lambda: M.DeepCrossing(50, 60, 8, [32, 16]),
     }[name]()
 
 
-NAMES = ["lr", "mf", "deepfm", "nfm", "afm", "ffm", "pnn_in", "pnn_out", "din", "dien", "neuralcf"]
+NAMES = ["lr", "mf", "deepfm", "nfm", "afm", "ffm", "pnn_in", "pnn_out", "din", "dien", "neuralcf",
+         "widedeep", "deepcross", "deepcrossing"]
 
 
 def close(got, want, atol, msg=""):
@@ -105,7 +109,7 @@ def test_pnn_out_raises_when_batch_differs_from_dim():
         m.cuda()(ins[0][:7].cuda())
 
 
-@pytest.mark.parametrize("name", ["lr", "deepfm", "nfm", "afm", "ffm", "pnn_in"])
+@pytest.mark.parametrize("name", ["lr", "deepfm", "nfm", "afm", "ffm", "pnn_in", "widedeep", "deepcross", "deepcrossing"])
 def test_against_oracle_on_fresh_inputs(name):
     """larger batch, more duplicates, different seed than the golden fixtures; also run twice for determinism."""
     _, _, sd0, _ = load_golden(name)

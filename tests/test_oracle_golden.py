@@ -6,9 +6,10 @@ import pytest
 import torch
 
 from conftest import load_golden
-from oracle import ml100k, optim, index, interactions as I
+from oracle import ml100k, optim, index, ranking, interactions as I
 
-MODELS = ["lr", "mf", "deepfm", "nfm", "afm", "ffm", "pnn_in", "pnn_out", "din", "dien", "neuralcf"]
+MODELS = ["lr", "mf", "deepfm", "nfm", "afm", "ffm", "pnn_in", "pnn_out", "din", "dien", "neuralcf",
+          "widedeep", "deepcross", "deepcrossing"]
 RTOL, ATOL = 1e-5, 1e-6       # north star: 1e-5 relative (fp32) for logits, loss, gradients
 
 
@@ -91,3 +92,51 @@ def test_sparse_sgd_equals_dense_sgd():
     want = table - 0.1 * dense
     got = optim.sgd_rows(table.clone(), ids, G, 0.1)
     assert torch.equal(got, want)
+
+
+# ---- catalogue ranking and the evaluator metrics
+def _npz(name):
+    import os
+    from conftest import GOLDEN
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def _unragged(flat, off):
+    return [flat[off[i]:off[i + 1]].tolist() for i in range(len(off) - 1)]
+
+
+@pytest.mark.parametrize("name", ["mf", "deepfm", "widedeep", "pnn_in", "pnn_out", "neuralcf", "din", "dien"])
+def test_rank_oracle_equals_reference_topk(name):
+    """rank_desc(scores) reproduces what the reference's recommendation() returned for the same scores."""
+    z = _npz("recommend.npz")
+    idx, scores = z[f"{name}/idx"], z[f"{name}/scores"]
+    for u in range(idx.shape[0]):
+        assert ranking.rank_desc(scores[u], idx.shape[1]).tolist() == idx[u].tolist(), (name, u)
+
+
+def test_mf_scores_oracle():
+    _, _, sd0, _ = load_golden("mf")
+    z = _npz("recommend.npz")
+    got = ranking.mf_scores(sd0["user_embeddings.weight"].numpy(), sd0["item_embeddings.weight"].numpy())
+    np.testing.assert_allclose(got, z["mf/scores"], rtol=RTOL, atol=1e-7)
+
+
+@pytest.mark.parametrize("k", [5, 50, 200])
+def test_ranking_metrics_oracle_and_mirror(k):
+    from deeplearningrecommendationsystem_b200.evaluator import Ranking
+    z = _npz("ranking.npz")
+    actual, predicted = _unragged(z["actual"], z["actual_off"]), _unragged(z["predicted"], z["predicted_off"])
+    np.testing.assert_allclose(ranking.ranking_metrics(actual, predicted, k), z[f"k{k}"], rtol=1e-12)
+    r = Ranking(actual, predicted, k)
+    got = [*r.precision_recall_f1(), r.mapk(), r.mean_ndcg(), r.mrr()]
+    np.testing.assert_allclose(got, z[f"k{k}"], rtol=1e-14)
+    assert Ranking.apk(actual[5], predicted[5], k) == 0.0 and Ranking.rr(actual[5], predicted[5]) == 0.0   # no hit at all
+    r.ranking_eval()
+
+
+def test_binary_metrics_oracle_and_mirror():
+    from deeplearningrecommendationsystem_b200.evaluator import Evaluator
+    z = _npz("evaluator.npz")
+    np.testing.assert_allclose(ranking.binary_metrics(z["y_true"], z["y_pred"]), z["metrics"], rtol=1e-12)
+    got = Evaluator.eval(torch.from_numpy(z["y_true"]), torch.from_numpy(z["y_pred"]))
+    np.testing.assert_allclose(got, z["metrics"], rtol=1e-12)
