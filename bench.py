@@ -453,6 +453,78 @@ def run_other(args):
         dist.destroy_process_group()
 
 
+def run_rank(args):
+    """SURVEY.md 8(f).1 -- catalogue ranking (`recommendation()`), one JSON line per case.  Not the headline metric.
+
+    mf:      fused rs_mf_rank over a (users x items) catalogue vs cuBLAS matmul + torch.topk (library route) and the
+             numpy oracle on the host (bounded sample of users).
+    deepfm:  DeepFM.recommendation(943, frame, 1682) -- the scripts' call (scripts/deepfm.py:67) -- wall clock including
+             the host-side grouping of the frame, vs the reference's one-forward-per-user loop on a sample of users."""
+    import time
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import catalogue_frame
+    from oracle import ranking as R
+    from deeplearningrecommendationsystem_b200 import model as M, ops
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    g = torch.Generator().manual_seed(5)
+
+    def dev_ms(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    for nu, ni, W, k, tag in ((943, 1682, 64, 1682, "ML-100k full ranking (scripts/mf.py:81)"),
+                              (65536, 16384, 64, 100, "synthetic 65536 users x 16384 items, top-100")):
+        U = (torch.randn(nu, W, generator=g) * 0.3).to(dev)
+        V = (torch.randn(ni, W, generator=g) * 0.3).to(dev)
+        ms = dev_ms(lambda: ops.mf_rank(U, V, k, check=False), args.steps, max(args.warmup, 3))
+        ms_lib = dev_ms(lambda: torch.topk(U @ V.T, k, dim=1), max(args.steps // 4, 2), 2)
+        ns = min(nu, 256)
+        Un, Vn = U[:ns].cpu().numpy(), V.cpu().numpy()
+        t0 = time.perf_counter()
+        sc = (Un @ Vn.T).astype(np.float32)
+        for u in range(ns):
+            R.rank_desc(sc[u], k)
+        cpu = ns / (time.perf_counter() - t0)
+        print(json.dumps({"metric": "ranked users/sec", "value": nu / (ms / 1e3), "unit": "users/s", "n_gpus": 1, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "config": {"workload": f"rank/mf: {tag}", "users": nu, "items": ni, "width": W, "k": k},
+                          "library_route_ms": ms_lib, "gpu_launches": args.steps,
+                          "cpu_baseline": {"value": cpu, "unit": "users/s", "cores": 1, "kind": "port", "sample": f"{ns} users, numpy"}}))
+
+    nu, ni = 943, 1682
+    torch.manual_seed(0)
+    m = M.DeepFM(nu, ni, [256, 128, 1], 128).to(dev).eval()          # scripts/deepfm.py:52
+    df = catalogue_frame(g, nu, ni, shuffle=False)
+    m.recommendation(32, df[df["user_id"] < 32], ni)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = m.recommendation(nu, df, ni)
+    torch.cuda.synchronize()
+    sec = time.perf_counter() - t0
+    ns = 24
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for u in range(ns):                                            # the reference's loop, model/deepfm.py:85-95, on this GPU
+            rows = torch.Tensor(df[df["user_id"] == u].values).to(dev)
+            torch.topk(m(rows), ni, dim=0).indices.view(1, -1).tolist()[0]
+    loop = ns / (time.perf_counter() - t0)
+    print(json.dumps({"metric": "ranked users/sec", "value": nu / sec, "unit": "users/s", "n_gpus": 1, "steps": 1, "warmup": 1,
+                      "ms_per_step": sec * 1e3, "higher_is_better": True, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": "rank/deepfm: DeepFM.recommendation(943, user_item, 1682), wall clock incl. host grouping",
+                                 "rows": int(len(df)), "shape": list(out.shape)},
+                      "per_user_loop_users_per_s": loop, "per_user_loop_sample": f"{ns} users, same GPU, reference control flow"}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -466,7 +538,7 @@ def main():
     ap.add_argument("--graph", dest="graph", action="store_true", default=None,
                     help="replay the train step as a CUDA graph (default for the single-GPU c2 headline)")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="eager Trainer.train_loop instead of graph replay")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5", "rank"],
                     help="c2 = headline (BASELINE.json configs[1]); c3/c4/c5 = the other synthetic configs, one line per model")
     args = ap.parse_args()
     if args.graph is None:
@@ -478,6 +550,8 @@ def main():
         run_reference(args)
     elif args.workload == "c2":
         run_gpu(args)
+    elif args.workload == "rank":
+        run_rank(args)
     else:
         run_other(args)
 

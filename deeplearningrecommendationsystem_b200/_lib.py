@@ -93,7 +93,8 @@ SIGNATURES = {
     "rs_xcol_to_ids": [_P, _L, _I, _I, _P, _P],
     "rs_sigmoid_bce": [_P, _P, _L, _P, _P, _P, _P, _P],
     "rs_rank_segments": [_P, _P, _L, _L, _I, _P, _P, _P, _P],
-    "rs_mf_rank": [_P, _P, _L, _L, _I, _I, _P, _P, _P, _P],
+    "rs_mf_rank_ws_bytes": [_L, _L, _I, _I, _PP(_Z)],
+    "rs_mf_rank": [_P, _P, _L, _L, _I, _I, _P, _P, _P, _P, _Z, _P],
     "rs_afm_num_parts": [_L, _I, _I, _I, _PP(_I)],
     "rs_afm_fwd": [_P, _L, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "rs_afm_bwd": [_P, _L, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P],

@@ -710,10 +710,13 @@ def mf_rank(user_rows, item_rows, k, values=False, check=True):
     val = torch.empty(nu, k, dtype=torch.float32, device=U.device) if values else None
     if nu > 0:
         st = torch.zeros(1, dtype=torch.int32, device=U.device)
+        lib, nbytes = _lib.load(), C.c_size_t(0)
+        _lib.check(lib.rs_mf_rank_ws_bytes(nu, ni, U.shape[1], k, C.byref(nbytes)), "rs_mf_rank_ws_bytes")
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=U.device) if nbytes.value else None
         with _timed("mf_rank"):
-            _lib.check(_lib.load().rs_mf_rank(U.data_ptr(), V.data_ptr(), nu, ni, U.shape[1], k, idx.data_ptr(),
-                                              _p(val), st.data_ptr(), _stream()), "rs_mf_rank")
-        _count()
+            _lib.check(lib.rs_mf_rank(U.data_ptr(), V.data_ptr(), nu, ni, U.shape[1], k, idx.data_ptr(), _p(val), st.data_ptr(),
+                                      _p(ws), nbytes.value, _stream()), "rs_mf_rank")
+        _count(2 if ws is not None else 1)
         if check:
             _rank_status(st, k, "mf_rank")
     return (idx, val) if values else idx

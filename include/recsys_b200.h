@@ -281,9 +281,12 @@ int rs_rank_segments(const float *scores, const int64_t *seg_start, int64_t num_
 
 /* ---- fused MF scoring + ranking (model/mf.py:28-35: `U @ V^T` then topk over items): scores never reach HBM.
  * user_rows (num_users, width), item_rows (num_items, width) row-major fp32; out_* as rs_rank_segments with
- * uniform segments of num_items.  Each score is a fixed-order fp32 dot product. */
+ * uniform segments of num_items.  Each score is a fixed-order fp32 dot product.  For a small k over a large catalogue
+ * (k <= 512, >= 64 users) a tiled kernel scores 8 users per CTA against a transposed copy of the item table held in
+ * the caller's workspace (rs_mf_rank_ws_bytes; 0 when that path does not apply). */
+int rs_mf_rank_ws_bytes(int64_t num_users, int64_t num_items, int32_t width, int32_t k, size_t *bytes);
 int rs_mf_rank(const float *user_rows, const float *item_rows, int64_t num_users, int64_t num_items, int32_t width, int32_t k,
-               int64_t *out_idx, float *out_val, int32_t *status, void *stream);
+               int64_t *out_idx, float *out_val, int32_t *status, void *ws, size_t ws_bytes, void *stream);
 
 #ifdef __cplusplus
 }

@@ -82,7 +82,9 @@ def test_k_out_of_range_raises_like_topk():
     assert ops.rank_segments(torch.empty(0, device="cuda"), 3, seg_start=torch.zeros(1, dtype=torch.int64).cuda()).shape == (0, 3)
 
 
-@pytest.mark.parametrize("nu,ni,W,k", [(50, 60, 16, 60), (943, 1682, 64, 1682), (33, 1682, 64, 50), (4, 20000, 32, 100), (9, 130, 10, 7)])
+@pytest.mark.parametrize("nu,ni,W,k", [(50, 60, 16, 60), (943, 1682, 64, 1682), (33, 1682, 64, 50), (4, 20000, 32, 100), (9, 130, 10, 7),
+                                       # the tiled kernel (>= 64 users, k <= 512 << items): ragged user tile, padded item chunk
+                                       (300, 5000, 32, 10), (65, 4100, 64, 100), (203, 20001, 64, 512), (64, 70000, 16, 1)])
 def test_mf_rank_matches_oracle(nu, ni, W, k):
     g = torch.Generator().manual_seed(nu + ni)
     U, V = torch.randn(nu, W, generator=g) * 0.3, torch.randn(ni, W, generator=g) * 0.3
