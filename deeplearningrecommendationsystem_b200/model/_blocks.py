@@ -261,10 +261,16 @@ def topk_per_user(model, num_users, user_item, k, batched=True):
     device = next(model.parameters()).device
     uid = np.asarray(user_item["user_id"].values).astype(np.int64)
     keep = (uid >= 0) & (uid < num_users)
-    order = np.flatnonzero(keep)
-    order = order[np.argsort(uid[order], kind="stable")]
-    counts = np.bincount(uid[order], minlength=num_users)
-    values = np.asarray(user_item.values, dtype=np.float32)
+    grouped = bool(keep.all()) and bool((uid[1:] >= uid[:-1]).all())   # data.user_item() is already user-major
+    if grouped:
+        order = slice(None)
+        counts = np.bincount(uid, minlength=num_users)
+    else:
+        order = np.flatnonzero(keep)
+        order = order[np.argsort(uid[order], kind="stable")]
+        counts = np.bincount(uid[order], minlength=num_users)
+    values = np.asarray(user_item.values, dtype=np.float32)[order]
+    n_rows = values.shape[0]
     seg = np.zeros(num_users + 1, dtype=np.int64)
     np.cumsum(counts, out=seg[1:])
     if num_users == 0:
@@ -272,12 +278,12 @@ def topk_per_user(model, num_users, user_item, k, batched=True):
     scores = []
     with torch.no_grad():
         if batched:
-            for r0 in range(0, len(order), RANK_CHUNK_ROWS):
-                rows = torch.from_numpy(values[order[r0:r0 + RANK_CHUNK_ROWS]]).to(device)
+            for r0 in range(0, n_rows, RANK_CHUNK_ROWS):
+                rows = torch.from_numpy(values[r0:r0 + RANK_CHUNK_ROWS]).to(device)
                 scores.append(model(rows).reshape(-1))
         else:
             for u in range(num_users):
-                rows = torch.from_numpy(values[order[seg[u]:seg[u + 1]]]).to(device)
+                rows = torch.from_numpy(values[seg[u]:seg[u + 1]]).to(device)
                 scores.append(model(rows).reshape(-1))
         scores = torch.cat(scores) if scores else torch.empty(0, device=device)
         idx = ops.rank_segments(scores, k, seg_start=torch.from_numpy(seg).to(device), max_len=int(counts.max()))

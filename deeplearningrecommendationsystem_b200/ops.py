@@ -720,3 +720,39 @@ def mf_rank(user_rows, item_rows, k, values=False, check=True):
         if check:
             _rank_status(st, k, "mf_rank")
     return (idx, val) if values else idx
+
+
+def sample_negatives(excluded_keys, num_user, num_item, num_negatives, seed, epoch=0):
+    """OPTIONAL device sampler (not the reference's python-`random` stream; see include/recsys_b200.h).
+    excluded_keys: ascending int64 CUDA tensor of user * num_item + item.  -> (users, items) int64, user-major."""
+    keys = _i64(excluded_keys).view(-1)
+    _need_cuda(keys)
+    total = num_user * num_negatives
+    users = torch.empty(total, dtype=torch.int64, device=keys.device)
+    items = torch.empty(total, dtype=torch.int64, device=keys.device)
+    if total:
+        st = torch.zeros(1, dtype=torch.int32, device=keys.device)
+        with _timed("sample_negatives"):
+            _lib.check(_lib.load().rs_sample_negatives(keys.data_ptr() if keys.numel() else None, keys.numel(), num_user, num_item,
+                                                       num_negatives, seed & (2 ** 64 - 1), epoch, users.data_ptr(), items.data_ptr(),
+                                                       st.data_ptr(), _stream()), "rs_sample_negatives")
+        _count()
+        if int(st.item()) & 8:
+            raise RuntimeError("sample_negatives: a user has (almost) every item observed; no free item found")
+    return users, items
+
+
+def assemble_features(users, items, user_feat, item_feat):
+    """(B, 2 + FU + FI) fp32 rows [user, item, user_feat[user], item_feat[item]] -- data/reader.py:98-101 on the device."""
+    users, items = _i64(users).view(-1), _i64(items).view(-1)
+    user_feat, item_feat = _f32(user_feat), _f32(item_feat)
+    _need_cuda(users, items, user_feat, item_feat)
+    B, FU, FI = users.numel(), user_feat.shape[1], item_feat.shape[1]
+    out = torch.empty(B, 2 + FU + FI, dtype=torch.float32, device=users.device)
+    if B:
+        with _timed("assemble_features"):
+            _lib.check(_lib.load().rs_assemble_features(users.data_ptr(), items.data_ptr(), user_feat.data_ptr(), user_feat.shape[0], FU,
+                                                        item_feat.data_ptr(), item_feat.shape[0], FI, B, out.data_ptr(),
+                                                        status_word(users.device).data_ptr(), _stream()), "rs_assemble_features")
+        _count()
+    return out

@@ -288,6 +288,22 @@ int rs_mf_rank_ws_bytes(int64_t num_users, int64_t num_items, int32_t width, int
 int rs_mf_rank(const float *user_rows, const float *item_rows, int64_t num_users, int64_t num_items, int32_t width, int32_t k,
                int64_t *out_idx, float *out_val, int32_t *status, void *ws, size_t ws_bytes, void *stream);
 
+/* ---- OPTIONAL device-side negative sampling (sampler/sampler.py:16-27: per user, num_negatives uniform items,
+ * redrawn while (user, item) is an observed pair).  NOT the reference's python-`random` stream (that stays on the host,
+ * sampler.Sampler); the stream is Philox4x32-10 with key = seed and counter = (sample index lo, hi, attempt block,
+ * epoch), item = (r * num_item) >> 32, four attempts per block, first accepted wins -- restated bit for bit in
+ * oracle/sampling.py.  excluded_keys: ascending int64 user * num_item + item.  out_* hold num_user * num_negatives
+ * entries, user-major (the reference's order).  status |= 8 if a slot found no free item in 65536 attempts. */
+int rs_sample_negatives(const int64_t *excluded_keys, int64_t num_excluded, int64_t num_user, int64_t num_item,
+                        int32_t num_negatives, uint64_t seed, uint32_t epoch, int64_t *out_users, int64_t *out_items,
+                        int32_t *status, void *stream);
+
+/* ---- feature-matrix assembly (data/reader.py:98-101, the two pd.merge calls): out (B, 2 + user_width + item_width)
+ * fp32 rows [user, item, user_feat[user, :], item_feat[item, :]].  status |= 1 on an out-of-range id. */
+int rs_assemble_features(const int64_t *users, const int64_t *items, const float *user_feat, int64_t num_user,
+                         int32_t user_width, const float *item_feat, int64_t num_item, int32_t item_width, int64_t B,
+                         float *out, int32_t *status, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

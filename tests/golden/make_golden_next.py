@@ -11,6 +11,7 @@ Run in the build container only (needs /root/reference):
                    that tests can tell a real ranking difference from an fp32 near-tie
   ranking.npz      evaluator/ranking.py metrics on seeded ragged lists
   evaluator.npz    evaluator/evaluator.py metrics (sklearn) on seeded labels / probabilities incl. values of exactly 0.5
+  features.npz     data/reader.py:98-101 MovieLens100K.feature (the two pd.merge calls) on seeded side-feature tables
 """
 import os
 import sys
@@ -119,6 +120,32 @@ def main():
     ev = {"y_true": yt.numpy(), "y_pred": yp.numpy(), "metrics": np.asarray(Evaluator.eval(yt, yp), dtype=np.float64)}
     np.savez_compressed(os.path.join(OUT, "evaluator.npz"), **ev)
     print("evaluator:", ev["metrics"])
+
+    # ---- feature-matrix assembly: the reference's own feature() on stand-in side tables (no dataset files needed)
+    import pandas as pd
+    from data.reader import MovieLens100K
+    nu, ni, B = 30, 40, 500
+    fu = feature_matrix(g, nu, nu, ni)[:, 2:26].numpy().astype(np.float64)          # age, gender(2), occupation(21)
+    fi = feature_matrix(g, ni, nu, ni)[:, 26:].numpy().astype(np.float64)           # genre(19)
+    user_data = pd.DataFrame(fu, columns=["age"] + [f"u{k}" for k in range(23)])
+    user_data.insert(0, "user_id", np.arange(nu))
+    item_data = pd.DataFrame(fi, columns=[f"m{k}" for k in range(19)])
+    item_data.insert(0, "item_id", np.arange(ni))
+    pairs = pd.DataFrame({"user_id": torch.randint(0, nu, (B,), generator=g).numpy(),
+                          "item_id": torch.randint(0, ni, (B,), generator=g).numpy(),
+                          "rating": (torch.rand(B, generator=g) < 0.5).long().numpy()})
+
+    class Stub:
+        pass
+    stub = Stub()
+    stub.user_data, stub.item_data = user_data, item_data
+    feat = MovieLens100K.feature(stub, pairs)
+    rating = feat.iloc[:, 2].values.astype(np.float32)                               # scripts/deepfm.py:42-44
+    feat = feat.drop("rating", axis=1)
+    np.savez_compressed(os.path.join(OUT, "features.npz"), users=pairs["user_id"].values, items=pairs["item_id"].values,
+                        pair_rating=pairs["rating"].values.astype(np.float32), user_feat=fu.astype(np.float32),
+                        item_feat=fi.astype(np.float32), x=feat.values.astype(np.float32), rating=rating)
+    print("features:", feat.shape)
 
 
 if __name__ == "__main__":

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from conftest import load_golden
-from oracle import ml100k, optim, index, ranking, interactions as I
+from oracle import ml100k, optim, index, ranking, sampling, interactions as I
 
 MODELS = ["lr", "mf", "deepfm", "nfm", "afm", "ffm", "pnn_in", "pnn_out", "din", "dien", "neuralcf",
           "widedeep", "deepcross", "deepcrossing"]
@@ -140,3 +140,44 @@ def test_binary_metrics_oracle_and_mirror():
     np.testing.assert_allclose(ranking.binary_metrics(z["y_true"], z["y_pred"]), z["metrics"], rtol=1e-12)
     got = Evaluator.eval(torch.from_numpy(z["y_true"]), torch.from_numpy(z["y_pred"]))
     np.testing.assert_allclose(got, z["metrics"], rtol=1e-12)
+
+
+# ---- device-side input preparation
+def test_philox_known_answers():
+    """Random123 kat_vectors for philox4x32-10."""
+    def run(ctr, key):
+        return [int(v) for v in sampling.philox4x32_10(np.array(ctr, np.uint32), np.array(key, np.uint32))]
+    assert run([0] * 4, [0] * 2) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert run([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert run([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_philox_negative_draws_follow_the_reference_rule():
+    z = _npz("sampler.npz")
+    excl = {tuple(p) for p in z["excl"].tolist()}
+    u, i = sampling.negative_draws_philox(20, 30, excl, 5, seed=9)
+    assert u.tolist() == np.repeat(np.arange(20), 5).tolist()                    # user-major, 5 per user (sampler.py:21-22)
+    assert all((a, b) not in excl for a, b in zip(u.tolist(), i.tolist()))       # never an observed pair (sampler.py:24-25)
+    assert i.min() >= 0 and i.max() < 30
+    u2, i2 = sampling.negative_draws_philox(20, 30, excl, 5, seed=9)
+    assert i.tolist() == i2.tolist()
+    assert i.tolist() != sampling.negative_draws_philox(20, 30, excl, 5, seed=9, epoch=1)[1].tolist()
+    # uniform over the free items: chi-square against the exact per-user free sets, 400 draws per user
+    u, i = sampling.negative_draws_philox(20, 30, excl, 400, seed=3)
+    chi = 0.0
+    dof = 0
+    for user in range(20):
+        free = [it for it in range(30) if (user, it) not in excl]
+        cnt = np.bincount(i[u == user], minlength=30)[free]
+        e = 400 / len(free)
+        chi += float(((cnt - e) ** 2 / e).sum())
+        dof += len(free) - 1
+    assert abs(chi - dof) < 5 * np.sqrt(2 * dof)
+
+
+def test_assemble_features_oracle_equals_reference_merge():
+    z = _npz("features.npz")
+    got = sampling.assemble_features(z["users"], z["items"], z["user_feat"], z["item_feat"])
+    assert np.array_equal(got, z["x"])                    # bit-exact, row order of the input pairs
+    assert np.array_equal(z["rating"], z["pair_rating"])
