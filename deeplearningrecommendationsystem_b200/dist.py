@@ -35,7 +35,7 @@ def _phase(name):
 
 @dataclass
 class Prims:
-    unique: callable      # (keys (n,) int64, total_rows) -> (uniq ascending (nu,), inverse (n,) int64)
+    unique: callable      # (keys (n,) int64, total_rows) -> (uniq ascending (nu,), inverse (n,) int64[, sort handle])
     gather: callable      # (table (R, W), idx (m,) int64) -> (m, W)
 
 
@@ -44,7 +44,8 @@ def cuda_prims():
 
     def unique(keys, total_rows):
         segs = ops.dedup_sort(keys, 1, None, total_rows, max_width=1, reuse_workspace=False)
-        return segs.uniq().clone(), segs.inverse().long()
+        # third value: the sort itself, which the backward re-uses for the per-row gradient reduce (Plan.segs)
+        return segs.uniq().clone(), segs.inverse().long(), segs
 
     def gather(table, idx):
         return ops.gather_rows(ops.make_tables([table]), idx.view(-1, 1)).view(idx.numel(), table.shape[1])
@@ -60,6 +61,7 @@ class Plan:
     send_counts: list
     recv_counts: list
     recv_local: torch.Tensor     # (m,) local row indices other ranks asked this rank for (grouped by requester)
+    segs: object = None          # CUDA path: the stable sort / segments of the batch's keys (ops.Segments), else None
 
 
 class RowExchange:
@@ -95,7 +97,7 @@ class RowExchange:
         # Sort key = owner * R + local index: ONE dedup then yields the unique rows already grouped by owner and
         # ascending inside each group, so `inverse` is directly the position inside the fetched block.
         okeys = (keys % N) * R + keys // N if N > 1 else keys
-        uniq, inverse = self.prims.unique(okeys, N * R)
+        uniq, inverse, *rest = self.prims.unique(okeys, N * R)
         bounds = torch.arange(N + 1, device=keys.device, dtype=uniq.dtype) * R
         send_counts_t = torch.diff(torch.searchsorted(uniq, bounds))
         recv_counts_t = torch.empty_like(send_counts_t)
@@ -110,7 +112,7 @@ class RowExchange:
             dist.all_to_all_single(recv_local, send_local, recv_counts, send_counts, group=self.group)
         else:
             recv_local.copy_(send_local)
-        return Plan(int(uniq.numel()), inverse, send_local, send_counts, recv_counts, recv_local)
+        return Plan(int(uniq.numel()), inverse, send_local, send_counts, recv_counts, recv_local, rest[0] if rest else None)
 
     def fetch(self, plan, local_table):
         """-> (n_uniq, W) block holding the rows this rank's batch needs, in the order `local_ids` indexes."""
@@ -169,7 +171,7 @@ class PeerRowExchange(RowExchange):
         N = self.world
         R = (total_rows + N - 1) // N
         okeys = (keys % N) * R + keys // N
-        uniq, inverse = self.prims.unique(okeys, N * R)
+        uniq, inverse, *rest = self.prims.unique(okeys, N * R)
         bounds = torch.arange(N + 1, device=keys.device, dtype=uniq.dtype) * R
         send_counts_t = torch.diff(torch.searchsorted(uniq, bounds))
         # every rank learns the whole (requester, owner) count matrix in ONE all-gather: that fixes all split sizes
@@ -182,7 +184,7 @@ class PeerRowExchange(RowExchange):
         send_local = uniq % R
         recv_local = torch.empty(sum(recv_counts), dtype=torch.int64, device=keys.device)
         dist.all_to_all_single(recv_local, send_local, recv_counts, send_counts, group=self.group)
-        plan = Plan(int(uniq.numel()), inverse, send_local, send_counts, recv_counts, recv_local)
+        plan = Plan(int(uniq.numel()), inverse, send_local, send_counts, recv_counts, recv_local, rest[0] if rest else None)
         plan.counts = counts
         return plan
 

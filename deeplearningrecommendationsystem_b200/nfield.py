@@ -180,7 +180,10 @@ class _FieldModel(nn.Module):
                 continue
             # row-sharded: reduce the batch's gradients per fetched row, send them to the owners, update there
             plan, ex = rec["plan"], self.exchange
-            segs = ops.dedup_sort(plan.local_ids, 1, None, plan.n_uniq, max_width=self.width)   # memoised per plan
+            if plan.segs is not None:      # the plan already sorted these lookups by row: no second sort
+                segs = ops.block_segments(plan.segs, plan.n_uniq, self.width)
+            else:
+                segs = ops.dedup_sort(plan.local_ids, 1, None, plan.n_uniq, max_width=self.width)   # memoised per plan
             if "scale" in src:
                 src["scale"] = src["scale"] * (1.0 / ex.world)          # gradients are averaged over the ranks
             else:
@@ -234,6 +237,9 @@ class _FieldModel(nn.Module):
         rec = {}
         if self.sharded:
             plan = self.exchange.plan_for(ids, self._offsets_key(), self.total_rows)
+            if train and self.fused and plan.recv_local.numel():
+                # the owner-side sort of the requested rows depends only on the plan: overlap it with fetch + forward
+                ops.prefetch_dedup(plan.recv_local, 1, None, self.weight.shape[0])
             block = self.exchange.fetch(plan, self.weight.data)
             ids = plan.local_ids.view(ids.shape)
             cross, stash = self._interact(ops.make_tables([block] * self.F), ids, want_stash=train)

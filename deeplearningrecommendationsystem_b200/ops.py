@@ -265,6 +265,10 @@ class Segments:
     def uniq(self):
         return self._view(self.seg.uniq, self.n, torch.int64)[: self.n_uniq]
 
+    def uniq_view(self, n_uniq):
+        """uniq()[:n_uniq] without the host read of the device-side count"""
+        return self._view(self.seg.uniq, self.n, torch.int64)[:n_uniq]
+
     def inverse(self):
         return self._view(self.seg.inverse, self.n, torch.int32)
 
@@ -340,6 +344,18 @@ def dedup_sort(ids, F=1, row_offset=None, total_rows=None, max_width=1, reuse_wo
             segs.ready.record()
     part = _partial_buffer(ids.device, n, int(max_width)) if reuse_workspace else \
         torch.empty(2 * (n // _lib.RS_CHUNK + 2) * int(max_width), dtype=torch.float32, device=ids.device)
+    segs.partial = part
+    segs.seg.partial = part.data_ptr()
+    segs.seg.partial_floats = part.numel()
+    return segs
+
+
+def block_segments(segs, n_uniq, width):
+    """Re-use the segments of a dedup over global keys for the rows of the fetched block: the j-th distinct key IS block
+    row j, so only the row ids change (uniq := 0..n_uniq-1, in place) -- the stable order, segment and chunk
+    boundaries are identical to what sorting the block-local ids again would give."""
+    segs.uniq_view(n_uniq).copy_(torch.arange(n_uniq, dtype=torch.int64, device=segs.device))
+    part = _partial_buffer(segs.device, segs.n, int(width))
     segs.partial = part
     segs.seg.partial = part.data_ptr()
     segs.seg.partial_floats = part.numel()
