@@ -85,6 +85,7 @@ SIGNATURES = {
     "rs_ffm_dense_bwd": [_P, _P, _L, _I, _I, _I, _PP(_I), _P, _P],
     "rs_dedup_workspace_bytes": [_L, _I, _PP(_Z)],
     "rs_dedup_sort": [_P, _L, _I, _PP(_L), _L, _P, _Z, _PP(rs_segments), _P, _P],
+    "rs_segments_relabel": [_PP(rs_segments), _L, _P],
     "rs_segment_update": [_PP(rs_segments), _L, _PP(rs_update), _P],
     "rs_adam_dense": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P],
     "rs_xembed_fwd": [_PP(rs_xslots), _P, _L, _P, _P, _P],

@@ -123,6 +123,15 @@ __global__ void __launch_bounds__(256) unit_start_kernel(const int4 *__restrict_
   unit_start[u] = (int32_t)(s < n ? s : n);
 }
 
+// Rename the rows of a finished sort to their rank among the distinct keys (row of segment g := g).
+__global__ void __launch_bounds__(256) relabel_kernel(int4 *__restrict__ desc, const int32_t *__restrict__ inverse,
+                                                     int64_t *__restrict__ uniq, const int32_t *__restrict__ n_uniq, int64_t n) {
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  desc[s].z = inverse[desc[s].x];
+  if (s < *n_uniq) uniq[s] = s;
+}
+
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 struct WsLayout {
@@ -252,6 +261,15 @@ RS_API int rs_dedup_sort(const int64_t *ids, int64_t n, int32_t F, const int64_t
   RS_CHECK_LAUNCH();
   const int nunits = (int)(n / RS_UNIT + 1);
   unit_start_kernel<<<(nunits + 256) / 256, 256, 0, st>>>((const int4 *)seg->lookup_desc, n, nunits, seg->unit_start);
+  RS_CHECK_LAUNCH();
+  return RS_OK;
+}
+
+RS_API int rs_segments_relabel(const rs_segments *seg, int64_t n, void *stream) {
+  RS_CHECK_ARG(seg && seg->lookup_desc && seg->inverse && seg->uniq && seg->n_uniq, RS_E_ARG, "rs_segments_relabel: incomplete segments");
+  if (n <= 0) return RS_OK;
+  relabel_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((int4 *)seg->lookup_desc, seg->inverse, seg->uniq,
+                                                                                seg->n_uniq, n);
   RS_CHECK_LAUNCH();
   return RS_OK;
 }

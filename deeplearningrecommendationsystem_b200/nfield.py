@@ -112,7 +112,7 @@ class _FieldModel(nn.Module):
                 raise ValueError("sharded tables are updated by the fused row optimizer (fused=True)")
             from . import dist as rsdist
             # Exchange over NVLink: kernels fused with the transfer through peer memory (PeerRowExchange), or NCCL
-            # all-to-alls (RowExchange).  Measured on 8xB200 (C2): fused 26.5 vs 20.5 M samples/s at N=2, 39.1 vs 36.4
+            # all-to-alls (RowExchange).  Measured on 8xB200 (C2): fused 27.7 vs 21.1 M samples/s at N=2, 39.1 vs 36.4
             # at N=4, but 56.5 vs 69.5 at N=8, where the simple peer-store kernels do not yet drive seven peers as
             # well as NCCL does -- so the fused path is the default up to 4 ranks.  RS_PEER_EXCHANGE=0/1 overrides.
             import os

@@ -265,10 +265,6 @@ class Segments:
     def uniq(self):
         return self._view(self.seg.uniq, self.n, torch.int64)[: self.n_uniq]
 
-    def uniq_view(self, n_uniq):
-        """uniq()[:n_uniq] without the host read of the device-side count"""
-        return self._view(self.seg.uniq, self.n, torch.int64)[:n_uniq]
-
     def inverse(self):
         return self._view(self.seg.inverse, self.n, torch.int32)
 
@@ -352,9 +348,12 @@ def dedup_sort(ids, F=1, row_offset=None, total_rows=None, max_width=1, reuse_wo
 
 def block_segments(segs, n_uniq, width):
     """Re-use the segments of a dedup over global keys for the rows of the fetched block: the j-th distinct key IS block
-    row j, so only the row ids change (uniq := 0..n_uniq-1, in place) -- the stable order, segment and chunk
-    boundaries are identical to what sorting the block-local ids again would give."""
-    segs.uniq_view(n_uniq).copy_(torch.arange(n_uniq, dtype=torch.int64, device=segs.device))
+    row j, so only the row ids change (rs_segments_relabel, once) -- the stable order, segment and chunk boundaries are
+    identical to what sorting the block-local ids again would give."""
+    if not getattr(segs, "relabelled", False):
+        _lib.check(_lib.load().rs_segments_relabel(C.byref(segs.seg), segs.n, _stream()), "rs_segments_relabel")
+        _count()
+        segs.relabelled = True
     part = _partial_buffer(segs.device, segs.n, int(width))
     segs.partial = part
     segs.seg.partial = part.data_ptr()

@@ -145,6 +145,11 @@ int rs_dedup_workspace_bytes(int64_t n, int32_t max_width, size_t *bytes);
 /* row_offset: HOST array of F int64 (NULL = all zero).  Fills `seg` with pointers carved from ws. */
 int rs_dedup_sort(const int64_t *ids, int64_t n, int32_t F, const int64_t *row_offset, int64_t total_rows,
                   void *ws, size_t ws_bytes, rs_segments *seg, int32_t *status, void *stream);
+/* Rename the rows of a finished sort to their rank among the distinct keys: uniq[g] := g and every lookup record
+ * points at g.  The row-sharded step (no reference counterpart) sorts the batch's GLOBAL rows once for
+ * the exchange plan; the j-th distinct row is row j of the fetched block, so after this call the same segments drive
+ * the per-row gradient reduce over the block -- no second sort. */
+int rs_segments_relabel(const rs_segments *seg, int64_t n, void *stream);
 
 /* ---- segment-reduce of duplicate rows fused with the row update.
  * Replaces embedding_dense_backward + optimizer.step() for embedding tables (trainer/trainer.py:38-39).

@@ -104,6 +104,34 @@ def test_segment_grad_and_sgd(W, hot):
     close(tc, ooptim.sgd_rows(table.clone(), ids, G, 0.05), rtol=1e-5, atol=atol)
 
 
+@pytest.mark.parametrize("W", [16, 416])           # 16: chunk kernel, 416: TMA streaming kernel (reads the lookup records)
+def test_relabelled_segments_equal_a_second_sort(W):
+    """rs_segments_relabel: the sort of a batch's global rows, renamed to block rows, drives the per-row gradient
+    reduce exactly like sorting the block-local ids again (what the row-sharded backward used to do)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(W)
+    total, n = 10 ** 7, 20000
+    keys = (torch.rand(n, generator=g) ** 4 * total).long().clamp_(max=total - 1)
+    keys[::5] = 123456                                     # a long multi-chunk segment
+    stash = torch.randn(n, W, generator=g).cuda()
+    scale = torch.randn(n, generator=g).cuda()
+    a = ops.dedup_sort(keys.cuda(), 1, None, total, max_width=1, reuse_workspace=False)
+    uniq, inverse = a.uniq().clone(), a.inverse().long()
+    nu = uniq.numel()
+    assert torch.equal(uniq.cpu(), torch.unique(keys))
+    a = ops.block_segments(a, nu, W)
+    b = ops.dedup_sort(inverse, 1, None, nu, max_width=W, reuse_workspace=False)
+    ga, gb = torch.zeros(nu, W).cuda(), torch.zeros(nu, W).cuda()
+    ops.segment_update(a, ops.RS_UPD_GRAD, W, 1, stash=stash, scale=scale, dense_grad=ga)
+    ops.segment_update(b, ops.RS_UPD_GRAD, W, 1, stash=stash, scale=scale, dense_grad=gb)
+    assert torch.equal(ga, gb)
+    G = (stash * scale[:, None]).cpu()
+    want = torch.zeros(nu, W).index_add_(0, inverse.cpu(), G)
+    atol = max(1e-6, 2e-7 * float(torch.zeros(nu, W).index_add_(0, inverse.cpu(), G.abs()).max()))   # see test_segment_grad_and_sgd
+    close(ga, want, rtol=1e-5, atol=atol)
+    ops.check_status()
+
+
 def test_segment_short_segments_bit_exact_vs_sequential():
     """segments <= RS_CHUNK are summed in ascending position, the CPU index_add order -> bit-identical."""
     ops = _ops()
