@@ -1,0 +1,296 @@
+// DIN / DIEN attention unit on the tensor cores (forward): score[b, l] = MLP([h, h-t, t]) for every history slot
+// (reference model/din.py:39-45, model/dien.py:27-35), the two hidden layers as fused tcgen05 GEMMs.
+//
+// One persistent CTA per SM walks tiles of 128 (b, l) rows; thread r owns row r of the tile end to end (operand
+// repack, TMEM lane, epilogues).
+//   layer 0   relu((Wa + Wb) h + tb[b])        tb[b] = b0 + (Wc - Wb) t_b is precomputed per sample (din_tbias_kernel),
+//             so the concat [h, h-t, t] is never built and K is D, not 3D.   MMA: M=128, N=H1, K=D  -> TMEM cols [0, H1)
+//   layer 1   relu(W1 a + b1)                  the layer-0 epilogue writes relu(.) split into tf32 hi/lo STRAIGHT into
+//             the A-operand chunk of the next GEMM (32 columns of D0 = one K chunk), and that chunk's MMAs are issued
+//             while the next 32 columns are being read back.               MMA: M=128, N=H2, K=H1 -> TMEM cols [H1, H1+H2)
+//   layer 2   w2 . relu(.) + b2                a per-row dot product in the final epilogue.
+// All weights stay resident in shared memory as tf32 hi/lo pairs (3xTF32: lo*hi + hi*lo + hi*hi, ~1e-6 relative) in
+// the canonical K-major core-matrix layout.  The softmax over L and the weighted sum run in din_softmax_pool_kernel.
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace {
+
+using namespace rs::tc;
+constexpr int NTH = 128;
+
+struct DinTcParams {
+  const float *rows;  // (B, L+1, D)
+  const float *tb;    // (B, H1)
+  const float *W0;    // (H1, 3D)
+  const float *W1;    // (H2, H1)
+  const float *b1;    // (H2)
+  const float *W2;    // (H2)
+  const float *b2;    // (1)
+  float *score;       // (B, L)
+  int64_t B;
+  int L, D, H1, H2, tmem_cols;
+};
+
+// tb[b][c] = b0[c] + sum_d (W0[c][2D+d] - W0[c][D+d]) * t_b[d]
+__global__ void __launch_bounds__(128) din_tbias_kernel(const float *__restrict__ rows, const float *__restrict__ W0,
+                                                        const float *__restrict__ b0, int64_t B, int L, int D, int H1,
+                                                        float *__restrict__ tb) {
+  extern __shared__ __align__(16) float smf[];
+  float *Wt = smf;                         // [H1][D + 1]
+  float *t = Wt + (size_t)H1 * (D + 1);    // [D]
+  for (int e = threadIdx.x; e < H1 * D; e += blockDim.x) {
+    const int c = e / D, d = e - c * D;
+    Wt[c * (D + 1) + d] = W0[(size_t)c * 3 * D + 2 * D + d] - W0[(size_t)c * 3 * D + D + d];
+  }
+  __syncthreads();
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    for (int d = threadIdx.x; d < D; d += blockDim.x) t[d] = rows[(b * (L + 1) + L) * D + d];
+    __syncthreads();
+    for (int c = threadIdx.x; c < H1; c += blockDim.x) {
+      float acc = b0[c];
+      for (int d = 0; d < D; ++d) acc = fmaf(Wt[c * (D + 1) + d], t[d], acc);
+      tb[b * H1 + c] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(NTH, 1) din_score_tc_kernel(const __grid_constant__ DinTcParams P) {
+  extern __shared__ __align__(128) uint32_t sm[];
+  __shared__ uint64_t bar[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int D = P.D, H1 = P.H1, H2 = P.H2;
+  uint32_t *w0h = sm, *w0l = w0h + D * H1;                    // layer 0: N = H1 rows, K = D
+  uint32_t *w1h = w0l + D * H1, *w1l = w1h + H1 * H2;         // layer 1: N = H2 rows, K = H1
+  uint32_t *abuf = w1l + H1 * H2;                             // [2][hi | lo][KC * MT]
+  float *b1s = reinterpret_cast<float *>(abuf + 4 * KC * MT), *w2s = b1s + H2;
+  if (warp == 0) tmem_alloc(&tmem_base_s, P.tmem_cols);
+  if (tid == 0) {
+    rs::mbar_init(&bar[0], 1);
+    rs::mbar_init(&bar[1], 1);
+    rs::mbar_fence_init();
+  }
+  for (int e = tid; e < D * H1; e += NTH) {
+    const int n = e / D, k = e - n * D;
+    const float x = P.W0[(size_t)n * 3 * D + k] + P.W0[(size_t)n * 3 * D + D + k];   // Wa + Wb
+    const uint32_t h = to_tf32(x);
+    w0h[tile_off(H1, n, k)] = h;
+    w0l[tile_off(H1, n, k)] = to_tf32(x - __uint_as_float(h));
+  }
+  for (int e = tid; e < H1 * H2; e += NTH) {
+    const int n = e / H1, k = e - n * H1;
+    const float x = P.W1[(size_t)n * H1 + k];
+    const uint32_t h = to_tf32(x);
+    w1h[tile_off(H2, n, k)] = h;
+    w1l[tile_off(H2, n, k)] = to_tf32(x - __uint_as_float(h));
+  }
+  for (int e = tid; e < H2; e += NTH) {
+    b1s[e] = P.b1[e];
+    w2s[e] = P.W2[e];
+  }
+  rs::fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t idesc0 = idesc_tf32(H1), idesc1 = idesc_tf32(H2);
+  const uint32_t lbo_a = MT * 16, lbo_w0 = (uint32_t)H1 * 16, lbo_w1 = (uint32_t)H2 * 16, sbo = 128;
+  const float b2 = P.b2[0];
+  const int nchunk0 = (D + KC - 1) / KC, nchunk1 = H1 / KC;
+  uint32_t uses[2] = {0, 0};   // commits so far on each A buffer's barrier (-> parity of the latest phase)
+  uint32_t cc = 0;             // running chunk counter: buffer = cc & 1
+  const int64_t nrows = P.B * P.L;
+  const int64_t ntiles = (nrows + MT - 1) / MT;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t r = tile * MT + tid;
+    const bool valid = r < nrows;
+    const int64_t b = valid ? r / P.L : 0;
+    const float *arow = valid ? P.rows + (b * (P.L + 1) + (r - b * P.L)) * D : nullptr;
+    // ---- layer 0: A = history rows
+    for (int c = 0; c < nchunk0; ++c, ++cc) {
+      const int bi = cc & 1;
+      uint32_t *ah = abuf + (size_t)bi * 2 * KC * MT, *al = ah + KC * MT;
+      if (uses[bi] > 0) rs::mbar_wait(&bar[bi], (uses[bi] - 1) & 1u);
+      const int kq = (D - c * KC) < KC ? (D - c * KC) / 4 : KC / 4;   // 16-byte K pieces in this chunk
+      for (int q = 0; q < kq; ++q) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (arow) v = rs::ldg_nc_f4(arow + c * KC + q * 4);
+        uint4 h, l;
+        split4(v, h, l);
+        *reinterpret_cast<uint4 *>(ah + (q * MT + tid) * 4) = h;
+        *reinterpret_cast<uint4 *>(al + (q * MT + tid) * 4) = l;
+      }
+      rs::fence_proxy_async();
+      __syncthreads();
+      if (tid == 0) {
+        fence_after_sync();
+        for (int s = 0; s < kq / 2; ++s) {
+          const uint32_t kb = (uint32_t)(c * (KC / 4) + s * 2);
+          const uint64_t dah = smem_desc(rs::smem_u32(ah) + s * 2 * lbo_a, lbo_a, sbo);
+          const uint64_t dal = smem_desc(rs::smem_u32(al) + s * 2 * lbo_a, lbo_a, sbo);
+          const uint64_t dbh = smem_desc(rs::smem_u32(w0h) + kb * lbo_w0, lbo_w0, sbo);
+          const uint64_t dbl = smem_desc(rs::smem_u32(w0l) + kb * lbo_w0, lbo_w0, sbo);
+          mma_tf32(tmem, dal, dbh, idesc0, (c == 0 && s == 0) ? 0u : 1u);
+          mma_tf32(tmem, dah, dbl, idesc0, 1u);
+          mma_tf32(tmem, dah, dbh, idesc0, 1u);
+        }
+        commit(&bar[bi]);
+      }
+      __syncwarp();   // warp 0 re-converges before its next aligned tcgen05.ld
+      uses[bi]++;
+    }
+    {  // D0 complete: the latest commit covers every earlier MMA
+      const int lb = (cc - 1) & 1;
+      rs::mbar_wait(&bar[lb], (uses[lb] - 1) & 1u);
+      fence_after_sync();
+    }
+    // ---- layer 1: 32 columns of D0 -> relu(. + tb) -> one K chunk of the next A operand
+    const float *tbrow = P.tb + b * H1;
+    for (int c = 0; c < nchunk1; ++c, ++cc) {
+      const int bi = cc & 1;
+      uint32_t *ah = abuf + (size_t)bi * 2 * KC * MT, *al = ah + KC * MT;
+      if (uses[bi] > 0) rs::mbar_wait(&bar[bi], (uses[bi] - 1) & 1u);
+      uint32_t v[32];
+      tmem_ld32(tmem, warp, c * KC, v);
+#pragma unroll
+      for (int q = 0; q < KC / 4; ++q) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) {
+          const float4 t4 = rs::ldg_f4(tbrow + c * KC + q * 4);
+          x.x = fmaxf(__uint_as_float(v[4 * q + 0]) + t4.x, 0.f);
+          x.y = fmaxf(__uint_as_float(v[4 * q + 1]) + t4.y, 0.f);
+          x.z = fmaxf(__uint_as_float(v[4 * q + 2]) + t4.z, 0.f);
+          x.w = fmaxf(__uint_as_float(v[4 * q + 3]) + t4.w, 0.f);
+        }
+        uint4 h, l;
+        split4(x, h, l);
+        *reinterpret_cast<uint4 *>(ah + (q * MT + tid) * 4) = h;
+        *reinterpret_cast<uint4 *>(al + (q * MT + tid) * 4) = l;
+      }
+      rs::fence_proxy_async();
+      fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        fence_after_sync();
+#pragma unroll
+        for (int s = 0; s < KC / 8; ++s) {
+          const uint32_t kb = (uint32_t)(c * (KC / 4) + s * 2);
+          const uint64_t dah = smem_desc(rs::smem_u32(ah) + s * 2 * lbo_a, lbo_a, sbo);
+          const uint64_t dal = smem_desc(rs::smem_u32(al) + s * 2 * lbo_a, lbo_a, sbo);
+          const uint64_t dbh = smem_desc(rs::smem_u32(w1h) + kb * lbo_w1, lbo_w1, sbo);
+          const uint64_t dbl = smem_desc(rs::smem_u32(w1l) + kb * lbo_w1, lbo_w1, sbo);
+          mma_tf32(tmem + (uint32_t)H1, dal, dbh, idesc1, (c == 0 && s == 0) ? 0u : 1u);
+          mma_tf32(tmem + (uint32_t)H1, dah, dbl, idesc1, 1u);
+          mma_tf32(tmem + (uint32_t)H1, dah, dbh, idesc1, 1u);
+        }
+        commit(&bar[bi]);
+      }
+      __syncwarp();   // warp 0 re-converges before its next aligned tcgen05.ld
+      uses[bi]++;
+    }
+    {
+      const int lb = (cc - 1) & 1;
+      rs::mbar_wait(&bar[lb], (uses[lb] - 1) & 1u);
+      fence_after_sync();
+    }
+    // ---- layer 2: per-row dot product over relu(D1 + b1)
+    float acc = b2;
+    for (int c0 = 0; c0 < H2; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem, warp, H1 + c0, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc = fmaf(w2s[c0 + j], fmaxf(__uint_as_float(v[j]) + b1s[c0 + j], 0.f), acc);
+    }
+    if (valid) P.score[r] = acc;
+    fence_before_sync();
+    __syncthreads();   // every warp has drained both accumulators before the next tile's MMAs overwrite them
+    fence_after_sync();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_free(tmem, P.tmem_cols);
+}
+
+// softmax over L (no mask, no scaling: model/din.py:46) and the weighted sum; one warp per sample
+__global__ void __launch_bounds__(256) din_softmax_pool_kernel(const float *__restrict__ rows, const float *__restrict__ score, int64_t B,
+                                                               int L, int D, int pool, float *__restrict__ out,
+                                                               float *__restrict__ attw) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t b = warp_global; b < B; b += nwarps) {
+    const float *s = score + b * L;
+    float mx = -INFINITY;
+    for (int l = lane; l < L; l += 32) mx = fmaxf(mx, s[l]);
+    mx = rs::warp_max(mx);
+    float sum = 0.f;
+    for (int l = lane; l < L; l += 32) sum += expf(s[l] - mx);
+    sum = rs::warp_sum(sum);
+    const float inv = 1.f / sum;
+    float *w = attw + b * L;
+    for (int l = lane; l < L; l += 32) w[l] = expf(s[l] - mx) * inv;
+    __syncwarp();
+    const float *h = rows + b * (int64_t)(L + 1) * D;
+    if (pool) {
+      for (int d = lane; d < D; d += 32) {
+        float acc = 0.f;
+        for (int l = 0; l < L; ++l) acc = fmaf(w[l], h[(int64_t)l * D + d], acc);
+        out[b * D + d] = acc;
+      }
+    } else {
+      float *o = out + b * (int64_t)L * D;
+      for (int e = lane; e < L * D; e += 32) o[e] = w[e / D] * h[e];
+    }
+  }
+}
+
+bool tc_shape_ok(int D, int H1, int H2) {
+  return (D == 16 || D == 32 || D == 64) && (H1 == 64 || H1 == 128) && (H2 == 32 || H2 == 64);
+}
+size_t tc_smem(int D, int H1, int H2) { return ((size_t)2 * D * H1 + (size_t)2 * H1 * H2 + (size_t)4 * KC * MT + 2 * H2) * 4; }
+
+}  // namespace
+
+RS_API int rs_din_fwd_tc_ws_bytes(int64_t B, int32_t L, int32_t D, int32_t H1, int32_t H2, size_t *bytes) {
+  RS_CHECK_ARG(bytes, RS_E_ARG, "rs_din_fwd_tc_ws_bytes: null bytes");
+  RS_CHECK_ARG(tc_shape_ok(D, H1, H2), RS_E_UNSUPPORTED, "rs_din_fwd_tc: built for D in {16,32,64}, H1 in {64,128}, H2 in {32,64}");
+  *bytes = ((size_t)B * H1 + (size_t)B * L) * sizeof(float);
+  return RS_OK;
+}
+
+RS_API int rs_din_fwd_tc(const float *rows, int64_t B, int32_t L, int32_t D, const rs_din_weights *w, int32_t pool, float *out,
+                         float *attw, void *ws, size_t ws_bytes, void *stream) {
+  RS_CHECK_ARG(rows && w && out && w->W0 && w->b0 && w->W1 && w->b1 && w->W2 && w->b2, RS_E_ARG, "rs_din_fwd_tc: null argument");
+  RS_CHECK_ARG(L >= 1, RS_E_SHAPE, "rs_din_fwd_tc: L=%d", L);
+  RS_CHECK_ARG(tc_shape_ok(D, w->H1, w->H2), RS_E_UNSUPPORTED,
+               "rs_din_fwd_tc: built for D in {16,32,64}, H1 in {64,128}, H2 in {32,64} (got %d, %d, %d)", D, w->H1, w->H2);
+  if (B == 0) return RS_OK;
+  const size_t need = ((size_t)B * w->H1 + (size_t)B * L) * sizeof(float);
+  RS_CHECK_ARG(ws && ws_bytes >= need, RS_E_WORKSPACE, "rs_din_fwd_tc: workspace of %zu bytes needed, got %zu", need, ws_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  float *tb = static_cast<float *>(ws), *score = tb + (size_t)B * w->H1;
+  const int sms = rs::num_sms();
+  {
+    const size_t smem = ((size_t)w->H1 * (D + 1) + D) * sizeof(float);
+    int64_t grid = B < 2 * sms ? B : 2 * sms;
+    din_tbias_kernel<<<(unsigned)grid, 128, smem, st>>>(rows, w->W0, w->b0, B, L, D, w->H1, tb);
+    RS_CHECK_LAUNCH();
+  }
+  DinTcParams P = {};
+  P.rows = rows, P.tb = tb, P.W0 = w->W0, P.W1 = w->W1, P.b1 = w->b1, P.W2 = w->W2, P.b2 = w->b2, P.score = score;
+  P.B = B, P.L = L, P.D = D, P.H1 = w->H1, P.H2 = w->H2;
+  P.tmem_cols = 32;
+  while (P.tmem_cols < w->H1 + w->H2) P.tmem_cols <<= 1;
+  const size_t smem = tc_smem(D, w->H1, w->H2);
+  RS_CUDA(cudaFuncSetAttribute(din_score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t ntiles = (B * L + MT - 1) / MT;
+  din_score_tc_kernel<<<(unsigned)(ntiles < sms ? ntiles : sms), NTH, smem, st>>>(P);
+  RS_CHECK_LAUNCH();
+  // attw doubles as the softmax output the backward needs; without it the scores are normalised in place
+  float *wout = attw ? attw : score;
+  int64_t blocks = (B + 7) / 8;
+  din_softmax_pool_kernel<<<(unsigned)(blocks < 8 * sms ? blocks : 8 * sms), 256, 0, st>>>(rows, score, B, L, D, pool, out, wout);
+  RS_CHECK_LAUNCH();
+  return RS_OK;
+}

@@ -9,42 +9,12 @@
 // them to an mbarrier, and the four warps read the accumulator back with tcgen05.ld (warp w owns TMEM lanes
 // 32w..32w+31).  Slab partials are added in slab order by a second kernel (deterministic).
 #include "common.cuh"
+#include "tc.cuh"
 
 namespace {
 
-constexpr int KC = 32;         // k depth per chunk (4 MMAs of K = 8)
-constexpr int MT = 128;        // UMMA M
+using namespace rs::tc;
 constexpr int NTHREADS = 128;
-
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm volatile("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
-
-// K-major, no swizzle (LayoutType::INTERLEAVE): ((8,n),2):((16 B,SBO),LBO)
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr >> 4) & 0x3fff);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
-  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
-  return d;
-}
-
-__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-// element (row, k) of a K-major core-matrix tile with `rows` rows: chunk k/4, row, k%4
-__device__ __forceinline__ int tile_off(int rows, int row, int k) { return ((k >> 2) * rows + row) * 4 + (k & 3); }
 
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_3xtf32_kernel(const float *__restrict__ A, const float *__restrict__ B, int64_t K,
                                                                     int M, int N, int NP /* N padded to 16 */, int tmem_cols,

@@ -2,6 +2,8 @@
 device memory and the stream; every op below is one call into librecsys_b200.so.  No CPU fallback."""
 import ctypes as C
 
+import os
+
 import torch
 
 from . import _lib
@@ -588,8 +590,19 @@ def _din_weights(ws):
     return w, (W0, b0, W1, b1, W2, b2)
 
 
-def din_fwd(rows, ws, pool, want_attw=False):
-    """rows (B, L+1, D) = [history | target]; ws = (W0, b0, W1, b1, W2, b2) -> out (B,D) | (B,L,D), attw (B,L) | None."""
+DIN_TC_MIN_ROWS = 128 * 64     # below this many (b, l) rows the tensor-core tiles cannot fill the machine
+
+
+def din_tc_supported(D, H1, H2):
+    return D in (16, 32, 64) and H1 in (64, 128) and H2 in (32, 64)
+
+
+def din_fwd(rows, ws, pool, want_attw=False, impl="auto"):
+    """rows (B, L+1, D) = [history | target]; ws = (W0, b0, W1, b1, W2, b2) -> out (B,D) | (B,L,D), attw (B,L) | None.
+
+    impl: "tc" = hidden layers on the tcgen05 tensor cores (rs_din_fwd_tc), "fused" = the CUDA-core kernel
+    (rs_din_fwd), "auto" = tc when the shape is built and there are enough rows to fill the SMs (RS_DIN_TC=0 forces
+    fused)."""
     rows = _f32(rows)
     _need_cuda(rows)
     B, L1, D = rows.shape
@@ -599,8 +612,21 @@ def din_fwd(rows, ws, pool, want_attw=False):
     attw = torch.empty(B, L, dtype=torch.float32, device=rows.device) if want_attw else None
     if B == 0:
         return out, attw
+    if impl == "auto":
+        impl = "tc" if (din_tc_supported(D, w.H1, w.H2) and B * L >= DIN_TC_MIN_ROWS
+                        and os.environ.get("RS_DIN_TC", "1") != "0") else "fused"
+    lib = _lib.load()
+    if impl == "tc":
+        nbytes = C.c_size_t(0)
+        _lib.check(lib.rs_din_fwd_tc_ws_bytes(B, L, D, w.H1, w.H2, C.byref(nbytes)), "rs_din_fwd_tc_ws_bytes")
+        scratch = torch.empty(nbytes.value, dtype=torch.uint8, device=rows.device)
+        with _timed("din_fwd_tc"):
+            _lib.check(lib.rs_din_fwd_tc(rows.data_ptr(), B, L, D, C.byref(w), int(bool(pool)), out.data_ptr(), _p(attw),
+                                         scratch.data_ptr(), nbytes.value, _stream()), "rs_din_fwd_tc")
+        _count(3)
+        return out, attw
     with _timed("din_fwd"):
-        _lib.check(_lib.load().rs_din_fwd(rows.data_ptr(), B, L, D, C.byref(w), int(bool(pool)), out.data_ptr(), _p(attw), _stream()),
+        _lib.check(lib.rs_din_fwd(rows.data_ptr(), B, L, D, C.byref(w), int(bool(pool)), out.data_ptr(), _p(attw), _stream()),
                    "rs_din_fwd")
     _count()
     return out, attw

@@ -231,6 +231,13 @@ typedef struct rs_din_weights {
 int rs_din_num_parts(int64_t B, int32_t *parts);
 int rs_din_fwd(const float *rows, int64_t B, int32_t L, int32_t D, const rs_din_weights *w, int32_t pool, float *out,
                float *attw /* (B, L) or NULL */, void *stream);
+/* Same contract as rs_din_fwd with the two hidden layers on the tcgen05 tensor cores (3xTF32, fp32 accumulation in
+ * tensor memory): 128 (b, l) rows per tile, layer-0 epilogue feeds layer 1's operand through shared memory, scores
+ * then softmax + weighted sum.  ws: rs_din_fwd_tc_ws_bytes (per-sample target bias (B, H1) + scores (B, L)).
+ * Built for D in {16,32,64}, H1 in {64,128}, H2 in {32,64}. */
+int rs_din_fwd_tc_ws_bytes(int64_t B, int32_t L, int32_t D, int32_t H1, int32_t H2, size_t *bytes);
+int rs_din_fwd_tc(const float *rows, int64_t B, int32_t L, int32_t D, const rs_din_weights *w, int32_t pool, float *out,
+                  float *attw /* (B, L) or NULL */, void *ws, size_t ws_bytes, void *stream);
 int rs_din_bwd(const float *rows, int64_t B, int32_t L, int32_t D, const rs_din_weights *w, int32_t pool,
                const float *g_out, float *d_rows, float *dWab_part, float *dWt_part, float *dW1_part, float *db0_part,
                float *db1_part, float *dW2_part, float *db2_part, int32_t num_parts, void *stream);

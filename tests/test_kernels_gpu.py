@@ -402,6 +402,12 @@ def test_din_attention_fwd_bwd(D, H1, H2, L, B, pool):
         close(got, ref, rtol=1e-5, atol=1e-5 * max(1e-3, float(ref.abs().max())), msg=name)
     scaled(attw, w.detach(), "attw")
     scaled(out, want.detach(), "out")
+    # the tensor-core forward (what "auto" picks for large batches) against the same oracle, with and without attw
+    out_tc, attw_tc = ops.din_fwd(rows.detach().cuda(), cw, pool, want_attw=True, impl="tc")
+    scaled(attw_tc, w.detach(), "attw (tc)")
+    scaled(out_tc, want.detach(), "out (tc)")
+    out_tc2, _ = ops.din_fwd(rows.detach().cuda(), cw, pool, want_attw=False, impl="tc")
+    assert torch.equal(out_tc, out_tc2)
     d_rows, dws = ops.din_bwd(rows.detach().cuda(), cw, pool, gup.cuda())
     scaled(d_rows, grads[0], "d_rows")
     for got, ref, name in zip(dws[:5], grads[1:6], ["dW0", "db0", "dW1", "db1", "dW2"]):
@@ -410,6 +416,23 @@ def test_din_attention_fwd_bwd(D, H1, H2, L, B, pool):
     assert float(dws[5].abs().max()) <= 1e-5 * max(1e-3, float(grads[5].abs().max()), float(grads[4].abs().max()))
     d2, dws2 = ops.din_bwd(rows.detach().cuda(), cw, pool, gup.cuda())
     assert torch.equal(d_rows, d2) and all(torch.equal(a, b_) for a, b_ in zip(dws, dws2))   # deterministic
+
+
+@pytest.mark.parametrize("D,H1,H2,L,B,pool", [(64, 128, 64, 100, 700, True), (32, 64, 32, 50, 1000, False), (16, 128, 64, 3, 9000, True)])
+def test_din_tc_forward_many_tiles(D, H1, H2, L, B, pool):
+    """more tiles than SMs (persistent loop, buffer/barrier parity across tiles, ragged last tile); tc == fused kernel"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(B)
+    rows = (torch.randn(B, L + 1, D, generator=g) * 0.5).cuda()
+    lin = lambda o, i: ((torch.rand(o, i, generator=g) * 2 - 1) / i ** 0.5).cuda()   # noqa: E731
+    vec = lambda o, i: ((torch.rand(o, generator=g) * 2 - 1) / i ** 0.5).cuda()      # noqa: E731
+    cw = [lin(H1, 3 * D), vec(H1, 3 * D), lin(H2, H1), vec(H2, H1), lin(1, H2), vec(1, H2)]
+    out_f, attw_f = ops.din_fwd(rows, cw, pool, want_attw=True, impl="fused")
+    out_t, attw_t = ops.din_fwd(rows, cw, pool, want_attw=True, impl="tc")
+    close(attw_t, attw_f.cpu(), rtol=1e-5, atol=1e-5 * float(attw_f.abs().max()), msg="attw")
+    close(out_t, out_f.cpu(), rtol=1e-5, atol=1e-5 * float(out_f.abs().max()), msg="out")
+    out_t2, attw_t2 = ops.din_fwd(rows, cw, pool, want_attw=True, impl="tc")
+    assert torch.equal(out_t, out_t2) and torch.equal(attw_t, attw_t2)       # deterministic
 
 
 # ------------------------------------------------------------------ tcgen05 3xTF32 A^T B (PNN "out")
