@@ -104,7 +104,8 @@ SIGNATURES = {
     "rs_din_num_parts": [_L, _PP(_I)],
     "rs_din_fwd": [_P, _L, _I, _I, _PP(rs_din_weights), _I, _P, _P, _P],
     "rs_din_fwd_tc_ws_bytes": [_L, _I, _I, _I, _I, _PP(_Z)],
-    "rs_din_fwd_tc": [_P, _L, _I, _I, _PP(rs_din_weights), _I, _P, _P, _P, _Z, _P],
+    "rs_din_fwd_tc": [_P, _L, _I, _I, _PP(rs_din_weights), _I, _P, _P, _P, _P, _P, _Z, _P],
+    "rs_din_bwd_tc": [_P, _L, _I, _I, _PP(rs_din_weights), _I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "rs_din_bwd": [_P, _L, _I, _I, _PP(rs_din_weights), _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P],
     "rs_gemm_tn_ws_bytes": [_L, _I, _I, _PP(_Z)],
     "rs_gemm_tn_3xtf32": [_P, _P, _L, _I, _I, _P, _P, _Z, _P],

@@ -28,22 +28,29 @@ def afm_pool(E, W, b, h):
 
 
 class _DINAttention(torch.autograd.Function):
-    """rs_din_fwd / rs_din_bwd on rows (B, L+1, D) = [history | target]."""
+    """rs_din_fwd / rs_din_bwd on rows (B, L+1, D) = [history | target].  Large batches run the hidden layers on the
+    tensor cores (rs_din_fwd_tc); that forward stashes its ReLU outputs and rs_din_bwd_tc consumes them, while the
+    CUDA-core kernel pair recomputes instead."""
 
     @staticmethod
     def forward(ctx, rows, pool, W0, b0, W1, b1, W2, b2):
         from . import ops
         ws = (W0, b0, W1, b1, W2, b2)
-        out, _ = ops.din_fwd(rows, [t.detach() for t in ws], pool)
-        ctx.pool = pool
-        ctx.save_for_backward(rows, *ws)
+        need = any(ctx.needs_input_grad)
+        out, _, stash = ops.din_fwd(rows, [t.detach() for t in ws], pool, want_stash=need)
+        ctx.pool, ctx.tc = pool, stash is not None
+        ctx.save_for_backward(rows, *ws, *(stash or ()))
         return out
 
     @staticmethod
     def backward(ctx, g):
         from . import ops
-        rows, *ws = ctx.saved_tensors
-        d_rows, dws = ops.din_bwd(rows, [t.detach() for t in ws], ctx.pool, g.contiguous())
+        rows, *rest = ctx.saved_tensors
+        ws, stash = rest[:6], rest[6:]
+        if ctx.tc:
+            d_rows, dws = ops.din_bwd_tc(rows, [t.detach() for t in ws], ctx.pool, g.contiguous(), stash)
+        else:
+            d_rows, dws = ops.din_bwd(rows, [t.detach() for t in ws], ctx.pool, g.contiguous())
         return (d_rows, None, *dws)
 
 

@@ -28,6 +28,8 @@ struct DinTcParams {
   const float *W2;    // (H2)
   const float *b2;    // (1)
   float *score;       // (B, L)
+  float *act0;        // (B*L, H1) relu output of layer 0, kept for the backward (or NULL)
+  float *act1;        // (B*L, H2) relu output of layer 1 (or NULL)
   int64_t B;
   int L, D, H1, H2, tmem_cols;
 };
@@ -164,6 +166,7 @@ __global__ void __launch_bounds__(NTH, 1) din_score_tc_kernel(const __grid_const
           x.z = fmaxf(__uint_as_float(v[4 * q + 2]) + t4.z, 0.f);
           x.w = fmaxf(__uint_as_float(v[4 * q + 3]) + t4.w, 0.f);
         }
+        if (P.act0 && valid) rs::stg_cs_f4(P.act0 + r * H1 + c * KC + q * 4, x);
         uint4 h, l;
         split4(x, h, l);
         *reinterpret_cast<uint4 *>(ah + (q * MT + tid) * 4) = h;
@@ -201,7 +204,17 @@ __global__ void __launch_bounds__(NTH, 1) din_score_tc_kernel(const __grid_const
       uint32_t v[32];
       tmem_ld32(tmem, warp, H1 + c0, v);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) acc = fmaf(w2s[c0 + j], fmaxf(__uint_as_float(v[j]) + b1s[c0 + j], 0.f), acc);
+      for (int j = 0; j < 32; ++j) {
+        const float a = fmaxf(__uint_as_float(v[j]) + b1s[c0 + j], 0.f);
+        v[j] = __float_as_uint(a);
+        acc = fmaf(w2s[c0 + j], a, acc);
+      }
+      if (P.act1 && valid) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          rs::stg_cs_f4(P.act1 + r * H2 + c0 + q * 4, make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                                                    __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])));
+      }
     }
     if (valid) P.score[r] = acc;
     fence_before_sync();
@@ -245,6 +258,223 @@ __global__ void __launch_bounds__(256) din_softmax_pool_kernel(const float *__re
   }
 }
 
+// ---------------------------------------------------------------------------------------------------- backward
+// ds[b][l] = d loss / d score: softmax backward of  out = sum_l w_l h_l  (pool)  or  out_l = w_l h_l.  Warp per sample.
+__global__ void __launch_bounds__(256) din_dscore_kernel(const float *__restrict__ rows, const float *__restrict__ attw,
+                                                         const float *__restrict__ g_out, int64_t B, int L, int D, int pool,
+                                                         float *__restrict__ ds) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t b = warp_global; b < B; b += nwarps) {
+    const float *h = rows + b * (int64_t)(L + 1) * D;
+    const float *w = attw + b * L;
+    float *o = ds + b * L;
+    float tsum = 0.f;
+    for (int l = 0; l < L; ++l) {
+      const float *g = pool ? g_out + b * D : g_out + (b * L + l) * (int64_t)D;
+      float part = 0.f;
+      for (int d = lane; d < D; d += 32) part = fmaf(g[d], h[(int64_t)l * D + d], part);
+      part = rs::warp_sum(part);                       // dw_l = <g, h_l>
+      tsum = fmaf(w[l], part, tsum);
+      if (lane == 0) o[l] = part;
+    }
+    __syncwarp();
+    for (int l = lane; l < L; l += 32) o[l] = w[l] * (o[l] - tsum);
+  }
+}
+
+struct DinTcBwdParams {
+  const float *rows, *attw, *g_out, *ds;   // (B, L+1, D), (B, L), (B, D) | (B, L, D), (B, L)
+  const float *act0, *act1;                // forward stashes
+  const float *W0, *W1, *W2;
+  float *d_rows;                           // (B, L+1, D): history rows written here, the target row by the caller
+  float *dz0;                              // (B, L+1, H1): d loss / d layer-0 pre-activation, zero row at l == L
+  float *dz1;                              // (B*L, H2)
+  int64_t B;
+  int L, D, H1, H2, pool, tmem_cols;
+};
+
+// Data-gradient chain of the attention unit, same tiling as the forward:
+//   dz1 = ds w2 [a1 > 0]          (built per row, also written out for the weight-gradient GEMM)
+//   da0 = dz1 W1                   MMA: M=128, N=H1, K=H2   (W1 resident as an (N=H1, K=H2) K-major image)
+//   dz0 = da0 [a0 > 0]             (epilogue -> written out, and straight into the next A operand)
+//   dx  = dz0 (Wa + Wb)            MMA: M=128, N=D,  K=H1   ((Wa+Wb) resident as (N=D, K=H1))
+//   d_rows[b, l] = dx + w_l g      (the direct path of the weighted sum)
+__global__ void __launch_bounds__(NTH, 1) din_bwd_tc_kernel(const __grid_constant__ DinTcBwdParams P) {
+  extern __shared__ __align__(128) uint32_t sm[];
+  __shared__ uint64_t bar[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int D = P.D, H1 = P.H1, H2 = P.H2;
+  uint32_t *w1h = sm, *w1l = w1h + H1 * H2;                   // N = H1 rows, K = H2
+  uint32_t *w0h = w1l + H1 * H2, *w0l = w0h + D * H1;         // N = D rows,  K = H1
+  uint32_t *abuf = w0l + D * H1;                              // [2][hi | lo][KC * MT]
+  float *w2s = reinterpret_cast<float *>(abuf + 4 * KC * MT);
+  if (warp == 0) tmem_alloc(&tmem_base_s, P.tmem_cols);
+  if (tid == 0) {
+    rs::mbar_init(&bar[0], 1);
+    rs::mbar_init(&bar[1], 1);
+    rs::mbar_fence_init();
+  }
+  for (int e = tid; e < H1 * H2; e += NTH) {
+    const int k = e / H1, n = e - k * H1;                     // W1 is (H2, H1): element (k = h2, n = h1), coalesced read
+    const float x = P.W1[e];
+    const uint32_t h = to_tf32(x);
+    w1h[tile_off(H1, n, k)] = h;
+    w1l[tile_off(H1, n, k)] = to_tf32(x - __uint_as_float(h));
+  }
+  for (int e = tid; e < D * H1; e += NTH) {
+    const int k = e / D, n = e - k * D;                       // (Wa + Wb) is (H1, D): element (k = h1, n = d)
+    const float x = P.W0[(size_t)k * 3 * D + n] + P.W0[(size_t)k * 3 * D + D + n];
+    const uint32_t h = to_tf32(x);
+    w0h[tile_off(D, n, k)] = h;
+    w0l[tile_off(D, n, k)] = to_tf32(x - __uint_as_float(h));
+  }
+  for (int e = tid; e < H2; e += NTH) w2s[e] = P.W2[e];
+  rs::fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t idescA = idesc_tf32(H1), idescB = idesc_tf32(D);
+  const uint32_t lbo_a = MT * 16, lbo_w1 = (uint32_t)H1 * 16, lbo_w0 = (uint32_t)D * 16, sbo = 128;
+  const int nchunkA = H2 / KC, nchunkB = H1 / KC;
+  uint32_t uses[2] = {0, 0};
+  uint32_t cc = 0;
+  const int64_t nrows = P.B * P.L;
+  const int64_t ntiles = (nrows + MT - 1) / MT;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t r = tile * MT + tid;
+    const bool valid = r < nrows;
+    const int64_t b = valid ? r / P.L : 0;
+    const int l = (int)(r - b * P.L);
+    const int64_t rr = b * (P.L + 1) + l;                     // row inside the (B, L+1, .) tensors
+    const float dsr = valid ? P.ds[r] : 0.f;
+    // ---- da0 = dz1 W1
+    for (int c = 0; c < nchunkA; ++c, ++cc) {
+      const int bi = cc & 1;
+      uint32_t *ah = abuf + (size_t)bi * 2 * KC * MT, *al = ah + KC * MT;
+      if (uses[bi] > 0) rs::mbar_wait(&bar[bi], (uses[bi] - 1) & 1u);
+#pragma unroll
+      for (int q = 0; q < KC / 4; ++q) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) {
+          const int k = c * KC + q * 4;
+          const float4 a1 = rs::ldg_nc_f4(P.act1 + r * H2 + k);
+          x.x = a1.x > 0.f ? dsr * w2s[k + 0] : 0.f;
+          x.y = a1.y > 0.f ? dsr * w2s[k + 1] : 0.f;
+          x.z = a1.z > 0.f ? dsr * w2s[k + 2] : 0.f;
+          x.w = a1.w > 0.f ? dsr * w2s[k + 3] : 0.f;
+          rs::stg_cs_f4(P.dz1 + r * H2 + k, x);
+        }
+        uint4 h, lo;
+        split4(x, h, lo);
+        *reinterpret_cast<uint4 *>(ah + (q * MT + tid) * 4) = h;
+        *reinterpret_cast<uint4 *>(al + (q * MT + tid) * 4) = lo;
+      }
+      rs::fence_proxy_async();
+      __syncthreads();
+      if (tid == 0) {
+        fence_after_sync();
+#pragma unroll
+        for (int s = 0; s < KC / 8; ++s) {
+          const uint32_t kb = (uint32_t)(c * (KC / 4) + s * 2);
+          const uint64_t dah = smem_desc(rs::smem_u32(ah) + s * 2 * lbo_a, lbo_a, sbo);
+          const uint64_t dal = smem_desc(rs::smem_u32(al) + s * 2 * lbo_a, lbo_a, sbo);
+          const uint64_t dbh = smem_desc(rs::smem_u32(w1h) + kb * lbo_w1, lbo_w1, sbo);
+          const uint64_t dbl = smem_desc(rs::smem_u32(w1l) + kb * lbo_w1, lbo_w1, sbo);
+          mma_tf32(tmem, dal, dbh, idescA, (c == 0 && s == 0) ? 0u : 1u);
+          mma_tf32(tmem, dah, dbl, idescA, 1u);
+          mma_tf32(tmem, dah, dbh, idescA, 1u);
+        }
+        commit(&bar[bi]);
+      }
+      __syncwarp();
+      uses[bi]++;
+    }
+    {
+      const int lb = (cc - 1) & 1;
+      rs::mbar_wait(&bar[lb], (uses[lb] - 1) & 1u);
+      fence_after_sync();
+    }
+    // ---- dz0 = da0 [a0 > 0]  ->  dx = dz0 (Wa + Wb)
+    for (int c = 0; c < nchunkB; ++c, ++cc) {
+      const int bi = cc & 1;
+      uint32_t *ah = abuf + (size_t)bi * 2 * KC * MT, *al = ah + KC * MT;
+      if (uses[bi] > 0) rs::mbar_wait(&bar[bi], (uses[bi] - 1) & 1u);
+      uint32_t v[32];
+      tmem_ld32(tmem, warp, c * KC, v);
+#pragma unroll
+      for (int q = 0; q < KC / 4; ++q) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) {
+          const int k = c * KC + q * 4;
+          const float4 a0 = rs::ldg_nc_f4(P.act0 + r * H1 + k);
+          x.x = a0.x > 0.f ? __uint_as_float(v[4 * q + 0]) : 0.f;
+          x.y = a0.y > 0.f ? __uint_as_float(v[4 * q + 1]) : 0.f;
+          x.z = a0.z > 0.f ? __uint_as_float(v[4 * q + 2]) : 0.f;
+          x.w = a0.w > 0.f ? __uint_as_float(v[4 * q + 3]) : 0.f;
+          rs::stg_cs_f4(P.dz0 + rr * H1 + k, x);
+          if (l == P.L - 1) rs::stg_cs_f4(P.dz0 + (rr + 1) * H1 + k, make_float4(0.f, 0.f, 0.f, 0.f));   // the target slot
+        }
+        uint4 h, lo;
+        split4(x, h, lo);
+        *reinterpret_cast<uint4 *>(ah + (q * MT + tid) * 4) = h;
+        *reinterpret_cast<uint4 *>(al + (q * MT + tid) * 4) = lo;
+      }
+      rs::fence_proxy_async();
+      fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        fence_after_sync();
+#pragma unroll
+        for (int s = 0; s < KC / 8; ++s) {
+          const uint32_t kb = (uint32_t)(c * (KC / 4) + s * 2);
+          const uint64_t dah = smem_desc(rs::smem_u32(ah) + s * 2 * lbo_a, lbo_a, sbo);
+          const uint64_t dal = smem_desc(rs::smem_u32(al) + s * 2 * lbo_a, lbo_a, sbo);
+          const uint64_t dbh = smem_desc(rs::smem_u32(w0h) + kb * lbo_w0, lbo_w0, sbo);
+          const uint64_t dbl = smem_desc(rs::smem_u32(w0l) + kb * lbo_w0, lbo_w0, sbo);
+          mma_tf32(tmem + (uint32_t)H1, dal, dbh, idescB, (c == 0 && s == 0) ? 0u : 1u);
+          mma_tf32(tmem + (uint32_t)H1, dah, dbl, idescB, 1u);
+          mma_tf32(tmem + (uint32_t)H1, dah, dbh, idescB, 1u);
+        }
+        commit(&bar[bi]);
+      }
+      __syncwarp();
+      uses[bi]++;
+    }
+    {
+      const int lb = (cc - 1) & 1;
+      rs::mbar_wait(&bar[lb], (uses[lb] - 1) & 1u);
+      fence_after_sync();
+    }
+    // ---- d_rows[b, l] = dx + w_l g
+    const float wl = valid ? P.attw[r] : 0.f;
+    const float *g = P.pool ? P.g_out + b * D : P.g_out + r * D;
+    for (int c0 = 0; c0 < D; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem, warp, H1 + c0, v);
+      if (valid) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (c0 + 4 * q < D) {
+            const float4 g4 = rs::ldg_f4(g + c0 + 4 * q);
+            rs::stg_f4(P.d_rows + rr * D + c0 + 4 * q,
+                       make_float4(fmaf(wl, g4.x, __uint_as_float(v[4 * q + 0])), fmaf(wl, g4.y, __uint_as_float(v[4 * q + 1])),
+                                   fmaf(wl, g4.z, __uint_as_float(v[4 * q + 2])), fmaf(wl, g4.w, __uint_as_float(v[4 * q + 3]))));
+          }
+        }
+      }
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_free(tmem, P.tmem_cols);
+}
+
 bool tc_shape_ok(int D, int H1, int H2) {
   return (D == 16 || D == 32 || D == 64) && (H1 == 64 || H1 == 128) && (H2 == 32 || H2 == 64);
 }
@@ -260,7 +490,7 @@ RS_API int rs_din_fwd_tc_ws_bytes(int64_t B, int32_t L, int32_t D, int32_t H1, i
 }
 
 RS_API int rs_din_fwd_tc(const float *rows, int64_t B, int32_t L, int32_t D, const rs_din_weights *w, int32_t pool, float *out,
-                         float *attw, void *ws, size_t ws_bytes, void *stream) {
+                         float *attw, float *act0, float *act1, void *ws, size_t ws_bytes, void *stream) {
   RS_CHECK_ARG(rows && w && out && w->W0 && w->b0 && w->W1 && w->b1 && w->W2 && w->b2, RS_E_ARG, "rs_din_fwd_tc: null argument");
   RS_CHECK_ARG(L >= 1, RS_E_SHAPE, "rs_din_fwd_tc: L=%d", L);
   RS_CHECK_ARG(tc_shape_ok(D, w->H1, w->H2), RS_E_UNSUPPORTED,
@@ -279,6 +509,7 @@ RS_API int rs_din_fwd_tc(const float *rows, int64_t B, int32_t L, int32_t D, con
   }
   DinTcParams P = {};
   P.rows = rows, P.tb = tb, P.W0 = w->W0, P.W1 = w->W1, P.b1 = w->b1, P.W2 = w->W2, P.b2 = w->b2, P.score = score;
+  P.act0 = act0, P.act1 = act1;
   P.B = B, P.L = L, P.D = D, P.H1 = w->H1, P.H2 = w->H2;
   P.tmem_cols = 32;
   while (P.tmem_cols < w->H1 + w->H2) P.tmem_cols <<= 1;
@@ -291,6 +522,34 @@ RS_API int rs_din_fwd_tc(const float *rows, int64_t B, int32_t L, int32_t D, con
   float *wout = attw ? attw : score;
   int64_t blocks = (B + 7) / 8;
   din_softmax_pool_kernel<<<(unsigned)(blocks < 8 * sms ? blocks : 8 * sms), 256, 0, st>>>(rows, score, B, L, D, pool, out, wout);
+  RS_CHECK_LAUNCH();
+  return RS_OK;
+}
+
+RS_API int rs_din_bwd_tc(const float *rows, int64_t B, int32_t L, int32_t D, const rs_din_weights *w, int32_t pool,
+                         const float *g_out, const float *attw, const float *act0, const float *act1, float *d_rows, float *dz0,
+                         float *dz1, float *ds, void *stream) {
+  RS_CHECK_ARG(rows && w && g_out && attw && act0 && act1 && d_rows && dz0 && dz1 && ds && w->W0 && w->W1 && w->W2, RS_E_ARG,
+               "rs_din_bwd_tc: null argument");
+  RS_CHECK_ARG(L >= 1, RS_E_SHAPE, "rs_din_bwd_tc: L=%d", L);
+  RS_CHECK_ARG(tc_shape_ok(D, w->H1, w->H2), RS_E_UNSUPPORTED,
+               "rs_din_bwd_tc: built for D in {16,32,64}, H1 in {64,128}, H2 in {32,64} (got %d, %d, %d)", D, w->H1, w->H2);
+  if (B == 0) return RS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int sms = rs::num_sms();
+  int64_t blocks = (B + 7) / 8;
+  din_dscore_kernel<<<(unsigned)(blocks < 8 * sms ? blocks : 8 * sms), 256, 0, st>>>(rows, attw, g_out, B, L, D, pool, ds);
+  RS_CHECK_LAUNCH();
+  DinTcBwdParams P = {};
+  P.rows = rows, P.attw = attw, P.g_out = g_out, P.ds = ds, P.act0 = act0, P.act1 = act1;
+  P.W0 = w->W0, P.W1 = w->W1, P.W2 = w->W2, P.d_rows = d_rows, P.dz0 = dz0, P.dz1 = dz1;
+  P.B = B, P.L = L, P.D = D, P.H1 = w->H1, P.H2 = w->H2, P.pool = pool;
+  P.tmem_cols = 32;
+  while (P.tmem_cols < w->H1 + (D < 32 ? 32 : D)) P.tmem_cols <<= 1;
+  const size_t smem = tc_smem(D, w->H1, w->H2);
+  RS_CUDA(cudaFuncSetAttribute(din_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t ntiles = (B * L + MT - 1) / MT;
+  din_bwd_tc_kernel<<<(unsigned)(ntiles < sms ? ntiles : sms), NTH, smem, st>>>(P);
   RS_CHECK_LAUNCH();
   return RS_OK;
 }

@@ -16,7 +16,7 @@ namespace {
 using namespace rs::tc;
 constexpr int NTHREADS = 128;
 
-__global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_3xtf32_kernel(const float *__restrict__ A, const float *__restrict__ B, int64_t K,
+__global__ void __launch_bounds__(NTHREADS, 4) gemm_tn_3xtf32_kernel(const float *__restrict__ A, const float *__restrict__ B, int64_t K,
                                                                     int M, int N, int NP /* N padded to 16 */, int tmem_cols,
                                                                     int64_t slab, float *__restrict__ partial) {
   extern __shared__ __align__(128) uint32_t sm[];
@@ -43,20 +43,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_3xtf32_kernel(const float
   const int64_t k_hi = (k_lo + slab < K) ? k_lo + slab : K;
   uint32_t phase = 0, first = 1;
   for (int64_t k0 = k_lo; k0 < k_hi; k0 += KC) {
-    // repack chunk [k0, k0+KC) of A (-> MT rows) and B (-> NP rows), zero padded, split hi/lo
-    for (int e = tid; e < KC * MT; e += NTHREADS) {
-      const int kk = e / MT, m = e - kk * MT;
-      const float x = (m < M && k0 + kk < k_hi) ? A[(k0 + kk) * M + m] : 0.f;
-      const uint32_t h = to_tf32(x);
-      a_hi[tile_off(MT, m, kk)] = h;
-      a_lo[tile_off(MT, m, kk)] = to_tf32(x - __uint_as_float(h));
+    // repack chunk [k0, k0+KC) of A (-> MT rows) and B (-> NP rows), zero padded, split hi/lo.  A thread owns one
+    // operand row and turns 4 consecutive k (four coalesced loads across the threads) into one 16-byte store, which
+    // is exactly one row of a core matrix: conflict-free.  Fully unrolled: all 32 loads of a row are in flight at once.
+#pragma unroll
+    for (int q = 0; q < KC / 4; ++q) {
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (tid < M) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int64_t kk = k0 + q * 4 + i;
+          if (kk < k_hi) v[i] = A[kk * M + tid];
+        }
+      }
+      uint4 h, l;
+      split4(make_float4(v[0], v[1], v[2], v[3]), h, l);
+      *reinterpret_cast<uint4 *>(a_hi + (q * MT + tid) * 4) = h;
+      *reinterpret_cast<uint4 *>(a_lo + (q * MT + tid) * 4) = l;
     }
-    for (int e = tid; e < KC * NP; e += NTHREADS) {
-      const int kk = e / NP, n = e - kk * NP;
-      const float x = (n < N && k0 + kk < k_hi) ? B[(k0 + kk) * N + n] : 0.f;
-      const uint32_t h = to_tf32(x);
-      b_hi[tile_off(NP, n, kk)] = h;
-      b_lo[tile_off(NP, n, kk)] = to_tf32(x - __uint_as_float(h));
+    for (int n = tid; n < NP; n += NTHREADS) {
+#pragma unroll
+      for (int q = 0; q < KC / 4; ++q) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (n < N) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int64_t kk = k0 + q * 4 + i;
+            if (kk < k_hi) v[i] = B[kk * N + n];
+          }
+        }
+        uint4 h, l;
+        split4(make_float4(v[0], v[1], v[2], v[3]), h, l);
+        *reinterpret_cast<uint4 *>(b_hi + (q * NP + n) * 4) = h;
+        *reinterpret_cast<uint4 *>(b_lo + (q * NP + n) * 4) = l;
+      }
     }
     rs::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core's async proxy
     __syncthreads();
@@ -260,9 +280,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_nt_3xtf32_kernel(const __gri
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(P.tmem_cols) : "memory");
 }
 
-int plan_slabs(int64_t K, int64_t *slab) {
+// K is cut into slabs, one CTA each.  Several CTAs per SM (48 KB of shared memory, <= 128 TMEM columns each) keep loads
+// in flight while another CTA's MMAs run; the slab partials are added in slab order afterwards.
+int plan_slabs(int64_t K, int N, int64_t *slab) {
   int64_t chunks = (K + KC - 1) / KC;
-  int64_t n = rs::num_sms();
+  int cols = 32;
+  while (cols < (N + 15) / 16 * 16) cols <<= 1;
+  int per_sm = 512 / cols < 4 ? 512 / cols : 4;
+  int64_t n = (int64_t)rs::num_sms() * per_sm;
   if (n > chunks) n = chunks;
   if (n < 1) n = 1;
   int64_t per = (chunks + n - 1) / n;  // chunks per slab
@@ -275,7 +300,7 @@ int plan_slabs(int64_t K, int64_t *slab) {
 RS_API int rs_gemm_tn_ws_bytes(int64_t K, int32_t M, int32_t N, size_t *bytes) {
   RS_CHECK_ARG(bytes && K >= 1 && M >= 1 && N >= 1, RS_E_ARG, "rs_gemm_tn_ws_bytes: bad argument");
   int64_t slab;
-  *bytes = (size_t)plan_slabs(K, &slab) * M * N * 4;
+  *bytes = (size_t)plan_slabs(K, N, &slab) * M * N * 4;
   return RS_OK;
 }
 
@@ -284,7 +309,7 @@ RS_API int rs_gemm_tn_3xtf32(const float *A, const float *B, int64_t K, int32_t 
   RS_CHECK_ARG(A && B && C && ws && K >= 1, RS_E_ARG, "rs_gemm_tn_3xtf32: bad argument");
   RS_CHECK_ARG(M >= 1 && M <= MT && N >= 1 && N <= 256, RS_E_UNSUPPORTED, "rs_gemm_tn_3xtf32: need M <= 128 and N <= 256 (got %d, %d)", M, N);
   int64_t slab;
-  const int nslabs = plan_slabs(K, &slab);
+  const int nslabs = plan_slabs(K, N, &slab);
   RS_CHECK_ARG(ws_bytes >= (size_t)nslabs * M * N * 4, RS_E_WORKSPACE, "rs_gemm_tn_3xtf32: workspace too small");
   const int NP = (N + 15) / 16 * 16;
   int tmem_cols = 32;

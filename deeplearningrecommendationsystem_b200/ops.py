@@ -597,39 +597,78 @@ def din_tc_supported(D, H1, H2):
     return D in (16, 32, 64) and H1 in (64, 128) and H2 in (32, 64)
 
 
-def din_fwd(rows, ws, pool, want_attw=False, impl="auto"):
+def din_fwd(rows, ws, pool, want_attw=False, impl="auto", want_stash=False):
     """rows (B, L+1, D) = [history | target]; ws = (W0, b0, W1, b1, W2, b2) -> out (B,D) | (B,L,D), attw (B,L) | None.
 
     impl: "tc" = hidden layers on the tcgen05 tensor cores (rs_din_fwd_tc), "fused" = the CUDA-core kernel
     (rs_din_fwd), "auto" = tc when the shape is built and there are enough rows to fill the SMs (RS_DIN_TC=0 forces
-    fused)."""
+    fused).  want_stash (training): a third value is returned -- (attw, act0 (B*L, H1), act1 (B*L, H2)), the forward
+    activations din_bwd_tc consumes -- or None when the fused kernel ran (its backward recomputes)."""
     rows = _f32(rows)
     _need_cuda(rows)
     B, L1, D = rows.shape
     L = L1 - 1
     w, keep = _din_weights(ws)
     out = torch.empty((B, D) if pool else (B, L, D), dtype=torch.float32, device=rows.device)
-    attw = torch.empty(B, L, dtype=torch.float32, device=rows.device) if want_attw else None
-    if B == 0:
-        return out, attw
     if impl == "auto":
         impl = "tc" if (din_tc_supported(D, w.H1, w.H2) and B * L >= DIN_TC_MIN_ROWS
                         and os.environ.get("RS_DIN_TC", "1") != "0") else "fused"
+    stash_tc = want_stash and impl == "tc"
+    attw = torch.empty(B, L, dtype=torch.float32, device=rows.device) if (want_attw or stash_tc) else None
+    if B == 0:
+        return (out, attw, None) if want_stash else (out, attw)
     lib = _lib.load()
     if impl == "tc":
         nbytes = C.c_size_t(0)
         _lib.check(lib.rs_din_fwd_tc_ws_bytes(B, L, D, w.H1, w.H2, C.byref(nbytes)), "rs_din_fwd_tc_ws_bytes")
         scratch = torch.empty(nbytes.value, dtype=torch.uint8, device=rows.device)
+        act0 = torch.empty(B * L, w.H1, dtype=torch.float32, device=rows.device) if stash_tc else None
+        act1 = torch.empty(B * L, w.H2, dtype=torch.float32, device=rows.device) if stash_tc else None
         with _timed("din_fwd_tc"):
-            _lib.check(lib.rs_din_fwd_tc(rows.data_ptr(), B, L, D, C.byref(w), int(bool(pool)), out.data_ptr(), _p(attw),
-                                         scratch.data_ptr(), nbytes.value, _stream()), "rs_din_fwd_tc")
+            _lib.check(lib.rs_din_fwd_tc(rows.data_ptr(), B, L, D, C.byref(w), int(bool(pool)), out.data_ptr(), _p(attw), _p(act0),
+                                         _p(act1), scratch.data_ptr(), nbytes.value, _stream()), "rs_din_fwd_tc")
         _count(3)
-        return out, attw
+        return (out, attw, (attw, act0, act1) if stash_tc else None) if want_stash else (out, attw)
     with _timed("din_fwd"):
         _lib.check(lib.rs_din_fwd(rows.data_ptr(), B, L, D, C.byref(w), int(bool(pool)), out.data_ptr(), _p(attw), _stream()),
                    "rs_din_fwd")
     _count()
-    return out, attw
+    return (out, attw, None) if want_stash else (out, attw)
+
+
+def din_bwd_tc(rows, ws, pool, g_out, stash):
+    """Backward of the tensor-core forward from its stash -> d_rows (B, L+1, D), (dW0, db0, dW1, db1, dW2, db2).
+    rs_din_bwd_tc runs the data-gradient chain (two fused tcgen05 GEMMs per 128-row tile); the weight gradients are
+    reductions over all B*L rows: two rs_gemm_tn_3xtf32 calls plus small sums / products on the per-sample terms."""
+    rows, g_out = _f32(rows), _f32(g_out)
+    attw, act0, act1 = stash
+    B, L1, D = rows.shape
+    L = L1 - 1
+    w, keep = _din_weights(ws)
+    W0 = keep[0]
+    H1, H2 = w.H1, w.H2
+    dev = rows.device
+    d_rows = torch.empty_like(rows)
+    dz0 = torch.empty(B, L1, H1, dtype=torch.float32, device=dev)
+    dz1 = torch.empty(B * L, H2, dtype=torch.float32, device=dev)
+    ds = torch.empty(B, L, dtype=torch.float32, device=dev)
+    with _timed("din_bwd_tc"):
+        _lib.check(_lib.load().rs_din_bwd_tc(rows.data_ptr(), B, L, D, C.byref(w), int(bool(pool)), g_out.data_ptr(), attw.data_ptr(),
+                                             act0.data_ptr(), act1.data_ptr(), d_rows.data_ptr(), dz0.data_ptr(), dz1.data_ptr(),
+                                             ds.data_ptr(), _stream()), "rs_din_bwd_tc")
+    _count(2)
+    with _timed("din_bwd_tc_weights"):
+        dW1 = gemm_tn(act0, dz1).t().contiguous()                    # (H2, H1)
+        dWab = gemm_tn(dz0.view(B * L1, H1), rows.view(B * L1, D))   # (H1, D): the target slots of dz0 are zero
+        db1 = dz1.sum(0)
+        dW2 = ds.view(1, B * L) @ act1                               # (1, H2)
+        db2 = ds.sum().view(1)
+        dtb = dz0.sum(1)                                             # (B, H1): gradient of the per-sample target term
+        t = rows[:, L]
+        dWt = dtb.t() @ t                                            # (H1, D)
+        d_rows[:, L] = dtb @ (W0[:, 2 * D:] - W0[:, D:2 * D])
+        dW0 = torch.cat([dWab, dWab - dWt, dWt], dim=1)
+    return d_rows, (dW0, dtb.sum(0), dW1, db1, dW2, db2)
 
 
 def din_bwd(rows, ws, pool, g_out):

@@ -237,7 +237,19 @@ int rs_din_fwd(const float *rows, int64_t B, int32_t L, int32_t D, const rs_din_
  * Built for D in {16,32,64}, H1 in {64,128}, H2 in {32,64}. */
 int rs_din_fwd_tc_ws_bytes(int64_t B, int32_t L, int32_t D, int32_t H1, int32_t H2, size_t *bytes);
 int rs_din_fwd_tc(const float *rows, int64_t B, int32_t L, int32_t D, const rs_din_weights *w, int32_t pool, float *out,
-                  float *attw /* (B, L) or NULL */, void *ws, size_t ws_bytes, void *stream);
+                  float *attw /* (B, L) or NULL */, float *act0 /* (B*L, H1) or NULL */, float *act1 /* (B*L, H2) or NULL */,
+                  void *ws, size_t ws_bytes, void *stream);
+/* Backward of rs_din_fwd_tc from its stashes (attw and the two ReLU outputs act0, act1), data-gradient chain on the
+ * tensor cores:  ds = softmax backward (scratch, (B, L));  dz1 = ds w2 [act1 > 0] (B*L, H2);  dz0 = (dz1 W1) [act0 > 0]
+ * written as (B, L+1, H1) with a zero row in the target slot;  d_rows[b, l<L] = dz0 (Wa+Wb) + w_l g  (the target row
+ * d_rows[b, L] is NOT written).  The weight gradients are reductions over all rows that the caller forms from the
+ * outputs with rs_gemm_tn_3xtf32 and small sums:
+ *   dW1 = dz1^T act0,  dWab = dz0^T rows,  db1 = sum dz1,  dW2 = ds^T act1,  db2 = sum ds,
+ *   dtb = sum_l dz0 (B, H1),  db0 = sum_b dtb,  dWt = dtb^T t,  d_rows[b, L] = dtb (Wc - Wb),
+ *   dW0 = [dWab | dWab - dWt | dWt]. */
+int rs_din_bwd_tc(const float *rows, int64_t B, int32_t L, int32_t D, const rs_din_weights *w, int32_t pool,
+                  const float *g_out, const float *attw, const float *act0, const float *act1, float *d_rows, float *dz0,
+                  float *dz1, float *ds, void *stream);
 int rs_din_bwd(const float *rows, int64_t B, int32_t L, int32_t D, const rs_din_weights *w, int32_t pool,
                const float *g_out, float *d_rows, float *dWab_part, float *dWt_part, float *dW1_part, float *db0_part,
                float *db1_part, float *dW2_part, float *db2_part, int32_t num_parts, void *stream);

@@ -416,6 +416,16 @@ def test_din_attention_fwd_bwd(D, H1, H2, L, B, pool):
     assert float(dws[5].abs().max()) <= 1e-5 * max(1e-3, float(grads[5].abs().max()), float(grads[4].abs().max()))
     d2, dws2 = ops.din_bwd(rows.detach().cuda(), cw, pool, gup.cuda())
     assert torch.equal(d_rows, d2) and all(torch.equal(a, b_) for a, b_ in zip(dws, dws2))   # deterministic
+    # tensor-core backward from the tensor-core forward's stash, same oracle gradients
+    _, _, stash = ops.din_fwd(rows.detach().cuda(), cw, pool, impl="tc", want_stash=True)
+    d_tc, dws_tc = ops.din_bwd_tc(rows.detach().cuda(), cw, pool, gup.cuda(), stash)
+    scaled(d_tc, grads[0], "d_rows (tc)")
+    for got, ref, name in zip(dws_tc[:5], grads[1:6], ["dW0", "db0", "dW1", "db1", "dW2"]):
+        assert got.shape == ref.shape, name
+        scaled(got, ref, name + " (tc)")
+    assert float(dws_tc[5].abs().max()) <= 1e-5 * max(1e-3, float(grads[5].abs().max()), float(grads[4].abs().max()))
+    d_tc2, dws_tc2 = ops.din_bwd_tc(rows.detach().cuda(), cw, pool, gup.cuda(), stash)
+    assert torch.equal(d_tc, d_tc2) and all(torch.equal(a, b_) for a, b_ in zip(dws_tc, dws_tc2))
 
 
 @pytest.mark.parametrize("D,H1,H2,L,B,pool", [(64, 128, 64, 100, 700, True), (32, 64, 32, 50, 1000, False), (16, 128, 64, 3, 9000, True)])
@@ -433,6 +443,44 @@ def test_din_tc_forward_many_tiles(D, H1, H2, L, B, pool):
     close(out_t, out_f.cpu(), rtol=1e-5, atol=1e-5 * float(out_f.abs().max()), msg="out")
     out_t2, attw_t2 = ops.din_fwd(rows, cw, pool, want_attw=True, impl="tc")
     assert torch.equal(out_t, out_t2) and torch.equal(attw_t, attw_t2)       # deterministic
+    gup = torch.randn(*out_f.shape, generator=g).cuda()
+    d_f, dws_f = ops.din_bwd(rows, cw, pool, gup)
+    _, _, stash = ops.din_fwd(rows, cw, pool, impl="tc", want_stash=True)
+    d_t, dws_t = ops.din_bwd_tc(rows, cw, pool, gup, stash)
+    # ReLU is not differentiable at 0: a pre-activation within rounding of zero can land on either side in two fp32
+    # implementations, which changes that one (b, l) row's gradient by a finite amount.  13 M activations here, so a
+    # handful of rows may differ; everything else must agree to 1e-5, and the outliers stay small.
+    err = (d_t - d_f).abs()
+    tol = 1e-5 * float(d_f.abs().max()) + 1e-5 * d_f.abs()
+    bad_rows = int((err > tol).any(dim=2).sum())
+    assert bad_rows <= max(2, int(2e-4 * B * L)), f"{bad_rows} history rows differ"
+    assert float(err.max()) <= 1e-2 * float(d_f.abs().max())
+    # Weight gradients sum those rows, so the same few kinks move them by more than 1e-5 between ANY two fp32
+    # evaluations; against the fused kernel only the aggregate can be bounded ...
+    for a, b_, name in zip(dws_t[:5], dws_f[:5], ["dW0", "db0", "dW1", "db1", "dW2"]):
+        assert float((a - b_).norm()) <= 1e-3 * float(b_.norm()), name
+        assert float((a - b_).abs().max()) <= 2e-3 * float(b_.abs().max()), name
+    # ... and the kernels themselves are checked exactly: with the ReLU masks FIXED to the ones the forward stashed,
+    # the gradient is a smooth function, and a float64 evaluation of it must agree to 1e-5 everywhere.
+    attw, act0, act1 = [t.double().cpu() for t in stash]
+    W0, b0, W1, b1, W2, b2 = [t.double().cpu() for t in cw]
+    X, G = rows.double().cpu(), gup.double().cpu()
+    h, t = X[:, :L], X[:, L]
+    dw = (G.unsqueeze(1) * h).sum(-1) if pool else (G * h).sum(-1)                   # (B, L)
+    ds = attw * (dw - (attw * dw).sum(1, keepdim=True))
+    dz1 = ds.reshape(-1, 1) * W2 * (act1 > 0)
+    dz0 = (dz1 @ W1) * (act0 > 0)
+    Wab, Wt = W0[:, :D] + W0[:, D:2 * D], W0[:, 2 * D:] - W0[:, D:2 * D]
+    direct = attw.unsqueeze(-1) * (G.unsqueeze(1) if pool else G)
+    dtb = dz0.view(B, L, H1).sum(1)
+    dWab, dWt = dz0.t() @ h.reshape(-1, D), dtb.t() @ t
+    want = {"d_hist": (dz0 @ Wab).view(B, L, D) + direct, "d_tgt": dtb @ Wt, "dW0": torch.cat([dWab, dWab - dWt, dWt], 1),
+            "db0": dtb.sum(0), "dW1": dz1.t() @ act0, "db1": dz1.sum(0), "dW2": ds.reshape(1, -1) @ act1}
+    got = {"d_hist": d_t[:, :L], "d_tgt": d_t[:, L], "dW0": dws_t[0], "db0": dws_t[1], "dW1": dws_t[2], "db1": dws_t[3],
+           "dW2": dws_t[4]}
+    for name in want:
+        ref = want[name]
+        close(got[name].double(), ref, rtol=1e-5, atol=1e-5 * float(ref.abs().max()), msg=name + " (fixed masks, f64)")
 
 
 # ------------------------------------------------------------------ tcgen05 3xTF32 A^T B (PNN "out")
