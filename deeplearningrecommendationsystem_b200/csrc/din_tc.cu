@@ -17,7 +17,7 @@
 namespace {
 
 using namespace rs::tc;
-constexpr int NTH = 128;
+constexpr int NTH = 256;   // two warpgroups per CTA, each owning its own tiles, operand buffer, barrier and TMEM half
 
 struct DinTcParams {
   const float *rows;  // (B, L+1, D)
@@ -60,35 +60,36 @@ __global__ void __launch_bounds__(128) din_tbias_kernel(const float *__restrict_
 
 __global__ void __launch_bounds__(NTH, 1) din_score_tc_kernel(const __grid_constant__ DinTcParams P) {
   extern __shared__ __align__(128) uint32_t sm[];
-  __shared__ uint64_t bar[2];
+  __shared__ uint64_t bar[2];   // one per warpgroup: that group's operand buffer has been read by its MMAs
   __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int warp = threadIdx.x >> 5;
+  const int grp = threadIdx.x >> 7, tid = threadIdx.x & (MT - 1);   // warpgroup, row inside its tile
   const int D = P.D, H1 = P.H1, H2 = P.H2;
   uint32_t *w0h = sm, *w0l = w0h + D * H1;                    // layer 0: N = H1 rows, K = D
   uint32_t *w1h = w0l + D * H1, *w1l = w1h + H1 * H2;         // layer 1: N = H2 rows, K = H1
-  uint32_t *abuf = w1l + H1 * H2;                             // [2][hi | lo][KC * MT]
+  uint32_t *abuf = w1l + H1 * H2;                             // [warpgroup][hi | lo][KC * MT]
   float *b1s = reinterpret_cast<float *>(abuf + 4 * KC * MT), *w2s = b1s + H2;
   if (warp == 0) tmem_alloc(&tmem_base_s, P.tmem_cols);
-  if (tid == 0) {
+  if (threadIdx.x == 0) {
     rs::mbar_init(&bar[0], 1);
     rs::mbar_init(&bar[1], 1);
     rs::mbar_fence_init();
   }
-  for (int e = tid; e < D * H1; e += NTH) {
+  for (int e = threadIdx.x; e < D * H1; e += NTH) {
     const int n = e / D, k = e - n * D;
     const float x = P.W0[(size_t)n * 3 * D + k] + P.W0[(size_t)n * 3 * D + D + k];   // Wa + Wb
     const uint32_t h = to_tf32(x);
     w0h[tile_off(H1, n, k)] = h;
     w0l[tile_off(H1, n, k)] = to_tf32(x - __uint_as_float(h));
   }
-  for (int e = tid; e < H1 * H2; e += NTH) {
+  for (int e = threadIdx.x; e < H1 * H2; e += NTH) {
     const int n = e / H1, k = e - n * H1;
     const float x = P.W1[(size_t)n * H1 + k];
     const uint32_t h = to_tf32(x);
     w1h[tile_off(H2, n, k)] = h;
     w1l[tile_off(H2, n, k)] = to_tf32(x - __uint_as_float(h));
   }
-  for (int e = tid; e < H2; e += NTH) {
+  for (int e = threadIdx.x; e < H2; e += NTH) {
     b1s[e] = P.b1[e];
     w2s[e] = P.W2[e];
   }
@@ -96,36 +97,76 @@ __global__ void __launch_bounds__(NTH, 1) din_score_tc_kernel(const __grid_const
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tmem = tmem_base_s;
+  const uint32_t tmem = tmem_base_s + (uint32_t)grp * (uint32_t)(P.tmem_cols / 2);
   const uint32_t idesc0 = idesc_tf32(H1), idesc1 = idesc_tf32(H2);
   const uint32_t lbo_a = MT * 16, lbo_w0 = (uint32_t)H1 * 16, lbo_w1 = (uint32_t)H2 * 16, sbo = 128;
   const float b2 = P.b2[0];
   const int nchunk0 = (D + KC - 1) / KC, nchunk1 = H1 / KC;
-  uint32_t uses[2] = {0, 0};   // commits so far on each A buffer's barrier (-> parity of the latest phase)
-  uint32_t cc = 0;             // running chunk counter: buffer = cc & 1
+  uint32_t uses = 0;   // commits so far on this group's barrier (-> parity of the latest phase)
   const int64_t nrows = P.B * P.L;
   const int64_t ntiles = (nrows + MT - 1) / MT;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t r = tile * MT + tid;
-    const bool valid = r < nrows;
-    const int64_t b = valid ? r / P.L : 0;
-    const float *arow = valid ? P.rows + (b * (P.L + 1) + (r - b * P.L)) * D : nullptr;
+  const int64_t first_tile = (int64_t)blockIdx.x * 2 + grp, tile_step = (int64_t)gridDim.x * 2;   // the two warpgroups take alternate tiles
+  const int nS = nchunk0 + nchunk1;   // stages of one tile that read global memory: history-row chunks, tb pieces
+  // Each stage's eight 16-byte pieces are fetched one stage AHEAD into `pre` (across tile boundaries too), so the
+  // load latency hides behind the previous stage's repack and MMAs.
+  float4 pre[KC / 4];
+  auto row_of = [&](int64_t tile, int64_t &r, int64_t &b) {
+    r = tile * MT + tid;
+    const bool ok = r < nrows;
+    b = ok ? r / P.L : 0;
+    return ok;
+  };
+  auto prefetch = [&](int stage, bool ok, int64_t r, int64_t b) {
+    const float *src;
+    int n4 = KC / 4;
+    if (stage < nchunk0) {
+      src = P.rows + (b * (P.L + 1) + (r - b * P.L)) * D + stage * KC;
+      n4 = (D - stage * KC) < KC ? (D - stage * KC) / 4 : KC / 4;
+    } else {
+      src = P.tb + b * H1 + (stage - nchunk0) * KC;
+    }
+#pragma unroll
+    for (int q = 0; q < KC / 4; ++q) pre[q] = (ok && q < n4) ? rs::ldg_nc_f4(src + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  {
+    int64_t r, b;
+    const bool ok = row_of(first_tile, r, b);
+    if (first_tile < ntiles) prefetch(0, ok, r, b);
+  }
+  for (int64_t tile = first_tile; tile < ntiles; tile += tile_step) {
+    int64_t r, b;
+    const bool valid = row_of(tile, r, b);
+    int stage = 0;
+    float4 cur[KC / 4];
+    auto advance = [&]() {
+#pragma unroll
+      for (int q = 0; q < KC / 4; ++q) cur[q] = pre[q];
+      ++stage;
+      if (stage < nS) {
+        prefetch(stage, valid, r, b);
+      } else if (tile + tile_step < ntiles) {
+        int64_t r2, b2;
+        const bool ok2 = row_of(tile + tile_step, r2, b2);
+        prefetch(0, ok2, r2, b2);
+      }
+    };
     // ---- layer 0: A = history rows
-    for (int c = 0; c < nchunk0; ++c, ++cc) {
-      const int bi = cc & 1;
-      uint32_t *ah = abuf + (size_t)bi * 2 * KC * MT, *al = ah + KC * MT;
-      if (uses[bi] > 0) rs::mbar_wait(&bar[bi], (uses[bi] - 1) & 1u);
+    for (int c = 0; c < nchunk0; ++c) {
+      uint32_t *ah = abuf + (size_t)grp * 2 * KC * MT, *al = ah + KC * MT;
+      advance();
+      if (uses > 0) rs::mbar_wait(&bar[grp], (uses - 1) & 1u);   // the previous chunk's MMAs have read the buffer
       const int kq = (D - c * KC) < KC ? (D - c * KC) / 4 : KC / 4;   // 16-byte K pieces in this chunk
-      for (int q = 0; q < kq; ++q) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (arow) v = rs::ldg_nc_f4(arow + c * KC + q * 4);
-        uint4 h, l;
-        split4(v, h, l);
-        *reinterpret_cast<uint4 *>(ah + (q * MT + tid) * 4) = h;
-        *reinterpret_cast<uint4 *>(al + (q * MT + tid) * 4) = l;
+#pragma unroll
+      for (int q = 0; q < KC / 4; ++q) {
+        if (q < kq) {
+          uint4 h, l;
+          split4(cur[q], h, l);
+          *reinterpret_cast<uint4 *>(ah + (q * MT + tid) * 4) = h;
+          *reinterpret_cast<uint4 *>(al + (q * MT + tid) * 4) = l;
+        }
       }
       rs::fence_proxy_async();
-      __syncthreads();
+      group_sync(grp);
       if (tid == 0) {
         fence_after_sync();
         for (int s = 0; s < kq / 2; ++s) {
@@ -138,29 +179,25 @@ __global__ void __launch_bounds__(NTH, 1) din_score_tc_kernel(const __grid_const
           mma_tf32(tmem, dah, dbl, idesc0, 1u);
           mma_tf32(tmem, dah, dbh, idesc0, 1u);
         }
-        commit(&bar[bi]);
+        commit(&bar[grp]);
       }
       __syncwarp();   // warp 0 re-converges before its next aligned tcgen05.ld
-      uses[bi]++;
+      uses++;
     }
-    {  // D0 complete: the latest commit covers every earlier MMA
-      const int lb = (cc - 1) & 1;
-      rs::mbar_wait(&bar[lb], (uses[lb] - 1) & 1u);
-      fence_after_sync();
-    }
+    rs::mbar_wait(&bar[grp], (uses - 1) & 1u);   // accumulator complete: the latest commit covers every earlier MMA
+    fence_after_sync();
     // ---- layer 1: 32 columns of D0 -> relu(. + tb) -> one K chunk of the next A operand
-    const float *tbrow = P.tb + b * H1;
-    for (int c = 0; c < nchunk1; ++c, ++cc) {
-      const int bi = cc & 1;
-      uint32_t *ah = abuf + (size_t)bi * 2 * KC * MT, *al = ah + KC * MT;
-      if (uses[bi] > 0) rs::mbar_wait(&bar[bi], (uses[bi] - 1) & 1u);
+    for (int c = 0; c < nchunk1; ++c) {
+      uint32_t *ah = abuf + (size_t)grp * 2 * KC * MT, *al = ah + KC * MT;
+      advance();
+      if (uses > 0) rs::mbar_wait(&bar[grp], (uses - 1) & 1u);   // the previous chunk's MMAs have read the buffer
       uint32_t v[32];
       tmem_ld32(tmem, warp, c * KC, v);
 #pragma unroll
       for (int q = 0; q < KC / 4; ++q) {
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
         if (valid) {
-          const float4 t4 = rs::ldg_f4(tbrow + c * KC + q * 4);
+          const float4 t4 = cur[q];
           x.x = fmaxf(__uint_as_float(v[4 * q + 0]) + t4.x, 0.f);
           x.y = fmaxf(__uint_as_float(v[4 * q + 1]) + t4.y, 0.f);
           x.z = fmaxf(__uint_as_float(v[4 * q + 2]) + t4.z, 0.f);
@@ -174,7 +211,7 @@ __global__ void __launch_bounds__(NTH, 1) din_score_tc_kernel(const __grid_const
       }
       rs::fence_proxy_async();
       fence_before_sync();
-      __syncthreads();
+      group_sync(grp);
       if (tid == 0) {
         fence_after_sync();
 #pragma unroll
@@ -188,16 +225,13 @@ __global__ void __launch_bounds__(NTH, 1) din_score_tc_kernel(const __grid_const
           mma_tf32(tmem + (uint32_t)H1, dah, dbl, idesc1, 1u);
           mma_tf32(tmem + (uint32_t)H1, dah, dbh, idesc1, 1u);
         }
-        commit(&bar[bi]);
+        commit(&bar[grp]);
       }
       __syncwarp();   // warp 0 re-converges before its next aligned tcgen05.ld
-      uses[bi]++;
+      uses++;
     }
-    {
-      const int lb = (cc - 1) & 1;
-      rs::mbar_wait(&bar[lb], (uses[lb] - 1) & 1u);
-      fence_after_sync();
-    }
+    rs::mbar_wait(&bar[grp], (uses - 1) & 1u);   // accumulator complete: the latest commit covers every earlier MMA
+    fence_after_sync();
     // ---- layer 2: per-row dot product over relu(D1 + b1)
     float acc = b2;
     for (int c0 = 0; c0 < H2; c0 += 32) {
@@ -218,11 +252,11 @@ __global__ void __launch_bounds__(NTH, 1) din_score_tc_kernel(const __grid_const
     }
     if (valid) P.score[r] = acc;
     fence_before_sync();
-    __syncthreads();   // every warp has drained both accumulators before the next tile's MMAs overwrite them
+    group_sync(grp);   // the group's warps have drained both accumulators before its next tile's MMAs overwrite them
     fence_after_sync();
   }
   __syncthreads();
-  if (warp == 0) tmem_free(tmem, P.tmem_cols);
+  if (warp == 0) tmem_free(tmem_base_s, P.tmem_cols);
 }
 
 // softmax over L (no mask, no scaling: model/din.py:46) and the weighted sum; one warp per sample
@@ -303,65 +337,118 @@ struct DinTcBwdParams {
 //   d_rows[b, l] = dx + w_l g      (the direct path of the weighted sum)
 __global__ void __launch_bounds__(NTH, 1) din_bwd_tc_kernel(const __grid_constant__ DinTcBwdParams P) {
   extern __shared__ __align__(128) uint32_t sm[];
-  __shared__ uint64_t bar[2];
+  __shared__ uint64_t bar[2];   // one per warpgroup: that group's operand buffer has been read by its MMAs
   __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int warp = threadIdx.x >> 5;
+  const int grp = threadIdx.x >> 7, tid = threadIdx.x & (MT - 1);   // warpgroup, row inside its tile
   const int D = P.D, H1 = P.H1, H2 = P.H2;
   uint32_t *w1h = sm, *w1l = w1h + H1 * H2;                   // N = H1 rows, K = H2
   uint32_t *w0h = w1l + H1 * H2, *w0l = w0h + D * H1;         // N = D rows,  K = H1
-  uint32_t *abuf = w0l + D * H1;                              // [2][hi | lo][KC * MT]
+  uint32_t *abuf = w0l + D * H1;                              // [warpgroup][hi | lo][KC * MT]
   float *w2s = reinterpret_cast<float *>(abuf + 4 * KC * MT);
   if (warp == 0) tmem_alloc(&tmem_base_s, P.tmem_cols);
-  if (tid == 0) {
+  if (threadIdx.x == 0) {
     rs::mbar_init(&bar[0], 1);
     rs::mbar_init(&bar[1], 1);
     rs::mbar_fence_init();
   }
-  for (int e = tid; e < H1 * H2; e += NTH) {
+  for (int e = threadIdx.x; e < H1 * H2; e += NTH) {
     const int k = e / H1, n = e - k * H1;                     // W1 is (H2, H1): element (k = h2, n = h1), coalesced read
     const float x = P.W1[e];
     const uint32_t h = to_tf32(x);
     w1h[tile_off(H1, n, k)] = h;
     w1l[tile_off(H1, n, k)] = to_tf32(x - __uint_as_float(h));
   }
-  for (int e = tid; e < D * H1; e += NTH) {
+  for (int e = threadIdx.x; e < D * H1; e += NTH) {
     const int k = e / D, n = e - k * D;                       // (Wa + Wb) is (H1, D): element (k = h1, n = d)
     const float x = P.W0[(size_t)k * 3 * D + n] + P.W0[(size_t)k * 3 * D + D + n];
     const uint32_t h = to_tf32(x);
     w0h[tile_off(D, n, k)] = h;
     w0l[tile_off(D, n, k)] = to_tf32(x - __uint_as_float(h));
   }
-  for (int e = tid; e < H2; e += NTH) w2s[e] = P.W2[e];
+  for (int e = threadIdx.x; e < H2; e += NTH) w2s[e] = P.W2[e];
   rs::fence_proxy_async();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tmem = tmem_base_s;
+  const uint32_t tmem = tmem_base_s + (uint32_t)grp * (uint32_t)(P.tmem_cols / 2);
   const uint32_t idescA = idesc_tf32(H1), idescB = idesc_tf32(D);
   const uint32_t lbo_a = MT * 16, lbo_w1 = (uint32_t)H1 * 16, lbo_w0 = (uint32_t)D * 16, sbo = 128;
   const int nchunkA = H2 / KC, nchunkB = H1 / KC;
-  uint32_t uses[2] = {0, 0};
-  uint32_t cc = 0;
+  uint32_t uses = 0;   // commits so far on this group's barrier (-> parity of the latest phase)
   const int64_t nrows = P.B * P.L;
   const int64_t ntiles = (nrows + MT - 1) / MT;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t r = tile * MT + tid;
-    const bool valid = r < nrows;
-    const int64_t b = valid ? r / P.L : 0;
-    const int l = (int)(r - b * P.L);
-    const int64_t rr = b * (P.L + 1) + l;                     // row inside the (B, L+1, .) tensors
-    const float dsr = valid ? P.ds[r] : 0.f;
+  const int64_t first_tile = (int64_t)blockIdx.x * 2 + grp, tile_step = (int64_t)gridDim.x * 2;   // the two warpgroups take alternate tiles
+  const int nG = (D + 31) / 32, nS = nchunkA + nchunkB + nG;   // stages of one tile: act1 chunks, act0 chunks, g pieces
+  // Every stage consumes eight 16-byte pieces of one row of a global array.  They are fetched one stage AHEAD into
+  // `pre` (across tile boundaries too), so the load latency hides behind the previous stage's repack and MMAs.
+  float4 pre[KC / 4];
+  float ds_pre = 0.f;
+  auto row_of = [&](int64_t tile, int64_t &r, int64_t &b, int &l, int64_t &rr) {
+    r = tile * MT + tid;
+    const bool ok = r < nrows;
+    b = ok ? r / P.L : 0;
+    l = (int)(r - b * P.L);
+    rr = b * (P.L + 1) + l;
+    return ok;
+  };
+  auto prefetch = [&](int stage, bool ok, int64_t r, int64_t b) {
+    const float *src;
+    int n4 = KC / 4;
+    if (stage < nchunkA) {
+      src = P.act1 + r * H2 + stage * KC;
+    } else if (stage < nchunkA + nchunkB) {
+      src = P.act0 + r * H1 + (stage - nchunkA) * KC;
+    } else {
+      const int c0 = (stage - nchunkA - nchunkB) * 32;
+      src = (P.pool ? P.g_out + b * D : P.g_out + r * D) + c0;
+      n4 = (D - c0) / 4 < 8 ? (D - c0) / 4 : 8;
+    }
+#pragma unroll
+    for (int q = 0; q < KC / 4; ++q) pre[q] = (ok && q < n4) ? rs::ldg_nc_f4(src + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  {
+    int64_t r, b, rr;
+    int l;
+    const bool ok = row_of(first_tile, r, b, l, rr);
+    if (first_tile < ntiles) {
+      prefetch(0, ok, r, b);
+      ds_pre = ok ? P.ds[r] : 0.f;
+    }
+  }
+  for (int64_t tile = first_tile; tile < ntiles; tile += tile_step) {
+    int64_t r, b, rr;
+    int l;
+    const bool valid = row_of(tile, r, b, l, rr);
+    const float dsr = ds_pre;
+    int stage = 0;
+    float4 cur[KC / 4];
+    // move the prefetched pieces into `cur` and start the loads of the next stage (or of the next tile's first)
+    auto advance = [&]() {
+#pragma unroll
+      for (int q = 0; q < KC / 4; ++q) cur[q] = pre[q];
+      ++stage;
+      if (stage < nS) {
+        prefetch(stage, valid, r, b);
+      } else if (tile + tile_step < ntiles) {
+        int64_t r2, b2, rr2;
+        int l2;
+        const bool ok2 = row_of(tile + tile_step, r2, b2, l2, rr2);
+        prefetch(0, ok2, r2, b2);
+        ds_pre = ok2 ? P.ds[r2] : 0.f;
+      }
+    };
     // ---- da0 = dz1 W1
-    for (int c = 0; c < nchunkA; ++c, ++cc) {
-      const int bi = cc & 1;
-      uint32_t *ah = abuf + (size_t)bi * 2 * KC * MT, *al = ah + KC * MT;
-      if (uses[bi] > 0) rs::mbar_wait(&bar[bi], (uses[bi] - 1) & 1u);
+    for (int c = 0; c < nchunkA; ++c) {
+      uint32_t *ah = abuf + (size_t)grp * 2 * KC * MT, *al = ah + KC * MT;
+      advance();
+      if (uses > 0) rs::mbar_wait(&bar[grp], (uses - 1) & 1u);   // the previous chunk's MMAs have read the buffer
 #pragma unroll
       for (int q = 0; q < KC / 4; ++q) {
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
         if (valid) {
           const int k = c * KC + q * 4;
-          const float4 a1 = rs::ldg_nc_f4(P.act1 + r * H2 + k);
+          const float4 a1 = cur[q];
           x.x = a1.x > 0.f ? dsr * w2s[k + 0] : 0.f;
           x.y = a1.y > 0.f ? dsr * w2s[k + 1] : 0.f;
           x.z = a1.z > 0.f ? dsr * w2s[k + 2] : 0.f;
@@ -374,7 +461,7 @@ __global__ void __launch_bounds__(NTH, 1) din_bwd_tc_kernel(const __grid_constan
         *reinterpret_cast<uint4 *>(al + (q * MT + tid) * 4) = lo;
       }
       rs::fence_proxy_async();
-      __syncthreads();
+      group_sync(grp);
       if (tid == 0) {
         fence_after_sync();
 #pragma unroll
@@ -388,21 +475,18 @@ __global__ void __launch_bounds__(NTH, 1) din_bwd_tc_kernel(const __grid_constan
           mma_tf32(tmem, dah, dbl, idescA, 1u);
           mma_tf32(tmem, dah, dbh, idescA, 1u);
         }
-        commit(&bar[bi]);
+        commit(&bar[grp]);
       }
       __syncwarp();
-      uses[bi]++;
+      uses++;
     }
-    {
-      const int lb = (cc - 1) & 1;
-      rs::mbar_wait(&bar[lb], (uses[lb] - 1) & 1u);
-      fence_after_sync();
-    }
+    rs::mbar_wait(&bar[grp], (uses - 1) & 1u);   // accumulator complete: the latest commit covers every earlier MMA
+    fence_after_sync();
     // ---- dz0 = da0 [a0 > 0]  ->  dx = dz0 (Wa + Wb)
-    for (int c = 0; c < nchunkB; ++c, ++cc) {
-      const int bi = cc & 1;
-      uint32_t *ah = abuf + (size_t)bi * 2 * KC * MT, *al = ah + KC * MT;
-      if (uses[bi] > 0) rs::mbar_wait(&bar[bi], (uses[bi] - 1) & 1u);
+    for (int c = 0; c < nchunkB; ++c) {
+      uint32_t *ah = abuf + (size_t)grp * 2 * KC * MT, *al = ah + KC * MT;
+      advance();
+      if (uses > 0) rs::mbar_wait(&bar[grp], (uses - 1) & 1u);   // the previous chunk's MMAs have read the buffer
       uint32_t v[32];
       tmem_ld32(tmem, warp, c * KC, v);
 #pragma unroll
@@ -410,7 +494,7 @@ __global__ void __launch_bounds__(NTH, 1) din_bwd_tc_kernel(const __grid_constan
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
         if (valid) {
           const int k = c * KC + q * 4;
-          const float4 a0 = rs::ldg_nc_f4(P.act0 + r * H1 + k);
+          const float4 a0 = cur[q];
           x.x = a0.x > 0.f ? __uint_as_float(v[4 * q + 0]) : 0.f;
           x.y = a0.y > 0.f ? __uint_as_float(v[4 * q + 1]) : 0.f;
           x.z = a0.z > 0.f ? __uint_as_float(v[4 * q + 2]) : 0.f;
@@ -425,7 +509,7 @@ __global__ void __launch_bounds__(NTH, 1) din_bwd_tc_kernel(const __grid_constan
       }
       rs::fence_proxy_async();
       fence_before_sync();
-      __syncthreads();
+      group_sync(grp);
       if (tid == 0) {
         fence_after_sync();
 #pragma unroll
@@ -439,27 +523,24 @@ __global__ void __launch_bounds__(NTH, 1) din_bwd_tc_kernel(const __grid_constan
           mma_tf32(tmem + (uint32_t)H1, dah, dbl, idescB, 1u);
           mma_tf32(tmem + (uint32_t)H1, dah, dbh, idescB, 1u);
         }
-        commit(&bar[bi]);
+        commit(&bar[grp]);
       }
       __syncwarp();
-      uses[bi]++;
+      uses++;
     }
-    {
-      const int lb = (cc - 1) & 1;
-      rs::mbar_wait(&bar[lb], (uses[lb] - 1) & 1u);
-      fence_after_sync();
-    }
+    rs::mbar_wait(&bar[grp], (uses - 1) & 1u);   // accumulator complete: the latest commit covers every earlier MMA
+    fence_after_sync();
     // ---- d_rows[b, l] = dx + w_l g
     const float wl = valid ? P.attw[r] : 0.f;
-    const float *g = P.pool ? P.g_out + b * D : P.g_out + r * D;
     for (int c0 = 0; c0 < D; c0 += 32) {
+      advance();
       uint32_t v[32];
       tmem_ld32(tmem, warp, H1 + c0, v);
       if (valid) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           if (c0 + 4 * q < D) {
-            const float4 g4 = rs::ldg_f4(g + c0 + 4 * q);
+            const float4 g4 = cur[q];
             rs::stg_f4(P.d_rows + rr * D + c0 + 4 * q,
                        make_float4(fmaf(wl, g4.x, __uint_as_float(v[4 * q + 0])), fmaf(wl, g4.y, __uint_as_float(v[4 * q + 1])),
                                    fmaf(wl, g4.z, __uint_as_float(v[4 * q + 2])), fmaf(wl, g4.w, __uint_as_float(v[4 * q + 3]))));
@@ -468,11 +549,11 @@ __global__ void __launch_bounds__(NTH, 1) din_bwd_tc_kernel(const __grid_constan
       }
     }
     fence_before_sync();
-    __syncthreads();
+    group_sync(grp);
     fence_after_sync();
   }
   __syncthreads();
-  if (warp == 0) tmem_free(tmem, P.tmem_cols);
+  if (warp == 0) tmem_free(tmem_base_s, P.tmem_cols);
 }
 
 bool tc_shape_ok(int D, int H1, int H2) {
@@ -513,10 +594,12 @@ RS_API int rs_din_fwd_tc(const float *rows, int64_t B, int32_t L, int32_t D, con
   P.B = B, P.L = L, P.D = D, P.H1 = w->H1, P.H2 = w->H2;
   P.tmem_cols = 32;
   while (P.tmem_cols < w->H1 + w->H2) P.tmem_cols <<= 1;
+  P.tmem_cols *= 2;   // one half per warpgroup
   const size_t smem = tc_smem(D, w->H1, w->H2);
   RS_CUDA(cudaFuncSetAttribute(din_score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t ntiles = (B * L + MT - 1) / MT;
-  din_score_tc_kernel<<<(unsigned)(ntiles < sms ? ntiles : sms), NTH, smem, st>>>(P);
+  const int64_t pairs = (ntiles + 1) / 2;   // a CTA's two warpgroups take alternate tiles
+  din_score_tc_kernel<<<(unsigned)(pairs < sms ? pairs : sms), NTH, smem, st>>>(P);
   RS_CHECK_LAUNCH();
   // attw doubles as the softmax output the backward needs; without it the scores are normalised in place
   float *wout = attw ? attw : score;
@@ -546,10 +629,12 @@ RS_API int rs_din_bwd_tc(const float *rows, int64_t B, int32_t L, int32_t D, con
   P.B = B, P.L = L, P.D = D, P.H1 = w->H1, P.H2 = w->H2, P.pool = pool;
   P.tmem_cols = 32;
   while (P.tmem_cols < w->H1 + (D < 32 ? 32 : D)) P.tmem_cols <<= 1;
+  P.tmem_cols *= 2;   // one half per warpgroup
   const size_t smem = tc_smem(D, w->H1, w->H2);
   RS_CUDA(cudaFuncSetAttribute(din_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t ntiles = (B * L + MT - 1) / MT;
-  din_bwd_tc_kernel<<<(unsigned)(ntiles < sms ? ntiles : sms), NTH, smem, st>>>(P);
+  const int64_t pairs = (ntiles + 1) / 2;
+  din_bwd_tc_kernel<<<(unsigned)(pairs < sms ? pairs : sms), NTH, smem, st>>>(P);
   RS_CHECK_LAUNCH();
   return RS_OK;
 }

@@ -12,7 +12,7 @@ constexpr int MT = 128;  // UMMA M: one accumulator row per TMEM lane
 
 __device__ __forceinline__ uint32_t to_tf32(float x) {
   uint32_t r;
-  asm volatile("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));   // pure: not volatile, so independent splits interleave
   return r;
 }
 
@@ -60,9 +60,10 @@ __device__ __forceinline__ void tmem_free(uint32_t base, int cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
 }
 
-// lane l of warp w receives columns [col, col+32) of accumulator row 32w + l
+// lane l of warp w receives columns [col, col+32) of accumulator row 32(w % 4) + l (a warp can only reach the TMEM
+// lane quarter given by its index inside its warpgroup)
 __device__ __forceinline__ void tmem_ld32(uint32_t tmem, int warp, int col, uint32_t (&v)[32]) {
-  const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)col;
+  const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col;
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
       "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
@@ -73,6 +74,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t tmem, int warp, int col, uint
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+
+// barrier over the 128 threads of one warpgroup (ids 1.. ; 0 is __syncthreads)
+__device__ __forceinline__ void group_sync(int group) { asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory"); }
 
 // split four fp32 values into tf32 hi and lo parts (x = hi + lo up to ~2^-22 relative)
 __device__ __forceinline__ void split4(float4 v, uint4 &h, uint4 &l) {
