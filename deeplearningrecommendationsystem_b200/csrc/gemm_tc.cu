@@ -45,37 +45,49 @@ __global__ void __launch_bounds__(NTHREADS, 4) gemm_tn_3xtf32_kernel(const float
   for (int64_t k0 = k_lo; k0 < k_hi; k0 += KC) {
     // repack chunk [k0, k0+KC) of A (-> MT rows) and B (-> NP rows), zero padded, split hi/lo.  A thread owns one
     // operand row and turns 4 consecutive k (four coalesced loads across the threads) into one 16-byte store, which
-    // is exactly one row of a core matrix: conflict-free.  Fully unrolled: all 32 loads of a row are in flight at once.
+    // is exactly one row of a core matrix: conflict-free.  Fully unrolled: all loads of a row are in flight at once;
+    // only the last chunk of a slab pays for bounds checks.
+    const bool full = k0 + KC <= k_hi;
+    {
+      const float *ap = A + k0 * M + tid;
+      float v[KC];
+      if (tid < M && full) {
 #pragma unroll
-    for (int q = 0; q < KC / 4; ++q) {
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
-      if (tid < M) {
+        for (int kk = 0; kk < KC; ++kk) v[kk] = ap[(int64_t)kk * M];
+      } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int64_t kk = k0 + q * 4 + i;
-          if (kk < k_hi) v[i] = A[kk * M + tid];
-        }
+        for (int kk = 0; kk < KC; ++kk) v[kk] = (tid < M && k0 + kk < k_hi) ? ap[(int64_t)kk * M] : 0.f;
       }
-      uint4 h, l;
-      split4(make_float4(v[0], v[1], v[2], v[3]), h, l);
-      *reinterpret_cast<uint4 *>(a_hi + (q * MT + tid) * 4) = h;
-      *reinterpret_cast<uint4 *>(a_lo + (q * MT + tid) * 4) = l;
-    }
-    for (int n = tid; n < NP; n += NTHREADS) {
 #pragma unroll
       for (int q = 0; q < KC / 4; ++q) {
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (n < N) {
+        uint4 h, l;
+        split4(make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]), h, l);
+        *reinterpret_cast<uint4 *>(a_hi + (q * MT + tid) * 4) = h;
+        *reinterpret_cast<uint4 *>(a_lo + (q * MT + tid) * 4) = l;
+      }
+    }
+    // B has NP <= 256 rows: with fewer rows than threads, NTHREADS / NP threads share a row and split its k range
+    {
+      const int nsub = NP < NTHREADS ? NTHREADS / NP : 1;   // NP is a multiple of 16: 1, 2, 4 or 8 when NP divides 128
+      const int qper = (KC / 4) / nsub;
+      for (int n = tid % (NP < NTHREADS ? NP : NTHREADS), sub = (NP < NTHREADS ? tid / NP : 0); n < NP && sub < nsub; n += NTHREADS) {
+        const float *bp = B + k0 * N + n;
+        float v[KC];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int64_t kk = k0 + q * 4 + i;
-            if (kk < k_hi) v[i] = B[kk * N + n];
+        for (int j = 0; j < KC; ++j) {   // j counts inside this thread's share of the row
+          const int kk = sub * qper * 4 + j;
+          v[j] = (j < qper * 4 && n < N && k0 + kk < k_hi) ? bp[(int64_t)kk * N] : 0.f;
+        }
+#pragma unroll
+        for (int qq = 0; qq < KC / 4; ++qq) {
+          if (qq < qper) {
+            const int q = sub * qper + qq;
+            uint4 h, l;
+            split4(make_float4(v[4 * qq], v[4 * qq + 1], v[4 * qq + 2], v[4 * qq + 3]), h, l);
+            *reinterpret_cast<uint4 *>(b_hi + (q * NP + n) * 4) = h;
+            *reinterpret_cast<uint4 *>(b_lo + (q * NP + n) * 4) = l;
           }
         }
-        uint4 h, l;
-        split4(make_float4(v[0], v[1], v[2], v[3]), h, l);
-        *reinterpret_cast<uint4 *>(b_hi + (q * NP + n) * 4) = h;
-        *reinterpret_cast<uint4 *>(b_lo + (q * NP + n) * 4) = l;
       }
     }
     rs::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core's async proxy
