@@ -113,8 +113,9 @@ def din_attention(rows, unit, pool, impl="fused"):
     """softmax_L(MLP([h, h-t, t])) applied to the history                               reference model/din.py:39-47.
     rows (B, L+1, D): gathered history rows followed by the target row; unit = Sequential(Linear, ReLU, Linear, ReLU,
     Linear).  pool=True -> (B, D) weighted sum; pool=False -> (B, L, D) scaled history (model/dien.py:33-37).
-    impl "fused" (default): the single-kernel fp32 version; "tc": the same unit as tcgen05 3xTF32 GEMMs over all
-    B*L rows (parity-tested; its un-pipelined GEMM kernels are not yet faster than the fused kernel)."""
+    impl "fused" (default): rs_din_fwd / rs_din_bwd -- for B*L >= 8192 rows the tcgen05 kernels of din_tc.cu (both hidden
+    layers fused per 128-row tile, 3xTF32), otherwise the CUDA-core kernel pair; "tc": the same unit written as separate
+    rs_gemm_nt_3xtf32 / rs_gemm_tn_3xtf32 calls per layer (kept as a parity cross-check; slower, intermediates in HBM)."""
     l0, l1, l2 = unit[0], unit[2], unit[4]
     fn = _DINAttentionTC if impl == "tc" else _DINAttention
     return fn.apply(rows.contiguous(), pool, l0.weight, l0.bias, l1.weight, l1.bias, l2.weight, l2.bias)
