@@ -9,6 +9,11 @@
 // host adds in warp order -> deterministic.
 #include "common.cuh"
 
+namespace rs {
+int afm_fwd_tc_try(const float *E, int64_t B, int F, int D, int A, const float *W, const float *bvec, const float *h, float *pooled,
+                   float *attw, cudaStream_t st);
+}
+
 namespace {
 
 constexpr int AW = 4;    // max warps per CTA (fewer when the per-warp shared-memory tiles are large)
@@ -641,6 +646,10 @@ RS_API int rs_afm_fwd(const float *E, int64_t B, int32_t F, int32_t D, int32_t A
   RS_CHECK_ARG(P.aw >= 1, RS_E_UNSUPPORTED, "rs_afm_fwd: F=%d D=%d A=%d do not fit in shared memory", F, D, A);
   const size_t smem = smem_bytes(P, false, P.aw);
   RS_CUDA(cudaFuncSetAttribute(afm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {  // large batches: the projection on the tensor cores (afm_tc.cu); same outputs
+    int rc3 = rs::afm_fwd_tc_try(E, B, F, D, A, W, bvec, h, pooled, attw, (cudaStream_t)stream);
+    if (rc3 != 1) return rc3;
+  }
   {
     int rc2 = try_reg(P, false, grid_for(P, P.aw), (cudaStream_t)stream);
     if (rc2 != 1) return rc2;

@@ -350,6 +350,47 @@ def test_afm_pool_fwd_bwd(F, D, A, B):
     assert torch.equal(dE, dE2) and torch.equal(dW, dW2)            # deterministic
 
 
+@pytest.mark.parametrize("F,D,A,B", [(39, 32, 64, 700), (17, 16, 32, 1500), (20, 32, 128, 333)])
+def test_afm_forward_tensor_cores(F, D, A, B):
+    """batches of >= 2 x SMs samples take the tcgen05 projection (afm_tc.cu): same outputs as the CUDA-core kernel
+    (forced with RS_AFM_NO_TC) and as the oracle; the unchanged backward consumes its attention weights."""
+    import os
+    ops = _ops()
+    g = torch.Generator().manual_seed(F + B)
+    E = (torch.randn(B, F, D, generator=g) * 0.5).requires_grad_(True)
+    W = (torch.randn(D, A, generator=g) * 0.3).requires_grad_(True)
+    b = torch.randn(A, generator=g).requires_grad_(True)
+    h = torch.randn(A, 1, generator=g).requires_grad_(True)
+    gp = torch.randn(B, D, generator=g)
+    want = OI.afm_pool(E, W, b, h)
+    gE, gW, gb, gh = torch.autograd.grad((want * gp).sum(), [E, W, b, h])
+    cu = [t.detach().cuda() for t in (E, W, b, h)]
+    pooled, attw = ops.afm_fwd(*cu)
+    os.environ["RS_AFM_NO_TC"] = "1"
+    try:
+        pooled_cc, attw_cc = ops.afm_fwd(*cu)
+    finally:
+        del os.environ["RS_AFM_NO_TC"]
+    assert not torch.equal(attw, attw_cc)           # two different kernels really ran
+    close(attw, attw_cc.cpu(), rtol=1e-5, atol=1e-5 * float(attw_cc.max()))
+    close(pooled, pooled_cc.cpu(), rtol=1e-5, atol=1e-5 * float(pooled_cc.abs().max()))
+    close(pooled, want.detach(), rtol=1e-5, atol=max(1e-6, 1e-5 * float(want.detach().abs().max())))
+    assert abs(float(attw.sum(1).mean()) - 1.0) < 1e-5
+    pooled2, attw2 = ops.afm_fwd(*cu)
+    assert torch.equal(pooled, pooled2) and torch.equal(attw, attw2)
+    no_w, _ = ops.afm_fwd(*cu, want_attw=False)
+    assert torch.equal(no_w, pooled)
+    dE, dW, db, dh = ops.afm_bwd(*cu, attw, gp.cuda())
+    # B*P*A = tens of millions of ReLU inputs: a few sit within rounding of zero and may fall on either side in two fp32
+    # evaluations, which moves the gradient of the two embeddings of that pair by a finite amount (see the DIN test)
+    err = (dE.cpu() - gE).abs()
+    bad = int((err > 1e-5 * gE.abs() + 2e-5 * float(gE.abs().max())).flatten(1).any(dim=1).sum())
+    assert bad <= 3 + B // 200, f"{bad} samples differ"
+    assert float(err.max()) <= 5e-2 * float(gE.abs().max())
+    for got, ref in ((dW, gW), (db, gb), (dh, gh.view(-1))):
+        assert float((got.cpu() - ref).norm()) <= 1e-3 * float(ref.norm())
+
+
 # ------------------------------------------------------------------ GRU recurrence
 @pytest.mark.parametrize("H,B,L", [(16, 50, 7), (64, 33, 100), (8, 17, 3), (32, 16, 20)])
 def test_gru_recurrence_fwd_bwd(H, B, L):
