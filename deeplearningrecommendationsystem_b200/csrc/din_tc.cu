@@ -281,9 +281,16 @@ __global__ void __launch_bounds__(256) din_softmax_pool_kernel(const float *__re
     const float *h = rows + b * (int64_t)(L + 1) * D;
     if (pool) {
       for (int d = lane; d < D; d += 32) {
-        float acc = 0.f;
-        for (int l = 0; l < L; ++l) acc = fmaf(w[l], h[(int64_t)l * D + d], acc);
-        out[b * D + d] = acc;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // four independent chains keep the (coalesced) loads in flight
+        int l = 0;
+        for (; l + 4 <= L; l += 4) {
+          a0 = fmaf(w[l + 0], h[(int64_t)(l + 0) * D + d], a0);
+          a1 = fmaf(w[l + 1], h[(int64_t)(l + 1) * D + d], a1);
+          a2 = fmaf(w[l + 2], h[(int64_t)(l + 2) * D + d], a2);
+          a3 = fmaf(w[l + 3], h[(int64_t)(l + 3) * D + d], a3);
+        }
+        for (; l < L; ++l) a0 = fmaf(w[l], h[(int64_t)l * D + d], a0);
+        out[b * D + d] = (a0 + a1) + (a2 + a3);
       }
     } else {
       float *o = out + b * (int64_t)L * D;
@@ -304,17 +311,23 @@ __global__ void __launch_bounds__(256) din_dscore_kernel(const float *__restrict
     const float *h = rows + b * (int64_t)(L + 1) * D;
     const float *w = attw + b * L;
     float *o = ds + b * L;
+    // lane <-> history slot: dw_l = <g, h_l> from 16-byte loads (D / 4 independent loads per slot), no shuffles
     float tsum = 0.f;
-    for (int l = 0; l < L; ++l) {
+    for (int l = lane; l < L; l += 32) {
       const float *g = pool ? g_out + b * D : g_out + (b * L + l) * (int64_t)D;
-      float part = 0.f;
-      for (int d = lane; d < D; d += 32) part = fmaf(g[d], h[(int64_t)l * D + d], part);
-      part = rs::warp_sum(part);                       // dw_l = <g, h_l>
-      tsum = fmaf(w[l], part, tsum);
-      if (lane == 0) o[l] = part;
+      const float *hl = h + (int64_t)l * D;
+      float p0 = 0.f, p1 = 0.f;
+      for (int q = 0; q + 8 <= D; q += 8) {
+        p0 += rs::f4_dot(rs::ldg_f4(g + q), rs::ldg_nc_f4(hl + q));
+        p1 += rs::f4_dot(rs::ldg_f4(g + q + 4), rs::ldg_nc_f4(hl + q + 4));
+      }
+      if (D & 4) p0 += rs::f4_dot(rs::ldg_f4(g + (D & ~7)), rs::ldg_nc_f4(hl + (D & ~7)));
+      const float dw = p0 + p1;
+      o[l] = dw;
+      tsum = fmaf(w[l], dw, tsum);
     }
-    __syncwarp();
-    for (int l = lane; l < L; l += 32) o[l] = w[l] * (o[l] - tsum);
+    tsum = rs::warp_sum(tsum);
+    for (int l = lane; l < L; l += 32) o[l] = w[l] * (o[l] - tsum);   // each lane re-reads only what it wrote
   }
 }
 
