@@ -101,6 +101,8 @@ SIGNATURES = {
     "rs_afm_num_parts": [_L, _I, _I, _I, _PP(_I)],
     "rs_afm_fwd": [_P, _L, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "rs_afm_bwd": [_P, _L, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P],
+    "rs_afm_bwd_tc_plan": [_L, _I, _I, _I, _PP(_I), _PP(_Z)],
+    "rs_afm_bwd_tc": [_P, _L, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _Z, _P],
     "rs_din_num_parts": [_L, _PP(_I)],
     "rs_din_fwd": [_P, _L, _I, _I, _PP(rs_din_weights), _I, _P, _P, _P],
     "rs_din_fwd_tc_ws_bytes": [_L, _I, _I, _I, _I, _PP(_Z)],

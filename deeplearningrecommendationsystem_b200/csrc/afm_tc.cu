@@ -232,6 +232,441 @@ __global__ void __launch_bounds__(NTH, 1) afm_fwd_tc_kernel(const __grid_constan
   if (warp == 0) tmem_free(tmem_base_s, P.tmem_cols);
 }
 
+// ---------------------------------------------------------------------------------------------------- backward
+// Three kernels, each with one simple data flow (workspace: ds (B, P), ReLU masks (B, P, A/32) bits, dP (B, P, D)):
+//   afm_bwd_chain_tc_kernel   ds = softmax backward;  z = P W + b (MMA) -> mask;  dz = ds h [z > 0];  dP = dz W^T (MMA) + w g
+//   afm_dw_tc_kernel          U[d][a] = sum over all pairs of P[.][d] * (ds [z > 0])[.][a]  -- a GEMM whose K runs over the
+//                             pairs, so both operands are built K(=pair)-major by "column owner" threads straight from
+//                             E, ds and the mask bits; the accumulator lives in TMEM for the whole kernel.  Also
+//                             m1[a] = sum ds [z > 0].  Then  dW = U * h,  db = h * m1,  dh[a] = sum_d W[d][a] U[d][a] + b[a] m1[a].
+//   afm_de_kernel             dE_i += dP_p * e_j, dE_j += dP_p * e_i  (CUDA cores, lane = coordinate d, pairs in order)
+struct AfmTcBwdParams {
+  const float *E, *W, *bvec, *h, *attw, *g;
+  float *ds;          // (B, NP)
+  uint32_t *mask;     // (B, NP, A / 32)
+  float *dP;          // (B, NP, D)
+  float *U_part;      // (parts, D, A)
+  float *m1_part;     // (parts, A)
+  float *dE;          // (B, F, D)
+  int64_t B;
+  int F, D, A, NP, tmem_cols;
+};
+
+__global__ void __launch_bounds__(NTH, 1) afm_bwd_chain_tc_kernel(const __grid_constant__ AfmTcBwdParams P) {
+  extern __shared__ __align__(128) uint32_t sm[];
+  __shared__ uint64_t bar[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float red[2][4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = threadIdx.x >> 7, tid = threadIdx.x & (MT - 1), w4 = warp & 3;
+  const int F = P.F, D = P.D, A = P.A, NP = P.NP, AW = A / 32;
+  const int DP = D + 4, nt = (NP + MT - 1) / MT;
+  uint32_t *wh = sm, *wl = wh + A * D;                     // z GEMM:  N = A rows, K = D
+  uint32_t *vh = wl + A * D, *vl = vh + A * D;             // dP GEMM: N = D rows, K = A
+  float *bs = reinterpret_cast<float *>(vl + A * D), *hs = bs + A;
+  uint16_t *pair = reinterpret_cast<uint16_t *>(hs + A);
+  uint32_t *gbase = reinterpret_cast<uint32_t *>(pair) + ((NP + 1) / 2 + 3) / 4 * 4;
+  const int ewords = (2 * F * DP + 3) / 4 * 4;
+  const int per_group = 2 * D * MT + 2 * KC * MT + ewords + 2 * nt * MT + 64;
+  uint32_t *mine = gbase + (size_t)grp * per_group;
+  uint32_t *opP = mine, *opZ = opP + 2 * D * MT;           // [hi | lo] operand tiles
+  float *Es = reinterpret_cast<float *>(opZ + 2 * KC * MT);
+  float *ds_s = Es + ewords, *w_s = ds_s + nt * MT, *g_s = w_s + nt * MT;
+  if (warp == 0) tmem_alloc(&tmem_base_s, P.tmem_cols);
+  if (threadIdx.x == 0) {
+    rs::mbar_init(&bar[0], 1);
+    rs::mbar_init(&bar[1], 1);
+    rs::mbar_fence_init();
+  }
+  for (int e = threadIdx.x; e < A * D; e += NTH) {
+    const int d = e / A, a = e - d * A;                    // W is (D, A)
+    const float x = P.W[e];
+    const uint32_t hh = to_tf32(x), ll = to_tf32(x - __uint_as_float(hh));
+    wh[tile_off(A, a, d)] = hh, wl[tile_off(A, a, d)] = ll;
+    vh[tile_off(D, d, a)] = hh, vl[tile_off(D, d, a)] = ll;
+  }
+  for (int e = threadIdx.x; e < A; e += NTH) bs[e] = P.bvec[e], hs[e] = P.h[e];
+  for (int p = threadIdx.x; p < NP; p += NTH) {
+    int i, j;
+    pair_of(F, p, i, j);
+    pair[p] = (uint16_t)((i << 8) | j);
+  }
+  rs::fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base_s + (uint32_t)grp * (uint32_t)(P.tmem_cols / 2);
+  const uint32_t idescZ = idesc_tf32(A), idescP = idesc_tf32(D);
+  const uint32_t lbo_a = MT * 16, lbo_w = (uint32_t)A * 16, lbo_v = (uint32_t)D * 16, sbo = 128;
+  const int64_t first = (int64_t)blockIdx.x * 2 + grp, step = (int64_t)gridDim.x * 2;
+  const int pieces = F * D / 4;
+  auto fetch = [&](int64_t b, int which) {
+    const float *src = P.E + b * (int64_t)F * D;
+    float *dst = Es + (size_t)which * F * DP;
+    for (int e = tid; e < pieces; e += MT) {
+      const int f = e / (D / 4), q = e - f * (D / 4);
+      rs::cp_async16(dst + f * DP + 4 * q, src + 4 * e);
+    }
+    rs::cp_async_commit();
+  };
+  uint32_t cnt = 0;   // commits on bar[grp]; every commit is waited before the next one is issued
+  int which = 0;
+  if (first < P.B) fetch(first, 0);
+  for (int64_t b = first; b < P.B; b += step, which ^= 1) {
+    if (b + step < P.B) {
+      fetch(b + step, which ^ 1);
+      rs::cp_async_wait<1>();
+    } else {
+      rs::cp_async_wait<0>();
+    }
+    for (int p = tid; p < nt * MT; p += MT) w_s[p] = p < NP ? P.attw[b * NP + p] : 0.f;
+    if (tid < D) g_s[tid] = P.g[b * D + tid];
+    group_sync(grp);
+    const float *Eb = Es + (size_t)which * F * DP;
+    // ---- softmax backward: dw_p = <g, P_p>,  ds_p = w_p (dw_p - sum_q w_q dw_q)
+    float tsum = 0.f;
+    for (int p = tid; p < NP; p += MT) {
+      const int ij = pair[p];
+      const float *ei = Eb + (ij >> 8) * DP, *ej = Eb + (ij & 255) * DP;
+      float dw = 0.f;
+      for (int q = 0; q < D / 4; ++q)
+        dw += rs::f4_dot(rs::f4_mul(*reinterpret_cast<const float4 *>(ei + 4 * q), *reinterpret_cast<const float4 *>(ej + 4 * q)),
+                         *reinterpret_cast<const float4 *>(g_s + 4 * q));
+      ds_s[p] = dw;
+      tsum = fmaf(w_s[p], dw, tsum);
+    }
+    tsum = rs::warp_sum(tsum);
+    if (lane == 0) red[grp][w4] = tsum;
+    group_sync(grp);
+    tsum = (red[grp][0] + red[grp][1]) + (red[grp][2] + red[grp][3]);
+    for (int p = tid; p < nt * MT; p += MT) {
+      const float v = p < NP ? w_s[p] * (ds_s[p] - tsum) : 0.f;
+      ds_s[p] = v;
+      if (p < NP) P.ds[b * NP + p] = v;
+    }
+    group_sync(grp);
+    for (int t = 0; t < nt; ++t) {
+      const int p = t * MT + tid;
+      const bool ok = p < NP;
+      const int ij = ok ? pair[p] : 0;
+      const float *ei = Eb + (ij >> 8) * DP, *ej = Eb + (ij & 255) * DP;
+      // ---- z = P W: pair products straight into the A operand
+      for (int q = 0; q < D / 4; ++q) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) x = rs::f4_mul(*reinterpret_cast<const float4 *>(ei + 4 * q), *reinterpret_cast<const float4 *>(ej + 4 * q));
+        uint4 hh, ll;
+        split4(x, hh, ll);
+        *reinterpret_cast<uint4 *>(opP + (q * MT + tid) * 4) = hh;
+        *reinterpret_cast<uint4 *>(opP + D * MT + (q * MT + tid) * 4) = ll;
+      }
+      rs::fence_proxy_async();
+      fence_before_sync();
+      group_sync(grp);
+      if (tid == 0) {
+        fence_after_sync();
+        for (int s = 0; s < D / 8; ++s) {
+          const uint64_t dah = smem_desc(rs::smem_u32(opP) + s * 2 * lbo_a, lbo_a, sbo);
+          const uint64_t dal = smem_desc(rs::smem_u32(opP + D * MT) + s * 2 * lbo_a, lbo_a, sbo);
+          const uint64_t dbh = smem_desc(rs::smem_u32(wh) + (uint32_t)(s * 2) * lbo_w, lbo_w, sbo);
+          const uint64_t dbl = smem_desc(rs::smem_u32(wl) + (uint32_t)(s * 2) * lbo_w, lbo_w, sbo);
+          mma_tf32(tmem, dal, dbh, idescZ, s == 0 ? 0u : 1u);
+          mma_tf32(tmem, dah, dbl, idescZ, 1u);
+          mma_tf32(tmem, dah, dbh, idescZ, 1u);
+        }
+        commit(&bar[grp]);
+      }
+      __syncwarp();
+      ++cnt;
+      rs::mbar_wait(&bar[grp], (cnt - 1) & 1u);
+      fence_after_sync();
+      // ---- dz = ds h [z > 0], 32 columns at a time = one K chunk of dP = dz W^T
+      const float dsp = ds_s[p];
+      for (int c = 0; c < AW; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem, warp, c * 32, v);
+        uint32_t bits = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 b4 = *reinterpret_cast<const float4 *>(bs + c * 32 + 4 * q), h4 = *reinterpret_cast<const float4 *>(hs + c * 32 + 4 * q);
+          float4 x;
+          const bool m0 = __uint_as_float(v[4 * q + 0]) + b4.x > 0.f, m1 = __uint_as_float(v[4 * q + 1]) + b4.y > 0.f;
+          const bool m2 = __uint_as_float(v[4 * q + 2]) + b4.z > 0.f, m3 = __uint_as_float(v[4 * q + 3]) + b4.w > 0.f;
+          bits |= (m0 ? 1u : 0u) << (4 * q) | (m1 ? 1u : 0u) << (4 * q + 1) | (m2 ? 1u : 0u) << (4 * q + 2) | (m3 ? 1u : 0u) << (4 * q + 3);
+          x.x = m0 ? dsp * h4.x : 0.f, x.y = m1 ? dsp * h4.y : 0.f, x.z = m2 ? dsp * h4.z : 0.f, x.w = m3 ? dsp * h4.w : 0.f;
+          uint4 hh, ll;
+          split4(x, hh, ll);
+          *reinterpret_cast<uint4 *>(opZ + (q * MT + tid) * 4) = hh;
+          *reinterpret_cast<uint4 *>(opZ + KC * MT + (q * MT + tid) * 4) = ll;
+        }
+        if (ok) P.mask[(b * NP + p) * AW + c] = bits;
+        rs::fence_proxy_async();
+        fence_before_sync();
+        group_sync(grp);
+        if (tid == 0) {
+          fence_after_sync();
+#pragma unroll
+          for (int s = 0; s < KC / 8; ++s) {
+            const uint32_t kb = (uint32_t)(c * (KC / 4) + s * 2);
+            const uint64_t dah = smem_desc(rs::smem_u32(opZ) + s * 2 * lbo_a, lbo_a, sbo);
+            const uint64_t dal = smem_desc(rs::smem_u32(opZ + KC * MT) + s * 2 * lbo_a, lbo_a, sbo);
+            const uint64_t dbh = smem_desc(rs::smem_u32(vh) + kb * lbo_v, lbo_v, sbo);
+            const uint64_t dbl = smem_desc(rs::smem_u32(vl) + kb * lbo_v, lbo_v, sbo);
+            mma_tf32(tmem + (uint32_t)A, dal, dbh, idescP, (c == 0 && s == 0) ? 0u : 1u);
+            mma_tf32(tmem + (uint32_t)A, dah, dbl, idescP, 1u);
+            mma_tf32(tmem + (uint32_t)A, dah, dbh, idescP, 1u);
+          }
+          commit(&bar[grp]);
+        }
+        __syncwarp();
+        ++cnt;
+        rs::mbar_wait(&bar[grp], (cnt - 1) & 1u);   // opZ is single-buffered: these MMAs must have read it
+        fence_after_sync();
+      }
+      // ---- dP_p = dz_p W^T + w_p g  -> workspace
+      {
+        uint32_t v[32];
+        tmem_ld32(tmem, warp, A, v);
+        if (ok) {
+          const float wp = w_s[p];
+          float *dst = P.dP + (b * NP + p) * (int64_t)D;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (4 * q < D) {
+              const float4 g4 = *reinterpret_cast<const float4 *>(g_s + 4 * q);
+              rs::stg_cs_f4(dst + 4 * q, make_float4(fmaf(wp, g4.x, __uint_as_float(v[4 * q + 0])), fmaf(wp, g4.y, __uint_as_float(v[4 * q + 1])),
+                                                     fmaf(wp, g4.z, __uint_as_float(v[4 * q + 2])), fmaf(wp, g4.w, __uint_as_float(v[4 * q + 3]))));
+            }
+          }
+        }
+      }
+      fence_before_sync();
+      group_sync(grp);   // accumulators drained before the next tile's MMAs
+      fence_after_sync();
+    }
+  }
+  __syncthreads();
+  if (warp == 0) tmem_free(tmem_base_s, P.tmem_cols);
+}
+
+// dE from the dP workspace: warp per sample, lane = coordinate d, pairs in order (deterministic, no atomics)
+__global__ void __launch_bounds__(256) afm_de_kernel(const __grid_constant__ AfmTcBwdParams P) {
+  extern __shared__ __align__(16) float smf[];
+  const int F = P.F, D = P.D, NP = P.NP;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  uint16_t *pair = reinterpret_cast<uint16_t *>(smf);
+  float *base = smf + ((NP + 1) / 2 + 3) / 4 * 4;
+  float *Ew = base + (size_t)warp * 2 * F * D, *dEw = Ew + F * D;
+  for (int p = threadIdx.x; p < NP; p += blockDim.x) {
+    int i, j;
+    pair_of(F, p, i, j);
+    pair[p] = (uint16_t)((i << 8) | j);
+  }
+  __syncthreads();
+  for (int64_t b = (int64_t)blockIdx.x * nw + warp; b < P.B; b += (int64_t)gridDim.x * nw) {
+    for (int e = lane; e < F * D; e += 32) Ew[e] = P.E[b * (int64_t)F * D + e], dEw[e] = 0.f;
+    __syncwarp();
+    const float *dp = P.dP + b * (int64_t)NP * D;
+    for (int d = lane; d < D; d += 32) {
+      int cur_i = 0;
+      float acc_i = 0.f;
+      for (int p0 = 0; p0 < NP; p0 += 4) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = p0 + u < NP ? dp[(int64_t)(p0 + u) * D + d] : 0.f;   // four loads in flight
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (p0 + u < NP) {
+            const int ij = pair[p0 + u], i = ij >> 8, j = ij & 255;
+            if (i != cur_i) {
+              dEw[cur_i * D + d] += acc_i;
+              acc_i = 0.f;
+              cur_i = i;
+            }
+            acc_i = fmaf(v[u], Ew[j * D + d], acc_i);
+            dEw[j * D + d] = fmaf(v[u], Ew[i * D + d], dEw[j * D + d]);
+          }
+        }
+      }
+      dEw[cur_i * D + d] += acc_i;
+    }
+    __syncwarp();
+    for (int e = lane; e < F * D; e += 32) P.dE[b * (int64_t)F * D + e] = dEw[e];
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(NTH, 1) afm_dw_tc_kernel(const __grid_constant__ AfmTcBwdParams P) {
+  extern __shared__ __align__(128) uint32_t sm[];
+  __shared__ uint64_t bar[2][2];
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5;
+  const int grp = threadIdx.x >> 7, tid = threadIdx.x & (MT - 1);
+  const int F = P.F, D = P.D, A = P.A, NP = P.NP, AW = A / 32;
+  const int DP = D + 4, nt = (NP + MT - 1) / MT, rows_pad = nt * MT;
+  uint16_t *pair = reinterpret_cast<uint16_t *>(sm);
+  uint32_t *gbase = sm + ((NP + 1) / 2 + 3) / 4 * 4;
+  const int ewords = (2 * F * DP + 3) / 4 * 4;
+  const int opA_words = 2 * KC * MT, opB_words = 2 * KC * D;                 // hi | lo of one 32-pair chunk
+  const int per_group = 2 * opA_words + 2 * opB_words + ewords + 2 * rows_pad + rows_pad * AW + MT;
+  uint32_t *mine = gbase + (size_t)grp * per_group;
+  uint32_t *opA = mine, *opB = opA + 2 * opA_words;
+  float *Es = reinterpret_cast<float *>(opB + 2 * opB_words);
+  uint32_t *dsh_s = reinterpret_cast<uint32_t *>(Es + ewords), *dsl_s = dsh_s + rows_pad;
+  uint32_t *mask_s = dsl_s + rows_pad;
+  float *m1_s = reinterpret_cast<float *>(mask_s + rows_pad * AW);
+  if (warp == 0) tmem_alloc(&tmem_base_s, P.tmem_cols);
+  if (threadIdx.x == 0) {
+    for (int x = 0; x < 2; ++x)
+      for (int y = 0; y < 2; ++y) rs::mbar_init(&bar[x][y], 1);
+    rs::mbar_fence_init();
+  }
+  for (int p = threadIdx.x; p < NP; p += NTH) {
+    int i, j;
+    pair_of(F, p, i, j);
+    pair[p] = (uint16_t)((i << 8) | j);
+  }
+  for (int e = tid; e < 2 * opA_words; e += MT) opA[e] = 0u;   // operand rows a >= A stay zero for the whole kernel
+  rs::fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base_s + (uint32_t)grp * (uint32_t)(P.tmem_cols / 2);
+  const uint32_t idesc = idesc_tf32(D);
+  const uint32_t lbo_a = MT * 16, lbo_b = (uint32_t)D * 16, sbo = 128;
+  const int64_t first = (int64_t)blockIdx.x * 2 + grp, step = (int64_t)gridDim.x * 2;
+  const int pieces = F * D / 4;
+  auto fetch = [&](int64_t b, int which) {
+    const float *src = P.E + b * (int64_t)F * D;
+    float *dst = Es + (size_t)which * F * DP;
+    for (int e = tid; e < pieces; e += MT) {
+      const int f = e / (D / 4), q = e - f * (D / 4);
+      rs::cp_async16(dst + f * DP + 4 * q, src + 4 * e);
+    }
+    rs::cp_async_commit();
+  };
+  // column-owner roles: A operand (u^T): column a, row groups [ja0, ja0 + jan);  B operand (P^T): coordinate d
+  const int a_col = tid % A, a_sub = tid / A, a_nsub = MT / A;     // A in {32, 64, 128}
+  const int jan = 8 / a_nsub, ja0 = a_sub * jan;
+  const int b_col = tid % D, b_sub = tid / D, b_nsub = MT / D;     // D in {16, 32}
+  const int jbn = 8 / b_nsub, jb0 = b_sub * jbn;
+  float m1 = 0.f;
+  uint32_t cnt[2] = {0, 0}, it = 0;
+  int which = 0;
+  if (first < P.B) fetch(first, 0);
+  for (int64_t b = first; b < P.B; b += step, which ^= 1) {
+    if (b + step < P.B) {
+      fetch(b + step, which ^ 1);
+      rs::cp_async_wait<1>();
+    } else {
+      rs::cp_async_wait<0>();
+    }
+    for (int p = tid; p < rows_pad; p += MT) {
+      const float v = p < NP ? P.ds[b * NP + p] : 0.f;
+      const uint32_t hh = to_tf32(v);
+      dsh_s[p] = hh;
+      dsl_s[p] = to_tf32(v - __uint_as_float(hh));
+    }
+    for (int e = tid; e < rows_pad * AW; e += MT) mask_s[e] = e < NP * AW ? P.mask[b * (int64_t)NP * AW + e] : 0u;
+    group_sync(grp);
+    const float *Eb = Es + (size_t)which * F * DP;
+    for (int ck = 0; ck < nt * 4; ++ck, ++it) {      // 32 pairs per chunk
+      const int ub = it & 1, r0 = ck * KC;
+      uint32_t *ah = opA + (size_t)ub * opA_words, *al = ah + KC * MT;
+      uint32_t *bh = opB + (size_t)ub * opB_words, *bl = bh + KC * D;
+      if (cnt[ub] > 0) rs::mbar_wait(&bar[grp][ub], (cnt[ub] - 1) & 1u);   // the MMAs that read this buffer pair are done
+      for (int jj = 0; jj < jan; ++jj) {
+        const int j = ja0 + jj, r = r0 + 4 * j;
+        uint32_t hv[4], lv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const bool on = (mask_s[(r + i) * AW + (a_col >> 5)] >> (a_col & 31)) & 1u;
+          hv[i] = on ? dsh_s[r + i] : 0u;
+          lv[i] = on ? dsl_s[r + i] : 0u;
+          m1 += __uint_as_float(hv[i]) + __uint_as_float(lv[i]);
+        }
+        *reinterpret_cast<uint4 *>(ah + (j * MT + a_col) * 4) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
+        *reinterpret_cast<uint4 *>(al + (j * MT + a_col) * 4) = make_uint4(lv[0], lv[1], lv[2], lv[3]);
+      }
+      for (int jj = 0; jj < jbn; ++jj) {
+        const int j = jb0 + jj, r = r0 + 4 * j;
+        float x[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int p = r + i;
+          const int ij = p < NP ? pair[p] : 0;
+          x[i] = p < NP ? Eb[(ij >> 8) * DP + b_col] * Eb[(ij & 255) * DP + b_col] : 0.f;
+        }
+        uint4 hh, ll;
+        split4(make_float4(x[0], x[1], x[2], x[3]), hh, ll);
+        *reinterpret_cast<uint4 *>(bh + (j * D + b_col) * 4) = hh;
+        *reinterpret_cast<uint4 *>(bl + (j * D + b_col) * 4) = ll;
+      }
+      rs::fence_proxy_async();
+      group_sync(grp);
+      if (tid == 0) {
+        fence_after_sync();
+#pragma unroll
+        for (int s = 0; s < KC / 8; ++s) {
+          const uint64_t dah = smem_desc(rs::smem_u32(ah) + s * 2 * lbo_a, lbo_a, sbo);
+          const uint64_t dal = smem_desc(rs::smem_u32(al) + s * 2 * lbo_a, lbo_a, sbo);
+          const uint64_t dbh = smem_desc(rs::smem_u32(bh) + s * 2 * lbo_b, lbo_b, sbo);
+          const uint64_t dbl = smem_desc(rs::smem_u32(bl) + s * 2 * lbo_b, lbo_b, sbo);
+          mma_tf32(tmem, dal, dbh, idesc, (it == 0 && s == 0) ? 0u : 1u);
+          mma_tf32(tmem, dah, dbl, idesc, 1u);
+          mma_tf32(tmem, dah, dbh, idesc, 1u);
+        }
+        commit(&bar[grp][ub]);
+      }
+      __syncwarp();
+      cnt[ub]++;
+    }
+    group_sync(grp);   // ds / mask / E of this sample are no longer read by this group's threads
+  }
+  // ---- drain: U[d][a] (accumulator lane = a, column = d) and m1[a] -> this group's partial
+  for (int ub = 0; ub < 2; ++ub)
+    if (cnt[ub] > 0) rs::mbar_wait(&bar[grp][ub], (cnt[ub] - 1) & 1u);
+  fence_after_sync();
+  const int part = blockIdx.x * 2 + grp;
+  m1_s[tid] = m1;
+  group_sync(grp);
+  {
+    uint32_t v[32];
+    if (it > 0) {
+      tmem_ld32(tmem, warp, 0, v);
+    } else {
+#pragma unroll
+      for (int d = 0; d < 32; ++d) v[d] = 0u;
+    }
+    if (tid < A) {
+      for (int d = 0; d < D; ++d) P.U_part[((int64_t)part * D + d) * A + tid] = __uint_as_float(v[d]);
+      float tot = 0.f;
+      for (int s2 = 0; s2 < a_nsub; ++s2) tot += m1_s[s2 * A + tid];
+      P.m1_part[(int64_t)part * A + tid] = tot;
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_free(tmem_base_s, P.tmem_cols);
+}
+
+size_t afm_chain_smem(int F, int D, int A, int NP) {
+  const int DP = D + 4, nt = (NP + MT - 1) / MT;
+  size_t words = (size_t)4 * A * D + 2 * A + ((NP + 1) / 2 + 3) / 4 * 4;
+  words += (size_t)2 * (2 * D * MT + 2 * KC * MT + (2 * F * DP + 3) / 4 * 4 + 2 * nt * MT + 64);
+  return words * 4;
+}
+size_t afm_dw_smem(int F, int D, int A, int NP) {
+  const int DP = D + 4, nt = (NP + MT - 1) / MT, rows_pad = nt * MT;
+  size_t words = ((NP + 1) / 2 + 3) / 4 * 4;
+  words += (size_t)2 * (2 * 2 * KC * MT + 2 * 2 * KC * D + (2 * F * DP + 3) / 4 * 4 + 2 * rows_pad + rows_pad * (A / 32) + MT);
+  return words * 4;
+}
+size_t ws_region(size_t bytes) { return (bytes + 255) / 256 * 256; }
+bool afm_tc_shape_ok(int64_t B, int F, int D, int A) {
+  const int NP = F * (F - 1) / 2;
+  return (D == 16 || D == 32) && (A == 32 || A == 64 || A == 128) && F >= 2 && F <= 255 && NP >= MT && B >= 2 * rs::num_sms();
+}
+
 size_t afm_tc_smem(int F, int D, int A, int NP) {
   const int DP = D + 4, nt = (NP + MT - 1) / MT;
   size_t words = (size_t)2 * A * D + 2 * A + ((NP + 1) / 2 + 3) / 4 * 4;
@@ -245,9 +680,8 @@ namespace rs {
 // RS_OK when the tensor-core forward handled the call, 1 when the shape is outside what it is built for
 int afm_fwd_tc_try(const float *E, int64_t B, int F, int D, int A, const float *W, const float *bvec, const float *h, float *pooled,
                    float *attw, cudaStream_t st) {
-  if (!(D == 16 || D == 32) || !(A == 32 || A == 64 || A == 128) || F < 2 || F > 255 || getenv("RS_AFM_NO_TC")) return 1;
+  if (!afm_tc_shape_ok(B, F, D, A) || getenv("RS_AFM_NO_TC")) return 1;   // else: too little work for persistent CTAs / a tile
   const int NP = F * (F - 1) / 2;
-  if (B < 2 * num_sms() || NP < MT) return 1;   // too little work to fill persistent CTAs / a tile
   const size_t smem = afm_tc_smem(F, D, A, NP);
   if (smem > 220 * 1024) return 1;
   AfmTcParams P = {};
@@ -263,3 +697,64 @@ int afm_fwd_tc_try(const float *E, int64_t B, int F, int D, int A, const float *
   return RS_OK;
 }
 }  // namespace rs
+
+// ---- C ABI of the tensor-core backward
+RS_API int rs_afm_bwd_tc_plan(int64_t B, int32_t F, int32_t D, int32_t A, int32_t *num_parts, size_t *ws_bytes) {
+  RS_CHECK_ARG(num_parts && ws_bytes, RS_E_ARG, "rs_afm_bwd_tc_plan: null output");
+  *num_parts = 0, *ws_bytes = 0;
+  if (!afm_tc_shape_ok(B, F, D, A) || getenv("RS_AFM_NO_TC")) return RS_OK;   // 0 parts: use rs_afm_bwd
+  const int NP = F * (F - 1) / 2;
+  if (afm_chain_smem(F, D, A, NP) > 220 * 1024 || afm_dw_smem(F, D, A, NP) > 220 * 1024) return RS_OK;
+  const int64_t pairs = (B + 1) / 2;
+  *num_parts = 2 * (int)(pairs < rs::num_sms() ? pairs : rs::num_sms());
+  *ws_bytes = ws_region((size_t)B * NP * 4) + ws_region((size_t)B * NP * 4 * (A / 32)) + ws_region((size_t)B * NP * 4 * D);
+  return RS_OK;
+}
+
+RS_API int rs_afm_bwd_tc(const float *E, int64_t B, int32_t F, int32_t D, int32_t A, const float *W, const float *bvec, const float *h,
+                         const float *attw, const float *g_pooled, float *dE, float *U_part, float *m1_part, int32_t num_parts,
+                         void *ws, size_t ws_bytes, void *stream) {
+  RS_CHECK_ARG(E && W && bvec && h && attw && g_pooled && dE && U_part && m1_part && ws, RS_E_ARG, "rs_afm_bwd_tc: null argument");
+  int32_t parts;
+  size_t need;
+  if (int rc = rs_afm_bwd_tc_plan(B, F, D, A, &parts, &need)) return rc;
+  RS_CHECK_ARG(parts > 0, RS_E_UNSUPPORTED, "rs_afm_bwd_tc: shape (B=%lld, F=%d, D=%d, A=%d) is served by rs_afm_bwd", (long long)B, F, D, A);
+  RS_CHECK_ARG(num_parts == parts, RS_E_ARG, "rs_afm_bwd_tc: num_parts %d != plan %d", num_parts, parts);
+  RS_CHECK_ARG(ws_bytes >= need, RS_E_WORKSPACE, "rs_afm_bwd_tc: workspace of %zu bytes needed, got %zu", need, ws_bytes);
+  const int NP = F * (F - 1) / 2;
+  cudaStream_t st = (cudaStream_t)stream;
+  AfmTcBwdParams P = {};
+  P.E = E, P.W = W, P.bvec = bvec, P.h = h, P.attw = attw, P.g = g_pooled, P.dE = dE, P.U_part = U_part, P.m1_part = m1_part;
+  char *wsb = static_cast<char *>(ws);
+  P.ds = reinterpret_cast<float *>(wsb);
+  P.mask = reinterpret_cast<uint32_t *>(wsb + ws_region((size_t)B * NP * 4));
+  P.dP = reinterpret_cast<float *>(wsb + ws_region((size_t)B * NP * 4) + ws_region((size_t)B * NP * 4 * (A / 32)));
+  P.B = B, P.F = F, P.D = D, P.A = A, P.NP = NP;
+  const int grid = parts / 2;
+  {
+    P.tmem_cols = 32;
+    while (P.tmem_cols < A + 32) P.tmem_cols <<= 1;
+    P.tmem_cols *= 2;
+    const size_t smem = afm_chain_smem(F, D, A, NP);
+    RS_CUDA(cudaFuncSetAttribute(afm_bwd_chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    afm_bwd_chain_tc_kernel<<<grid, NTH, smem, st>>>(P);
+    RS_CHECK_LAUNCH();
+  }
+  {
+    const int nw = 8;
+    const size_t smem = ((size_t)((NP + 1) / 2 + 3) / 4 * 4 + (size_t)nw * 2 * F * D) * 4;
+    RS_CUDA(cudaFuncSetAttribute(afm_de_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t blocks = (B + nw - 1) / nw;
+    const int64_t cap = (int64_t)rs::num_sms() * 2;
+    afm_de_kernel<<<(unsigned)(blocks < cap ? blocks : cap), nw * 32, smem, st>>>(P);
+    RS_CHECK_LAUNCH();
+  }
+  {
+    P.tmem_cols = 64;   // 32 accumulator columns per warpgroup
+    const size_t smem = afm_dw_smem(F, D, A, NP);
+    RS_CUDA(cudaFuncSetAttribute(afm_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    afm_dw_tc_kernel<<<grid, NTH, smem, st>>>(P);
+    RS_CHECK_LAUNCH();
+  }
+  return RS_OK;
+}

@@ -560,16 +560,31 @@ def afm_fwd(E, W, b, h, want_attw=True):
     return pooled, attw
 
 
-def afm_bwd(E, W, b, h, attw, g_pooled):
-    """-> dE (B,F,D), dW (D,A), db (A), dh (A)  (per-warp partials added in warp order)."""
+def afm_bwd(E, W, b, h, attw, g_pooled, impl="auto"):
+    """-> dE (B,F,D), dW (D,A), db (A), dh (A)  (per-warp partials added in warp order).
+    impl "auto": the tcgen05 kernels of afm_tc.cu when rs_afm_bwd_tc_plan accepts the shape; "cuda_cores": rs_afm_bwd."""
     E, W, b, h, g_pooled = _f32(E), _f32(W), _f32(b), _f32(h).reshape(-1), _f32(g_pooled)
     B, F, D = E.shape
     A = W.shape[1]
     lib = _lib.load()
-    parts = C.c_int32(0)
+    parts, nbytes = C.c_int32(0), C.c_size_t(0)
+    dE = torch.empty_like(E)
+    _lib.check(lib.rs_afm_bwd_tc_plan(B, F, D, A, C.byref(parts), C.byref(nbytes)), "rs_afm_bwd_tc_plan")
+    if parts.value > 0 and impl != "cuda_cores":
+        # tensor-core backward (large batches): partial sums of U = P^T (ds [z > 0]) and m1 = sum ds [z > 0]
+        n = parts.value
+        Up = torch.empty(n, D, A, dtype=torch.float32, device=E.device)
+        m1p = torch.empty(n, A, dtype=torch.float32, device=E.device)
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=E.device)
+        with _timed("afm_bwd_tc"):
+            _lib.check(lib.rs_afm_bwd_tc(E.data_ptr(), B, F, D, A, W.data_ptr(), b.data_ptr(), h.data_ptr(), attw.data_ptr(),
+                                         g_pooled.data_ptr(), dE.data_ptr(), Up.data_ptr(), m1p.data_ptr(), n, ws.data_ptr(),
+                                         nbytes.value, _stream()), "rs_afm_bwd_tc")
+        _count(3)
+        U, m1 = Up.sum(dim=0), m1p.sum(dim=0)
+        return dE, U * h, h * m1, (W * U).sum(dim=0) + b * m1
     _lib.check(lib.rs_afm_num_parts(B, F, D, A, C.byref(parts)), "rs_afm_num_parts")
     n = parts.value
-    dE = torch.empty_like(E)
     dWp = torch.empty(n, D, A, dtype=torch.float32, device=E.device)
     dbp = torch.empty(n, A, dtype=torch.float32, device=E.device)
     dhp = torch.empty(n, A, dtype=torch.float32, device=E.device)

@@ -214,6 +214,16 @@ int rs_afm_bwd(const float *E, int64_t B, int32_t F, int32_t D, int32_t A, const
                const float *h, const float *attw, const float *g_pooled, float *dE, float *dW_part, float *db_part,
                float *dh_part, int32_t num_parts, void *stream);
 
+/* Tensor-core backward of the AFM pooling (afm_tc.cu) for the shapes its forward serves (D in {16, 32}, A in {32, 64,
+ * 128}, >= 128 pairs, B >= 2 x SMs).  rs_afm_bwd_tc_plan returns num_parts == 0 when the shape is served by rs_afm_bwd
+ * instead.  dE (B, F, D) is complete; the parameter gradients come back as per-warpgroup partials U_part (parts, D, A)
+ * and m1_part (parts, A), to be added in index order:  with U = sum U_part, m1 = sum m1_part,
+ *   dW = U * h[a],   db = h * m1,   dh[a] = sum_d W[d][a] U[d][a] + b[a] m1[a]. */
+int rs_afm_bwd_tc_plan(int64_t B, int32_t F, int32_t D, int32_t A, int32_t *num_parts, size_t *ws_bytes);
+int rs_afm_bwd_tc(const float *E, int64_t B, int32_t F, int32_t D, int32_t A, const float *W, const float *bvec,
+                  const float *h, const float *attw, const float *g_pooled, float *dE, float *U_part, float *m1_part,
+                  int32_t num_parts, void *ws, size_t ws_bytes, void *stream);
+
 /* ---- DIN target attention (model/din.py:39-47; model/dien.py:27-37 with pool == 0), forward and backward.
  * rows (B, L+1, D): the L gathered history rows followed by the target row (the layout rs_gather_rows produces for
  * ids = [hist | target]).  Attention unit 3D -> H1 -> H2 -> 1 with ReLU (torch Linear layout (out, in)), softmax over

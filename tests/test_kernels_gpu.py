@@ -380,15 +380,22 @@ def test_afm_forward_tensor_cores(F, D, A, B):
     assert torch.equal(pooled, pooled2) and torch.equal(attw, attw2)
     no_w, _ = ops.afm_fwd(*cu, want_attw=False)
     assert torch.equal(no_w, pooled)
-    dE, dW, db, dh = ops.afm_bwd(*cu, attw, gp.cuda())
     # B*P*A = tens of millions of ReLU inputs: a few sit within rounding of zero and may fall on either side in two fp32
-    # evaluations, which moves the gradient of the two embeddings of that pair by a finite amount (see the DIN test)
-    err = (dE.cpu() - gE).abs()
-    bad = int((err > 1e-5 * gE.abs() + 2e-5 * float(gE.abs().max())).flatten(1).any(dim=1).sum())
-    assert bad <= 3 + B // 200, f"{bad} samples differ"
-    assert float(err.max()) <= 5e-2 * float(gE.abs().max())
-    for got, ref in ((dW, gW), (db, gb), (dh, gh.view(-1))):
-        assert float((got.cpu() - ref).norm()) <= 1e-3 * float(ref.norm())
+    # evaluations, which moves the gradient of the two embeddings of that pair by a finite amount (see the DIN test).
+    # Both backward implementations -- tcgen05 (what "auto" picks here) and CUDA cores -- against the oracle:
+    for impl in ("auto", "cuda_cores"):
+        n0 = ops.launches()
+        dE, dW, db, dh = ops.afm_bwd(*cu, attw, gp.cuda(), impl=impl)
+        assert ops.launches() - n0 == (3 if impl == "auto" else 1)          # chain + dE + dW kernels vs the single one
+        err = (dE.cpu() - gE).abs()
+        bad = int((err > 1e-5 * gE.abs() + 2e-5 * float(gE.abs().max())).flatten(1).any(dim=1).sum())
+        assert bad <= 3 + B // 200, f"{impl}: {bad} samples differ"
+        assert float(err.max()) <= 5e-2 * float(gE.abs().max()), impl
+        for got, ref, name in ((dW, gW, "dW"), (db, gb, "db"), (dh, gh.view(-1), "dh")):
+            assert got.shape == ref.shape, (impl, name)
+            assert float((got.cpu() - ref).norm()) <= 1e-3 * float(ref.norm()), (impl, name)
+        again = ops.afm_bwd(*cu, attw, gp.cuda(), impl=impl)
+        assert all(torch.equal(x, y_) for x, y_ in zip((dE, dW, db, dh), again)), f"{impl}: not deterministic"
 
 
 # ------------------------------------------------------------------ GRU recurrence
