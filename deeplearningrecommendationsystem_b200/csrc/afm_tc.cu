@@ -448,46 +448,38 @@ __global__ void __launch_bounds__(NTH, 1) afm_bwd_chain_tc_kernel(const __grid_c
   if (warp == 0) tmem_free(tmem_base_s, P.tmem_cols);
 }
 
-// dE from the dP workspace: warp per sample, lane = coordinate d, pairs in order (deterministic, no atomics)
+// dE from the dP workspace: warp per sample, lane = coordinate d; pairs are walked in their (i < j) order, so the row
+// of feature i accumulates in a register while every partner j is updated in shared memory (deterministic, no atomics)
 __global__ void __launch_bounds__(256) afm_de_kernel(const __grid_constant__ AfmTcBwdParams P) {
   extern __shared__ __align__(16) float smf[];
   const int F = P.F, D = P.D, NP = P.NP;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  uint16_t *pair = reinterpret_cast<uint16_t *>(smf);
-  float *base = smf + ((NP + 1) / 2 + 3) / 4 * 4;
-  float *Ew = base + (size_t)warp * 2 * F * D, *dEw = Ew + F * D;
-  for (int p = threadIdx.x; p < NP; p += blockDim.x) {
-    int i, j;
-    pair_of(F, p, i, j);
-    pair[p] = (uint16_t)((i << 8) | j);
-  }
-  __syncthreads();
+  float *Ew = smf + (size_t)warp * 2 * F * D, *dEw = Ew + F * D;
   for (int64_t b = (int64_t)blockIdx.x * nw + warp; b < P.B; b += (int64_t)gridDim.x * nw) {
     for (int e = lane; e < F * D; e += 32) Ew[e] = P.E[b * (int64_t)F * D + e], dEw[e] = 0.f;
     __syncwarp();
-    const float *dp = P.dP + b * (int64_t)NP * D;
-    for (int d = lane; d < D; d += 32) {
-      int cur_i = 0;
-      float acc_i = 0.f;
-      for (int p0 = 0; p0 < NP; p0 += 4) {
-        float v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = p0 + u < NP ? dp[(int64_t)(p0 + u) * D + d] : 0.f;   // four loads in flight
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (p0 + u < NP) {
-            const int ij = pair[p0 + u], i = ij >> 8, j = ij & 255;
-            if (i != cur_i) {
-              dEw[cur_i * D + d] += acc_i;
-              acc_i = 0.f;
-              cur_i = i;
-            }
-            acc_i = fmaf(v[u], Ew[j * D + d], acc_i);
-            dEw[j * D + d] = fmaf(v[u], Ew[i * D + d], dEw[j * D + d]);
-          }
+    if (lane < D) {
+      const int d = lane;
+      const float *dp = P.dP + b * (int64_t)NP * D + d;
+      for (int i = 0; i + 1 < F; ++i) {
+        const float ei = Ew[i * D + d];
+        float acc = 0.f;
+        int j = i + 1;
+        for (; j + 4 <= F; j += 4) {
+          const float v0 = dp[0], v1 = dp[D], v2 = dp[2 * D], v3 = dp[3 * D];   // four loads in flight
+          dp += 4 * D;
+          acc = fmaf(v0, Ew[(j + 0) * D + d], acc), dEw[(j + 0) * D + d] = fmaf(v0, ei, dEw[(j + 0) * D + d]);
+          acc = fmaf(v1, Ew[(j + 1) * D + d], acc), dEw[(j + 1) * D + d] = fmaf(v1, ei, dEw[(j + 1) * D + d]);
+          acc = fmaf(v2, Ew[(j + 2) * D + d], acc), dEw[(j + 2) * D + d] = fmaf(v2, ei, dEw[(j + 2) * D + d]);
+          acc = fmaf(v3, Ew[(j + 3) * D + d], acc), dEw[(j + 3) * D + d] = fmaf(v3, ei, dEw[(j + 3) * D + d]);
         }
+        for (; j < F; ++j) {
+          const float v = dp[0];
+          dp += D;
+          acc = fmaf(v, Ew[j * D + d], acc), dEw[j * D + d] = fmaf(v, ei, dEw[j * D + d]);
+        }
+        dEw[i * D + d] += acc;
       }
-      dEw[cur_i * D + d] += acc_i;
     }
     __syncwarp();
     for (int e = lane; e < F * D; e += 32) P.dE[b * (int64_t)F * D + e] = dEw[e];
@@ -495,6 +487,9 @@ __global__ void __launch_bounds__(256) afm_de_kernel(const __grid_constant__ Afm
   }
 }
 
+// U^T[a][d] = sum over pairs of mask[pair][a] * (ds[pair] P[pair][d]),  and with one extra operand column holding ds
+// itself, U^T[a][D] = m1[a].  The A operand is the 0/1 ReLU mask: exact in tf32, so it needs no lo part and each K step
+// costs two MMAs (mask x Q_lo, mask x Q_hi) instead of three.
 __global__ void __launch_bounds__(NTH, 1) afm_dw_tc_kernel(const __grid_constant__ AfmTcBwdParams P) {
   extern __shared__ __align__(128) uint32_t sm[];
   __shared__ uint64_t bar[2][2];
@@ -502,18 +497,18 @@ __global__ void __launch_bounds__(NTH, 1) afm_dw_tc_kernel(const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int grp = threadIdx.x >> 7, tid = threadIdx.x & (MT - 1);
   const int F = P.F, D = P.D, A = P.A, NP = P.NP, AW = A / 32;
+  const int ND = D + 16;                                                   // Q columns: D products, ds, zero padding
   const int DP = D + 4, nt = (NP + MT - 1) / MT, rows_pad = nt * MT;
   uint16_t *pair = reinterpret_cast<uint16_t *>(sm);
   uint32_t *gbase = sm + ((NP + 1) / 2 + 3) / 4 * 4;
   const int ewords = (2 * F * DP + 3) / 4 * 4;
-  const int opA_words = 2 * KC * MT, opB_words = 2 * KC * D;                 // hi | lo of one 32-pair chunk
-  const int per_group = 2 * opA_words + 2 * opB_words + ewords + 2 * rows_pad + rows_pad * AW + MT;
+  const int opA_words = KC * MT, opB_words = 2 * KC * ND;                  // mask (hi only); Q hi | lo
+  const int per_group = 2 * opA_words + 2 * opB_words + ewords + rows_pad + rows_pad * AW;
   uint32_t *mine = gbase + (size_t)grp * per_group;
   uint32_t *opA = mine, *opB = opA + 2 * opA_words;
   float *Es = reinterpret_cast<float *>(opB + 2 * opB_words);
-  uint32_t *dsh_s = reinterpret_cast<uint32_t *>(Es + ewords), *dsl_s = dsh_s + rows_pad;
-  uint32_t *mask_s = dsl_s + rows_pad;
-  float *m1_s = reinterpret_cast<float *>(mask_s + rows_pad * AW);
+  float *ds_s = Es + ewords;
+  uint32_t *mask_s = reinterpret_cast<uint32_t *>(ds_s + rows_pad);
   if (warp == 0) tmem_alloc(&tmem_base_s, P.tmem_cols);
   if (threadIdx.x == 0) {
     for (int x = 0; x < 2; ++x)
@@ -525,14 +520,15 @@ __global__ void __launch_bounds__(NTH, 1) afm_dw_tc_kernel(const __grid_constant
     pair_of(F, p, i, j);
     pair[p] = (uint16_t)((i << 8) | j);
   }
-  for (int e = tid; e < 2 * opA_words; e += MT) opA[e] = 0u;   // operand rows a >= A stay zero for the whole kernel
+  // operand rows that never change: mask rows a >= A, Q columns d > D
+  for (int e = tid; e < 2 * opA_words + 2 * opB_words; e += MT) opA[e] = 0u;
   rs::fence_proxy_async();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_base_s + (uint32_t)grp * (uint32_t)(P.tmem_cols / 2);
-  const uint32_t idesc = idesc_tf32(D);
-  const uint32_t lbo_a = MT * 16, lbo_b = (uint32_t)D * 16, sbo = 128;
+  const uint32_t idesc = idesc_tf32(ND);
+  const uint32_t lbo_a = MT * 16, lbo_b = (uint32_t)ND * 16, sbo = 128;
   const int64_t first = (int64_t)blockIdx.x * 2 + grp, step = (int64_t)gridDim.x * 2;
   const int pieces = F * D / 4;
   auto fetch = [&](int64_t b, int which) {
@@ -544,12 +540,11 @@ __global__ void __launch_bounds__(NTH, 1) afm_dw_tc_kernel(const __grid_constant
     }
     rs::cp_async_commit();
   };
-  // column-owner roles: A operand (u^T): column a, row groups [ja0, ja0 + jan);  B operand (P^T): coordinate d
+  // column-owner roles: A operand (mask^T): column a, row groups [ja0, ja0 + jan);  B operand (Q^T): coordinate d
   const int a_col = tid % A, a_sub = tid / A, a_nsub = MT / A;     // A in {32, 64, 128}
   const int jan = 8 / a_nsub, ja0 = a_sub * jan;
   const int b_col = tid % D, b_sub = tid / D, b_nsub = MT / D;     // D in {16, 32}
   const int jbn = 8 / b_nsub, jb0 = b_sub * jbn;
-  float m1 = 0.f;
   uint32_t cnt[2] = {0, 0}, it = 0;
   int which = 0;
   if (first < P.B) fetch(first, 0);
@@ -560,32 +555,21 @@ __global__ void __launch_bounds__(NTH, 1) afm_dw_tc_kernel(const __grid_constant
     } else {
       rs::cp_async_wait<0>();
     }
-    for (int p = tid; p < rows_pad; p += MT) {
-      const float v = p < NP ? P.ds[b * NP + p] : 0.f;
-      const uint32_t hh = to_tf32(v);
-      dsh_s[p] = hh;
-      dsl_s[p] = to_tf32(v - __uint_as_float(hh));
-    }
+    for (int p = tid; p < rows_pad; p += MT) ds_s[p] = p < NP ? P.ds[b * NP + p] : 0.f;
     for (int e = tid; e < rows_pad * AW; e += MT) mask_s[e] = e < NP * AW ? P.mask[b * (int64_t)NP * AW + e] : 0u;
     group_sync(grp);
     const float *Eb = Es + (size_t)which * F * DP;
     for (int ck = 0; ck < nt * 4; ++ck, ++it) {      // 32 pairs per chunk
       const int ub = it & 1, r0 = ck * KC;
-      uint32_t *ah = opA + (size_t)ub * opA_words, *al = ah + KC * MT;
-      uint32_t *bh = opB + (size_t)ub * opB_words, *bl = bh + KC * D;
+      uint32_t *am = opA + (size_t)ub * opA_words;
+      uint32_t *bh = opB + (size_t)ub * opB_words, *bl = bh + KC * ND;
       if (cnt[ub] > 0) rs::mbar_wait(&bar[grp][ub], (cnt[ub] - 1) & 1u);   // the MMAs that read this buffer pair are done
       for (int jj = 0; jj < jan; ++jj) {
         const int j = ja0 + jj, r = r0 + 4 * j;
-        uint32_t hv[4], lv[4];
+        uint32_t mv[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const bool on = (mask_s[(r + i) * AW + (a_col >> 5)] >> (a_col & 31)) & 1u;
-          hv[i] = on ? dsh_s[r + i] : 0u;
-          lv[i] = on ? dsl_s[r + i] : 0u;
-          m1 += __uint_as_float(hv[i]) + __uint_as_float(lv[i]);
-        }
-        *reinterpret_cast<uint4 *>(ah + (j * MT + a_col) * 4) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
-        *reinterpret_cast<uint4 *>(al + (j * MT + a_col) * 4) = make_uint4(lv[0], lv[1], lv[2], lv[3]);
+        for (int i = 0; i < 4; ++i) mv[i] = ((mask_s[(r + i) * AW + (a_col >> 5)] >> (a_col & 31)) & 1u) ? 0x3f800000u : 0u;
+        *reinterpret_cast<uint4 *>(am + (j * MT + a_col) * 4) = make_uint4(mv[0], mv[1], mv[2], mv[3]);
       }
       for (int jj = 0; jj < jbn; ++jj) {
         const int j = jb0 + jj, r = r0 + 4 * j;
@@ -594,12 +578,19 @@ __global__ void __launch_bounds__(NTH, 1) afm_dw_tc_kernel(const __grid_constant
         for (int i = 0; i < 4; ++i) {
           const int p = r + i;
           const int ij = p < NP ? pair[p] : 0;
-          x[i] = p < NP ? Eb[(ij >> 8) * DP + b_col] * Eb[(ij & 255) * DP + b_col] : 0.f;
+          x[i] = ds_s[p] * (Eb[(ij >> 8) * DP + b_col] * Eb[(ij & 255) * DP + b_col]);   // ds is 0 on padding rows
         }
         uint4 hh, ll;
         split4(make_float4(x[0], x[1], x[2], x[3]), hh, ll);
-        *reinterpret_cast<uint4 *>(bh + (j * D + b_col) * 4) = hh;
-        *reinterpret_cast<uint4 *>(bl + (j * D + b_col) * 4) = ll;
+        *reinterpret_cast<uint4 *>(bh + (j * ND + b_col) * 4) = hh;
+        *reinterpret_cast<uint4 *>(bl + (j * ND + b_col) * 4) = ll;
+      }
+      if (tid < 8) {   // column D of Q: ds itself -> m1 = mask^T ds comes out of the same accumulator
+        const int r = r0 + 4 * tid;
+        uint4 hh, ll;
+        split4(make_float4(ds_s[r], ds_s[r + 1], ds_s[r + 2], ds_s[r + 3]), hh, ll);
+        *reinterpret_cast<uint4 *>(bh + (tid * ND + D) * 4) = hh;
+        *reinterpret_cast<uint4 *>(bl + (tid * ND + D) * 4) = ll;
       }
       rs::fence_proxy_async();
       group_sync(grp);
@@ -607,13 +598,11 @@ __global__ void __launch_bounds__(NTH, 1) afm_dw_tc_kernel(const __grid_constant
         fence_after_sync();
 #pragma unroll
         for (int s = 0; s < KC / 8; ++s) {
-          const uint64_t dah = smem_desc(rs::smem_u32(ah) + s * 2 * lbo_a, lbo_a, sbo);
-          const uint64_t dal = smem_desc(rs::smem_u32(al) + s * 2 * lbo_a, lbo_a, sbo);
+          const uint64_t dam = smem_desc(rs::smem_u32(am) + s * 2 * lbo_a, lbo_a, sbo);
           const uint64_t dbh = smem_desc(rs::smem_u32(bh) + s * 2 * lbo_b, lbo_b, sbo);
           const uint64_t dbl = smem_desc(rs::smem_u32(bl) + s * 2 * lbo_b, lbo_b, sbo);
-          mma_tf32(tmem, dal, dbh, idesc, (it == 0 && s == 0) ? 0u : 1u);
-          mma_tf32(tmem, dah, dbl, idesc, 1u);
-          mma_tf32(tmem, dah, dbh, idesc, 1u);
+          mma_tf32(tmem, dam, dbl, idesc, (it == 0 && s == 0) ? 0u : 1u);
+          mma_tf32(tmem, dam, dbh, idesc, 1u);
         }
         commit(&bar[grp][ub]);
       }
@@ -622,26 +611,25 @@ __global__ void __launch_bounds__(NTH, 1) afm_dw_tc_kernel(const __grid_constant
     }
     group_sync(grp);   // ds / mask / E of this sample are no longer read by this group's threads
   }
-  // ---- drain: U[d][a] (accumulator lane = a, column = d) and m1[a] -> this group's partial
+  // ---- drain: accumulator lane = a, columns 0..D-1 = U[.][a], column D = m1[a] -> this group's partial
   for (int ub = 0; ub < 2; ++ub)
     if (cnt[ub] > 0) rs::mbar_wait(&bar[grp][ub], (cnt[ub] - 1) & 1u);
   fence_after_sync();
   const int part = blockIdx.x * 2 + grp;
-  m1_s[tid] = m1;
-  group_sync(grp);
-  {
+  for (int c0 = 0; c0 < ND; c0 += 32) {
     uint32_t v[32];
     if (it > 0) {
-      tmem_ld32(tmem, warp, 0, v);
+      tmem_ld32(tmem, warp, c0, v);
     } else {
 #pragma unroll
       for (int d = 0; d < 32; ++d) v[d] = 0u;
     }
     if (tid < A) {
-      for (int d = 0; d < D; ++d) P.U_part[((int64_t)part * D + d) * A + tid] = __uint_as_float(v[d]);
-      float tot = 0.f;
-      for (int s2 = 0; s2 < a_nsub; ++s2) tot += m1_s[s2 * A + tid];
-      P.m1_part[(int64_t)part * A + tid] = tot;
+#pragma unroll
+      for (int d = 0; d < 32; ++d) {
+        if (c0 + d < D) P.U_part[((int64_t)part * D + c0 + d) * A + tid] = __uint_as_float(v[d]);
+        if (c0 + d == D) P.m1_part[(int64_t)part * A + tid] = __uint_as_float(v[d]);
+      }
     }
   }
   fence_before_sync();
@@ -656,9 +644,9 @@ size_t afm_chain_smem(int F, int D, int A, int NP) {
   return words * 4;
 }
 size_t afm_dw_smem(int F, int D, int A, int NP) {
-  const int DP = D + 4, nt = (NP + MT - 1) / MT, rows_pad = nt * MT;
+  const int DP = D + 4, nt = (NP + MT - 1) / MT, rows_pad = nt * MT, ND = D + 16;
   size_t words = ((NP + 1) / 2 + 3) / 4 * 4;
-  words += (size_t)2 * (2 * 2 * KC * MT + 2 * 2 * KC * D + (2 * F * DP + 3) / 4 * 4 + 2 * rows_pad + rows_pad * (A / 32) + MT);
+  words += (size_t)2 * (2 * KC * MT + 2 * 2 * KC * ND + (2 * F * DP + 3) / 4 * 4 + rows_pad + rows_pad * (A / 32));
   return words * 4;
 }
 size_t ws_region(size_t bytes) { return (bytes + 255) / 256 * 256; }
@@ -742,15 +730,15 @@ RS_API int rs_afm_bwd_tc(const float *E, int64_t B, int32_t F, int32_t D, int32_
   }
   {
     const int nw = 8;
-    const size_t smem = ((size_t)((NP + 1) / 2 + 3) / 4 * 4 + (size_t)nw * 2 * F * D) * 4;
+    const size_t smem = (size_t)nw * 2 * F * D * 4;
     RS_CUDA(cudaFuncSetAttribute(afm_de_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t blocks = (B + nw - 1) / nw;
-    const int64_t cap = (int64_t)rs::num_sms() * 2;
+    const int64_t cap = (int64_t)rs::num_sms() * 4;
     afm_de_kernel<<<(unsigned)(blocks < cap ? blocks : cap), nw * 32, smem, st>>>(P);
     RS_CHECK_LAUNCH();
   }
   {
-    P.tmem_cols = 64;   // 32 accumulator columns per warpgroup
+    P.tmem_cols = 128;   // D + 16 <= 48 accumulator columns per warpgroup
     const size_t smem = afm_dw_smem(F, D, A, NP);
     RS_CUDA(cudaFuncSetAttribute(afm_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     afm_dw_tc_kernel<<<grid, NTH, smem, st>>>(P);
