@@ -16,6 +16,7 @@ namespace {
 
 using namespace rs::tc;
 constexpr int NTH = 256;
+constexpr int NG3 = 3;   // warpgroups per CTA in the backward kernels (384 threads): more latency hiding per SM
 
 struct AfmTcParams {
   const float *E, *W, *bvec, *h;
@@ -249,14 +250,14 @@ struct AfmTcBwdParams {
   float *m1_part;     // (parts, A)
   float *dE;          // (B, F, D)
   int64_t B;
-  int F, D, A, NP, tmem_cols;
+  int F, D, A, NP, tmem_cols, tmem_slot;   // tmem_slot: accumulator columns reserved per warpgroup
 };
 
-__global__ void __launch_bounds__(NTH, 1) afm_bwd_chain_tc_kernel(const __grid_constant__ AfmTcBwdParams P) {
+__global__ void __launch_bounds__(NG3 * MT, 1) afm_bwd_chain_tc_kernel(const __grid_constant__ AfmTcBwdParams P) {
   extern __shared__ __align__(128) uint32_t sm[];
-  __shared__ uint64_t bar[2];
+  __shared__ uint64_t bar[NG3];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float red[2][4];
+  __shared__ float red[NG3][4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = threadIdx.x >> 7, tid = threadIdx.x & (MT - 1), w4 = warp & 3;
   const int F = P.F, D = P.D, A = P.A, NP = P.NP, AW = A / 32;
@@ -267,26 +268,26 @@ __global__ void __launch_bounds__(NTH, 1) afm_bwd_chain_tc_kernel(const __grid_c
   uint16_t *pair = reinterpret_cast<uint16_t *>(hs + A);
   uint32_t *gbase = reinterpret_cast<uint32_t *>(pair) + ((NP + 1) / 2 + 3) / 4 * 4;
   const int ewords = (2 * F * DP + 3) / 4 * 4;
-  const int per_group = 2 * D * MT + 2 * KC * MT + ewords + 2 * nt * MT + 64;
+  const int op_words = 2 * (D > KC ? D : KC) * MT;           // the P tile and the dz chunks take turns in one buffer
+  const int per_group = op_words + ewords + 2 * nt * MT + 64;
   uint32_t *mine = gbase + (size_t)grp * per_group;
-  uint32_t *opP = mine, *opZ = opP + 2 * D * MT;           // [hi | lo] operand tiles
-  float *Es = reinterpret_cast<float *>(opZ + 2 * KC * MT);
+  uint32_t *opP = mine, *opZ = mine;                       // [hi | lo]; dz is built only after the z MMAs have read P
+  float *Es = reinterpret_cast<float *>(mine + op_words);
   float *ds_s = Es + ewords, *w_s = ds_s + nt * MT, *g_s = w_s + nt * MT;
   if (warp == 0) tmem_alloc(&tmem_base_s, P.tmem_cols);
   if (threadIdx.x == 0) {
-    rs::mbar_init(&bar[0], 1);
-    rs::mbar_init(&bar[1], 1);
+    for (int x = 0; x < NG3; ++x) rs::mbar_init(&bar[x], 1);
     rs::mbar_fence_init();
   }
-  for (int e = threadIdx.x; e < A * D; e += NTH) {
+  for (int e = threadIdx.x; e < A * D; e += NG3 * MT) {
     const int d = e / A, a = e - d * A;                    // W is (D, A)
     const float x = P.W[e];
     const uint32_t hh = to_tf32(x), ll = to_tf32(x - __uint_as_float(hh));
     wh[tile_off(A, a, d)] = hh, wl[tile_off(A, a, d)] = ll;
     vh[tile_off(D, d, a)] = hh, vl[tile_off(D, d, a)] = ll;
   }
-  for (int e = threadIdx.x; e < A; e += NTH) bs[e] = P.bvec[e], hs[e] = P.h[e];
-  for (int p = threadIdx.x; p < NP; p += NTH) {
+  for (int e = threadIdx.x; e < A; e += NG3 * MT) bs[e] = P.bvec[e], hs[e] = P.h[e];
+  for (int p = threadIdx.x; p < NP; p += NG3 * MT) {
     int i, j;
     pair_of(F, p, i, j);
     pair[p] = (uint16_t)((i << 8) | j);
@@ -295,10 +296,10 @@ __global__ void __launch_bounds__(NTH, 1) afm_bwd_chain_tc_kernel(const __grid_c
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tmem = tmem_base_s + (uint32_t)grp * (uint32_t)(P.tmem_cols / 2);
+  const uint32_t tmem = tmem_base_s + (uint32_t)grp * (uint32_t)P.tmem_slot;
   const uint32_t idescZ = idesc_tf32(A), idescP = idesc_tf32(D);
   const uint32_t lbo_a = MT * 16, lbo_w = (uint32_t)A * 16, lbo_v = (uint32_t)D * 16, sbo = 128;
-  const int64_t first = (int64_t)blockIdx.x * 2 + grp, step = (int64_t)gridDim.x * 2;
+  const int64_t first = (int64_t)blockIdx.x * NG3 + grp, step = (int64_t)gridDim.x * NG3;
   const int pieces = F * D / 4;
   auto fetch = [&](int64_t b, int which) {
     const float *src = P.E + b * (int64_t)F * D;
@@ -490,9 +491,9 @@ __global__ void __launch_bounds__(256) afm_de_kernel(const __grid_constant__ Afm
 // U^T[a][d] = sum over pairs of mask[pair][a] * (ds[pair] P[pair][d]),  and with one extra operand column holding ds
 // itself, U^T[a][D] = m1[a].  The A operand is the 0/1 ReLU mask: exact in tf32, so it needs no lo part and each K step
 // costs two MMAs (mask x Q_lo, mask x Q_hi) instead of three.
-__global__ void __launch_bounds__(NTH, 1) afm_dw_tc_kernel(const __grid_constant__ AfmTcBwdParams P) {
+__global__ void __launch_bounds__(NG3 * MT, 1) afm_dw_tc_kernel(const __grid_constant__ AfmTcBwdParams P) {
   extern __shared__ __align__(128) uint32_t sm[];
-  __shared__ uint64_t bar[2][2];
+  __shared__ uint64_t bar[NG3][2];
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5;
   const int grp = threadIdx.x >> 7, tid = threadIdx.x & (MT - 1);
@@ -501,7 +502,7 @@ __global__ void __launch_bounds__(NTH, 1) afm_dw_tc_kernel(const __grid_constant
   const int DP = D + 4, nt = (NP + MT - 1) / MT, rows_pad = nt * MT;
   uint16_t *pair = reinterpret_cast<uint16_t *>(sm);
   uint32_t *gbase = sm + ((NP + 1) / 2 + 3) / 4 * 4;
-  const int ewords = (2 * F * DP + 3) / 4 * 4;
+  const int ewords = (F * DP + 3) / 4 * 4;                                 // one sample's embeddings (single buffer)
   const int opA_words = KC * MT, opB_words = 2 * KC * ND;                  // mask (hi only); Q hi | lo
   const int per_group = 2 * opA_words + 2 * opB_words + ewords + rows_pad + rows_pad * AW;
   uint32_t *mine = gbase + (size_t)grp * per_group;
@@ -511,11 +512,11 @@ __global__ void __launch_bounds__(NTH, 1) afm_dw_tc_kernel(const __grid_constant
   uint32_t *mask_s = reinterpret_cast<uint32_t *>(ds_s + rows_pad);
   if (warp == 0) tmem_alloc(&tmem_base_s, P.tmem_cols);
   if (threadIdx.x == 0) {
-    for (int x = 0; x < 2; ++x)
+    for (int x = 0; x < NG3; ++x)
       for (int y = 0; y < 2; ++y) rs::mbar_init(&bar[x][y], 1);
     rs::mbar_fence_init();
   }
-  for (int p = threadIdx.x; p < NP; p += NTH) {
+  for (int p = threadIdx.x; p < NP; p += NG3 * MT) {
     int i, j;
     pair_of(F, p, i, j);
     pair[p] = (uint16_t)((i << 8) | j);
@@ -526,14 +527,14 @@ __global__ void __launch_bounds__(NTH, 1) afm_dw_tc_kernel(const __grid_constant
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tmem = tmem_base_s + (uint32_t)grp * (uint32_t)(P.tmem_cols / 2);
+  const uint32_t tmem = tmem_base_s + (uint32_t)grp * (uint32_t)P.tmem_slot;
   const uint32_t idesc = idesc_tf32(ND);
   const uint32_t lbo_a = MT * 16, lbo_b = (uint32_t)ND * 16, sbo = 128;
-  const int64_t first = (int64_t)blockIdx.x * 2 + grp, step = (int64_t)gridDim.x * 2;
+  const int64_t first = (int64_t)blockIdx.x * NG3 + grp, step = (int64_t)gridDim.x * NG3;
   const int pieces = F * D / 4;
-  auto fetch = [&](int64_t b, int which) {
+  auto fetch = [&](int64_t b) {
     const float *src = P.E + b * (int64_t)F * D;
-    float *dst = Es + (size_t)which * F * DP;
+    float *dst = Es;
     for (int e = tid; e < pieces; e += MT) {
       const int f = e / (D / 4), q = e - f * (D / 4);
       rs::cp_async16(dst + f * DP + 4 * q, src + 4 * e);
@@ -546,19 +547,13 @@ __global__ void __launch_bounds__(NTH, 1) afm_dw_tc_kernel(const __grid_constant
   const int b_col = tid % D, b_sub = tid / D, b_nsub = MT / D;     // D in {16, 32}
   const int jbn = 8 / b_nsub, jb0 = b_sub * jbn;
   uint32_t cnt[2] = {0, 0}, it = 0;
-  int which = 0;
-  if (first < P.B) fetch(first, 0);
-  for (int64_t b = first; b < P.B; b += step, which ^= 1) {
-    if (b + step < P.B) {
-      fetch(b + step, which ^ 1);
-      rs::cp_async_wait<1>();
-    } else {
-      rs::cp_async_wait<0>();
-    }
+  for (int64_t b = first; b < P.B; b += step) {
+    fetch(b);
     for (int p = tid; p < rows_pad; p += MT) ds_s[p] = p < NP ? P.ds[b * NP + p] : 0.f;
     for (int e = tid; e < rows_pad * AW; e += MT) mask_s[e] = e < NP * AW ? P.mask[b * (int64_t)NP * AW + e] : 0u;
+    rs::cp_async_wait<0>();
     group_sync(grp);
-    const float *Eb = Es + (size_t)which * F * DP;
+    const float *Eb = Es;
     for (int ck = 0; ck < nt * 4; ++ck, ++it) {      // 32 pairs per chunk
       const int ub = it & 1, r0 = ck * KC;
       uint32_t *am = opA + (size_t)ub * opA_words;
@@ -615,7 +610,7 @@ __global__ void __launch_bounds__(NTH, 1) afm_dw_tc_kernel(const __grid_constant
   for (int ub = 0; ub < 2; ++ub)
     if (cnt[ub] > 0) rs::mbar_wait(&bar[grp][ub], (cnt[ub] - 1) & 1u);
   fence_after_sync();
-  const int part = blockIdx.x * 2 + grp;
+  const int part = blockIdx.x * NG3 + grp;
   for (int c0 = 0; c0 < ND; c0 += 32) {
     uint32_t v[32];
     if (it > 0) {
@@ -640,13 +635,13 @@ __global__ void __launch_bounds__(NTH, 1) afm_dw_tc_kernel(const __grid_constant
 size_t afm_chain_smem(int F, int D, int A, int NP) {
   const int DP = D + 4, nt = (NP + MT - 1) / MT;
   size_t words = (size_t)4 * A * D + 2 * A + ((NP + 1) / 2 + 3) / 4 * 4;
-  words += (size_t)2 * (2 * D * MT + 2 * KC * MT + (2 * F * DP + 3) / 4 * 4 + 2 * nt * MT + 64);
+  words += (size_t)NG3 * (2 * (D > KC ? D : KC) * MT + (2 * F * DP + 3) / 4 * 4 + 2 * nt * MT + 64);
   return words * 4;
 }
 size_t afm_dw_smem(int F, int D, int A, int NP) {
   const int DP = D + 4, nt = (NP + MT - 1) / MT, rows_pad = nt * MT, ND = D + 16;
   size_t words = ((NP + 1) / 2 + 3) / 4 * 4;
-  words += (size_t)2 * (2 * KC * MT + 2 * 2 * KC * ND + (2 * F * DP + 3) / 4 * 4 + rows_pad + rows_pad * (A / 32));
+  words += (size_t)NG3 * (2 * KC * MT + 2 * 2 * KC * ND + (F * DP + 3) / 4 * 4 + rows_pad + rows_pad * (A / 32));
   return words * 4;
 }
 size_t ws_region(size_t bytes) { return (bytes + 255) / 256 * 256; }
@@ -693,8 +688,8 @@ RS_API int rs_afm_bwd_tc_plan(int64_t B, int32_t F, int32_t D, int32_t A, int32_
   if (!afm_tc_shape_ok(B, F, D, A) || getenv("RS_AFM_NO_TC")) return RS_OK;   // 0 parts: use rs_afm_bwd
   const int NP = F * (F - 1) / 2;
   if (afm_chain_smem(F, D, A, NP) > 220 * 1024 || afm_dw_smem(F, D, A, NP) > 220 * 1024) return RS_OK;
-  const int64_t pairs = (B + 1) / 2;
-  *num_parts = 2 * (int)(pairs < rs::num_sms() ? pairs : rs::num_sms());
+  const int64_t ctas = (B + NG3 - 1) / NG3;
+  *num_parts = NG3 * (int)(ctas < rs::num_sms() ? ctas : rs::num_sms());
   *ws_bytes = ws_region((size_t)B * NP * 4) + ws_region((size_t)B * NP * 4 * (A / 32)) + ws_region((size_t)B * NP * 4 * D);
   return RS_OK;
 }
@@ -718,14 +713,14 @@ RS_API int rs_afm_bwd_tc(const float *E, int64_t B, int32_t F, int32_t D, int32_
   P.mask = reinterpret_cast<uint32_t *>(wsb + ws_region((size_t)B * NP * 4));
   P.dP = reinterpret_cast<float *>(wsb + ws_region((size_t)B * NP * 4) + ws_region((size_t)B * NP * 4 * (A / 32)));
   P.B = B, P.F = F, P.D = D, P.A = A, P.NP = NP;
-  const int grid = parts / 2;
+  const int grid = parts / NG3;
   {
+    P.tmem_slot = A + 32;   // z (A columns) + dP (up to 32)
     P.tmem_cols = 32;
-    while (P.tmem_cols < A + 32) P.tmem_cols <<= 1;
-    P.tmem_cols *= 2;
+    while (P.tmem_cols < NG3 * P.tmem_slot) P.tmem_cols <<= 1;
     const size_t smem = afm_chain_smem(F, D, A, NP);
     RS_CUDA(cudaFuncSetAttribute(afm_bwd_chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    afm_bwd_chain_tc_kernel<<<grid, NTH, smem, st>>>(P);
+    afm_bwd_chain_tc_kernel<<<grid, NG3 * MT, smem, st>>>(P);
     RS_CHECK_LAUNCH();
   }
   {
@@ -738,10 +733,11 @@ RS_API int rs_afm_bwd_tc(const float *E, int64_t B, int32_t F, int32_t D, int32_
     RS_CHECK_LAUNCH();
   }
   {
-    P.tmem_cols = 128;   // D + 16 <= 48 accumulator columns per warpgroup
+    P.tmem_slot = 64;       // D + 16 <= 48 accumulator columns
+    P.tmem_cols = 256;
     const size_t smem = afm_dw_smem(F, D, A, NP);
     RS_CUDA(cudaFuncSetAttribute(afm_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    afm_dw_tc_kernel<<<grid, NTH, smem, st>>>(P);
+    afm_dw_tc_kernel<<<grid, NG3 * MT, smem, st>>>(P);
     RS_CHECK_LAUNCH();
   }
   return RS_OK;
