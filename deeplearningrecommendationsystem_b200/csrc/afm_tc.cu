@@ -466,6 +466,17 @@ __global__ void __launch_bounds__(256) afm_de_kernel(const __grid_constant__ Afm
         const float ei = Ew[i * D + d];
         float acc = 0.f;
         int j = i + 1;
+        for (; j + 8 <= F; j += 8) {   // eight independent loads in flight per lane
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = dp[u * D];
+          dp += 8 * D;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            acc = fmaf(v[u], Ew[(j + u) * D + d], acc);
+            dEw[(j + u) * D + d] = fmaf(v[u], ei, dEw[(j + u) * D + d]);
+          }
+        }
         for (; j + 4 <= F; j += 4) {
           const float v0 = dp[0], v1 = dp[D], v2 = dp[2 * D], v3 = dp[3 * D];   // four loads in flight
           dp += 4 * D;
