@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(NTH, 1) afm_fwd_tc_kernel(const __grid_constan
 
 // ---------------------------------------------------------------------------------------------------- backward
 // Three kernels, each with one simple data flow (workspace: ds (B, P), ReLU masks (B, P, A/32) bits, dP (B, P, D)):
-//   afm_bwd_chain_tc_kernel   ds = softmax backward;  z = P W + b (MMA) -> mask;  dz = ds h [z > 0];  dP = dz W^T (MMA) + w g
+//   afm_bwd_chain_tc_kernel   ds = softmax backward;  z = P W + b (MMA) -> mask m = [z > 0];  dP = ds (m (h*W)^T) (MMA) + w g
 //   afm_dw_tc_kernel          U[d][a] = sum over all pairs of P[.][d] * (ds [z > 0])[.][a]  -- a GEMM whose K runs over the
 //                             pairs, so both operands are built K(=pair)-major by "column owner" threads straight from
 //                             E, ds and the mask bits; the accumulator lives in TMEM for the whole kernel.  Also
@@ -284,7 +284,9 @@ __global__ void __launch_bounds__(NG3 * MT, 1) afm_bwd_chain_tc_kernel(const __g
     const float x = P.W[e];
     const uint32_t hh = to_tf32(x), ll = to_tf32(x - __uint_as_float(hh));
     wh[tile_off(A, a, d)] = hh, wl[tile_off(A, a, d)] = ll;
-    vh[tile_off(D, d, a)] = hh, vl[tile_off(D, d, a)] = ll;
+    const float y = x * P.h[a];                              // dP = ds * ([z > 0] . (h * W)^T): h is folded into the operand
+    const uint32_t yh = to_tf32(y);
+    vh[tile_off(D, d, a)] = yh, vl[tile_off(D, d, a)] = to_tf32(y - __uint_as_float(yh));
   }
   for (int e = threadIdx.x; e < A; e += NG3 * MT) bs[e] = P.bvec[e], hs[e] = P.h[e];
   for (int p = threadIdx.x; p < NP; p += NG3 * MT) {
@@ -380,7 +382,8 @@ __global__ void __launch_bounds__(NG3 * MT, 1) afm_bwd_chain_tc_kernel(const __g
       ++cnt;
       rs::mbar_wait(&bar[grp], (cnt - 1) & 1u);
       fence_after_sync();
-      // ---- dz = ds h [z > 0], 32 columns at a time = one K chunk of dP = dz W^T
+      // ---- [z > 0], 32 columns at a time = one K chunk of  dP = ds * ([z > 0] (h * W)^T).  The 0/1 mask is exact in
+      // tf32: no lo part, no split, two MMAs per K step.
       const float dsp = ds_s[p];
       for (int c = 0; c < AW; ++c) {
         uint32_t v[32];
@@ -388,16 +391,12 @@ __global__ void __launch_bounds__(NG3 * MT, 1) afm_bwd_chain_tc_kernel(const __g
         uint32_t bits = 0;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const float4 b4 = *reinterpret_cast<const float4 *>(bs + c * 32 + 4 * q), h4 = *reinterpret_cast<const float4 *>(hs + c * 32 + 4 * q);
-          float4 x;
+          const float4 b4 = *reinterpret_cast<const float4 *>(bs + c * 32 + 4 * q);
           const bool m0 = __uint_as_float(v[4 * q + 0]) + b4.x > 0.f, m1 = __uint_as_float(v[4 * q + 1]) + b4.y > 0.f;
           const bool m2 = __uint_as_float(v[4 * q + 2]) + b4.z > 0.f, m3 = __uint_as_float(v[4 * q + 3]) + b4.w > 0.f;
           bits |= (m0 ? 1u : 0u) << (4 * q) | (m1 ? 1u : 0u) << (4 * q + 1) | (m2 ? 1u : 0u) << (4 * q + 2) | (m3 ? 1u : 0u) << (4 * q + 3);
-          x.x = m0 ? dsp * h4.x : 0.f, x.y = m1 ? dsp * h4.y : 0.f, x.z = m2 ? dsp * h4.z : 0.f, x.w = m3 ? dsp * h4.w : 0.f;
-          uint4 hh, ll;
-          split4(x, hh, ll);
-          *reinterpret_cast<uint4 *>(opZ + (q * MT + tid) * 4) = hh;
-          *reinterpret_cast<uint4 *>(opZ + KC * MT + (q * MT + tid) * 4) = ll;
+          *reinterpret_cast<uint4 *>(opZ + (q * MT + tid) * 4) =
+              make_uint4(m0 ? 0x3f800000u : 0u, m1 ? 0x3f800000u : 0u, m2 ? 0x3f800000u : 0u, m3 ? 0x3f800000u : 0u);
         }
         if (ok) P.mask[(b * NP + p) * AW + c] = bits;
         rs::fence_proxy_async();
@@ -408,13 +407,11 @@ __global__ void __launch_bounds__(NG3 * MT, 1) afm_bwd_chain_tc_kernel(const __g
 #pragma unroll
           for (int s = 0; s < KC / 8; ++s) {
             const uint32_t kb = (uint32_t)(c * (KC / 4) + s * 2);
-            const uint64_t dah = smem_desc(rs::smem_u32(opZ) + s * 2 * lbo_a, lbo_a, sbo);
-            const uint64_t dal = smem_desc(rs::smem_u32(opZ + KC * MT) + s * 2 * lbo_a, lbo_a, sbo);
+            const uint64_t dam = smem_desc(rs::smem_u32(opZ) + s * 2 * lbo_a, lbo_a, sbo);
             const uint64_t dbh = smem_desc(rs::smem_u32(vh) + kb * lbo_v, lbo_v, sbo);
             const uint64_t dbl = smem_desc(rs::smem_u32(vl) + kb * lbo_v, lbo_v, sbo);
-            mma_tf32(tmem + (uint32_t)A, dal, dbh, idescP, (c == 0 && s == 0) ? 0u : 1u);
-            mma_tf32(tmem + (uint32_t)A, dah, dbl, idescP, 1u);
-            mma_tf32(tmem + (uint32_t)A, dah, dbh, idescP, 1u);
+            mma_tf32(tmem + (uint32_t)A, dam, dbl, idescP, (c == 0 && s == 0) ? 0u : 1u);
+            mma_tf32(tmem + (uint32_t)A, dam, dbh, idescP, 1u);
           }
           commit(&bar[grp]);
         }
@@ -423,7 +420,7 @@ __global__ void __launch_bounds__(NG3 * MT, 1) afm_bwd_chain_tc_kernel(const __g
         rs::mbar_wait(&bar[grp], (cnt - 1) & 1u);   // opZ is single-buffered: these MMAs must have read it
         fence_after_sync();
       }
-      // ---- dP_p = dz_p W^T + w_p g  -> workspace
+      // ---- dP_p = ds_p * acc + w_p g  -> workspace
       {
         uint32_t v[32];
         tmem_ld32(tmem, warp, A, v);
@@ -434,8 +431,8 @@ __global__ void __launch_bounds__(NG3 * MT, 1) afm_bwd_chain_tc_kernel(const __g
           for (int q = 0; q < 8; ++q) {
             if (4 * q < D) {
               const float4 g4 = *reinterpret_cast<const float4 *>(g_s + 4 * q);
-              rs::stg_cs_f4(dst + 4 * q, make_float4(fmaf(wp, g4.x, __uint_as_float(v[4 * q + 0])), fmaf(wp, g4.y, __uint_as_float(v[4 * q + 1])),
-                                                     fmaf(wp, g4.z, __uint_as_float(v[4 * q + 2])), fmaf(wp, g4.w, __uint_as_float(v[4 * q + 3]))));
+              rs::stg_cs_f4(dst + 4 * q, make_float4(fmaf(wp, g4.x, dsp * __uint_as_float(v[4 * q + 0])), fmaf(wp, g4.y, dsp * __uint_as_float(v[4 * q + 1])),
+                                                     fmaf(wp, g4.z, dsp * __uint_as_float(v[4 * q + 2])), fmaf(wp, g4.w, dsp * __uint_as_float(v[4 * q + 3]))));
             }
           }
         }
