@@ -567,14 +567,18 @@ __global__ void __launch_bounds__(NG3 * MT, 1) afm_dw_tc_kernel(const __grid_con
       uint32_t *am = opA + (size_t)ub * opA_words;
       uint32_t *bh = opB + (size_t)ub * opB_words, *bl = bh + KC * ND;
       if (cnt[ub] > 0) rs::mbar_wait(&bar[grp][ub], (cnt[ub] - 1) & 1u);   // the MMAs that read this buffer pair are done
-      for (int jj = 0; jj < jan; ++jj) {
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {   // jan <= 8: unrolled with a predicate so the units' loads overlap
+        if (jj >= jan) break;
         const int j = ja0 + jj, r = r0 + 4 * j;
         uint32_t mv[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) mv[i] = ((mask_s[(r + i) * AW + (a_col >> 5)] >> (a_col & 31)) & 1u) ? 0x3f800000u : 0u;
         *reinterpret_cast<uint4 *>(am + (j * MT + a_col) * 4) = make_uint4(mv[0], mv[1], mv[2], mv[3]);
       }
-      for (int jj = 0; jj < jbn; ++jj) {
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {   // jbn <= 2
+        if (jj >= jbn) break;
         const int j = jb0 + jj, r = r0 + 4 * j;
         float x[4];
 #pragma unroll
