@@ -383,41 +383,50 @@ __global__ void __launch_bounds__(NG3 * MT, 1) afm_bwd_chain_tc_kernel(const __g
       rs::mbar_wait(&bar[grp], (cnt - 1) & 1u);
       fence_after_sync();
       // ---- [z > 0], 32 columns at a time = one K chunk of  dP = ds * ([z > 0] (h * W)^T).  The 0/1 mask is exact in
-      // tf32: no lo part, no split, two MMAs per K step.
+      // tf32: no lo part, no split, two MMAs per K step -- and two chunks fit in the operand buffer at once, so they
+      // share one barrier round trip.
       const float dsp = ds_s[p];
-      for (int c = 0; c < AW; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem, warp, c * 32, v);
-        uint32_t bits = 0;
+      for (int c0 = 0; c0 < AW; c0 += 2) {
+        const int nc = AW - c0 < 2 ? AW - c0 : 2;
+        for (int cl = 0; cl < nc; ++cl) {
+          const int c = c0 + cl;
+          uint32_t *om = opZ + (size_t)cl * KC * MT;
+          uint32_t v[32];
+          tmem_ld32(tmem, warp, c * 32, v);
+          uint32_t bits = 0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 b4 = *reinterpret_cast<const float4 *>(bs + c * 32 + 4 * q);
-          const bool m0 = __uint_as_float(v[4 * q + 0]) + b4.x > 0.f, m1 = __uint_as_float(v[4 * q + 1]) + b4.y > 0.f;
-          const bool m2 = __uint_as_float(v[4 * q + 2]) + b4.z > 0.f, m3 = __uint_as_float(v[4 * q + 3]) + b4.w > 0.f;
-          bits |= (m0 ? 1u : 0u) << (4 * q) | (m1 ? 1u : 0u) << (4 * q + 1) | (m2 ? 1u : 0u) << (4 * q + 2) | (m3 ? 1u : 0u) << (4 * q + 3);
-          *reinterpret_cast<uint4 *>(opZ + (q * MT + tid) * 4) =
-              make_uint4(m0 ? 0x3f800000u : 0u, m1 ? 0x3f800000u : 0u, m2 ? 0x3f800000u : 0u, m3 ? 0x3f800000u : 0u);
+          for (int q = 0; q < 8; ++q) {
+            const float4 b4 = *reinterpret_cast<const float4 *>(bs + c * 32 + 4 * q);
+            const bool m0 = __uint_as_float(v[4 * q + 0]) + b4.x > 0.f, m1 = __uint_as_float(v[4 * q + 1]) + b4.y > 0.f;
+            const bool m2 = __uint_as_float(v[4 * q + 2]) + b4.z > 0.f, m3 = __uint_as_float(v[4 * q + 3]) + b4.w > 0.f;
+            bits |= (m0 ? 1u : 0u) << (4 * q) | (m1 ? 1u : 0u) << (4 * q + 1) | (m2 ? 1u : 0u) << (4 * q + 2) | (m3 ? 1u : 0u) << (4 * q + 3);
+            *reinterpret_cast<uint4 *>(om + (q * MT + tid) * 4) =
+                make_uint4(m0 ? 0x3f800000u : 0u, m1 ? 0x3f800000u : 0u, m2 ? 0x3f800000u : 0u, m3 ? 0x3f800000u : 0u);
+          }
+          if (ok) P.mask[(b * NP + p) * AW + c] = bits;
         }
-        if (ok) P.mask[(b * NP + p) * AW + c] = bits;
         rs::fence_proxy_async();
         fence_before_sync();
         group_sync(grp);
         if (tid == 0) {
           fence_after_sync();
+          for (int cl = 0; cl < nc; ++cl) {
+            const uint32_t om = rs::smem_u32(opZ + (size_t)cl * KC * MT);
 #pragma unroll
-          for (int s = 0; s < KC / 8; ++s) {
-            const uint32_t kb = (uint32_t)(c * (KC / 4) + s * 2);
-            const uint64_t dam = smem_desc(rs::smem_u32(opZ) + s * 2 * lbo_a, lbo_a, sbo);
-            const uint64_t dbh = smem_desc(rs::smem_u32(vh) + kb * lbo_v, lbo_v, sbo);
-            const uint64_t dbl = smem_desc(rs::smem_u32(vl) + kb * lbo_v, lbo_v, sbo);
-            mma_tf32(tmem + (uint32_t)A, dam, dbl, idescP, (c == 0 && s == 0) ? 0u : 1u);
-            mma_tf32(tmem + (uint32_t)A, dam, dbh, idescP, 1u);
+            for (int s = 0; s < KC / 8; ++s) {
+              const uint32_t kb = (uint32_t)((c0 + cl) * (KC / 4) + s * 2);
+              const uint64_t dam = smem_desc(om + s * 2 * lbo_a, lbo_a, sbo);
+              const uint64_t dbh = smem_desc(rs::smem_u32(vh) + kb * lbo_v, lbo_v, sbo);
+              const uint64_t dbl = smem_desc(rs::smem_u32(vl) + kb * lbo_v, lbo_v, sbo);
+              mma_tf32(tmem + (uint32_t)A, dam, dbl, idescP, (c0 + cl == 0 && s == 0) ? 0u : 1u);
+              mma_tf32(tmem + (uint32_t)A, dam, dbh, idescP, 1u);
+            }
           }
           commit(&bar[grp]);
         }
         __syncwarp();
         ++cnt;
-        rs::mbar_wait(&bar[grp], (cnt - 1) & 1u);   // opZ is single-buffered: these MMAs must have read it
+        rs::mbar_wait(&bar[grp], (cnt - 1) & 1u);   // the operand buffer is reused: these MMAs must have read it
         fence_after_sync();
       }
       // ---- dP_p = ds_p * acc + w_p g  -> workspace
