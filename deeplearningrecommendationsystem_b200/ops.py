@@ -626,8 +626,9 @@ def din_fwd(rows, ws, pool, want_attw=False, impl="auto", want_stash=False):
     w, keep = _din_weights(ws)
     out = torch.empty((B, D) if pool else (B, L, D), dtype=torch.float32, device=rows.device)
     if impl == "auto":
-        impl = "tc" if (din_tc_supported(D, w.H1, w.H2) and B * L >= DIN_TC_MIN_ROWS
-                        and os.environ.get("RS_DIN_TC", "1") != "0") else "fused"
+        fused_ok = D in (16, 32, 64) and (w.H1, w.H2) in ((128, 64), (64, 32))
+        big = B * L >= DIN_TC_MIN_ROWS and os.environ.get("RS_DIN_TC", "1") != "0"
+        impl = "tc" if din_tc_supported(D, w.H1, w.H2) and (big or not fused_ok) else "fused"
     stash_tc = want_stash and impl == "tc"
     attw = torch.empty(B, L, dtype=torch.float32, device=rows.device) if (want_attw or stash_tc) else None
     if B == 0:

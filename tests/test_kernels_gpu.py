@@ -476,6 +476,35 @@ def test_din_attention_fwd_bwd(D, H1, H2, L, B, pool):
     assert torch.equal(d_tc, d_tc2) and all(torch.equal(a, b_) for a, b_ in zip(dws_tc, dws_tc2))
 
 
+@pytest.mark.parametrize("D,H1,H2,L,B,pool", [(16, 64, 64, 5, 40, True), (32, 128, 32, 9, 30, False), (64, 64, 64, 1, 300, True)])
+def test_din_tc_shapes_the_cuda_core_kernels_do_not_build(D, H1, H2, L, B, pool):
+    """(H1, H2) in {(64,64), (128,32)} exist only on the tensor-core path: forward and backward against the oracle"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(D + H1 + H2)
+    rows = (torch.randn(B, L + 1, D, generator=g) * 0.5).requires_grad_(True)
+    lin = lambda o, i: ((torch.rand(o, i, generator=g) * 2 - 1) / i ** 0.5).requires_grad_(True)   # noqa: E731
+    vec = lambda o, i: ((torch.rand(o, generator=g) * 2 - 1) / i ** 0.5).requires_grad_(True)      # noqa: E731
+    ws = [lin(H1, 3 * D), vec(H1, 3 * D), lin(H2, H1), vec(H2, H1), lin(1, H2), vec(1, H2)]
+    h, t = rows[:, :-1], rows[:, -1]
+    w = OI.din_attention(h, t, [(ws[0], ws[1]), (ws[2], ws[3]), (ws[4], ws[5])])
+    want = (h * w.unsqueeze(-1)).sum(1) if pool else h * w.unsqueeze(-1)
+    gup = torch.randn(*want.shape, generator=g)
+    grads = torch.autograd.grad((want * gup).sum(), [rows] + ws)
+    cw = [t_.detach().cuda() for t_ in ws]
+    out, attw, stash = ops.din_fwd(rows.detach().cuda(), cw, pool, want_attw=True, impl="tc", want_stash=True)
+
+    def scaled(got, ref, name=""):
+        close(got, ref, rtol=1e-5, atol=1e-5 * max(1e-3, float(ref.abs().max())), msg=name)
+    scaled(attw, w.detach(), "attw")
+    scaled(out, want.detach(), "out")
+    d_rows, dws = ops.din_bwd_tc(rows.detach().cuda(), cw, pool, gup.cuda(), stash)
+    scaled(d_rows, grads[0], "d_rows")
+    for got, ref, name in zip(dws[:5], grads[1:6], ["dW0", "db0", "dW1", "db1", "dW2"]):
+        scaled(got, ref, name)
+    with pytest.raises(RuntimeError):
+        ops.din_fwd(rows.detach().cuda(), cw, pool, impl="fused")
+
+
 @pytest.mark.parametrize("D,H1,H2,L,B,pool", [(64, 128, 64, 100, 700, True), (32, 64, 32, 50, 1000, False), (16, 128, 64, 3, 9000, True)])
 def test_din_tc_forward_many_tiles(D, H1, H2, L, B, pool):
     """more tiles than SMs (persistent loop, buffer/barrier parity across tiles, ragged last tile); tc == fused kernel"""
