@@ -461,15 +461,16 @@ __global__ void __launch_bounds__(256) afm_de_kernel(const __grid_constant__ Afm
   extern __shared__ __align__(16) float smf[];
   const int F = P.F, D = P.D, NP = P.NP;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  float *Ew = smf + (size_t)warp * 2 * F * D, *dEw = Ew + F * D;
+  float *dEw = smf + (size_t)warp * F * D;   // only the accumulators live in shared memory: more warps per SM
   for (int64_t b = (int64_t)blockIdx.x * nw + warp; b < P.B; b += (int64_t)gridDim.x * nw) {
-    for (int e = lane; e < F * D; e += 32) Ew[e] = P.E[b * (int64_t)F * D + e], dEw[e] = 0.f;
+    const float *Ew = P.E + b * (int64_t)F * D;   // 5 KB per sample, re-read through L1
+    for (int e = lane; e < F * D; e += 32) dEw[e] = 0.f;
     __syncwarp();
     if (lane < D) {
       const int d = lane;
       const float *dp = P.dP + b * (int64_t)NP * D + d;
       for (int i = 0; i + 1 < F; ++i) {
-        const float ei = Ew[i * D + d];
+        const float ei = __ldg(Ew + i * D + d);
         float acc = 0.f;
         int j = i + 1;
         for (; j + 8 <= F; j += 8) {   // eight independent loads in flight per lane
@@ -479,22 +480,22 @@ __global__ void __launch_bounds__(256) afm_de_kernel(const __grid_constant__ Afm
           dp += 8 * D;
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            acc = fmaf(v[u], Ew[(j + u) * D + d], acc);
+            acc = fmaf(v[u], __ldg(Ew + (j + u) * D + d), acc);
             dEw[(j + u) * D + d] = fmaf(v[u], ei, dEw[(j + u) * D + d]);
           }
         }
         for (; j + 4 <= F; j += 4) {
           const float v0 = dp[0], v1 = dp[D], v2 = dp[2 * D], v3 = dp[3 * D];   // four loads in flight
           dp += 4 * D;
-          acc = fmaf(v0, Ew[(j + 0) * D + d], acc), dEw[(j + 0) * D + d] = fmaf(v0, ei, dEw[(j + 0) * D + d]);
-          acc = fmaf(v1, Ew[(j + 1) * D + d], acc), dEw[(j + 1) * D + d] = fmaf(v1, ei, dEw[(j + 1) * D + d]);
-          acc = fmaf(v2, Ew[(j + 2) * D + d], acc), dEw[(j + 2) * D + d] = fmaf(v2, ei, dEw[(j + 2) * D + d]);
-          acc = fmaf(v3, Ew[(j + 3) * D + d], acc), dEw[(j + 3) * D + d] = fmaf(v3, ei, dEw[(j + 3) * D + d]);
+          acc = fmaf(v0, __ldg(Ew + (j + 0) * D + d), acc), dEw[(j + 0) * D + d] = fmaf(v0, ei, dEw[(j + 0) * D + d]);
+          acc = fmaf(v1, __ldg(Ew + (j + 1) * D + d), acc), dEw[(j + 1) * D + d] = fmaf(v1, ei, dEw[(j + 1) * D + d]);
+          acc = fmaf(v2, __ldg(Ew + (j + 2) * D + d), acc), dEw[(j + 2) * D + d] = fmaf(v2, ei, dEw[(j + 2) * D + d]);
+          acc = fmaf(v3, __ldg(Ew + (j + 3) * D + d), acc), dEw[(j + 3) * D + d] = fmaf(v3, ei, dEw[(j + 3) * D + d]);
         }
         for (; j < F; ++j) {
           const float v = dp[0];
           dp += D;
-          acc = fmaf(v, Ew[j * D + d], acc), dEw[j * D + d] = fmaf(v, ei, dEw[j * D + d]);
+          acc = fmaf(v, __ldg(Ew + j * D + d), acc), dEw[j * D + d] = fmaf(v, ei, dEw[j * D + d]);
         }
         dEw[i * D + d] += acc;
       }
@@ -746,10 +747,10 @@ RS_API int rs_afm_bwd_tc(const float *E, int64_t B, int32_t F, int32_t D, int32_
   }
   {
     const int nw = 8;
-    const size_t smem = (size_t)nw * 2 * F * D * 4;
+    const size_t smem = (size_t)nw * F * D * 4;
     RS_CUDA(cudaFuncSetAttribute(afm_de_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t blocks = (B + nw - 1) / nw;
-    const int64_t cap = (int64_t)rs::num_sms() * 4;
+    const int64_t cap = (int64_t)rs::num_sms() * 5;
     afm_de_kernel<<<(unsigned)(blocks < cap ? blocks : cap), nw * 32, smem, st>>>(P);
     RS_CHECK_LAUNCH();
   }
