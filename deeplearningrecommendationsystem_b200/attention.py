@@ -54,71 +54,14 @@ class _DINAttention(torch.autograd.Function):
         return (d_rows, None, *dws)
 
 
-class _DINAttentionTC(torch.autograd.Function):
-    """The attention unit as tensor-core GEMMs over all B*L (sample, position) rows: rs_gemm_nt_3xtf32 for the layer
-    products (bias / per-sample target term / ReLU / ReLU-mask fused in the epilogue) and rs_gemm_tn_3xtf32 for the
-    weight gradients (reductions over B*L).  The concat is never built: W0 z = (Wa+Wb) h + (Wc-Wb) t.  Softmax and the
-    (B, L, D) weighting are small elementwise ops."""
-
-    @staticmethod
-    def forward(ctx, rows, pool, W0, b0, W1, b1, W2, b2):
-        from . import ops
-        B, L1, D = rows.shape
-        L = L1 - 1
-        Wab = (W0[:, :D] + W0[:, D:2 * D]).contiguous()
-        Wcb = (W0[:, 2 * D:] - W0[:, D:2 * D]).contiguous()
-        hist_view = (L, L1 * D, D)                                            # row r -> rows[r // L, r % L]
-        c = ops.gemm_nt(rows[:, L], Wcb, bias=b0, M=B, a_rows=(1, L1 * D, D))                      # (B, H1) target part
-        a1 = ops.gemm_nt(rows, Wab, rowbias=c, rb_group=L, relu=True, M=B * L, a_rows=hist_view)  # (B*L, H1)
-        a2 = ops.gemm_nt(a1, W1, bias=b1, relu=True)                                              # (B*L, H2)
-        s = ops.gemm_nt(a2, W2, bias=b2).view(B, L)
-        w = torch.softmax(s, dim=1)
-        h = rows[:, :L]
-        out = torch.einsum("bl,bld->bd", w, h) if pool else h * w.unsqueeze(-1)
-        ctx.pool = pool
-        ctx.save_for_backward(rows, a1, a2, w, Wab, Wcb, W1, W2)
-        return out
-
-    @staticmethod
-    def backward(ctx, g):
-        from . import ops
-        rows, a1, a2, w, Wab, Wcb, W1, W2 = ctx.saved_tensors
-        B, L1, D = rows.shape
-        L = L1 - 1
-        h, t = rows[:, :L], rows[:, L]
-        if ctx.pool:
-            dw = torch.einsum("bld,bd->bl", h, g)
-            dh = w.unsqueeze(-1) * g.unsqueeze(1)
-        else:
-            dw = (h * g).sum(dim=-1)
-            dh = w.unsqueeze(-1) * g
-        ds = (w * (dw - (w * dw).sum(dim=1, keepdim=True))).reshape(B * L, 1)
-        dW2 = ops.gemm_tn(ds, a2)                                             # (1, H2)
-        db2 = ds.sum().view(1)
-        da2 = torch.where(a2 > 0, ds * W2, torch.zeros((), device=a2.device))  # (B*L, H2)
-        dW1 = ops.gemm_tn(da2, a1)                                            # (H2, H1)
-        db1 = da2.sum(dim=0)
-        da1 = ops.gemm_nt(da2, W1.t().contiguous(), mask=a1)                  # (da2 W1) * [a1 > 0]
-        dWab = ops.gemm_tn(da1, h.reshape(B * L, D))                          # (H1, D)
-        db0 = da1.sum(dim=0)
-        s1 = da1.view(B, L, -1).sum(dim=1)                                    # (B, H1)
-        dWt = ops.gemm_tn(s1, t.contiguous())                                 # (H1, D)
-        dW0 = torch.cat([dWab, dWab - dWt, dWt], dim=1)
-        dh = dh + ops.gemm_nt(da1, Wab.t().contiguous()).view(B, L, D)
-        dt = ops.gemm_nt(s1, Wcb.t().contiguous())                            # (B, D)
-        return torch.cat([dh, dt.unsqueeze(1)], dim=1), None, dW0, db0, dW1, db1, dW2, db2
-
-
-def din_attention(rows, unit, pool, impl="fused"):
+def din_attention(rows, unit, pool):
     """softmax_L(MLP([h, h-t, t])) applied to the history                               reference model/din.py:39-47.
     rows (B, L+1, D): gathered history rows followed by the target row; unit = Sequential(Linear, ReLU, Linear, ReLU,
     Linear).  pool=True -> (B, D) weighted sum; pool=False -> (B, L, D) scaled history (model/dien.py:33-37).
-    impl "fused" (default): rs_din_fwd / rs_din_bwd -- for B*L >= 8192 rows the tcgen05 kernels of din_tc.cu (both hidden
-    layers fused per 128-row tile, 3xTF32), otherwise the CUDA-core kernel pair; "tc": the same unit written as separate
-    rs_gemm_nt_3xtf32 / rs_gemm_tn_3xtf32 calls per layer (kept as a parity cross-check; slower, intermediates in HBM)."""
+    rs_din_fwd / rs_din_bwd: for B*L >= 8192 rows the tcgen05 kernels of din_tc.cu (both hidden layers fused per
+    128-row tile, 3xTF32), otherwise the CUDA-core kernel pair (ops.din_fwd picks)."""
     l0, l1, l2 = unit[0], unit[2], unit[4]
-    fn = _DINAttentionTC if impl == "tc" else _DINAttention
-    return fn.apply(rows.contiguous(), pool, l0.weight, l0.bias, l1.weight, l1.bias, l2.weight, l2.bias)
+    return _DINAttention.apply(rows.contiguous(), pool, l0.weight, l0.bias, l1.weight, l1.bias, l2.weight, l2.bias)
 
 
 class _GRURecurrence(torch.autograd.Function):
