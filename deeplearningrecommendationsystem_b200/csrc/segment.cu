@@ -4,6 +4,9 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "segment.cuh"
 
@@ -132,11 +135,21 @@ __global__ void __launch_bounds__(256) relabel_kernel(int4 *__restrict__ desc, c
   if (s < *n_uniq) uniq[s] = s;
 }
 
+}  // namespace
+namespace rs {   // sort.cu
+size_t radix_sort_ws_ints(int64_t n);
+size_t scan_ws_ints(int64_t n);
+int radix_sort_pairs(const uint32_t *kin, const int32_t *vin, uint32_t *kout, int32_t *vout, uint32_t *ktmp, int32_t *vtmp,
+                     int32_t *hist_ws, int64_t n, int end_bit, cudaStream_t st);
+int inclusive_sum_i32(const int32_t *in, int32_t *out, int64_t n, int32_t *ws, cudaStream_t st);
+}  // namespace rs
+namespace {
+
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 struct WsLayout {
   size_t sorted_key, sorted_pos, uniq, inverse, counts, seg_start, seg_first_chunk, chunk_start, chunk_seg, multi_seg, lookup_desc, unit_start, scale_sorted, scalars;
-  size_t keys_in, pos_in, head, segidx1, chead, chunkidx1, cub, partial, total;
+  size_t keys_in, pos_in, head, segidx1, chead, chunkidx1, cub, sort_hist, scan_ws, partial, total;
   size_t cub_bytes, partial_floats;
 };
 
@@ -175,6 +188,8 @@ WsLayout layout(int64_t n, int max_width) {
   cub::DeviceScan::InclusiveSum(nullptr, scan_b, (const int32_t *)nullptr, (int32_t *)nullptr, (int)n);
   L.cub_bytes = sort_b > scan_b ? sort_b : scan_b;
   L.cub = take(L.cub_bytes);
+  L.sort_hist = take(rs::radix_sort_ws_ints(n) * 4);   // per-tile digit counts of the hand-written radix sort
+  L.scan_ws = take(rs::scan_ws_ints(n) * 4);
   // Only chunks of multi-chunk segments store a partial.  Such chunks are all full (RS_CHUNK lookups) except the
   // tail of each segment, so slot = 2*(chunk_start/RS_CHUNK) + is_tail is injective and < 2*(n/RS_CHUNK + 1)
   // (see partial_slot below).
@@ -240,16 +255,37 @@ RS_API int rs_dedup_sort(const int64_t *ids, int64_t n, int32_t F, const int64_t
   RS_CHECK_LAUNCH();
   int end_bit = 1;
   while (end_bit < 32 && (1ull << end_bit) < (uint64_t)total_rows) ++end_bit;
-  RS_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, keys_in, seg->sorted_key, pos_in, seg->sorted_pos, (int)n, 0, end_bit, st));
+  // Stable sort by row key.  Default: cub::DeviceRadixSort (onesweep) + cub::DeviceScan -- library plumbing, like cuBLAS
+  // for the towers.  RS_SORT=own selects the hand-written LSD radix sort and prefix sums of sort.cu: bit-identical
+  // results (tests/test_kernels_gpu.py), but 15 small launches per sort instead of 4, which measured 3 % slower on the
+  // whole C2 step, so it is not the default yet.  head / segidx1 are free until the sort ends (its scratch).
+  const bool use_cub = !(getenv("RS_SORT") && !strcmp(getenv("RS_SORT"), "own"));
+  int32_t *sort_hist = (int32_t *)(w + L.sort_hist), *scan_ws = (int32_t *)(w + L.scan_ws);
+  if (use_cub) {
+    RS_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, keys_in, seg->sorted_key, pos_in, seg->sorted_pos, (int)n, 0, end_bit, st));
+  } else {
+    int rc = rs::radix_sort_pairs(keys_in, pos_in, seg->sorted_key, seg->sorted_pos, (uint32_t *)head, segidx1, sort_hist, n, end_bit, st);
+    if (rc) return rc;
+  }
   head_flags_kernel<<<blocks, 256, 0, st>>>(seg->sorted_key, n, head);
   RS_CHECK_LAUNCH();
-  RS_CUDA(cub::DeviceScan::InclusiveSum(cub_ws, cub_bytes, head, segidx1, (int)n, st));
+  if (use_cub) {
+    RS_CUDA(cub::DeviceScan::InclusiveSum(cub_ws, cub_bytes, head, segidx1, (int)n, st));
+  } else {
+    int rc = rs::inclusive_sum_i32(head, segidx1, n, scan_ws, st);
+    if (rc) return rc;
+  }
   seg_scatter_kernel<<<blocks, 256, 0, st>>>(seg->sorted_key, seg->sorted_pos, head, segidx1, n, seg->uniq, seg->seg_start,
                                              seg->inverse, seg->n_uniq);
   RS_CHECK_LAUNCH();
   chunk_flags_kernel<<<blocks, 256, 0, st>>>(head, segidx1, seg->seg_start, n, chead, seg->counts);
   RS_CHECK_LAUNCH();
-  RS_CUDA(cub::DeviceScan::InclusiveSum(cub_ws, cub_bytes, chead, chunkidx1, (int)n, st));
+  if (use_cub) {
+    RS_CUDA(cub::DeviceScan::InclusiveSum(cub_ws, cub_bytes, chead, chunkidx1, (int)n, st));
+  } else {
+    int rc = rs::inclusive_sum_i32(chead, chunkidx1, n, scan_ws, st);
+    if (rc) return rc;
+  }
   chunk_scatter_kernel<<<blocks, 256, 0, st>>>(head, segidx1, chead, chunkidx1, n, seg->chunk_start, seg->chunk_seg,
                                                seg->seg_first_chunk, seg->n_chunks);
   RS_CHECK_LAUNCH();

@@ -75,6 +75,31 @@ def test_dedup_matches_unique(n, F, card):
     assert np.array_equal(segs.sorted_pos().cpu().numpy().astype(np.int64), oidx.stable_order(keys))
 
 
+@pytest.mark.parametrize("n,total", [(1, 7), (33, 2 ** 31 + 5), (4095, 300), (4096, 2 ** 9), (4097, 2 ** 9 + 1), (70001, 2 ** 18), (1703936, 33762577),
+                                     (3000017, 2 ** 32 - 1)])
+def test_radix_sort_is_stable_and_equals_library_sort(n, total):
+    """the hand-written LSD radix sort + prefix sums (sort.cu, RS_SORT=own) against numpy's stable argsort, and -- array
+    by array -- against the default dedup driven by cub: tile edges, 1..4 digit passes, heavy duplicates, 32-bit keys"""
+    import os
+    ops = _ops()
+    g = torch.Generator().manual_seed(n)
+    ids = (torch.rand(n, generator=g, dtype=torch.float64) ** 3 * total).long().clamp_(max=total - 1)
+    ids[::7] = total - 1
+    cu = ids.cuda()
+    lib = ops.dedup_sort(cu, 1, None, total, reuse_workspace=False)
+    os.environ["RS_SORT"] = "own"
+    try:
+        own = ops.dedup_sort(cu, 1, None, total, reuse_workspace=False)
+    finally:
+        del os.environ["RS_SORT"]
+    order = np.argsort(ids.numpy(), kind="stable")
+    assert np.array_equal(own.sorted_pos().cpu().numpy().astype(np.int64), order)
+    assert own.n_uniq == lib.n_uniq == len(np.unique(ids.numpy()))
+    for name in ("sorted_pos", "inverse", "counts", "uniq"):
+        assert torch.equal(getattr(own, name)(), getattr(lib, name)()), name
+    ops.check_status()
+
+
 # ------------------------------------------------------------------ segment reduce + update
 @pytest.mark.parametrize("W", [1, 4, 8, 16, 64, 128, 416, 10, 1248])
 @pytest.mark.parametrize("hot", [False, True])
