@@ -176,21 +176,36 @@ def test_eval_mode_and_no_grad():
 
 @pytest.mark.parametrize("pool", [True, False])
 def test_din_attention_tc_equals_fused(pool):
-    """tensor-core (GEMM) and fused CUDA-core implementations of the attention unit agree on outputs and gradients."""
-    from deeplearningrecommendationsystem_b200 import attention
+    """the tcgen05 kernels (what din_attention picks for B*L >= 8192 rows) and the CUDA-core kernel pair (RS_DIN_TC=0)
+    agree on outputs and gradients through autograd."""
+    import os
+    from deeplearningrecommendationsystem_b200 import attention, ops
     g = torch.Generator().manual_seed(0)
-    B, L, D = 70, 100, 64
+    B, L, D = 90, 100, 64
     unit = torch.nn.Sequential(torch.nn.Linear(3 * D, 128), torch.nn.ReLU(), torch.nn.Linear(128, 64), torch.nn.ReLU(),
                                torch.nn.Linear(64, 1)).cuda()
     rows = (torch.randn(B, L + 1, D, generator=g) * 0.5).cuda()
     gup = torch.randn((B, D) if pool else (B, L, D), generator=g).cuda()
     res = {}
     for impl in ("tc", "fused"):
-        r = rows.clone().requires_grad_(True)
-        unit.zero_grad()
-        out = attention.din_attention(r, unit, pool, impl=impl)
-        (out * gup).sum().backward()
-        res[impl] = [out.detach(), r.grad] + [p.grad.clone() for p in unit.parameters()]
-    for a, b in list(zip(res["tc"], res["fused"]))[:-1]:          # the last entry is d/d b2, analytically zero (softmax shift)
-        np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-5, atol=1e-5 * max(1e-3, float(b.abs().max())))
+        if impl == "fused":
+            os.environ["RS_DIN_TC"] = "0"
+        try:
+            r = rows.clone().requires_grad_(True)
+            unit.zero_grad()
+            n0 = ops.launches()
+            out = attention.din_attention(r, unit, pool)
+            (out * gup).sum().backward()
+            res[impl] = [out.detach(), r.grad] + [p.grad.clone() for p in unit.parameters()]
+            res[impl + "_launches"] = ops.launches() - n0
+        finally:
+            os.environ.pop("RS_DIN_TC", None)
+    assert res["tc_launches"] > res["fused_launches"]                      # two different kernel sets really ran
+    for k, (a, b) in enumerate(list(zip(res["tc"], res["fused"]))[:-1]):   # the last entry is d/d b2, analytically zero
+        tol = 1e-5 * max(1e-3, float(b.abs().max()))
+        if k == 1:   # d rows: a ReLU input within rounding of zero may flip between the two evaluations (see kernel tests)
+            bad = int(((a - b).abs() > tol + 1e-5 * b.abs()).flatten(1).any(dim=1).sum())
+            assert bad <= 1, f"{bad} samples differ"
+        else:
+            assert float((a - b).norm()) <= 1e-4 * float(b.norm()) + tol, k
     assert float(res["tc"][-1].abs().max()) < 1e-4 and float(res["fused"][-1].abs().max()) < 1e-4
