@@ -181,3 +181,17 @@ def test_assemble_features_oracle_equals_reference_merge():
     got = sampling.assemble_features(z["users"], z["items"], z["user_feat"], z["item_feat"])
     assert np.array_equal(got, z["x"])                    # bit-exact, row order of the input pairs
     assert np.array_equal(z["rating"], z["pair_rating"])
+
+
+def test_rank_oracle_tie_and_nan_conventions():
+    """distinct scores: exactly torch.topk; ties: the lower position first (torch.sort(stable=True, descending=True));
+    NaN ranks above everything, as in torch.topk."""
+    g = torch.Generator().manual_seed(1)
+    s = torch.randn(500, generator=g)
+    assert ranking.rank_desc(s.numpy(), 37).tolist() == torch.topk(s, 37).indices.tolist()
+    t = (s * 2).round() / 2                                    # heavy ties
+    assert ranking.rank_desc(t.numpy(), 500).tolist() == torch.sort(t, stable=True, descending=True).indices.tolist()
+    t[17] = float("nan")
+    assert int(ranking.rank_desc(t.numpy(), 1)[0]) == 17 == int(torch.topk(t, 1).indices[0])
+    with pytest.raises(RuntimeError):
+        ranking.rank_desc(s.numpy()[:5], 6)
