@@ -135,13 +135,16 @@ __global__ void __launch_bounds__(NTH, 1) afm_fwd_tc_kernel(const __grid_constan
       const int p = t * MT + tid;
       const int ij = p < NP ? pair[p] : 0;
       const float *ei = Eb + (ij >> 8) * DP, *ej = Eb + (ij & 255) * DP;
-      for (int q = 0; q < D / 4; ++q) {
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p < NP) x = rs::f4_mul(*reinterpret_cast<const float4 *>(ei + 4 * q), *reinterpret_cast<const float4 *>(ej + 4 * q));
-        uint4 hh, ll;
-        split4(x, hh, ll);
-        *reinterpret_cast<uint4 *>(ah + (q * MT + tid) * 4) = hh;
-        *reinterpret_cast<uint4 *>(al + (q * MT + tid) * 4) = ll;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {   // D <= 32: unrolled with a predicate so the eight products overlap
+        if (4 * q < D) {
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p < NP) x = rs::f4_mul(*reinterpret_cast<const float4 *>(ei + 4 * q), *reinterpret_cast<const float4 *>(ej + 4 * q));
+          uint4 hh, ll;
+          split4(x, hh, ll);
+          *reinterpret_cast<uint4 *>(ah + (q * MT + tid) * 4) = hh;
+          *reinterpret_cast<uint4 *>(al + (q * MT + tid) * 4) = ll;
+        }
       }
       rs::fence_proxy_async();
       fence_before_sync();
@@ -332,6 +335,7 @@ __global__ void __launch_bounds__(NG3 * MT, 1) afm_bwd_chain_tc_kernel(const __g
       const int ij = pair[p];
       const float *ei = Eb + (ij >> 8) * DP, *ej = Eb + (ij & 255) * DP;
       float dw = 0.f;
+#pragma unroll 4
       for (int q = 0; q < D / 4; ++q)
         dw += rs::f4_dot(rs::f4_mul(*reinterpret_cast<const float4 *>(ei + 4 * q), *reinterpret_cast<const float4 *>(ej + 4 * q)),
                          *reinterpret_cast<const float4 *>(g_s + 4 * q));
@@ -354,13 +358,16 @@ __global__ void __launch_bounds__(NG3 * MT, 1) afm_bwd_chain_tc_kernel(const __g
       const int ij = ok ? pair[p] : 0;
       const float *ei = Eb + (ij >> 8) * DP, *ej = Eb + (ij & 255) * DP;
       // ---- z = P W: pair products straight into the A operand
-      for (int q = 0; q < D / 4; ++q) {
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok) x = rs::f4_mul(*reinterpret_cast<const float4 *>(ei + 4 * q), *reinterpret_cast<const float4 *>(ej + 4 * q));
-        uint4 hh, ll;
-        split4(x, hh, ll);
-        *reinterpret_cast<uint4 *>(opP + (q * MT + tid) * 4) = hh;
-        *reinterpret_cast<uint4 *>(opP + D * MT + (q * MT + tid) * 4) = ll;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {   // D <= 32
+        if (4 * q < D) {
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok) x = rs::f4_mul(*reinterpret_cast<const float4 *>(ei + 4 * q), *reinterpret_cast<const float4 *>(ej + 4 * q));
+          uint4 hh, ll;
+          split4(x, hh, ll);
+          *reinterpret_cast<uint4 *>(opP + (q * MT + tid) * 4) = hh;
+          *reinterpret_cast<uint4 *>(opP + D * MT + (q * MT + tid) * 4) = ll;
+        }
       }
       rs::fence_proxy_async();
       fence_before_sync();
