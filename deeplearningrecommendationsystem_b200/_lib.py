@@ -26,7 +26,20 @@ RS_MAX_RANKS = 64
 
 class rs_routes(C.Structure):
     _fields_ = [("n", C.c_int32), ("start", C.c_int64 * (RS_MAX_RANKS + 1)), ("base", C.c_void_p * RS_MAX_RANKS),
-                ("row0", C.c_int64 * RS_MAX_RANKS)]
+                ("row0", C.c_int64 * RS_MAX_RANKS), ("dyn_start", C.c_void_p), ("dyn_row0", C.c_void_p), ("cap_rows", C.c_int64)]
+
+
+class rs_dedup_opts(C.Structure):
+    _fields_ = [("n_valid", C.c_void_p), ("shard_world", C.c_int32), ("shard_rows", C.c_int64)]
+
+
+RS_SHARD_CTL_WORDS = 384
+RS_CTL_CNT_IN, RS_CTL_BLK0_IN, RS_CTL_G0_IN, RS_CTL_SEND_START, RS_CTL_RECV_START, RS_CTL_M_TOTAL = 0, 64, 128, 192, 257, 322
+
+
+class rs_shard(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("rows_per_rank", C.c_int64), ("cap_req", C.c_int64),
+                ("cap_recv", C.c_int64), ("req", C.c_void_p * RS_MAX_RANKS), ("ctl", C.c_void_p * RS_MAX_RANKS)]
 
 
 class rs_fields_io(C.Structure):
@@ -85,7 +98,11 @@ SIGNATURES = {
     "rs_ffm_dense_bwd": [_P, _P, _L, _I, _I, _I, _PP(_I), _P, _P],
     "rs_dedup_workspace_bytes": [_L, _I, _PP(_Z)],
     "rs_dedup_sort": [_P, _L, _I, _PP(_L), _L, _P, _Z, _PP(rs_segments), _P, _P],
+    "rs_dedup_sort_ex": [_P, _L, _I, _PP(_L), _L, _PP(rs_dedup_opts), _P, _Z, _PP(rs_segments), _P, _P],
     "rs_segments_relabel": [_PP(rs_segments), _L, _P],
+    "rs_shard_post": [_PP(rs_shard), _PP(rs_segments), _L, _P, _P],
+    "rs_shard_collect": [_PP(rs_shard), _P, _P, _P, _P],
+    "rs_shard_serve": [_PP(rs_shard), _P, _L, _I, _P, _PP(_P), _L, _P, _P],
     "rs_segment_update": [_PP(rs_segments), _L, _PP(rs_update), _P],
     "rs_adam_dense": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P],
     "rs_xembed_fwd": [_PP(rs_xslots), _P, _L, _P, _P, _P],

@@ -146,12 +146,22 @@ struct Routes {
   int64_t start[RS_MAX_RANKS + 1];
   float *base[RS_MAX_RANKS];
   int64_t row0[RS_MAX_RANKS];
+  const int64_t *dyn_start, *dyn_row0;  // device-resident ranges (host-sync-free sharded step), else nullptr
+  int64_t cap_rows;                     // > 0: destination rows >= cap_rows are dropped
 };
-// destination of logical row r (floats): linear scan over at most n <= 64 ranges
+// destination of logical row r (floats): linear scan over at most n <= 64 ranges; nullptr = drop the row
 __device__ __forceinline__ float *route_row(const Routes &R, int64_t r, int W) {
   int k = 0;
-  while (k + 1 < R.n && r >= R.start[k + 1]) ++k;
-  return R.base[k] + (R.row0[k] + (r - R.start[k])) * W;
+  int64_t dst;
+  if (R.dyn_start) {
+    while (k + 1 < R.n && r >= R.dyn_start[k + 1]) ++k;
+    dst = R.dyn_row0[k] + (r - R.dyn_start[k]);
+  } else {
+    while (k + 1 < R.n && r >= R.start[k + 1]) ++k;
+    dst = R.row0[k] + (r - R.start[k]);
+  }
+  if (R.cap_rows > 0 && dst >= R.cap_rows) return nullptr;
+  return R.base[k] + dst * W;
 }
 
 __device__ __forceinline__ int64_t clamp_id(int64_t id, int64_t rows, int32_t *status) {

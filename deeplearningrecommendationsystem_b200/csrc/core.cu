@@ -106,6 +106,10 @@ int fill_routes(Routes &R, const rs_routes *r, const char *who) {
     R.row0[k] = r->row0[k];
   }
   R.start[r->n] = r->start[r->n];
+  R.dyn_start = r->dyn_start;
+  R.dyn_row0 = r->dyn_row0;
+  R.cap_rows = r->cap_rows;
+  RS_CHECK_ARG(!r->dyn_start || r->dyn_row0, RS_E_ARG, "%s: dyn_start without dyn_row0", who);
   return RS_OK;
 }
 }  // namespace rs
@@ -131,7 +135,8 @@ __global__ void __launch_bounds__(256) gather_rows_peer_kernel(const float *__re
         const int v = (int)(e - i * wv);
         const int64_t id = rs::clamp_id(idx[i], rows, status);
         val[u] = rs::ldg_nc_f4(table + (id * wv + v) * 4);
-        dst[u] = rs::route_row(R, i, wv * 4) + v * 4;
+        dst[u] = rs::route_row(R, i, wv * 4);
+        if (dst[u]) dst[u] += v * 4;
       }
     }
 #pragma unroll

@@ -19,35 +19,49 @@ struct Offsets {
   int64_t off[RS_MAX_FIELDS];
 };
 
+// Padding (p >= *n_valid) gets the key `pad_key` = one past the largest real key: it sorts behind every real lookup and is
+// then ignored by all the kernels below, which stop at *n_valid.
 __global__ void __launch_bounds__(256) make_keys_kernel(const int64_t *__restrict__ ids, int64_t n, int F, const __grid_constant__ Offsets O,
                                                        int64_t total_rows, uint32_t *__restrict__ keys, int32_t *__restrict__ pos,
-                                                       int32_t *status) {
+                                                       int32_t *status, const int32_t *__restrict__ n_valid, int shard_world,
+                                                       int64_t shard_rows, uint32_t pad_key) {
   __shared__ int64_t s_off[RS_MAX_FIELDS + 1];
   for (int i = threadIdx.x; i < F; i += blockDim.x) s_off[i] = O.off[i];
   if (threadIdx.x == 0) s_off[F] = total_rows;
   __syncthreads();
   int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
+  pos[p] = (int32_t)p;
+  if (n_valid && p >= *n_valid) {
+    keys[p] = pad_key;
+    return;
+  }
   int f = (int)(p % F);
   int64_t lo = s_off[f];
   int64_t hi = (f + 1 < F ? s_off[f + 1] : total_rows);
   int64_t id = rs::clamp_id(ids[p], hi - lo, status);
-  keys[p] = (uint32_t)(lo + id);
-  pos[p] = (int32_t)p;
+  int64_t g = lo + id;
+  if (shard_world > 1) g = (g % shard_world) * shard_rows + g / shard_world;   // owner-major: owner * R + local index
+  keys[p] = (uint32_t)g;
 }
 
-__global__ void __launch_bounds__(256) head_flags_kernel(const uint32_t *__restrict__ k, int64_t n, int32_t *__restrict__ head) {
+#define RS_NV(nvp, n) ((nvp) ? (int64_t) * (nvp) : (n))   /* number of real (non-padding) lookups */
+
+__global__ void __launch_bounds__(256) head_flags_kernel(const uint32_t *__restrict__ k, int64_t n, int32_t *__restrict__ head,
+                                                        const int32_t *__restrict__ nvp) {
   int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
-  head[s] = (s == 0 || k[s] != k[s - 1]) ? 1 : 0;
+  head[s] = (s < RS_NV(nvp, n) && (s == 0 || k[s] != k[s - 1])) ? 1 : 0;
 }
 
 // segidx1 = inclusive scan of head flags (1-based segment index)
 __global__ void __launch_bounds__(256) seg_scatter_kernel(const uint32_t *__restrict__ k, const int32_t *__restrict__ pos,
                                                          const int32_t *__restrict__ head, const int32_t *__restrict__ segidx1, int64_t n,
                                                          int64_t *__restrict__ uniq, int32_t *__restrict__ seg_start,
-                                                         int32_t *__restrict__ inverse, int32_t *__restrict__ n_uniq) {
+                                                         int32_t *__restrict__ inverse, int32_t *__restrict__ n_uniq,
+                                                         const int32_t *__restrict__ nvp) {
   int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  n = RS_NV(nvp, n);
   if (s >= n) return;
   int g = segidx1[s] - 1;
   if (head[s]) {
@@ -63,9 +77,13 @@ __global__ void __launch_bounds__(256) seg_scatter_kernel(const uint32_t *__rest
 
 __global__ void __launch_bounds__(256) chunk_flags_kernel(const int32_t *__restrict__ head, const int32_t *__restrict__ segidx1,
                                                          const int32_t *__restrict__ seg_start, int64_t n, int32_t *__restrict__ chead,
-                                                         int32_t *__restrict__ counts) {
+                                                         int32_t *__restrict__ counts, const int32_t *__restrict__ nvp) {
   int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
+  if (s >= RS_NV(nvp, n)) {
+    chead[s] = 0;
+    return;
+  }
   int g = segidx1[s] - 1;
   int st = seg_start[g];
   chead[s] = (((int)s - st) % RS_CHUNK == 0) ? 1 : 0;
@@ -75,8 +93,10 @@ __global__ void __launch_bounds__(256) chunk_flags_kernel(const int32_t *__restr
 __global__ void __launch_bounds__(256) chunk_scatter_kernel(const int32_t *__restrict__ head, const int32_t *__restrict__ segidx1,
                                                            const int32_t *__restrict__ chead, const int32_t *__restrict__ chunkidx1,
                                                            int64_t n, int32_t *__restrict__ chunk_start, int32_t *__restrict__ chunk_seg,
-                                                           int32_t *__restrict__ seg_first_chunk, int32_t *__restrict__ n_chunks) {
+                                                           int32_t *__restrict__ seg_first_chunk, int32_t *__restrict__ n_chunks,
+                                                           const int32_t *__restrict__ nvp) {
   int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  n = RS_NV(nvp, n);
   if (s >= n) return;
   int g = segidx1[s] - 1;
   int c = chunkidx1[s] - 1;
@@ -105,9 +125,13 @@ __global__ void __launch_bounds__(256) multi_list_kernel(const int32_t *__restri
 __global__ void __launch_bounds__(256) lookup_desc_kernel(const int32_t *__restrict__ sorted_pos, const int32_t *__restrict__ chunkidx1,
                                                          const int32_t *__restrict__ chunk_start, const int32_t *__restrict__ chunk_seg,
                                                          const int32_t *__restrict__ seg_first_chunk, const int64_t *__restrict__ uniq,
-                                                         int64_t n, int4 *__restrict__ desc) {
+                                                         int64_t n, int4 *__restrict__ desc, const int32_t *__restrict__ nvp) {
   int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
+  if (s >= RS_NV(nvp, n)) {
+    desc[s] = make_int4(0, 0, 0, 0);
+    return;
+  }
   const int c = chunkidx1[s] - 1;
   const int s0 = chunk_start[c], s1 = chunk_start[c + 1];
   const int g = chunk_seg[c];
@@ -118,9 +142,11 @@ __global__ void __launch_bounds__(256) lookup_desc_kernel(const int32_t *__restr
 
 // Work units of the streaming kernel start on chunk boundaries: unit u = chunks whose first lookup is in
 // [u*RS_UNIT, (u+1)*RS_UNIT).  unit_start[u] = first chunk start >= u*RS_UNIT (n past the end).
-__global__ void __launch_bounds__(256) unit_start_kernel(const int4 *__restrict__ desc, int64_t n, int nunits, int32_t *__restrict__ unit_start) {
+__global__ void __launch_bounds__(256) unit_start_kernel(const int4 *__restrict__ desc, int64_t n, int nunits, int32_t *__restrict__ unit_start,
+                                                        const int32_t *__restrict__ nvp) {
   int u = blockIdx.x * blockDim.x + threadIdx.x;
   if (u > nunits) return;
+  n = RS_NV(nvp, n);
   int64_t s = (int64_t)u * RS_UNIT;
   while (s < n && !(desc[s].y & 1)) ++s;  // a chunk has at most RS_CHUNK lookups, so this stops within RS_CHUNK steps
   unit_start[u] = (int32_t)(s < n ? s : n);
@@ -209,7 +235,22 @@ RS_API int rs_dedup_workspace_bytes(int64_t n, int32_t max_width, size_t *bytes)
 
 RS_API int rs_dedup_sort(const int64_t *ids, int64_t n, int32_t F, const int64_t *row_offset, int64_t total_rows, void *ws,
                          size_t ws_bytes, rs_segments *seg, int32_t *status, void *stream) {
+  return rs_dedup_sort_ex(ids, n, F, row_offset, total_rows, nullptr, ws, ws_bytes, seg, status, stream);
+}
+
+RS_API int rs_dedup_sort_ex(const int64_t *ids, int64_t n, int32_t F, const int64_t *row_offset, int64_t total_rows,
+                            const rs_dedup_opts *opts, void *ws, size_t ws_bytes, rs_segments *seg, int32_t *status, void *stream) {
   RS_CHECK_ARG(ids && ws && seg, RS_E_ARG, "rs_dedup_sort: null argument");
+  const int32_t *nvp = opts ? opts->n_valid : nullptr;
+  const int shard_world = opts ? opts->shard_world : 0;
+  const int64_t shard_rows = opts ? opts->shard_rows : 0;
+  int64_t key_space = total_rows;                  // keys live in [0, key_space)
+  if (shard_world > 1) {
+    RS_CHECK_ARG(shard_rows >= (total_rows + shard_world - 1) / shard_world, RS_E_ARG, "rs_dedup_sort_ex: shard_rows too small");
+    key_space = (int64_t)shard_world * shard_rows;
+  }
+  if (nvp) key_space += 1;                         // the padding key
+  RS_CHECK_ARG(key_space < (1ll << 32), RS_E_SHAPE, "rs_dedup_sort_ex: key space must be < 2^32");
   RS_CHECK_ARG(n > 0 && n < (1ll << 31), RS_E_SHAPE, "rs_dedup_sort: n must be in [1, 2^31)");
   RS_CHECK_ARG(F >= 1 && F <= RS_MAX_FIELDS && n % F == 0, RS_E_SHAPE, "rs_dedup_sort: bad F");
   RS_CHECK_ARG(total_rows > 0 && total_rows < (1ll << 32), RS_E_SHAPE, "rs_dedup_sort: total_rows must be < 2^32");
@@ -251,10 +292,14 @@ RS_API int rs_dedup_sort(const int64_t *ids, int64_t n, int32_t F, const int64_t
   if (!row_offset) RS_CHECK_ARG(F == 1, RS_E_ARG, "rs_dedup_sort: row_offset required when F > 1");
   cudaStream_t st = (cudaStream_t)stream;
   int blocks = (int)((n + 255) / 256);
-  make_keys_kernel<<<blocks, 256, 0, st>>>(ids, n, F, O, total_rows, keys_in, pos_in, status);
+  // scalars start at zero so that an empty (all padding) list leaves n_uniq = n_chunks = 0 and seg_start[0] = 0
+  RS_CUDA(cudaMemsetAsync(seg->n_uniq, 0, 4 * sizeof(int32_t), st));
+  if (nvp) RS_CUDA(cudaMemsetAsync(seg->seg_start, 0, sizeof(int32_t), st));
+  make_keys_kernel<<<blocks, 256, 0, st>>>(ids, n, F, O, total_rows, keys_in, pos_in, status, nvp, shard_world, shard_rows,
+                                           (uint32_t)(key_space - 1));
   RS_CHECK_LAUNCH();
   int end_bit = 1;
-  while (end_bit < 32 && (1ull << end_bit) < (uint64_t)total_rows) ++end_bit;
+  while (end_bit < 32 && (1ull << end_bit) < (uint64_t)key_space) ++end_bit;
   // Stable sort by row key.  Default: cub::DeviceRadixSort (onesweep) + cub::DeviceScan -- library plumbing, like cuBLAS
   // for the towers.  RS_SORT=own selects the hand-written LSD radix sort and prefix sums of sort.cu: bit-identical
   // results (tests/test_kernels_gpu.py), but 15 small launches per sort instead of 4, which measured 3 % slower on the
@@ -267,7 +312,7 @@ RS_API int rs_dedup_sort(const int64_t *ids, int64_t n, int32_t F, const int64_t
     int rc = rs::radix_sort_pairs(keys_in, pos_in, seg->sorted_key, seg->sorted_pos, (uint32_t *)head, segidx1, sort_hist, n, end_bit, st);
     if (rc) return rc;
   }
-  head_flags_kernel<<<blocks, 256, 0, st>>>(seg->sorted_key, n, head);
+  head_flags_kernel<<<blocks, 256, 0, st>>>(seg->sorted_key, n, head, nvp);
   RS_CHECK_LAUNCH();
   if (use_cub) {
     RS_CUDA(cub::DeviceScan::InclusiveSum(cub_ws, cub_bytes, head, segidx1, (int)n, st));
@@ -276,9 +321,9 @@ RS_API int rs_dedup_sort(const int64_t *ids, int64_t n, int32_t F, const int64_t
     if (rc) return rc;
   }
   seg_scatter_kernel<<<blocks, 256, 0, st>>>(seg->sorted_key, seg->sorted_pos, head, segidx1, n, seg->uniq, seg->seg_start,
-                                             seg->inverse, seg->n_uniq);
+                                             seg->inverse, seg->n_uniq, nvp);
   RS_CHECK_LAUNCH();
-  chunk_flags_kernel<<<blocks, 256, 0, st>>>(head, segidx1, seg->seg_start, n, chead, seg->counts);
+  chunk_flags_kernel<<<blocks, 256, 0, st>>>(head, segidx1, seg->seg_start, n, chead, seg->counts, nvp);
   RS_CHECK_LAUNCH();
   if (use_cub) {
     RS_CUDA(cub::DeviceScan::InclusiveSum(cub_ws, cub_bytes, chead, chunkidx1, (int)n, st));
@@ -287,16 +332,15 @@ RS_API int rs_dedup_sort(const int64_t *ids, int64_t n, int32_t F, const int64_t
     if (rc) return rc;
   }
   chunk_scatter_kernel<<<blocks, 256, 0, st>>>(head, segidx1, chead, chunkidx1, n, seg->chunk_start, seg->chunk_seg,
-                                               seg->seg_first_chunk, seg->n_chunks);
+                                               seg->seg_first_chunk, seg->n_chunks, nvp);
   RS_CHECK_LAUNCH();
-  RS_CUDA(cudaMemsetAsync(seg->n_multi, 0, sizeof(int32_t), st));
   multi_list_kernel<<<blocks, 256, 0, st>>>(seg->seg_first_chunk, seg->n_uniq, seg->multi_seg, seg->n_multi);
   RS_CHECK_LAUNCH();
   lookup_desc_kernel<<<blocks, 256, 0, st>>>(seg->sorted_pos, chunkidx1, seg->chunk_start, seg->chunk_seg, seg->seg_first_chunk,
-                                             seg->uniq, n, (int4 *)seg->lookup_desc);
+                                             seg->uniq, n, (int4 *)seg->lookup_desc, nvp);
   RS_CHECK_LAUNCH();
   const int nunits = (int)(n / RS_UNIT + 1);
-  unit_start_kernel<<<(nunits + 256) / 256, 256, 0, st>>>((const int4 *)seg->lookup_desc, n, nunits, seg->unit_start);
+  unit_start_kernel<<<(nunits + 256) / 256, 256, 0, st>>>((const int4 *)seg->lookup_desc, n, nunits, seg->unit_start, nvp);
   RS_CHECK_LAUNCH();
   return RS_OK;
 }
@@ -348,9 +392,10 @@ __device__ __forceinline__ void apply_row(const UpdParams &P, int64_t row, int e
   using V = Vec<VEC>;
   int64_t off = (row * P.W) + (int64_t)e * VEC;
   if (MODE == RS_UPD_GRAD) {
-    if (P.routes.n > 0)
-      V::st(rs::route_row(P.routes, row, P.W) + (int64_t)e * VEC, g);
-    else
+    if (P.routes.n > 0) {
+      float *d = rs::route_row(P.routes, row, P.W);
+      if (d) V::st(d + (int64_t)e * VEC, g);
+    } else
       V::st(P.dense_grad + off, g);
   } else if (MODE == RS_UPD_SGD) {
     typename V::T w = V::ld(P.table + off);
@@ -573,6 +618,8 @@ RS_API int rs_segment_update(const rs_segments *seg, int64_t n, const rs_update 
   P.v = u->v;
   P.dense_grad = u->dense_grad;
   P.routes.n = 0;
+  P.routes.dyn_start = P.routes.dyn_row0 = nullptr;
+  P.routes.cap_rows = 0;
   if (u->mode == RS_UPD_GRAD && u->grad_routes) {
     int rc = rs::fill_routes(P.routes, u->grad_routes, "rs_segment_update");
     if (rc) return rc;

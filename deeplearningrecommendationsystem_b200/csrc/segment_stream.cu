@@ -189,14 +189,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) seg_stream_kernel(const __grid_co
                 uint32_t row;
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(row) : "r"(h + (uint32_t)offsetof(StageHdr, row) + 4u * e));
                 float *dst = (MODE == RS_UPD_GRAD ? (P.routes.n > 0 ? route_row(P.routes, row, P.W) : P.dense_grad + (int64_t)row * P.W)
-                                                  : P.table + (int64_t)row * P.W) + col * 4;
+                                                  : P.table + (int64_t)row * P.W);
+                if (dst) dst += col * 4;   // nullptr: the routed destination is beyond the receiver's capacity (flagged there)
                 if (MODE == RS_UPD_SGD) {
                   int ts;
                   asm volatile("ld.shared.s32 %0, [%1];" : "=r"(ts) : "r"(h + (uint32_t)offsetof(StageHdr, tslot) + 4u * e));
                   const float4 w = lds_f4(col_s + (uint32_t)(SR + ts) * row_bytes);
                   stg_f4(dst, upd_sgd(w, acc[a], P));
                 } else if (MODE == RS_UPD_GRAD) {
-                  stg_f4(dst, acc[a]);
+                  if (dst) stg_f4(dst, acc[a]);
                 } else {
                   float wv[4], mv[4], vv[4], gv[4];
                   *reinterpret_cast<float4 *>(wv) = ldg_f4(dst);

@@ -1,0 +1,280 @@
+// Row-sharded tables: the exchange plan of a step, kept entirely on the device (no reference counterpart).
+//
+// Global row g lives on rank g % N at local index g / N.  A requester's distinct rows arrive here already sorted
+// owner-major (rs_dedup_sort_ex with shard_world), so the rows wanted from owner o are the contiguous range
+// [bounds[o], bounds[o+1]) of `uniq`.  Counts, offsets and request lists are written straight into the owners' symmetric
+// (peer-mapped) `req` / `ctl` buffers over NVLink; after one cross-rank barrier every owner knows what to serve and
+// where each requester's gradients will land.  Nothing is read back by the host, so the whole sharded train step is a
+// fixed launch sequence (CUDA-graph capturable).
+//
+// rs_shard_serve is the "rows" all-to-all fused into the owner's gather: for wide rows (FFM, 1664 B) each warp runs a
+// TMA pipeline -- cp.async.bulk global->shared of up to SERVE_C table rows into a stage, then ONE cp.async.bulk
+// shared->global of the whole stage into the requester's block (contiguous there), so the SM issues two bulk copies per
+// 16 rows and the payload never touches registers.  Narrow rows (FM, 64 B) use 128-bit loads/stores.
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace {
+
+struct ShardDev {
+  int world, rank;
+  int64_t R, cap_req, cap_recv;
+  int32_t *req[RS_MAX_RANKS];
+  int64_t *ctl[RS_MAX_RANKS];
+};
+
+int fill_shard(ShardDev &D, const rs_shard *S, const char *who) {
+  RS_CHECK_ARG(S && S->world >= 1 && S->world <= RS_MAX_RANKS && S->rank >= 0 && S->rank < S->world, RS_E_ARG, "%s: bad world/rank", who);
+  RS_CHECK_ARG(S->rows_per_rank > 0 && S->cap_req > 0 && S->cap_recv > 0, RS_E_ARG, "%s: bad capacities", who);
+  D.world = S->world, D.rank = S->rank, D.R = S->rows_per_rank, D.cap_req = S->cap_req, D.cap_recv = S->cap_recv;
+  for (int k = 0; k < S->world; ++k) {
+    RS_CHECK_ARG(S->req[k] && S->ctl[k], RS_E_ARG, "%s: null peer buffer for rank %d", who, k);
+    D.req[k] = S->req[k];
+    D.ctl[k] = S->ctl[k];
+  }
+  return RS_OK;
+}
+
+// first index j in [0, n) with a[j] >= key
+__device__ __forceinline__ int64_t lower_bound(const int64_t *__restrict__ a, int64_t n, int64_t key) {
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// ------------------------------------------------------------------ requester: post the request lists
+__global__ void __launch_bounds__(256) shard_post_kernel(const __grid_constant__ ShardDev S, const int64_t *__restrict__ uniq,
+                                                        const int32_t *__restrict__ n_uniq) {
+  __shared__ int64_t bounds[RS_MAX_RANKS + 1];
+  const int64_t nu = *n_uniq;
+  if (threadIdx.x <= S.world) bounds[threadIdx.x] = lower_bound(uniq, nu, (int64_t)threadIdx.x * S.R);
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x <= S.world) {
+    const int o = threadIdx.x;
+    S.ctl[S.rank][RS_CTL_SEND_START + o] = bounds[o];
+    if (o < S.world) {
+      S.ctl[o][RS_CTL_CNT_IN + S.rank] = bounds[o + 1] - bounds[o];   // rows I want from owner o
+      S.ctl[o][RS_CTL_BLK0_IN + S.rank] = bounds[o];                  // ... and where they belong inside my block
+    }
+  }
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nu; j += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t key = uniq[j];
+    const int o = (int)(key / S.R);
+    S.req[o][(int64_t)S.rank * S.cap_req + (j - bounds[o])] = (int32_t)(key - (int64_t)o * S.R);
+  }
+}
+
+// ------------------------------------------------------------------ owner: prefix of the counts + compact receive list
+__global__ void __launch_bounds__(256) shard_collect_kernel(const __grid_constant__ ShardDev S, int64_t *__restrict__ recv_local,
+                                                           int32_t *__restrict__ m_total, int32_t *status) {
+  __shared__ int64_t start[RS_MAX_RANKS + 1];
+  int64_t *ctl = S.ctl[S.rank];
+  if (threadIdx.x == 0) {
+    int64_t acc = 0;
+    for (int r = 0; r < S.world; ++r) {
+      start[r] = acc < S.cap_recv ? acc : S.cap_recv;
+      acc += ctl[RS_CTL_CNT_IN + r];
+    }
+    if (acc > S.cap_recv) {      // more rows than the receive buffers hold: flagged, the surplus is dropped everywhere
+      if (status && blockIdx.x == 0) atomicOr(status, 16);
+      acc = S.cap_recv;
+    }
+    start[S.world] = acc;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    if (threadIdx.x <= S.world) ctl[RS_CTL_RECV_START + threadIdx.x] = start[threadIdx.x];
+    if (threadIdx.x < S.world) S.ctl[threadIdx.x][RS_CTL_G0_IN + S.rank] = start[threadIdx.x];   // requester r pushes its gradients here
+    if (threadIdx.x == 0) {
+      ctl[RS_CTL_M_TOTAL] = start[S.world];
+      *m_total = (int32_t)start[S.world];
+    }
+  }
+  const int64_t m = start[S.world];
+  const int32_t *req = S.req[S.rank];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+    int r = 0;
+    while (r + 1 < S.world && i >= start[r + 1]) ++r;
+    recv_local[i] = (int64_t)req[(int64_t)r * S.cap_req + (i - start[r])];
+  }
+}
+
+// ------------------------------------------------------------------ owner: serve the rows
+struct Blocks {
+  float *base[RS_MAX_RANKS];
+};
+
+// generic 128-bit path (any width that is a multiple of 4 floats): one 16-byte piece per thread iteration, four in flight
+__global__ void __launch_bounds__(256) shard_serve_kernel(const __grid_constant__ ShardDev S, const float *__restrict__ table, int64_t rows,
+                                                         int wv, const int64_t *__restrict__ recv_local,
+                                                         const __grid_constant__ Blocks B, int64_t cap_block, int32_t *status) {
+  __shared__ int64_t start[RS_MAX_RANKS + 1], blk0[RS_MAX_RANKS];
+  const int64_t *ctl = S.ctl[S.rank];
+  if (threadIdx.x <= S.world) start[threadIdx.x] = ctl[RS_CTL_RECV_START + threadIdx.x];
+  if (threadIdx.x < S.world) blk0[threadIdx.x] = ctl[RS_CTL_BLK0_IN + threadIdx.x];
+  __syncthreads();
+  const int64_t total = start[S.world] * wv;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e0 < total; e0 += 4 * stride) {
+    float4 val[4];
+    float *dst[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t e = e0 + u * stride;
+      dst[u] = nullptr;
+      if (e < total) {
+        const int64_t i = e / wv;
+        const int v = (int)(e - i * wv);
+        int r = 0;
+        while (r + 1 < S.world && i >= start[r + 1]) ++r;
+        const int64_t id = rs::clamp_id(recv_local[i], rows, status);
+        const int64_t drow = blk0[r] + (i - start[r]);
+        val[u] = rs::ldg_nc_f4(table + (id * wv + v) * 4);
+        if (drow < cap_block) dst[u] = B.base[r] + (drow * wv + v) * 4;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (dst[u]) rs::stg_f4(dst[u], val[u]);
+  }
+}
+
+// TMA path.  Every warp owns SERVE_NST stages of SERVE_C rows.  Work item = up to SERVE_C consecutive rows of ONE
+// requester's list (they are consecutive in its block, so a stage leaves in a single bulk store).
+constexpr int SERVE_C = 16, SERVE_NST = 2, SERVE_WARPS = 4;
+
+__global__ void __launch_bounds__(SERVE_WARPS * 32, 1) shard_serve_tma_kernel(const __grid_constant__ ShardDev S, const float *__restrict__ table,
+                                                                             int64_t rows, int W, const int64_t *__restrict__ recv_local,
+                                                                             const __grid_constant__ Blocks B, int64_t cap_block,
+                                                                             int32_t *status) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint64_t full_bar[SERVE_WARPS][SERVE_NST];
+  __shared__ int64_t start[RS_MAX_RANKS + 1], blk0[RS_MAX_RANKS], cstart[RS_MAX_RANKS + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t row_bytes = (uint32_t)W * 4u;
+  const int64_t *ctl = S.ctl[S.rank];
+  if (threadIdx.x <= S.world) start[threadIdx.x] = ctl[RS_CTL_RECV_START + threadIdx.x];
+  if (threadIdx.x < S.world) blk0[threadIdx.x] = ctl[RS_CTL_BLK0_IN + threadIdx.x];
+  if (threadIdx.x < SERVE_WARPS * SERVE_NST) rs::mbar_init(&full_bar[threadIdx.x / SERVE_NST][threadIdx.x % SERVE_NST], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int64_t acc = 0;
+    for (int r = 0; r < S.world; ++r) {
+      cstart[r] = acc;
+      acc += (start[r + 1] - start[r] + SERVE_C - 1) / SERVE_C;
+    }
+    cstart[S.world] = acc;
+    rs::mbar_fence_init();
+  }
+  __syncthreads();
+  const int64_t nchunks = cstart[S.world];
+  float *ring = reinterpret_cast<float *>(smem_raw) + (size_t)warp * SERVE_NST * SERVE_C * W;
+  const int64_t gw = (int64_t)blockIdx.x * SERVE_WARPS + warp, nw = (int64_t)gridDim.x * SERVE_WARPS;
+  const int64_t mine = gw < nchunks ? (nchunks - gw + nw - 1) / nw : 0;   // chunks gw, gw + nw, ...
+
+  // chunk k of this warp -> (first compact row, row count, destination)
+  auto describe = [&](int64_t k, int64_t &i0, int &cnt, float *&dst) {
+    const int64_t c = gw + k * nw;
+    int r = 0;
+    while (r + 1 < S.world && c >= cstart[r + 1]) ++r;
+    i0 = start[r] + (c - cstart[r]) * SERVE_C;
+    const int64_t left = start[r + 1] - i0;
+    cnt = (int)(left < SERVE_C ? left : SERVE_C);
+    const int64_t drow = blk0[r] + (i0 - start[r]);
+    if (drow + cnt > cap_block) cnt = drow < cap_block ? (int)(cap_block - drow) : 0;
+    dst = B.base[r] + drow * W;
+  };
+
+  // iteration k: [stage k % NST is free once the store of chunk k - NST has read it] -> loads of chunk k ->
+  // [wait for the loads of chunk k - 1] -> store of chunk k - 1.  The store of chunk k - NST was committed NST - 2
+  // groups ago, so at most NST - 2 newer groups may still be reading.
+  for (int64_t k = 0; k <= mine; ++k) {
+    if (k < mine) {
+      const int st = (int)(k % SERVE_NST);
+      if (lane == 0) rs::bulk_wait_read<SERVE_NST - 2>();
+      __syncwarp();
+      int64_t i0;
+      int cnt;
+      float *dst;
+      describe(k, i0, cnt, dst);
+      if (lane == 0) rs::mbar_arrive_expect_tx(&full_bar[warp][st], row_bytes * (uint32_t)cnt);
+      __syncwarp();
+      if (lane < cnt) {
+        const int64_t id = rs::clamp_id(recv_local[i0 + lane], rows, status);
+        rs::bulk_g2s(ring + ((size_t)st * SERVE_C + lane) * W, table + id * W, row_bytes, &full_bar[warp][st]);
+      }
+    }
+    const int64_t j = k - 1;
+    if (j >= 0 && lane == 0) {
+      const int st = (int)(j % SERVE_NST);
+      int64_t i0;
+      int cnt;
+      float *dst;
+      describe(j, i0, cnt, dst);
+      rs::mbar_wait(&full_bar[warp][st], (uint32_t)(j / SERVE_NST) & 1u);
+      if (cnt > 0) rs::bulk_s2g(dst, ring + (size_t)st * SERVE_C * W, row_bytes * (uint32_t)cnt);
+      rs::bulk_commit();
+    }
+    __syncwarp();
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+}  // namespace
+
+RS_API int rs_shard_post(const rs_shard *S, const rs_segments *seg, int64_t n, int32_t *status, void *stream) {
+  ShardDev D;
+  if (int rc = fill_shard(D, S, "rs_shard_post")) return rc;
+  RS_CHECK_ARG(seg && seg->uniq && seg->n_uniq, RS_E_ARG, "rs_shard_post: incomplete segments");
+  RS_CHECK_ARG(n > 0 && n <= S->cap_req, RS_E_SHAPE, "rs_shard_post: %lld lookups exceed the request-slot capacity %lld", (long long)n,
+               (long long)S->cap_req);
+  (void)status;
+  int64_t blocks = (n + 255) / 256;
+  const int cap = rs::num_sms() * 8;
+  shard_post_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(D, seg->uniq, seg->n_uniq);
+  RS_CHECK_LAUNCH();
+  return RS_OK;
+}
+
+RS_API int rs_shard_collect(const rs_shard *S, int64_t *recv_local, int32_t *m_total, int32_t *status, void *stream) {
+  ShardDev D;
+  if (int rc = fill_shard(D, S, "rs_shard_collect")) return rc;
+  RS_CHECK_ARG(recv_local && m_total, RS_E_ARG, "rs_shard_collect: null output");
+  int64_t blocks = (S->cap_recv + 255) / 256;
+  const int cap = rs::num_sms() * 8;
+  shard_collect_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(D, recv_local, m_total, status);
+  RS_CHECK_LAUNCH();
+  return RS_OK;
+}
+
+RS_API int rs_shard_serve(const rs_shard *S, const float *table, int64_t rows, int32_t width, const int64_t *recv_local,
+                          float *const *block, int64_t cap_block_rows, int32_t *status, void *stream) {
+  ShardDev D;
+  if (int rc = fill_shard(D, S, "rs_shard_serve")) return rc;
+  RS_CHECK_ARG(table && rows > 0 && width >= 4 && width % 4 == 0 && recv_local && block && cap_block_rows > 0, RS_E_ARG,
+               "rs_shard_serve: bad argument");
+  Blocks B;
+  for (int k = 0; k < S->world; ++k) {
+    RS_CHECK_ARG(block[k], RS_E_ARG, "rs_shard_serve: null block pointer for rank %d", k);
+    B.base[k] = block[k];
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const char *mode = getenv("RS_SERVE");                       // "st" forces the 128-bit load/store kernel
+  const size_t smem = (size_t)SERVE_WARPS * SERVE_NST * SERVE_C * width * 4;
+  if (width * 4 >= 512 && smem <= 220 * 1024 && !(mode && !strcmp(mode, "st"))) {
+    RS_CUDA(cudaFuncSetAttribute(shard_serve_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    shard_serve_tma_kernel<<<rs::num_sms(), SERVE_WARPS * 32, smem, st>>>(D, table, rows, width, recv_local, B, cap_block_rows, status);
+  } else {
+    const int wv = width / 4;
+    int64_t blocks = (S->cap_recv * wv + 1023) / 1024;
+    const int cap = rs::num_sms() * 8;
+    shard_serve_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(D, table, rows, wv, recv_local, B, cap_block_rows, status);
+  }
+  RS_CHECK_LAUNCH();
+  return RS_OK;
+}

@@ -136,97 +136,294 @@ class RowExchange:
         return out
 
 
-class PeerRowExchange(RowExchange):
-    """RowExchange whose two heavy all-to-alls are fused into the kernels over NVLink peer memory.
+# ---------------------------------------------------------------------------------------------------------------------
+# Device-side exchange: no host synchronisation anywhere in the step
+class Fabric:
+    """What the device-side exchange needs from the interconnect: symmetric (peer-mapped) buffers and a stream-ordered
+    cross-rank barrier.  ``alloc`` must be called in the same order with the same sizes on every rank."""
+    world, rank = 1, 0
 
-    Every rank owns two symmetric (peer-mapped) buffers per row width: `block` (the rows its batch needs) and `grads`
-    (the per-row gradients other ranks push to it).  Forward: the OWNER's gather kernel stores each requested row
-    straight into the requester's `block` (rs_gather_rows_peer) -- no staging buffer, no NCCL copy.  Backward: the
-    requester's segment-reduce kernel stores each reduced row gradient straight into the owner's `grads`
-    (RS_UPD_GRAD with grad_routes).  A device-side barrier on the symmetric-memory signal pads orders the phases.
-    Only the small id/count messages still go through NCCL.
-    """
+    def alloc(self, shape, dtype, device):
+        """-> (this rank's tensor, [device address of every rank's tensor, indexed by rank])"""
+        raise NotImplementedError
 
-    def __init__(self, prims, group=None, grads_slack=2.0):
-        super().__init__(prims, group)
-        self.grads_slack = grads_slack
-        self._bufs = {}
+    def barrier(self):
+        raise NotImplementedError
 
-    def _buffers(self, width, cap_rows, device):
+    def max_over_ranks(self, value):
+        return int(value)
+
+
+class LocalFabric(Fabric):
+    """world == 1: the same kernels and the same launch sequence, buffers are plain device memory."""
+
+    def alloc(self, shape, dtype, device):
+        t = torch.zeros(shape, dtype=dtype, device=device)
+        return t, [t.data_ptr()]
+
+    def barrier(self):
+        pass
+
+
+class SymmFabric(Fabric):
+    """torch symmetric memory over NVLink / NVSwitch (plumbing: allocation, peer pointers and the signal-pad barrier
+    kernel; every byte of payload is moved by this package's own kernels through those pointers)."""
+
+    def __init__(self, group=None):
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self._handles, self._hb = [], None
+
+    def alloc(self, shape, dtype, device):
         import torch.distributed._symmetric_memory as symm
-        key = (width, device)
-        ent = self._bufs.get(key)
-        if ent is None or ent["cap"] < cap_rows:
-            group = self.group if self.group is not None else dist.group.WORLD
-            gcap = int(cap_rows * self.grads_slack)
-            block = symm.empty((cap_rows, width), dtype=torch.float32, device=device)
-            grads = symm.empty((gcap, width), dtype=torch.float32, device=device)
-            hb = symm.rendezvous(block, group.group_name)
-            hg = symm.rendezvous(grads, group.group_name)
-            ent = {"cap": cap_rows, "gcap": gcap, "block": block, "grads": grads, "hb": hb, "hg": hg}
-            self._bufs[key] = ent
+        t = symm.empty(shape, dtype=dtype, device=device)
+        h = symm.rendezvous(t, self.group.group_name)
+        t.zero_()
+        self._handles.append(h)
+        if self._hb is None:
+            self._hb = h
+        return t, [int(h.buffer_ptrs[r]) for r in range(self.world)]
+
+    def barrier(self):
+        self._hb.barrier()
+
+    def max_over_ranks(self, value):
+        t = torch.tensor([int(value)], dtype=torch.int64, device=torch.cuda.current_device())
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return int(t.item())
+
+
+class ThreadFabric(Fabric):
+    """N virtual ranks as N python threads on ONE GPU (tests and the single-GPU verification leg of bench.py): the
+    kernels only ever see pointers, so 'peer' buffers are simply the other threads' tensors.  Ranks take turns (one lock),
+    every barrier drains the rank's stream before the next rank runs -- slow, but it executes exactly the kernels and
+    the launch order of the multi-GPU step."""
+
+    class Shared:
+        def __init__(self, world):
+            import threading
+            self.world = world
+            self.lock = threading.Lock()
+            self.bar = threading.Barrier(world)
+            self.allocs = {}
+
+    def __init__(self, shared, rank):
+        self.shared, self.world, self.rank = shared, shared.world, rank
+        self._seq = 0
+
+    def alloc(self, shape, dtype, device):
+        key, self._seq = self._seq, self._seq + 1
+        sh = self.shared
+        if key not in sh.allocs:                 # the first rank to get here allocates for everyone (the lock is held)
+            sh.allocs[key] = [torch.zeros(shape, dtype=dtype, device=device) for _ in range(self.world)]
+        ts = sh.allocs[key]
+        return ts[self.rank], [t.data_ptr() for t in ts]
+
+    def barrier(self):
+        torch.cuda.current_stream().synchronize()
+        self.shared.lock.release()
+        try:
+            self.shared.bar.wait(timeout=120)
+        finally:
+            self.shared.lock.acquire()
+
+    def allreduce_mean(self, grads):
+        """average the given gradient tensors over the virtual ranks (rank order, so every rank gets the same bits)"""
+        sh = self.shared
+        sh.allocs.setdefault("ar", [None] * self.world)[self.rank] = [g.clone() for g in grads]
+        self.barrier()
+        for i, g in enumerate(grads):
+            acc = sh.allocs["ar"][0][i].clone()
+            for r in range(1, self.world):
+                acc += sh.allocs["ar"][r][i]
+            g.copy_(acc / self.world)
+        self.barrier()
+
+    @staticmethod
+    def run(world, fn):
+        """fn(fabric) on `world` threads; returns the list of results by rank (exceptions re-raised)."""
+        import threading
+        shared = ThreadFabric.Shared(world)
+        out, err = [None] * world, [None] * world
+
+        def body(r):
+            fab = ThreadFabric(shared, r)
+            try:
+                with shared.lock:
+                    s = torch.cuda.Stream()
+                    with torch.cuda.stream(s):
+                        out[r] = fn(fab)
+                        s.synchronize()
+            except BaseException as e:            # noqa: BLE001
+                err[r] = e
+                shared.bar.abort()
+        ts = [threading.Thread(target=body, args=(r,)) for r in range(world)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        for e in err:
+            if e is not None and not isinstance(e, threading.BrokenBarrierError):
+                raise e
+        for e in err:
+            if e is not None:
+                raise e
+        return out
+
+
+class DevPlan:
+    """One step's exchange plan; every count lives on the device.  Valid until the exchange plans the next batch."""
+
+    def __init__(self, gen, n, segs, local_ids, recv_local, m_total):
+        self.gen, self.n, self.segs, self.local_ids, self.recv_local, self.m_total = gen, n, segs, local_ids, recv_local, m_total
+        self.osegs, self.osegs_ready = None, None
+
+    @property
+    def n_uniq(self):             # capacity stand-in: callers only use it to size things
+        return self.n
+
+
+class DeviceRowExchange:
+    """Row exchange of a sharded table with the plan kept on the device (rs_shard_* kernels, csrc/shard.cu).
+
+    Every rank owns symmetric buffers: `req` / `ctl` (request lists and counts, written by the requesters), and per row
+    width a `block` (the rows its batch needs, written by the owners' rs_shard_serve) and a `grads` buffer (reduced row
+    gradients, written by the requesters' segment-reduce through rs_routes).  Payload moves only inside this package's
+    kernels over NVLink peer pointers; barriers are stream ordered; there is no NCCL call and no host read in a step, so
+    the whole train step can be captured into a CUDA graph.
+
+    Capacities are fixed at first use from the number of lookups per batch (agreed over the ranks): a batch can never
+    need more distinct rows than lookups, and an owner is given room for recv_slack x that many incoming rows; an
+    overflow sets bit 16 of the status word (ops.check_status raises)."""
+
+    device_plan = True
+
+    def __init__(self, fabric=None, recv_slack=1.25):
+        if fabric is None:
+            fabric = SymmFabric() if dist.is_initialized() and dist.get_world_size() > 1 else LocalFabric()
+        self.fabric, self.world, self.rank, self.recv_slack = fabric, fabric.world, fabric.rank, recv_slack
+        self._ctl = None
+        self._bufs = {}
+        self._gen, self._memo = 0, None
+        self._side, self._unjoined = None, None
+
+    def local_rows(self, total_rows):
+        return (total_rows - self.rank + self.world - 1) // self.world
+
+    # ---- buffers
+    def _control(self, n, total_rows, device):
+        from . import _lib, ops
+        R = (total_rows + self.world - 1) // self.world
+        if self._ctl is not None:
+            c = self._ctl
+            if n > c["cap_req"] or R != c["R"]:
+                raise RuntimeError(f"DeviceRowExchange was sized for {c['cap_req']} lookups per batch over {c['R']} rows per rank; "
+                                   f"got {n} lookups / {R} rows (build a new exchange for a different table or a larger batch)")
+            return c
+        cap_req = self.fabric.max_over_ranks(n)
+        cap_recv = int(cap_req * self.recv_slack) + 64
+        req, req_ptrs = self.fabric.alloc((self.world * cap_req,), torch.int32, device)
+        ctl, ctl_ptrs = self.fabric.alloc((_lib.RS_SHARD_CTL_WORDS,), torch.int64, device)
+        self._ctl = {"cap_req": cap_req, "cap_recv": cap_recv, "R": R, "req": req, "ctl": ctl,
+                     "S": ops.make_shard(self.world, self.rank, R, cap_req, cap_recv, req_ptrs, ctl_ptrs),
+                     "recv_local": torch.zeros(cap_recv, dtype=torch.int64, device=device),
+                     "m_total": torch.zeros(1, dtype=torch.int32, device=device)}
+        self.fabric.barrier()                      # every rank's buffers exist (and are zeroed) before anyone writes to them
+        return self._ctl
+
+    def _buffers(self, width, device):
+        ent = self._bufs.get(width)
+        if ent is None:
+            c = self._ctl
+            block, block_ptrs = self.fabric.alloc((c["cap_req"], width), torch.float32, device)
+            grads, grad_ptrs = self.fabric.alloc((c["cap_recv"], width), torch.float32, device)
+            ent = self._bufs[width] = {"block": block, "block_ptrs": block_ptrs, "grads": grads, "grad_ptrs": grad_ptrs}
+            self.fabric.barrier()
         return ent
 
-    def _plan(self, keys, total_rows):
-        N = self.world
-        R = (total_rows + N - 1) // N
-        okeys = (keys % N) * R + keys // N
-        uniq, inverse, *rest = self.prims.unique(okeys, N * R)
-        bounds = torch.arange(N + 1, device=keys.device, dtype=uniq.dtype) * R
-        send_counts_t = torch.diff(torch.searchsorted(uniq, bounds))
-        # every rank learns the whole (requester, owner) count matrix in ONE all-gather: that fixes all split sizes
-        # and all destination offsets of both fused exchanges
-        allc = torch.empty(N, N, dtype=send_counts_t.dtype, device=keys.device)
-        dist.all_gather_into_tensor(allc, send_counts_t, group=self.group)
-        counts = allc.tolist()                                        # the one host sync of the plan
-        send_counts = counts[self.rank]
-        recv_counts = [counts[r][self.rank] for r in range(N)]
-        send_local = uniq % R
-        recv_local = torch.empty(sum(recv_counts), dtype=torch.int64, device=keys.device)
-        dist.all_to_all_single(recv_local, send_local, recv_counts, send_counts, group=self.group)
-        plan = Plan(int(uniq.numel()), inverse, send_local, send_counts, recv_counts, recv_local, rest[0] if rest else None)
-        plan.counts = counts
+    # ---- forward
+    def plan_for(self, ids, offsets, total_rows):
+        """ids (B, F) local ids, offsets: HOST list of the F row offsets.  Memoised on the identity of `ids` while it is
+        the exchange's latest plan (the FM and the FFM model of one batch share it)."""
+        m = self._memo
+        if m is not None and m[0] is ids and m[1] == ids._version and m[2] == total_rows and m[3] == tuple(offsets):
+            return m[4]
+        with _phase("exchange_plan"):
+            plan = self._plan(ids, offsets, total_rows)
+        self._memo = (ids, ids._version, total_rows, tuple(offsets), plan)
         return plan
 
-    def fetch(self, plan, local_table):
+    def _plan(self, ids, offsets, total_rows):
         from . import ops
-        N, me, W = self.world, self.rank, local_table.shape[1]
-        cap = plan.local_ids.numel()                                  # a batch cannot need more distinct rows than lookups
-        ent = self._buffers(W, cap, local_table.device)
-        counts = plan.counts
-        # rows requested by rank r start at sum(recv_counts[:r]) in my request list and belong at
-        # sum(counts[r][:me]) in r's block
-        starts, row0s = [0], []
-        for r in range(N):
-            starts.append(starts[-1] + counts[r][me])
-            row0s.append(sum(counts[r][:me]))
-        routes = ops.make_routes(starts, [ent["hb"].buffer_ptrs[r] for r in range(N)], row0s)
-        ops.gather_rows_peer(local_table, plan.recv_local, routes)
+        F = ids.shape[1] if ids.dim() == 2 else 1
+        n = ids.numel()
+        c = self._control(n, total_rows, ids.device)
+        if self._unjoined is not None:             # an unconsumed owner-side sort of the previous plan still reads recv_local
+            torch.cuda.current_stream(ids.device).wait_event(self._unjoined)
+            self._unjoined = None
+        segs = ops.dedup_sort(ids, F, list(offsets) if F > 1 or offsets else None, total_rows, shard=(self.world, c["R"]))
+        ops.shard_post(c["S"], segs)
+        self.fabric.barrier()
+        ops.shard_collect(c["S"], c["recv_local"], c["m_total"])
+        self._gen += 1
+        return DevPlan(self._gen, n, segs, segs.inverse().long(), c["recv_local"], c["m_total"])
+
+    def _check(self, plan):
+        if plan.gen != self._gen:
+            raise RuntimeError("stale exchange plan: the exchange has planned another batch since (one batch in flight per exchange)")
+
+    def fetch(self, plan, local_table):
+        """-> (cap, W) block; rows [0, n_uniq) hold the rows this rank's batch needs, in the order `local_ids` indexes."""
+        from . import ops
+        self._check(plan)
+        c, ent = self._ctl, self._buffers(local_table.shape[1], local_table.device)
+        ops.shard_serve(c["S"], local_table, plan.recv_local, ent["block_ptrs"], c["cap_req"])
         with _phase("exchange_barrier"):
-            ent["hb"].barrier()
-        return ent["block"][: plan.n_uniq]
+            self.fabric.barrier()
+        return ent["block"]
+
+    # ---- backward
+    def prefetch_owner_segments(self, plan, local_rows):
+        """The owner-side sort depends only on the plan: run it on a side stream under the forward kernels."""
+        from . import ops
+        if plan.osegs is not None:
+            return
+        dev = plan.recv_local.device
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=dev)
+        self._side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self._side):
+            plan.osegs = ops.dedup_sort(plan.recv_local, 1, None, local_rows, n_valid=plan.m_total)
+            plan.osegs_ready = torch.cuda.Event()
+            plan.osegs_ready.record()
+        self._unjoined = plan.osegs_ready
+
+    def owner_segments(self, plan, local_rows, width):
+        from . import ops
+        self._check(plan)
+        if plan.osegs is None:
+            plan.osegs = ops.dedup_sort(plan.recv_local, 1, None, local_rows, n_valid=plan.m_total)
+        elif plan.osegs_ready is not None:
+            torch.cuda.current_stream().wait_event(plan.osegs_ready)
+            if self._unjoined is plan.osegs_ready:
+                self._unjoined = None
+            plan.osegs_ready = None
+        return ops.attach_partial(plan.osegs, width)
 
     def grad_routes(self, plan, width, device):
-        """Routes for the reduced row gradients of the fetched block: block rows of owner o go to o's `grads` buffer at
-        the offset where this rank's rows start in o's request list."""
-        from . import ops
-        N, me = self.world, self.rank
-        ent = self._bufs[(width, device)]
-        counts = plan.counts
-        need = max(sum(counts[r][o] for r in range(N)) for o in range(N))
-        if need > ent["gcap"]:
-            raise RuntimeError(f"PeerRowExchange: an owner receives {need} rows > capacity {ent['gcap']}; raise grads_slack")
-        starts, row0s = [0], []
-        for o in range(N):
-            starts.append(starts[-1] + counts[me][o])
-            row0s.append(sum(counts[r][o] for r in range(me)))
-        return ops.make_routes(starts, [ent["hg"].buffer_ptrs[o] for o in range(N)], row0s), ent
+        """Routes of the reduced row gradients of the fetched block: block rows of owner o (a device-resident range) go to
+        o's `grads` buffer at the offset o announced during rs_shard_collect."""
+        from . import _lib, ops
+        self._check(plan)
+        c, ent = self._ctl, self._bufs[width]
+        base = c["ctl"].data_ptr()
+        return ops.make_routes(None, ent["grad_ptrs"], None, dyn_start=base + 8 * _lib.RS_CTL_SEND_START,
+                               dyn_row0=base + 8 * _lib.RS_CTL_G0_IN, cap_rows=c["cap_recv"]), ent
 
     def finish_push(self, plan, ent):
-        """After the routed segment-reduce: barrier, then this rank's received gradients (aligned with recv_local)."""
         with _phase("exchange_barrier"):
-            ent["hg"].barrier()
-        return ent["grads"][: plan.recv_local.numel()]
+            self.fabric.barrier()
+        return ent["grads"]
 
 
 def shard_rows(global_table, rank, world):
@@ -244,8 +441,11 @@ def unshard_rows(shards):
     return out
 
 
-def allreduce_dense_grads(params, group=None):
+def allreduce_dense_grads(params, group=None, fabric=None):
     """Average the gradients of the replicated dense parameters with ONE all-reduce over a flat bucket."""
+    if fabric is not None and hasattr(fabric, "allreduce_mean"):          # virtual ranks (ThreadFabric)
+        fabric.allreduce_mean([p.grad for p in params if p.grad is not None])
+        return
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
     grads = [p.grad for p in params if p.grad is not None]

@@ -36,7 +36,26 @@ class GraphedTrainStep:
         self.optimizer.step()
         return pred, loss
 
+    def _check_capturable(self):
+        """Adam's bias correction is computed on the host from a python step counter and handed to the kernels by value
+        (rs_segment_update / rs_adam_dense), so a captured Adam step would replay with the correction frozen at the
+        capture step.  Refuse instead of training silently wrong; SGD (and torch optimizers built with
+        capturable=True, whose step lives on the device) capture fine."""
+        from .optim import DenseAdam, FusedRowOptimizer
+        opts = [self.optimizer]
+        if isinstance(self.optimizer, FusedRowOptimizer):
+            if self.optimizer.kind == "adam":
+                raise RuntimeError("GraphedTrainStep: FusedRowOptimizer(kind='adam') keeps its step count on the host and "
+                                   "cannot be captured; run it eagerly or use kind='sgd'")
+            opts = [self.optimizer.dense]
+        for o in opts:
+            if isinstance(o, DenseAdam):
+                raise RuntimeError("GraphedTrainStep: DenseAdam keeps its step count on the host and cannot be captured")
+            if isinstance(o, (torch.optim.Adam, torch.optim.AdamW)) and not all(g.get("capturable") for g in o.param_groups):
+                raise RuntimeError("GraphedTrainStep: torch Adam must be built with capturable=True to be captured")
+
     def _capture(self, inputs, rating):
+        self._check_capturable()
         self.static_in = [t.clone() for t in inputs]
         self.static_rating = rating.clone()
         torch.cuda.synchronize()

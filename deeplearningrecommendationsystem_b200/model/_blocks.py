@@ -229,7 +229,9 @@ def rank_catalogue(score_fn, num_users, num_items, k):
             u1 = min(num_users, u0 + step)
             scores = score_fn(u0, u1).reshape(-1)
             out.append(ops.rank_segments(scores, k, seg_len=num_items))
-    return torch.cat(out).cpu().numpy()
+    out = torch.cat(out).cpu().numpy()
+    ops.check_status(scores.device)          # an out-of-range id raises IndexError, as nn.Embedding does on CPU
+    return out
 
 
 def history_scores(model, hist_list, num_items, device):
@@ -287,4 +289,7 @@ def topk_per_user(model, num_users, user_item, k, batched=True):
                 scores.append(model(rows).reshape(-1))
         scores = torch.cat(scores) if scores else torch.empty(0, device=device)
         idx = ops.rank_segments(scores, k, seg_start=torch.from_numpy(seg).to(device), max_len=int(counts.max()))
-    return idx.cpu().numpy()
+    idx = idx.cpu().numpy()
+    if device.type == "cuda":
+        ops.check_status(device)             # an out-of-range id raises IndexError, as nn.Embedding does on CPU
+    return idx

@@ -98,7 +98,8 @@ class _EmbedFn(torch.autograd.Function):
 
 
 class _FieldModel(nn.Module):
-    def __init__(self, cardinalities, width, row_dim, fused=True, seed=None, device=None, sharded=False, group=None):
+    def __init__(self, cardinalities, width, row_dim, fused=True, seed=None, device=None, sharded=False, group=None,
+                 fabric=None, exchange=None):
         super().__init__()
         self.cards = [int(c) for c in cardinalities]
         self.F, self.width, self.fused = len(self.cards), width, fused
@@ -111,14 +112,17 @@ class _FieldModel(nn.Module):
             if not fused:
                 raise ValueError("sharded tables are updated by the fused row optimizer (fused=True)")
             from . import dist as rsdist
-            # Exchange over NVLink: kernels fused with the transfer through peer memory (PeerRowExchange), or NCCL
-            # all-to-alls (RowExchange).  Measured on 8xB200 (C2): fused 27.7 vs 21.1 M samples/s at N=2, 39.1 vs 36.4
-            # at N=4, but 56.5 vs 69.5 at N=8, where the simple peer-store kernels do not yet drive seven peers as
-            # well as NCCL does -- so the fused path is the default up to 4 ranks.  RS_PEER_EXCHANGE=0/1 overrides.
+            # Default: the device-side exchange (dist.DeviceRowExchange) -- plan, row fetch and gradient push are this
+            # package's kernels over NVLink peer memory, no host sync, CUDA-graph capturable, at every world size.
+            # RS_PEER_EXCHANGE=0 selects the NCCL all-to-all formulation (dist.RowExchange, host-synchronised split sizes),
+            # which is also what the gloo CPU tests drive.  `exchange` may also be passed in (shared by several models).
             import os
-            n = torch.distributed.get_world_size(group) if torch.distributed.is_initialized() else 1
-            peer = n > 1 and os.environ.get("RS_PEER_EXCHANGE", "1" if n <= 4 else "0") == "1"
-            self.exchange = (rsdist.PeerRowExchange if peer else rsdist.RowExchange)(rsdist.cuda_prims(), group)
+            if exchange is not None:
+                self.exchange = exchange
+            elif os.environ.get("RS_PEER_EXCHANGE", "1") == "1":
+                self.exchange = rsdist.DeviceRowExchange(fabric)
+            else:
+                self.exchange = rsdist.RowExchange(rsdist.cuda_prims(), group)
             rows = self.exchange.local_rows(self.total_rows)
             std = math.sqrt(2.0 / (self.total_rows / self.F + row_dim))
             w = torch.empty(rows, width, dtype=torch.float32, device=device)
@@ -188,20 +192,36 @@ class _FieldModel(nn.Module):
                 src["scale"] = src["scale"] * (1.0 / ex.world)          # gradients are averaged over the ranks
             else:
                 src["dense"] = src["dense"] * (1.0 / ex.world)
-            if hasattr(ex, "grad_routes"):
-                # segment-reduce fused with the push: reduced rows are stored straight into the owners' buffers
+            if getattr(ex, "device_plan", False):
+                # segment-reduce fused with the push: every reduced row is stored straight into its owner's buffer over
+                # NVLink (device-resident routes); after the barrier the owner runs the same sort / segment-reduce /
+                # update kernels over what it received (the fill level of that buffer is a device scalar: n_valid)
                 routes, ent = ex.grad_routes(plan, self.width, rec["g"].device)
                 ops.segment_update(segs, ops.RS_UPD_GRAD, self.width, self.F, grad_routes=routes, **src)
                 recv = ex.finish_push(plan, ent)
-            else:
-                # every fetched row has at least one lookup in this batch, so RS_UPD_GRAD writes every row of the block
-                block_grad = torch.empty(plan.n_uniq, self.width, dtype=torch.float32, device=rec["g"].device)
-                ops.segment_update(segs, ops.RS_UPD_GRAD, self.width, self.F, dense_grad=block_grad, **src)
-                recv = ex.push_grads(plan, block_grad)
+                osegs = ex.owner_segments(plan, self.weight.shape[0], self.width)
+                self._row_update(opt, osegs, 1, dense=recv)
+                continue
+            # NCCL formulation: every fetched row has at least one lookup in this batch, so RS_UPD_GRAD writes every row
+            block_grad = torch.empty(plan.n_uniq, self.width, dtype=torch.float32, device=rec["g"].device)
+            ops.segment_update(segs, ops.RS_UPD_GRAD, self.width, self.F, dense_grad=block_grad, **src)
+            recv = ex.push_grads(plan, block_grad)
             if recv.shape[0]:
                 osegs = ops.dedup_sort(plan.recv_local, 1, None, self.weight.shape[0], max_width=self.width)
                 self._row_update(opt, osegs, 1, dense=recv)
         self._pending.clear()
+
+    def _plan(self, ids, train):
+        ex = self.exchange
+        if getattr(ex, "device_plan", False):
+            plan = ex.plan_for(ids, self.offsets_host, self.total_rows)
+            if train:      # the owner-side sort of the requested rows depends only on the plan: overlap it with fetch + forward
+                ex.prefetch_owner_segments(plan, self.weight.shape[0])
+            return plan
+        plan = ex.plan_for(ids, self._offsets_key(), self.total_rows)
+        if train and plan.recv_local.numel():
+            ops.prefetch_dedup(plan.recv_local, 1, None, self.weight.shape[0])
+        return plan
 
     def _interact(self, T, ids, want_stash):
         raise NotImplementedError
@@ -215,7 +235,7 @@ class _FieldModel(nn.Module):
             raise ValueError(f"ids must be (B, {self.F})")
         rec = {}
         if self.sharded:
-            plan = self.exchange.plan_for(ids, self._offsets_key(), self.total_rows)
+            plan = self._plan(ids, torch.is_grad_enabled())
             block = self.exchange.fetch(plan, self.weight.data)
             ids, T, rec = plan.local_ids.view(ids.shape), ops.make_tables([block] * self.F), {"plan": plan, "block": block}
         else:
@@ -236,10 +256,7 @@ class _FieldModel(nn.Module):
         train = torch.is_grad_enabled()
         rec = {}
         if self.sharded:
-            plan = self.exchange.plan_for(ids, self._offsets_key(), self.total_rows)
-            if train and self.fused and plan.recv_local.numel():
-                # the owner-side sort of the requested rows depends only on the plan: overlap it with fetch + forward
-                ops.prefetch_dedup(plan.recv_local, 1, None, self.weight.shape[0])
+            plan = self._plan(ids, train and self.fused)
             block = self.exchange.fetch(plan, self.weight.data)
             ids = plan.local_ids.view(ids.shape)
             cross, stash = self._interact(ops.make_tables([block] * self.F), ids, want_stash=train)
@@ -267,8 +284,8 @@ class _FieldModel(nn.Module):
 class FieldFM(_FieldModel):
     """sigmoid(b + 0.5 * sum_d[(sum_f e_f)^2 - sum_f e_f^2]) over F id-fields, D-dim rows."""
 
-    def __init__(self, cardinalities, embedding_dim, fused=True, seed=None, device=None, sharded=False, group=None):
-        super().__init__(cardinalities, embedding_dim, embedding_dim, fused, seed, device, sharded, group)
+    def __init__(self, cardinalities, embedding_dim, fused=True, seed=None, device=None, sharded=False, group=None, **kw):
+        super().__init__(cardinalities, embedding_dim, embedding_dim, fused, seed, device, sharded, group, **kw)
 
     def _interact(self, T, ids, want_stash):
         out = ops.fields_fwd(T, ids.shape[0], ids.device, ids=ids, cross=True, stash=want_stash)
@@ -278,9 +295,9 @@ class FieldFM(_FieldModel):
 class FieldFFM(_FieldModel):
     """sigmoid(b + sum_{i<j} <v_{i,j}, v_{j,i}>): feature i's table row is (F, D), slot j aimed at field j."""
 
-    def __init__(self, cardinalities, num_vector, fused=True, seed=None, device=None, sharded=False, group=None):
+    def __init__(self, cardinalities, num_vector, fused=True, seed=None, device=None, sharded=False, group=None, **kw):
         F = len(cardinalities)
-        super().__init__(cardinalities, F * num_vector, num_vector, fused, seed, device, sharded, group)
+        super().__init__(cardinalities, F * num_vector, num_vector, fused, seed, device, sharded, group, **kw)
         self.D = num_vector
 
     def _interact(self, T, ids, want_stash):
@@ -295,8 +312,8 @@ class FieldMF(_FieldModel):
 
     use_bias = False
 
-    def __init__(self, num_users, num_items, embedding_size, fused=True, seed=None, device=None, sharded=False, group=None):
-        super().__init__([num_users, num_items], embedding_size, embedding_size, fused, seed, device, sharded, group)
+    def __init__(self, num_users, num_items, embedding_size, fused=True, seed=None, device=None, sharded=False, group=None, **kw):
+        super().__init__([num_users, num_items], embedding_size, embedding_size, fused, seed, device, sharded, group, **kw)
         self.bias.requires_grad_(False)
 
     def _interact(self, T, ids, want_stash):
@@ -314,8 +331,8 @@ class FieldPNN(_FieldModel):
 
     use_bias = False
 
-    def __init__(self, cardinalities, embed_dim, hidden_units, fused=True, seed=None, device=None, sharded=False, group=None):
-        super().__init__(cardinalities, embed_dim, embed_dim, fused, seed, device, sharded, group)
+    def __init__(self, cardinalities, embed_dim, hidden_units, fused=True, seed=None, device=None, sharded=False, group=None, **kw):
+        super().__init__(cardinalities, embed_dim, embed_dim, fused, seed, device, sharded, group, **kw)
         F = self.F
         self.bias.requires_grad_(False)
         self.linear1 = nn.Linear(F * embed_dim, hidden_units[0], device=device)
@@ -337,8 +354,8 @@ class FieldAFM(_FieldModel):
 
     use_bias = False
 
-    def __init__(self, cardinalities, embed_dim, attention_dim, fused=True, seed=None, device=None, sharded=False, group=None):
-        super().__init__(cardinalities, embed_dim, embed_dim, fused, seed, device, sharded, group)
+    def __init__(self, cardinalities, embed_dim, attention_dim, fused=True, seed=None, device=None, sharded=False, group=None, **kw):
+        super().__init__(cardinalities, embed_dim, embed_dim, fused, seed, device, sharded, group, **kw)
         self.bias.requires_grad_(False)
         g = torch.Generator(device="cpu").manual_seed(seed or 0)
         self.attention_W = nn.Parameter((torch.randn(embed_dim, attention_dim, generator=g) * 0.1).to(device))

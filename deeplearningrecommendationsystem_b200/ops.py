@@ -81,6 +81,9 @@ def check_status(device=None):
     v = int(w.item())
     if v:
         w.zero_()
+        if v & 16:
+            raise RuntimeError("row exchange: an owner was asked for more rows than its receive capacity "
+                               "(raise recv_slack of the DeviceRowExchange); the step's update is incomplete")
         raise IndexError("index out of range in embedding lookup")
 
 
@@ -293,8 +296,11 @@ def _partial_buffer(device, n, width):
     return buf
 
 
-def dedup_sort(ids, F=1, row_offset=None, total_rows=None, max_width=1, reuse_workspace=True):
+def dedup_sort(ids, F=1, row_offset=None, total_rows=None, max_width=1, reuse_workspace=True, shard=None, n_valid=None):
     """Stable sort of the lookups by global table row + segment/chunk boundaries (no host sync).
+
+    shard=(world, rows_per_rank): owner-major keys for row-sharded tables (rs_dedup_sort_ex); n_valid: int32 device
+    scalar, only the first n_valid ids are real (fixed-capacity receive lists).  Both bypass the memo.
 
     The result depends only on (ids, F, row_offset, total_rows), so a second request for the SAME ids tensor (same
     storage, same version counter -- e.g. the FM and the FFM model stepping on one batch) returns the memoised
@@ -304,6 +310,8 @@ def dedup_sort(ids, F=1, row_offset=None, total_rows=None, max_width=1, reuse_wo
     _need_cuda(ids)
     n = ids.numel()
     lib = _lib.load()
+    if shard is not None or n_valid is not None:
+        reuse_workspace = False
     memo_key = (ids.data_ptr(), ids._version, n, F, tuple(int(o) for o in row_offset) if row_offset is not None else None,
                 int(total_rows)) if reuse_workspace else None
     slots = _seg_memo.setdefault(ids.device, []) if reuse_workspace else None
@@ -330,9 +338,15 @@ def dedup_sort(ids, F=1, row_offset=None, total_rows=None, max_width=1, reuse_wo
         offs = None
         if row_offset is not None:
             offs = (C.c_int64 * F)(*[int(o) for o in row_offset])
+        opts = None
+        if shard is not None or n_valid is not None:
+            opts = _lib.rs_dedup_opts()
+            opts.n_valid = _p(n_valid)
+            opts.shard_world, opts.shard_rows = (int(shard[0]), int(shard[1])) if shard is not None else (0, 0)
+            opts = C.byref(opts)
         with _timed("dedup_sort"):
-            _lib.check(lib.rs_dedup_sort(ids.data_ptr(), n, F, offs, int(total_rows), ws.data_ptr(), ws.numel(), C.byref(seg),
-                                         status_word(ids.device).data_ptr(), _stream()), "rs_dedup_sort")
+            _lib.check(lib.rs_dedup_sort_ex(ids.data_ptr(), n, F, offs, int(total_rows), opts, ws.data_ptr(), ws.numel(), C.byref(seg),
+                                            status_word(ids.device).data_ptr(), _stream()), "rs_dedup_sort")
         _count(10)
         segs = Segments(ws, seg, n, ids.device)
         if reuse_workspace:
@@ -342,6 +356,15 @@ def dedup_sort(ids, F=1, row_offset=None, total_rows=None, max_width=1, reuse_wo
             segs.ready.record()
     part = _partial_buffer(ids.device, n, int(max_width)) if reuse_workspace else \
         torch.empty(2 * (n // _lib.RS_CHUNK + 2) * int(max_width), dtype=torch.float32, device=ids.device)
+    segs.partial = part
+    segs.seg.partial = part.data_ptr()
+    segs.seg.partial_floats = part.numel()
+    return segs
+
+
+def attach_partial(segs, width):
+    """(Re)attach the chunk-partial scratch for rows of `width` floats to finished segments."""
+    part = _partial_buffer(segs.device, segs.n, int(width))
     segs.partial = part
     segs.seg.partial = part.data_ptr()
     segs.seg.partial_floats = part.numel()
@@ -384,15 +407,59 @@ def prefetch_dedup(ids, F=1, row_offset=None, total_rows=None):
         _prefetching = False
 
 
-def make_routes(starts, bases, row0s):
+def make_routes(starts, bases, row0s, dyn_start=None, dyn_row0=None, cap_rows=0):
     """rs_routes: logical rows [starts[k], starts[k+1]) go to bases[k] (device pointer, peer-mapped or local) at row
-    offset row0s[k].  len(starts) == len(bases) + 1."""
+    offset row0s[k].  len(starts) == len(bases) + 1.  dyn_start / dyn_row0: device addresses of the same two arrays
+    (int64) when they only exist on the device (host-sync-free sharded step); starts / row0s are then ignored."""
     R = _lib.rs_routes()
     R.n = len(bases)
-    for k, (s0, b, r0) in enumerate(zip(starts, bases, row0s)):
-        R.start[k], R.base[k], R.row0[k] = int(s0), int(b), int(r0)
-    R.start[R.n] = int(starts[-1])
+    for k, b in enumerate(bases):
+        R.base[k] = int(b)
+    if dyn_start is None:
+        for k, (s0, r0) in enumerate(zip(starts, row0s)):
+            R.start[k], R.row0[k] = int(s0), int(r0)
+        R.start[R.n] = int(starts[-1])
+    else:
+        R.dyn_start, R.dyn_row0 = int(dyn_start), int(dyn_row0)
+    R.cap_rows = int(cap_rows)
     return R
+
+
+def make_shard(world, rank, rows_per_rank, cap_req, cap_recv, req_ptrs, ctl_ptrs):
+    """rs_shard: the per-exchange constants + the peer-mapped request / control buffers of every rank."""
+    S = _lib.rs_shard()
+    S.world, S.rank, S.rows_per_rank, S.cap_req, S.cap_recv = world, rank, int(rows_per_rank), int(cap_req), int(cap_recv)
+    for k in range(world):
+        S.req[k], S.ctl[k] = int(req_ptrs[k]), int(ctl_ptrs[k])
+    return S
+
+
+def shard_post(S, segs):
+    """requester: request lists + counts written straight into the owners' buffers (follow with a cross-rank barrier)"""
+    with _timed("shard_post"):
+        _lib.check(_lib.load().rs_shard_post(C.byref(S), C.byref(segs.seg), segs.n, status_word(segs.device).data_ptr(), _stream()),
+                   "rs_shard_post")
+    _count()
+
+
+def shard_collect(S, recv_local, m_total):
+    """owner: prefix of the received counts, compact receive list (first m_total entries of recv_local), gradient
+    offsets sent back to the requesters"""
+    _need_cuda(recv_local, m_total)
+    with _timed("shard_collect"):
+        _lib.check(_lib.load().rs_shard_collect(C.byref(S), recv_local.data_ptr(), m_total.data_ptr(),
+                                                status_word(recv_local.device).data_ptr(), _stream()), "rs_shard_collect")
+    _count()
+
+
+def shard_serve(S, table, recv_local, block_ptrs, cap_block_rows):
+    """owner: table[recv_local[i]] -> the requesters' blocks over NVLink (follow with a cross-rank barrier)"""
+    _need_cuda(table, recv_local)
+    ptrs = (C.c_void_p * S.world)(*[int(p) for p in block_ptrs])
+    with _timed(f"shard_serve[w{table.shape[1]}]"):
+        _lib.check(_lib.load().rs_shard_serve(C.byref(S), table.data_ptr(), table.shape[0], table.shape[1], recv_local.data_ptr(), ptrs,
+                                              int(cap_block_rows), status_word(table.device).data_ptr(), _stream()), "rs_shard_serve")
+    _count()
 
 
 def gather_rows_peer(table, idx, routes):
@@ -560,9 +627,13 @@ def afm_fwd(E, W, b, h, want_attw=True):
     return pooled, attw
 
 
-def afm_bwd(E, W, b, h, attw, g_pooled, impl="auto"):
+_afm_ws = {}
+
+
+def afm_bwd(E, W, b, h, attw, g_pooled, impl="auto", return_masks=False):
     """-> dE (B,F,D), dW (D,A), db (A), dh (A)  (per-warp partials added in warp order).
-    impl "auto": the tcgen05 kernels of afm_tc.cu when rs_afm_bwd_tc_plan accepts the shape; "cuda_cores": rs_afm_bwd."""
+    impl "auto": the tcgen05 kernels of afm_tc.cu when rs_afm_bwd_tc_plan accepts the shape; "cuda_cores": rs_afm_bwd.
+    return_masks (tensor-core path, tests): a fifth value, the ReLU masks [z > 0] the chain kernel used, (B, P, A) bool."""
     E, W, b, h, g_pooled = _f32(E), _f32(W), _f32(b), _f32(h).reshape(-1), _f32(g_pooled)
     B, F, D = E.shape
     A = W.shape[1]
@@ -575,14 +646,25 @@ def afm_bwd(E, W, b, h, attw, g_pooled, impl="auto"):
         n = parts.value
         Up = torch.empty(n, D, A, dtype=torch.float32, device=E.device)
         m1p = torch.empty(n, A, dtype=torch.float32, device=E.device)
-        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=E.device)
+        # the workspace (ds, mask bits, dP: 3.1 GB at C3) is cached per device instead of being allocated every backward
+        ws = _afm_ws.get(E.device)
+        if ws is None or ws.numel() < nbytes.value:
+            _afm_ws[E.device] = None
+            ws = _afm_ws[E.device] = torch.empty(nbytes.value, dtype=torch.uint8, device=E.device)
         with _timed("afm_bwd_tc"):
             _lib.check(lib.rs_afm_bwd_tc(E.data_ptr(), B, F, D, A, W.data_ptr(), b.data_ptr(), h.data_ptr(), attw.data_ptr(),
                                          g_pooled.data_ptr(), dE.data_ptr(), Up.data_ptr(), m1p.data_ptr(), n, ws.data_ptr(),
                                          nbytes.value, _stream()), "rs_afm_bwd_tc")
         _count(3)
         U, m1 = Up.sum(dim=0), m1p.sum(dim=0)
-        return dE, U * h, h * m1, (W * U).sum(dim=0) + b * m1
+        out = (dE, U * h, h * m1, (W * U).sum(dim=0) + b * m1)
+        if return_masks:
+            NP, AW = F * (F - 1) // 2, A // 32
+            off = (B * NP * 4 + 255) // 256 * 256                     # ws layout of rs_afm_bwd_tc: ds | mask bits | dP
+            bits = ws[off:off + B * NP * AW * 4].view(torch.int32).view(B, NP, AW, 1)
+            masks = ((bits >> torch.arange(32, device=E.device, dtype=torch.int32)) & 1).bool().view(B, NP, A)
+            out += (masks,)
+        return out
     _lib.check(lib.rs_afm_num_parts(B, F, D, A, C.byref(parts)), "rs_afm_num_parts")
     n = parts.value
     dWp = torch.empty(n, D, A, dtype=torch.float32, device=E.device)

@@ -38,7 +38,9 @@ class FusedRowOptimizer:
             m.apply_pending(self)
         if self.dense is not None:
             from .dist import allreduce_dense_grads
-            allreduce_dense_grads([p for g in self.dense.param_groups for p in g["params"]])
+            fabric = next((m.exchange.fabric for m in self._sparse_modules()
+                           if getattr(m, "exchange", None) is not None and hasattr(m.exchange, "fabric")), None)
+            allreduce_dense_grads([p for g in self.dense.param_groups for p in g["params"]], fabric=fabric)
             self.dense.step()
 
 

@@ -7,9 +7,27 @@ anything else -> ValueError); the ``*_loop2(matrix, mask)`` AutoRec variants; re
 ``FusedRowOptimizer`` drops in.  ``model_eval`` computes the reference Evaluator's five metrics
 (evaluator/evaluator.py:13-20: predictions thresholded at >= 0.5 *before* AUC) on the device, one host read per split.
 """
+import os
+
 import torch
 
 from ..evaluator.evaluator import binary_metrics
+
+# Out-of-range ids never fault on the device (they are clamped and a status bit is set); the reference raises
+# IndexError from nn.Embedding.  The Trainer turns the bit back into that IndexError: on every valid/test pass and
+# metrics() call (per-epoch, they read results back anyway) and every RS_CHECK_EVERY train steps (one 4-byte read).
+CHECK_EVERY = int(os.environ.get("RS_CHECK_EVERY", "64"))
+
+
+def _check_ids(model):
+    try:
+        dev = next(model.parameters()).device
+    except StopIteration:
+        return
+    if dev.type != "cuda" or torch.cuda.is_current_stream_capturing():
+        return
+    from .. import ops
+    ops.check_status(dev)
 
 
 _binary_metrics = binary_metrics
@@ -19,6 +37,7 @@ class Trainer:
     def __init__(self, model, loss_fn, optimizer):
         self.model, self.loss_fn, self.optimizer = model, loss_fn, optimizer
         self.train_loss = self.valid_loss = self.test_loss = None
+        self._steps = 0
         self.predictions_train = self.predictions_valid = self.predictions_test = None
         self.train_rating = self.valid_rating = self.test_rating = None
 
@@ -35,12 +54,16 @@ class Trainer:
         self.train_loss.backward()
         self.optimizer.step()
         self.train_rating = train_rating
+        self._steps += 1
+        if CHECK_EVERY > 0 and self._steps % CHECK_EVERY == 0:
+            _check_ids(self.model)
 
     def _eval(self, args, rating, who):
         self.model.eval()
         with torch.no_grad():
             pred = self._forward(args, who)
             loss = self.loss_fn(pred, rating)
+        _check_ids(self.model)
         return pred, loss
 
     def valid_loop(self, *args, valid_rating):
@@ -77,6 +100,7 @@ class Trainer:
     def metrics(self):
         """{'train'|'valid'|'test': [acc, precision, recall, f1, auc]} for the splits that have run."""
         out = {}
+        _check_ids(self.model)
         for split in ("train", "valid", "test"):
             pred, rating = getattr(self, f"predictions_{split}"), getattr(self, f"{split}_rating")
             if pred is not None:

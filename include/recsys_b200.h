@@ -51,6 +51,12 @@ typedef struct rs_routes {
   int64_t start[RS_MAX_RANKS + 1];
   float *base[RS_MAX_RANKS];
   int64_t row0[RS_MAX_RANKS];
+  /* Optional DEVICE-resident ranges (the host-sync-free sharded step: the split sizes only ever exist on the device).
+   * When dyn_start != NULL the kernels read start[0..n] from dyn_start and row0[0..n-1] from dyn_row0 instead of the
+   * host arrays above; a destination row index >= cap_rows (cap_rows > 0) is dropped, not stored. */
+  const int64_t *dyn_start;
+  const int64_t *dyn_row0;
+  int64_t cap_rows;
 } rs_routes;
 
 int rs_version(void);
@@ -145,6 +151,19 @@ int rs_dedup_workspace_bytes(int64_t n, int32_t max_width, size_t *bytes);
 /* row_offset: HOST array of F int64 (NULL = all zero).  Fills `seg` with pointers carved from ws. */
 int rs_dedup_sort(const int64_t *ids, int64_t n, int32_t F, const int64_t *row_offset, int64_t total_rows,
                   void *ws, size_t ws_bytes, rs_segments *seg, int32_t *status, void *stream);
+/* Extended form used by the row-sharded step (no reference counterpart):
+ *   n_valid      DEVICE int32 (NULL = n): only the first *n_valid ids exist; the rest of the n-entry buffer is padding
+ *                (a fixed-capacity receive list whose fill level is only known on the device).  Padding sorts last and
+ *                produces no segment, chunk or work unit, so rs_segment_update over the same n touches valid rows only.
+ *   shard_world  > 1: keys become owner-major, key = (g % shard_world) * shard_rows + g / shard_world for global row
+ *                g = row_offset[p % F] + ids[p] -- one sort then yields the distinct rows grouped by owning rank. */
+typedef struct rs_dedup_opts {
+  const int32_t *n_valid;
+  int32_t shard_world;
+  int64_t shard_rows;
+} rs_dedup_opts;
+int rs_dedup_sort_ex(const int64_t *ids, int64_t n, int32_t F, const int64_t *row_offset, int64_t total_rows,
+                     const rs_dedup_opts *opts, void *ws, size_t ws_bytes, rs_segments *seg, int32_t *status, void *stream);
 /* Rename the rows of a finished sort to their rank among the distinct keys: uniq[g] := g and every lookup record
  * points at g.  The row-sharded step (no reference counterpart) sorts the batch's GLOBAL rows once for
  * the exchange plan; the j-th distinct row is row j of the fetched block, so after this call the same segments drive
@@ -176,6 +195,40 @@ typedef struct rs_update {
                                    (routes) instead of dense_grad[r] -- segment-reduce fused with the gradient push */
 } rs_update;
 int rs_segment_update(const rs_segments *seg, int64_t n, const rs_update *u, void *stream);
+
+/* ---- row-sharded tables: the exchange plan lives on the DEVICE (no reference counterpart).
+ * Global row g is owned by rank g % world at local index g / world.  Every rank owns two small symmetric (peer-mapped)
+ * buffers: `req` (world slots of cap_req int32 local row indices, slot r written by requester r) and `ctl`
+ * (RS_SHARD_CTL_WORDS int64 control words).  One step:
+ *   rs_dedup_sort_ex(shard_world)   distinct rows of the local batch, grouped by owner
+ *   rs_shard_post                   requester: writes its request list and counts straight into every owner's req/ctl
+ *   -- cross-rank barrier --
+ *   rs_shard_collect                owner: prefix of the counts, compact receive list, tells every requester where its
+ *                                   gradients will go (ctl of the requester)
+ *   rs_shard_serve                  owner: table rows -> the requesters' blocks over NVLink (TMA bulk copies for wide rows)
+ *   -- barrier --  forward / backward on the fetched block  --
+ *   rs_segment_update(RS_UPD_GRAD, grad_routes with dyn_start = ctl + RS_CTL_SEND_START, dyn_row0 = ctl + RS_CTL_G0_IN)
+ *   -- barrier --
+ *   rs_dedup_sort_ex(n_valid = m_total) + rs_segment_update on the received rows.
+ * Nothing in this sequence reads a count on the host, so the whole step can be captured in a CUDA graph.
+ * Bit 4 (16) of `status` is set when an owner is asked for more rows than cap_recv. */
+#define RS_SHARD_CTL_WORDS 384
+enum { RS_CTL_CNT_IN = 0, RS_CTL_BLK0_IN = 64, RS_CTL_G0_IN = 128, RS_CTL_SEND_START = 192, RS_CTL_RECV_START = 257, RS_CTL_M_TOTAL = 322 };
+typedef struct rs_shard {
+  int32_t world, rank;
+  int64_t rows_per_rank; /* R = ceil(total_rows / world) */
+  int64_t cap_req;       /* ids per (requester, owner) slot; >= lookups per batch */
+  int64_t cap_recv;      /* rows one owner can receive per step */
+  int32_t *req[RS_MAX_RANKS];
+  int64_t *ctl[RS_MAX_RANKS];
+} rs_shard;
+int rs_shard_post(const rs_shard *S, const rs_segments *seg, int64_t n, int32_t *status, void *stream);
+int rs_shard_collect(const rs_shard *S, int64_t *recv_local /* [cap_recv] */, int32_t *m_total /* device */,
+                     int32_t *status, void *stream);
+/* block[r]: base of rank r's receive block (cap_block_rows x width fp32), peer-mapped. */
+int rs_shard_serve(const rs_shard *S, const float *table, int64_t rows, int32_t width, const int64_t *recv_local,
+                   float *const *block, int64_t cap_block_rows, int32_t *status, void *stream);
+
 
 /* Fused DENSE Adam sweep with torch.optim.Adam's exact arithmetic order ("reference-Adam" mode for the
  * MovieLens-sized tables; scripts/deepfm.py:55). */

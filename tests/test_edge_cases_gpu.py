@@ -69,6 +69,61 @@ def test_out_of_range_id_raises_index_error_like_the_reference():
         ops.check_status()
 
 
+def test_trainer_turns_a_bad_id_into_index_error():
+    """the product path polls the device status word itself: valid/test passes and metrics() always, train_loop every
+    RS_CHECK_EVERY steps (nothing but tests used to read the flag)"""
+    from deeplearningrecommendationsystem_b200.model import MatrixFactorization
+    from deeplearningrecommendationsystem_b200.trainer import Trainer, trainer as tmod
+    m = MatrixFactorization(5, 5, 8).cuda()
+    tr = Trainer(m, torch.nn.BCELoss(), torch.optim.SGD(m.parameters(), lr=0.1))
+    y = torch.tensor([0.0, 1.0]).cuda()
+    good, bad = (torch.tensor([1, 2]).cuda(), torch.tensor([0, 1]).cuda()), (torch.tensor([1, 9]).cuda(), torch.tensor([0, 1]).cuda())
+    tr.valid_loop(*good, valid_rating=y)
+    with pytest.raises(IndexError):
+        tr.valid_loop(*bad, valid_rating=y)
+    with pytest.raises(IndexError):
+        tr.test_loop(*bad, test_rating=y)
+    old = tmod.CHECK_EVERY
+    tmod.CHECK_EVERY = 2
+    try:
+        tr._steps = 0
+        tr.train_loop(*bad, train_rating=y)          # step 1: not polled yet
+        with pytest.raises(IndexError):
+            tr.train_loop(*good, train_rating=y)     # step 2: the flag raised by step 1 surfaces
+    finally:
+        tmod.CHECK_EVERY = old
+    tr.valid_loop(*good, valid_rating=y)             # the flag was cleared by the raise
+
+
+def test_graphed_adam_is_refused_not_silently_frozen():
+    """Adam's bias correction comes from a host step counter, so a captured Adam step would replay with
+    it frozen; GraphedTrainStep refuses, SGD captures and N graphed steps == N eager steps."""
+    from deeplearningrecommendationsystem_b200.graph import GraphedTrainStep
+    from deeplearningrecommendationsystem_b200.nfield import FieldFM
+    from deeplearningrecommendationsystem_b200.optim import DenseAdam, FusedRowOptimizer
+    cards = [50, 7, 300]
+    g = torch.Generator().manual_seed(0)
+    ids = torch.stack([torch.randint(0, c, (256,), generator=g) for c in cards], dim=1).cuda()
+    y = (torch.rand(256, 1, generator=g) < 0.3).float().cuda()
+    m = FieldFM(cards, 16, seed=1, device="cuda")
+    for opt in (FusedRowOptimizer(m, None, lr=0.1, kind="adam"), FusedRowOptimizer(m, DenseAdam([m.bias]), lr=0.1),
+                FusedRowOptimizer(m, torch.optim.Adam([m.bias]), lr=0.1)):
+        gs = GraphedTrainStep(m, torch.nn.BCELoss(), opt, warmup=0)
+        with pytest.raises(RuntimeError, match="captur"):
+            gs(ids, rating=y)
+    a, b = FieldFM(cards, 16, seed=2, device="cuda"), FieldFM(cards, 16, seed=2, device="cuda")
+    oa = FusedRowOptimizer(a, torch.optim.SGD([a.bias], lr=0.1), lr=0.1)
+    ob = FusedRowOptimizer(b, torch.optim.SGD([b.bias], lr=0.1), lr=0.1)
+    gs = GraphedTrainStep(a, torch.nn.BCELoss(), oa, warmup=1)
+    from deeplearningrecommendationsystem_b200.trainer import Trainer
+    tr = Trainer(b, torch.nn.BCELoss(), ob)
+    for _ in range(5):
+        gs(ids, rating=y)
+        tr.train_loop(ids, train_rating=y)
+    torch.cuda.synchronize()
+    assert torch.equal(a.weight.data, b.weight.data) and torch.equal(a.bias.data, b.bias.data)
+
+
 def test_unsupported_shapes_fail_loudly():
     ops = _ops()
     with pytest.raises(RuntimeError, match="power of two"):

@@ -421,6 +421,28 @@ def test_afm_forward_tensor_cores(F, D, A, B):
             assert float((got.cpu() - ref).norm()) <= 1e-3 * float(ref.norm()), (impl, name)
         again = ops.afm_bwd(*cu, attw, gp.cuda(), impl=impl)
         assert all(torch.equal(x, y_) for x, y_ in zip((dE, dW, db, dh), again)), f"{impl}: not deterministic"
+    # ... and the tcgen05 backward itself is checked EXACTLY (north star: 1e-5 everywhere): with the ReLU masks fixed to
+    # the bits its chain kernel produced, the gradient is a smooth function of the inputs, and a float64 evaluation of it
+    # (from the same attention weights the forward handed over) must agree element by element.
+    dE, dW, db, dh, masks = ops.afm_bwd(*cu, attw, gp.cuda(), impl="auto", return_masks=True)
+    i, j = OI.pair_index(F)
+    E64, W64, b64, h64, g64 = [t.detach().double() for t in (E, W, b, h.view(-1), gp)]
+    w64, m64 = attw.double().cpu(), masks.double().cpu()
+    P = E64[:, i] * E64[:, j]                                           # (B, P, D)
+    z = P @ W64 + b64
+    assert float(((z > 0).double() - m64).abs().mean()) < 1e-4           # the masks are the ReLU's, up to kinks at |z| ~ 0
+    assert float(torch.cat([z[(z > 0).double() != m64].abs().flatten(), torch.zeros(1, dtype=torch.float64)]).max()) < 1e-5
+    dwp = (P * g64.unsqueeze(1)).sum(-1)                                # d loss / d w_p
+    ds = w64 * (dwp - (w64 * dwp).sum(1, keepdim=True))
+    dz = ds.unsqueeze(-1) * h64 * m64                                   # (B, P, A)
+    dP = dz @ W64.t() + w64.unsqueeze(-1) * g64.unsqueeze(1)
+    want_dE = torch.zeros_like(E64)
+    want_dE.index_add_(1, i, dP * E64[:, j])
+    want_dE.index_add_(1, j, dP * E64[:, i])
+    want = {"dE": want_dE, "dW": torch.einsum("bpd,bpa->da", P, dz), "db": dz.sum((0, 1)), "dh": torch.einsum("bp,bpa->a", ds, m64 * z)}
+    for name, got in (("dE", dE), ("dW", dW), ("db", db), ("dh", dh)):
+        ref = want[name]
+        close(got.double(), ref, rtol=1e-5, atol=1e-5 * float(ref.abs().max()), msg=name + " (fixed masks, f64)")
 
 
 # ------------------------------------------------------------------ GRU recurrence

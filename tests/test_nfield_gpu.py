@@ -45,6 +45,42 @@ def test_fused_sgd_steps_match_oracle(kind, D, zipf):
     ops.check_status()
 
 
+C2_CARDS = [1460, 583, 10131227, 2202608, 305, 24, 12517, 633, 3, 93145, 5683, 8351593, 3194, 27, 14992, 5461306, 10, 5652,
+            2173, 4, 7046547, 18, 15, 286181, 105, 142572]
+
+
+@pytest.mark.parametrize("kind", ["fm", "ffm"])
+@pytest.mark.parametrize("zipf", [False, True])
+def test_c2_shape_train_steps_match_oracle(kind, zipf):
+    """BASELINE.json configs[1] at its own shape -- F = 26 Criteo fields, D = 16 (FFM rows of 416 floats, the TMA-fed
+    ffm_fwd_kernel and seg_stream_kernel) -- with every cardinality capped at 3000 rows so the CPU oracle's dense
+    gradient stays small; three fused SGD steps through Trainer.train_loop vs oracle/nfield.train_step."""
+    from deeplearningrecommendationsystem_b200 import ops
+    from deeplearningrecommendationsystem_b200.nfield import FieldFFM, FieldFM
+    from deeplearningrecommendationsystem_b200.optim import FusedRowOptimizer
+    from deeplearningrecommendationsystem_b200.trainer import Trainer
+    cards = [min(c, 3000) for c in C2_CARDS]
+    B, D, lr = 2048, 16, 0.5
+    g = torch.Generator().manual_seed(26)
+    model = (FieldFM if kind == "fm" else FieldFFM)(cards, D, fused=True, seed=7, device="cuda")
+    if zipf:
+        ids = torch.stack([(torch.rand(B, generator=g) ** 3 * c).long().clamp_(max=c - 1) for c in cards], dim=1)
+    else:
+        ids = torch.stack([torch.randint(0, c, (B,), generator=g) for c in cards], dim=1)
+    y = (torch.rand(B, 1, generator=g) < 0.3).float()
+    table, bias = model.weight.detach().cpu().clone(), model.bias.detach().cpu().clone()
+    offsets = torch.tensor(model.offsets_host)
+    opt = FusedRowOptimizer(model, torch.optim.SGD([model.bias], lr=lr), lr=lr, kind="sgd")
+    tr = Trainer(model, torch.nn.BCELoss(), opt)
+    for step in range(3):
+        tr.train_loop(ids.cuda(), train_rating=y.cuda())
+        pred, loss = onf.train_step(kind, table, bias, ids, offsets, y[:, 0], lr)
+        np.testing.assert_allclose(tr.predictions_train.detach().cpu().numpy()[:, 0], pred.numpy(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(tr.train_loss.item(), loss.item(), rtol=1e-5)
+        np.testing.assert_allclose(model.weight.detach().cpu().numpy(), table.numpy(), rtol=1e-5, atol=2e-6)
+    ops.check_status()
+
+
 @pytest.mark.parametrize("kind,D", [("fm", 16), ("ffm", 8)])
 def test_dense_grad_mode_matches_autograd(kind, D):
     """fused=False: the table is an ordinary dense-gradient Parameter (reference semantics, any torch optimizer)."""
