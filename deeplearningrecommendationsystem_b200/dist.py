@@ -26,7 +26,7 @@ def _phase(name):
     import contextlib
     try:
         from . import ops
-        if ops.PROFILE is not None and torch.cuda.is_available():
+        if (ops.PROFILE is not None or ops.NVTX) and torch.cuda.is_available():
             return ops._timed(name)
     except Exception:
         pass
@@ -192,6 +192,41 @@ class SymmFabric(Fabric):
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
         return int(t.item())
 
+    AR_MAX = 4096      # floats; larger dense buckets go through NCCL (NVLS), small ones are latency bound
+
+    def allreduce_mean(self, grads):
+        """Average a SMALL set of dense gradients (the FM/FFM/MF bias, a few floats) through a symmetric buffer: every rank
+        copies its flat bucket into slot [rank] of every peer, barrier, fixed-order sum.  No NCCL call, so the sharded
+        step stays one launch sequence.  Returns False (caller falls back to NCCL) for big buckets."""
+        K = sum(g.numel() for g in grads)
+        if K == 0:
+            return True
+        if K > self.AR_MAX or getattr(self, "_ar_broken", False):
+            return False
+        dev = grads[0].device
+        if getattr(self, "_ar", None) is None:
+            try:
+                buf, _ = self.alloc((self.world, self.AR_MAX), torch.float32, dev)
+                h = self._handles[-1]
+                views = [h.get_buffer(r, (self.world, self.AR_MAX), torch.float32) for r in range(self.world)]
+                self._ar = (buf, views)
+                self.barrier()
+            except Exception:                      # symmetric-memory API without get_buffer: use NCCL
+                self._ar_broken = True
+                return False
+        buf, views = self._ar
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        for r in range(self.world):
+            views[r][self.rank, :K].copy_(flat)
+        self.barrier()
+        mean = buf[:, :K].sum(0) / self.world
+        off = 0
+        for g in grads:
+            g.copy_(mean[off:off + g.numel()].view_as(g))
+            off += g.numel()
+        self.barrier()
+        return True
+
 
 class ThreadFabric(Fabric):
     """N virtual ranks as N python threads on ONE GPU (tests and the single-GPU verification leg of bench.py): the
@@ -331,13 +366,16 @@ class DeviceRowExchange:
         self.fabric.barrier()                      # every rank's buffers exist (and are zeroed) before anyone writes to them
         return self._ctl
 
-    def _buffers(self, width, device):
-        ent = self._bufs.get(width)
+    def _buffers(self, table, device):
+        """block / grads buffers of one table (keyed by the table, not just its width: the fetched block must survive
+        until that table's backward, and a model may shard two tables of equal width)"""
+        width, key = table.shape[1], (table.shape[1], table.data_ptr())
+        ent = self._bufs.get(key)
         if ent is None:
             c = self._ctl
             block, block_ptrs = self.fabric.alloc((c["cap_req"], width), torch.float32, device)
             grads, grad_ptrs = self.fabric.alloc((c["cap_recv"], width), torch.float32, device)
-            ent = self._bufs[width] = {"block": block, "block_ptrs": block_ptrs, "grads": grads, "grad_ptrs": grad_ptrs}
+            ent = self._bufs[key] = {"block": block, "block_ptrs": block_ptrs, "grads": grads, "grad_ptrs": grad_ptrs}
             self.fabric.barrier()
         return ent
 
@@ -376,7 +414,7 @@ class DeviceRowExchange:
         """-> (cap, W) block; rows [0, n_uniq) hold the rows this rank's batch needs, in the order `local_ids` indexes."""
         from . import ops
         self._check(plan)
-        c, ent = self._ctl, self._buffers(local_table.shape[1], local_table.device)
+        c, ent = self._ctl, self._buffers(local_table, local_table.device)
         ops.shard_serve(c["S"], local_table, plan.recv_local, ent["block_ptrs"], c["cap_req"])
         with _phase("exchange_barrier"):
             self.fabric.barrier()
@@ -410,12 +448,12 @@ class DeviceRowExchange:
             plan.osegs_ready = None
         return ops.attach_partial(plan.osegs, width)
 
-    def grad_routes(self, plan, width, device):
+    def grad_routes(self, plan, table, device):
         """Routes of the reduced row gradients of the fetched block: block rows of owner o (a device-resident range) go to
         o's `grads` buffer at the offset o announced during rs_shard_collect."""
         from . import _lib, ops
         self._check(plan)
-        c, ent = self._ctl, self._bufs[width]
+        c, ent = self._ctl, self._bufs[(table.shape[1], table.data_ptr())]
         base = c["ctl"].data_ptr()
         return ops.make_routes(None, ent["grad_ptrs"], None, dyn_start=base + 8 * _lib.RS_CTL_SEND_START,
                                dyn_row0=base + 8 * _lib.RS_CTL_G0_IN, cap_rows=c["cap_recv"]), ent
@@ -443,9 +481,9 @@ def unshard_rows(shards):
 
 def allreduce_dense_grads(params, group=None, fabric=None):
     """Average the gradients of the replicated dense parameters with ONE all-reduce over a flat bucket."""
-    if fabric is not None and hasattr(fabric, "allreduce_mean"):          # virtual ranks (ThreadFabric)
-        fabric.allreduce_mean([p.grad for p in params if p.grad is not None])
-        return
+    if fabric is not None and hasattr(fabric, "allreduce_mean"):          # symmetric-memory bucket / virtual ranks
+        if fabric.allreduce_mean([p.grad for p in params if p.grad is not None]) is not False:
+            return
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
     grads = [p.grad for p in params if p.grad is not None]

@@ -22,19 +22,28 @@ class GraphedTrainStep:
     until the next call).
     """
 
-    def __init__(self, model, loss_fn, optimizer, warmup=2):
+    def __init__(self, model, loss_fn, optimizer, warmup=2, also=()):
+        """also: further (model, loss_fn, optimizer) triples stepped on the SAME inputs inside the same graph (the C2
+        benchmark's FFM + FM pair, which share one dedup / one exchange plan per batch); the first triple's
+        (predictions, loss) are returned."""
         self.model, self.loss_fn, self.optimizer, self.warmup = model, loss_fn, optimizer, warmup
+        self.jobs = [(model, loss_fn, optimizer)] + [tuple(j) for j in also]
         self.graph, self.calls, self.side = None, 0, None
         self.static_in = self.static_rating = self.pred = self.loss = None
+        self.all_losses = None
 
     def _eager(self, inputs, rating):
-        self.model.train()
-        self.optimizer.zero_grad()
-        pred = self.model(*inputs)
-        loss = self.loss_fn(pred, rating)
-        loss.backward()
-        self.optimizer.step()
-        return pred, loss
+        outs = []
+        for model, loss_fn, optimizer in self.jobs:
+            model.train()
+            optimizer.zero_grad()
+            pred = model(*inputs)
+            loss = loss_fn(pred, rating)
+            loss.backward()
+            optimizer.step()
+            outs.append((pred, loss))
+        self.all_losses = [l for _, l in outs]
+        return outs[0]
 
     def _check_capturable(self):
         """Adam's bias correction is computed on the host from a python step counter and handed to the kernels by value
@@ -42,12 +51,15 @@ class GraphedTrainStep:
         capture step.  Refuse instead of training silently wrong; SGD (and torch optimizers built with
         capturable=True, whose step lives on the device) capture fine."""
         from .optim import DenseAdam, FusedRowOptimizer
-        opts = [self.optimizer]
-        if isinstance(self.optimizer, FusedRowOptimizer):
-            if self.optimizer.kind == "adam":
-                raise RuntimeError("GraphedTrainStep: FusedRowOptimizer(kind='adam') keeps its step count on the host and "
-                                   "cannot be captured; run it eagerly or use kind='sgd'")
-            opts = [self.optimizer.dense]
+        opts = []
+        for _, _, opt in self.jobs:
+            if isinstance(opt, FusedRowOptimizer):
+                if opt.kind == "adam":
+                    raise RuntimeError("GraphedTrainStep: FusedRowOptimizer(kind='adam') keeps its step count on the host and "
+                                       "cannot be captured; run it eagerly or use kind='sgd'")
+                opts.append(opt.dense)
+            else:
+                opts.append(opt)
         for o in opts:
             if isinstance(o, DenseAdam):
                 raise RuntimeError("GraphedTrainStep: DenseAdam keeps its step count on the host and cannot be captured")

@@ -54,7 +54,110 @@ class EmbeddingLookup(torch.autograd.Function):
 
 
 def lookup(weight, ids):
+    sink = getattr(weight, "_rs_sink", None)
+    if sink is not None and torch.is_grad_enabled():
+        return _FusedLookup.apply(sink.anchor(weight.device), weight, ids)
     return EmbeddingLookup.apply(weight, ids)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# Opt-in FUSED SPARSE mode for the id-indexed drop-in modules (DIN, DIEN, MatrixFactorization, NeuralCF).
+# Reference semantics (nn.Embedding + a dense optimizer, model/din.py:35-36 + trainer/trainer.py:38-39) cost a table-sized
+# zero-fill, a table-sized gradient and a full-table optimizer sweep every step -- proportional to the ROW COUNT, not to the
+# batch.  After ``model.fuse_embedding_updates()`` the tables stop being autograd leaves: backward hands the per-lookup row
+# gradients to a RowSink and ``FusedRowOptimizer.step()`` runs rs_dedup_sort + rs_segment_update (sort / segment-reduce
+# fused with the SGD or lazy-Adam row update) on the touched rows only.  SGD without weight decay is exactly the
+# reference's update (untouched rows have zero gradient); Adam / weight decay become row-wise (lazy) -- see optim.py.
+class RowSink:
+    def __init__(self):
+        self.groups, self.pending, self._anchor = [], [], None
+
+    def anchor(self, device):
+        if self._anchor is None or self._anchor.device != device:
+            self._anchor = torch.zeros(1, device=device, requires_grad=True)
+        return self._anchor
+
+    def add_group(self, embeddings):
+        """Tables of equal width that are looked up together (MF user + item) move into ONE concatenated buffer (each
+        nn.Embedding.weight becomes a view of it, state_dict keys and shapes unchanged), so one sort covers them."""
+        ws = [e.weight for e in embeddings]
+        W, dev = ws[0].shape[1], ws[0].device
+        if any(w.shape[1] != W or w.device != dev for w in ws) or dev.type != "cuda":
+            raise ValueError("fuse_embedding_updates: move the model to its CUDA device first; grouped tables need one width")
+        rows = [w.shape[0] for w in ws]
+        buf = torch.empty(sum(rows), W, dtype=torch.float32, device=dev)
+        grp = {"buf": buf, "rows": rows, "offsets": [sum(rows[:k]) for k in range(len(rows))], "m": None, "v": None}
+        for k, e in enumerate(embeddings):
+            o = grp["offsets"][k]
+            buf[o:o + rows[k]].copy_(e.weight.data)
+            e.weight = torch.nn.Parameter(buf[o:o + rows[k]], requires_grad=False)
+            e.weight._rs_sink, e.weight._rs_group, e.weight._rs_field = self, grp, k
+        self.groups.append(grp)
+        return grp
+
+    def record(self, weights, ids, dE):
+        """weights: the looked-up tables, all of one group, in the column order of ids (N, F); dE (N, F, W)."""
+        grp = weights[0]._rs_group
+        for w in weights:
+            if w._rs_group is not grp:
+                raise RuntimeError("tables looked up together must belong to one fused group")
+            if w.data_ptr() != grp["buf"].data_ptr() + grp["offsets"][w._rs_field] * grp["buf"].shape[1] * 4:
+                raise RuntimeError("an embedding table was moved after fuse_embedding_updates(); call it after .to(device)")
+        self.pending.append((grp, [w._rs_field for w in weights], ids, dE))
+
+    def apply(self, opt):
+        for grp, fields, ids, dE in self.pending:
+            F, W = len(fields), grp["buf"].shape[1]
+            offs = [grp["offsets"][f] for f in fields]
+            segs = ops.dedup_sort(ids.reshape(-1, F), F, offs, sum(grp["rows"]), max_width=W)
+            if opt.kind == "sgd":
+                ops.segment_update(segs, ops.RS_UPD_SGD, W, F, dense=dE.reshape(-1, W), table=grp["buf"], lr=opt.lr, wd=opt.weight_decay)
+            else:
+                if grp["m"] is None:
+                    grp["m"], grp["v"] = torch.zeros_like(grp["buf"]), torch.zeros_like(grp["buf"])
+                ops.segment_update(segs, ops.RS_UPD_ADAM, W, F, dense=dE.reshape(-1, W), table=grp["buf"], m=grp["m"], v=grp["v"],
+                                   lr=opt.lr, wd=opt.weight_decay, betas=opt.betas, eps=opt.eps, step=opt.step_count)
+        self.pending.clear()
+
+
+class FusedRows:
+    """Mixin: ``fuse_embedding_updates()`` + the apply_pending / clear_pending protocol FusedRowOptimizer drives."""
+    _row_sink = None
+
+    def _fused_groups(self):
+        raise NotImplementedError
+
+    def fuse_embedding_updates(self):
+        if self._row_sink is None:
+            self._row_sink = RowSink()
+            for group in self._fused_groups():
+                self._row_sink.add_group(group)
+        return self
+
+    def apply_pending(self, opt):
+        if self._row_sink is not None:
+            self._row_sink.apply(opt)
+
+    def clear_pending(self):
+        if self._row_sink is not None:
+            self._row_sink.pending.clear()
+
+
+class _FusedLookup(torch.autograd.Function):
+    """weight[ids] whose backward records (ids, row gradients) for the fused row optimizer instead of a dense gradient"""
+
+    @staticmethod
+    def forward(ctx, anchor, weight, ids):
+        ctx.weight = weight
+        ctx.save_for_backward(ids)
+        out = ops.gather_rows(ops.make_tables([weight.detach()]), ids.reshape(-1, 1))
+        return out.view(*ids.shape, weight.shape[1])
+
+    @staticmethod
+    def backward(ctx, g):
+        (ids,) = ctx.saved_tensors
+        ctx.weight._rs_sink.record([ctx.weight], ids.reshape(-1, 1), g.contiguous().view(-1, 1, g.shape[-1]))
+        return torch.zeros(1, device=g.device), None, None
 
 
 class XEmbed(torch.autograd.Function):
@@ -156,20 +259,34 @@ class PairLookup(torch.autograd.Function):
     (model/neuralcf.py:37-39) or the MLP-tower concat (model/neuralcf.py:43-46)."""
 
     @staticmethod
-    def forward(ctx, wu, wi, u, i, what):
+    def forward(ctx, wu, wi, u, i, what, anchor=None):
         ids = torch.stack([u, i], dim=1).contiguous()
         T = ops.make_tables([wu.detach(), wi.detach()])
-        ctx.what, ctx.rows = what, (wu.shape[0], wi.shape[0])
-        ctx.save_for_backward(ids, wu, wi)
+        ctx.what, ctx.rows, ctx.fused = what, (wu.shape[0], wi.shape[0]), anchor is not None
+        ctx.tables = (wu, wi)
+        ctx.save_for_backward(ids)
         return ops.fields_fwd(T, ids.shape[0], ids.device, ids=ids, **{what: True})[what]
 
     @staticmethod
     def backward(ctx, g):
-        ids, wu, wi = ctx.saved_tensors
+        (ids,) = ctx.saved_tensors
+        wu, wi = ctx.tables
         T = ops.make_tables([wu.detach(), wi.detach()])
         dE = ops.fields_bwd(T, ids.shape[0], ids.device, ids=ids, **{"g_" + ctx.what: g.contiguous()})
+        if ctx.fused:          # fused sparse mode: the row optimizer consumes (ids, dE); no table-sized gradient exists
+            wu._rs_sink.record([wu, wi], ids, dE)
+            return None, None, None, None, None, torch.zeros(1, device=g.device)
+        if not (wu.requires_grad or wi.requires_grad):
+            return None, None, None, None, None, None
         gu, gi = table_grads(ids, dE, list(ctx.rows))
-        return gu, gi, None, None, None
+        return gu, gi, None, None, None, None
+
+
+def pair_lookup(wu, wi, u, i, what):
+    sink = getattr(wu, "_rs_sink", None)
+    if sink is not None and torch.is_grad_enabled():
+        return PairLookup.apply(wu, wi, u, i, what, sink.anchor(wu.device))
+    return PairLookup.apply(wu, wi, u, i, what, None)
 
 
 class OuterPooled(torch.autograd.Function):

@@ -10,7 +10,7 @@ from . import _blocks as K
 from .. import attention
 
 
-class DIN(nn.Module):
+class DIN(nn.Module, K.FusedRows):
     """Attention front half of DIEN: returns (history * attention weight (B, L, D), target embedding (B, D))."""
 
     def __init__(self, num_items, embed_size):
@@ -18,6 +18,9 @@ class DIN(nn.Module):
         self.item_embedding = nn.Embedding(num_items, embed_size)
         self.attention = nn.Sequential(nn.Linear(embed_size * 3, 64), nn.ReLU(), nn.Linear(64, 32), nn.ReLU(), nn.Linear(32, 1))
         xavier_normal_(self.item_embedding.weight.data)
+
+    def _fused_groups(self):
+        return [[self.item_embedding]]
 
     def forward(self, hist, target_item):
         rows = K.lookup(self.item_embedding.weight, torch.cat([hist, target_item.unsqueeze(1)], dim=1))
@@ -31,6 +34,11 @@ class DIEN(nn.Module):
         self.interest_evolution = nn.GRU(embed_size, embed_size, batch_first=True)
         self.fc = nn.Sequential(nn.Linear(embed_size * 2, 128), nn.ReLU(), nn.Linear(128, 64), nn.ReLU(), nn.Linear(64, 1),
                                 nn.Sigmoid())
+
+    def fuse_embedding_updates(self):
+        """opt-in fused sparse rows for the item table (see model/_blocks.RowSink); FusedRowOptimizer finds self.din"""
+        self.din.fuse_embedding_updates()
+        return self
 
     def forward(self, hist, target_item):
         att_hist, target_embed = self.din(hist, target_item)

@@ -11,7 +11,7 @@ from . import _blocks as K
 from .. import attention
 
 
-class DIN(nn.Module):
+class DIN(nn.Module, K.FusedRows):
     def __init__(self, num_items, embed_size):
         super().__init__()
         self.item_embedding = nn.Embedding(num_items, embed_size)
@@ -19,6 +19,9 @@ class DIN(nn.Module):
         self.fc = nn.Sequential(nn.Linear(embed_size * 2, 256), nn.ReLU(), nn.Linear(256, 128), nn.ReLU(), nn.Linear(128, 1),
                                 nn.Sigmoid())
         xavier_normal_(self.item_embedding.weight.data)
+
+    def _fused_groups(self):
+        return [[self.item_embedding]]
 
     def forward(self, hist, target_item):
         rows = K.lookup(self.item_embedding.weight, torch.cat([hist, target_item.unsqueeze(1)], dim=1))   # (B, L+1, D)

@@ -7,7 +7,7 @@ from . import _blocks as K
 from .. import ops
 
 
-class MatrixFactorization(nn.Module):
+class MatrixFactorization(nn.Module, K.FusedRows):
     def __init__(self, num_users: int, num_items: int, embedding_size: int):
         super().__init__()
         self.user_embeddings = nn.Embedding(num_users, embedding_size)
@@ -15,8 +15,11 @@ class MatrixFactorization(nn.Module):
         xavier_normal_(self.user_embeddings.weight.data)
         xavier_normal_(self.item_embeddings.weight.data)
 
+    def _fused_groups(self):
+        return [[self.user_embeddings, self.item_embeddings]]
+
     def forward(self, user_indices: torch.Tensor, item_indices: torch.Tensor) -> torch.Tensor:
-        dot = K.PairLookup.apply(self.user_embeddings.weight, self.item_embeddings.weight, user_indices, item_indices, "dot2")
+        dot = K.pair_lookup(self.user_embeddings.weight, self.item_embeddings.weight, user_indices, item_indices, "dot2")
         return torch.sigmoid(dot)                                   # (B,)
 
     def recommendation(self, num_users, num_items):

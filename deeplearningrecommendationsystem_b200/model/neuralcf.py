@@ -6,7 +6,7 @@ from torch.nn.init import xavier_normal_
 from . import _blocks as K
 
 
-class NeuralCF(nn.Module):
+class NeuralCF(nn.Module, K.FusedRows):
     def __init__(self, num_user, num_item, mf_dim, layers):
         super().__init__()
         self.GMF_Embedding_User = nn.Embedding(num_user, mf_dim)
@@ -21,9 +21,12 @@ class NeuralCF(nn.Module):
         self.linear2 = nn.Linear(2 * mf_dim, 1)
         self.sigmoid = nn.Sigmoid()
 
+    def _fused_groups(self):
+        return [[self.GMF_Embedding_User, self.GMF_Embedding_Item], [self.MLP_Embedding_User, self.MLP_Embedding_Item]]
+
     def forward(self, user_indices, item_indices):
-        gmf = K.PairLookup.apply(self.GMF_Embedding_User.weight, self.GMF_Embedding_Item.weight, user_indices, item_indices, "had2")
-        x = K.PairLookup.apply(self.MLP_Embedding_User.weight, self.MLP_Embedding_Item.weight, user_indices, item_indices, "concat")
+        gmf = K.pair_lookup(self.GMF_Embedding_User.weight, self.GMF_Embedding_Item.weight, user_indices, item_indices, "had2")
+        x = K.pair_lookup(self.MLP_Embedding_User.weight, self.MLP_Embedding_Item.weight, user_indices, item_indices, "concat")
         for layer in self.dnn_network:
             x = self.relu(layer(x))
         vector = torch.cat([gmf, self.linear(x)], dim=1)

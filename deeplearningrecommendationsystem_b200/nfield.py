@@ -196,7 +196,7 @@ class _FieldModel(nn.Module):
                 # segment-reduce fused with the push: every reduced row is stored straight into its owner's buffer over
                 # NVLink (device-resident routes); after the barrier the owner runs the same sort / segment-reduce /
                 # update kernels over what it received (the fill level of that buffer is a device scalar: n_valid)
-                routes, ent = ex.grad_routes(plan, self.width, rec["g"].device)
+                routes, ent = ex.grad_routes(plan, self.weight.data, rec["g"].device)
                 ops.segment_update(segs, ops.RS_UPD_GRAD, self.width, self.F, grad_routes=routes, **src)
                 recv = ex.finish_push(plan, ent)
                 osegs = ex.owner_segments(plan, self.weight.shape[0], self.width)
@@ -368,3 +368,45 @@ class FieldAFM(_FieldModel):
         concat, _ = self.embed(ids)
         pooled = attention.afm_pool(concat.view(ids.shape[0], self.F, self.width), self.attention_W, self.attention_b, self.attention_h)
         return torch.sigmoid(self.output_layer(pooled))
+
+
+class _PairTable(_FieldModel):
+    """user + item tables of one embedding width in one concatenated (optionally row-sharded) buffer; only embed() is used"""
+    use_bias = False
+
+    def __init__(self, num_users, num_items, width, **kw):
+        super().__init__([num_users, num_items], width, width, **kw)
+        self.bias.requires_grad_(False)
+
+
+class FieldNeuralCF(nn.Module):
+    """NeuralCF (reference model/neuralcf.py:7-59: GMF Hadamard * MLP tower on [u_mlp, i_mlp], Linear(layers[-1], mf_dim),
+    Linear(2 mf_dim, 1), sigmoid) for the synthetic 100 M-row configs (BASELINE.json configs[4]): the four embedding tables
+    live in two concatenated buffers (GMF user+item, MLP user+item), updated by the fused row optimizer and -- with
+    ``sharded=True`` -- row-sharded over the ranks with ONE exchange plan per batch shared by both buffers (same ids, same
+    row layout).  Same forward signature and (B, 1) output as the reference module."""
+
+    def __init__(self, num_user, num_item, mf_dim, layers, fused=True, seed=None, device=None, sharded=False, group=None,
+                 fabric=None, exchange=None):
+        super().__init__()
+        if sharded and exchange is None:
+            from . import dist as rsdist
+            import os
+            if os.environ.get("RS_PEER_EXCHANGE", "1") == "1":
+                exchange = rsdist.DeviceRowExchange(fabric)
+        kw = dict(fused=fused, device=device, sharded=sharded, group=group, exchange=exchange)
+        self.gmf = _PairTable(num_user, num_item, mf_dim, seed=seed, **kw)
+        self.mlp = _PairTable(num_user, num_item, int(layers[0] / 2), seed=None if seed is None else seed + 1, **kw)
+        self.mf_dim = mf_dim
+        self.dnn_network = nn.ModuleList([nn.Linear(a, b, device=device) for a, b in zip(layers[:-1], layers[1:])])
+        self.linear = nn.Linear(layers[-1], mf_dim, device=device)
+        self.linear2 = nn.Linear(2 * mf_dim, 1, device=device)
+
+    def forward(self, user_indices, item_indices):
+        ids = torch.stack([user_indices, item_indices], dim=1)
+        g, _ = self.gmf.embed(ids)                               # (B, 2 mf_dim) = [U_g[u] | V_g[i]]
+        gmf = g[:, :self.mf_dim] * g[:, self.mf_dim:]
+        x, _ = self.mlp.embed(ids)                               # (B, layers[0]) = cat[U_m[u], V_m[i]]
+        for layer in self.dnn_network:
+            x = torch.relu(layer(x))
+        return torch.sigmoid(self.linear2(torch.cat([gmf, self.linear(x)], dim=1)))

@@ -12,6 +12,7 @@ from ._lib import RS_MAX_FIELDS, RS_UPD_ADAM, RS_UPD_GRAD, RS_UPD_SGD  # noqa: F
 _status = {}
 _launches = 0
 PROFILE = None   # bench.py sets this to a list; ops then bracket their C-ABI call with CUDA events on the launching stream
+NVTX = os.environ.get("RS_NVTX", "0") == "1"   # every C-ABI call and every exchange phase becomes an NVTX range (nsys / ncu --nvtx)
 
 
 class _timed:
@@ -19,11 +20,15 @@ class _timed:
         self.name = name
 
     def __enter__(self):
+        if NVTX:
+            torch.cuda.nvtx.range_push(self.name)
         if PROFILE is not None:
             self.a = torch.cuda.Event(enable_timing=True)
             self.a.record()
 
     def __exit__(self, *exc):
+        if NVTX:
+            torch.cuda.nvtx.range_pop()
         if PROFILE is not None:
             b = torch.cuda.Event(enable_timing=True)
             b.record()

@@ -1,4 +1,7 @@
-"""N-GPU row-sharded FM / FFM train steps == the 1-GPU step on the concatenated global batch (needs >= 2 GPUs)."""
+"""N-GPU row-sharded FM / FFM train steps == the 1-GPU step on the concatenated global batch (needs >= 2 GPUs), for both
+exchange implementations: dist.DeviceRowExchange (this package's kernels over NVLink peer memory, the default) and
+dist.RowExchange (NCCL all-to-alls).  On a 1-GPU box these skip; tests/test_shard_gpu.py runs the same comparison with
+virtual ranks, and `bench.py --gpus N` prints the same check ("sharded_equals_single") in its JSON line."""
 import os
 import socket
 
@@ -24,8 +27,8 @@ def _batch(rank, B):
     return ids, (torch.rand(B, 1, generator=g) < 0.3).float()
 
 
-def _worker(rank, world, port, kind, D, B, steps, lr, out):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+def _worker(rank, world, port, kind, D, B, steps, lr, out, exchange):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RS_PEER_EXCHANGE="1" if exchange == "device" else "0")
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
@@ -44,8 +47,7 @@ def _worker(rank, world, port, kind, D, B, steps, lr, out):
             tr.train_loop(ids.cuda(), train_rating=y.cuda())
             preds.append(tr.predictions_train.detach().cpu())
         ops.check_status()
-        shards = [torch.empty(rsdist.RowExchange(None).local_rows(m.total_rows) if r == rank else
-                              (m.total_rows - r + world - 1) // world, m.width, device=f"cuda:{rank}") for r in range(world)]
+        shards = [torch.empty((m.total_rows - r + world - 1) // world, m.width, device=f"cuda:{rank}") for r in range(world)]
         # gather every shard on rank 0 through padded all_gather
         maxr = max(s.shape[0] for s in shards)
         pad = torch.zeros(maxr, m.width, device=f"cuda:{rank}")
@@ -59,17 +61,18 @@ def _worker(rank, world, port, kind, D, B, steps, lr, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kind,D", [("fm", 16), ("ffm", 8)])
-def test_sharded_equals_single_gpu(kind, D, tmp_path):
-    world = 2
+@pytest.mark.parametrize("world", [2, 8])
+@pytest.mark.parametrize("exchange", ["device", "nccl"])
+@pytest.mark.parametrize("kind,D", [("fm", 16), ("ffm", 8), ("ffm", 16)])
+def test_sharded_equals_single_gpu(kind, D, exchange, world, tmp_path):
     if torch.cuda.device_count() < world:
-        pytest.skip("needs 2 GPUs")
+        pytest.skip(f"needs {world} GPUs")
     from deeplearningrecommendationsystem_b200.nfield import FieldFFM, FieldFM
     from deeplearningrecommendationsystem_b200.optim import FusedRowOptimizer
     from deeplearningrecommendationsystem_b200.trainer import Trainer
     B, steps, lr = 300, 3, 0.5
     out = str(tmp_path / "res.pt")
-    mp.spawn(_worker, args=(world, _free_port(), kind, D, B, steps, lr, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), kind, D, B, steps, lr, out, exchange), nprocs=world, join=True)
     res = torch.load(out)
     cls = FieldFM if kind == "fm" else FieldFFM
     m = cls(CARDS, D, fused=True, seed=4, device="cpu")
