@@ -115,6 +115,12 @@ class ClockSampler:
         return out
 
 
+def progress(msg):
+    """stage markers on stderr (rank 0): a hung multi-GPU run can then be located from its log"""
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def env():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -300,6 +306,7 @@ def run_legs(step, pool, B, args, world, dev, local, graph_step=None, extra_warm
     for k in range(args.warmup + extra_warmup):
         step(*pool[k % len(pool)])
     ops.check_status(dev)
+    progress("  warm-up done")
     ops.PROFILE = []
     clocks = ClockSampler(local)
     sync()
@@ -316,12 +323,14 @@ def run_legs(step, pool, B, args, world, dev, local, graph_step=None, extra_warm
     last_loss_eager = float(loss.detach())
     del loss            # keeps the eager autograd graph (AccumulateGrad nodes bound to this stream) alive otherwise: breaks capture
 
+    progress("  eager leg done")
     run = step
     api = "trainer.Trainer.train_loop (eager)"
     if graph_step is not None:
         run, api = graph_step, "graph.GraphedTrainStep (CUDA graph replay of the same step)"
         for k in range(3):                              # untimed: eager warm-up call(s), the capture, one replay
             run(*pool[k % len(pool)])
+        progress("  graph captured")
     host_pool = [(tuple(t.cpu().pin_memory() for t in ins), y.cpu().pin_memory()) for ins, y in pool]
     copy_stream = torch.cuda.Stream(device=dev)
     main = torch.cuda.current_stream()
@@ -507,6 +516,7 @@ def verify_sharded(dev, world, rank):
     dist.all_gather(all_y, y)
     out = {}
     for name in ("device", "nccl"):
+        progress(f"  verify: {name} exchange")
         os.environ["RS_PEER_EXCHANGE"] = "1" if name == "device" else "0"
         ex = rsdist.DeviceRowExchange() if name == "device" else None
         errs = []
@@ -528,7 +538,7 @@ def verify_sharded(dev, world, rank):
                 full = rsdist.unshard_rows([got[r][: rows[r]] for r in range(world)])
                 s = cls(cards, D, seed=5, device=dev)
                 s.weight.data.copy_(glob)
-                ts = Trainer(s, torch.nn.BCELoss(), FusedRowOptimizer(s, torch.optim.SGD([s.bias], lr=lr), lr=lr))
+                ts = Trainer(s, torch.nn.BCELoss(), FusedRowOptimizer(s, torch.optim.SGD([s.bias], lr=lr), lr=lr, data_parallel=False))
                 gi, gy = torch.cat(all_ids), torch.cat(all_y)
                 for k in range(steps):
                     ts.train_loop(gi, train_rating=gy)
@@ -571,7 +581,9 @@ def run_c2(args):
     cards = [min(c, 1 << 17) for c in CRITEO] if args.light else CRITEO
     B = args.batch
     graph = args.graph
+    progress(f"c2 headline: tables built, world={world}")
     legs, n_uniq = c2_job(cards, B, args.dist, dev, world, rank, args, local, graph=graph)
+    progress(f"c2 headline done: {legs['ms_step']:.3f} ms eager, {legs['ms_e2e']:.3f} ms e2e")
     line = base_line(args, world, B, legs, WORKLOADS["c2"],
                      {"fields": F, "dim": D, "rows": sum(cards), "ids": args.dist, "light": bool(args.light),
                       "l2": "8 distinct id batches cycled; per-step traffic (>8 GB) far exceeds the 126 MB L2",
@@ -590,6 +602,7 @@ def run_c2(args):
         if not args.quick:
             # Zipf(1.05) ids beside uniform: same tables, heavy duplicates
             other = "zipf" if args.dist == "uniform" else "uniform"
+            progress(f"{other} leg")
             zl, zu = c2_job(cards, B, other, dev, world, rank, sub_args, local, graph=graph)
             zr = c2_rooflines(zl, B, zu, f"{'light' if args.light else 'full'}-{other}")
             line[other] = {"value": world * B / (zl["ms_step"] / 1e3), "ms_per_step": zl["ms_step"], "e2e": world * B / (zl["ms_e2e"] / 1e3),
@@ -601,9 +614,12 @@ def run_c2(args):
                 line["light"] = {"value": B / (ll["ms_step"] / 1e3), "ms_per_step": ll["ms_step"], "e2e": B / (ll["ms_e2e"] / 1e3),
                                  "unique_rows_per_batch": lu, "rows": sum(min(c, 1 << 17) for c in CRITEO), "steps": sub_args.steps,
                                  "note": "same config as cpu_baseline.sample / the --impl reference arm"}
+            progress("c5 sub-record")
             line["c5"] = c5_subrecord(sub_args, dev, world, rank, local)
             if world > 1:
+                progress("sharded == single check")
                 line["sharded_equals_single"] = verify_sharded(dev, world, rank)
+            progress("sub-records done")
     if rank == 0:
         if world == 1 and not args.no_cpu:
             cb = time_cpu("c2", "FM+FFM", 2, 1)

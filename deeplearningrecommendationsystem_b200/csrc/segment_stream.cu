@@ -11,6 +11,7 @@
 // at chunk boundaries, so the summation order -- and therefore every bit of the result -- does not depend on the
 // schedule.
 #include <cstddef>
+#include <stdlib.h>
 
 #include "segment.cuh"
 
@@ -24,6 +25,7 @@ constexpr int NCT = NCW * 32;  // consumer threads: thread t owns float4 columns
 constexpr int NTHREADS = NCT + 32;
 constexpr int UNIT = RS_UNIT;   // sorted lookups per work unit
 constexpr int MAX_ST = 12;
+constexpr int OUT_SLOTS = 4;   // staging rows of the pusher warp (routed RS_UPD_GRAD)
 
 struct __align__(16) StageHdr {
   int flags[SR];      // 1 first | 2 last lookup of its chunk | 4 segment is a single chunk
@@ -45,10 +47,17 @@ __device__ __forceinline__ int4 lds_i4(uint32_t addr) {
   return v;
 }
 
+// out_slots > 0 (routed RS_UPD_GRAD, NA == 1): reduced rows leave through a PUSHER warp.  Remote (NVLink peer) stores issued
+// by the consumer warps themselves stall those warps until the link accepts them, which backs the whole ring up -- the
+// kernel then costs HBM time PLUS link time.  Instead the consumers drop each finished row into a small shared-memory
+// staging ring and the pusher warp sends it with one cp.async.bulk shared -> (peer) global, so the link transfer overlaps
+// the gradient stream.
 template <int NA, int MODE>
-__global__ void __launch_bounds__(NTHREADS, 1) seg_stream_kernel(const __grid_constant__ UpdParams P, int n, int nst) {
+__global__ void __launch_bounds__(NTHREADS + 32, 1) seg_stream_kernel(const __grid_constant__ UpdParams P, int n, int nst, int out_slots) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t full_bar[MAX_ST], empty_bar[MAX_ST];
+  __shared__ uint64_t out_full[OUT_SLOTS], out_empty[OUT_SLOTS];
+  __shared__ float *out_dst[OUT_SLOTS];
   __shared__ StageHdr hdr[MAX_ST];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int WV = P.W >> 2;
@@ -60,12 +69,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) seg_stream_kernel(const __grid_co
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], NCW);
     }
+    for (int s = 0; s < OUT_SLOTS; ++s) {
+      mbar_init(&out_full[s], NCW);
+      mbar_init(&out_empty[s], 1);
+    }
     mbar_fence_init();
   }
   __syncthreads();
   const float *src = P.stash ? P.stash : P.dense;
+  float *oring = ring + (size_t)nst * stage_floats;        // OUT_SLOTS staging rows behind the stage ring
+  float *const OUT_DONE = reinterpret_cast<float *>(uintptr_t(1));
+  const bool pushing = MODE == RS_UPD_GRAD && NA == 1 && out_slots > 0;
 
-  if (warp == NCW) {
+  if (warp == NCW + 1) {
+    // ===================== pusher =====================
+    if (pushing) {
+      for (int oc = 0;; ++oc) {
+        const int os = oc % out_slots;
+        mbar_wait(&out_full[os], (uint32_t)(oc / out_slots) & 1u);
+        float *dst = *reinterpret_cast<float *volatile *>(&out_dst[os]);
+        if (dst == OUT_DONE) break;
+        if (lane == 0) {
+          if (dst) bulk_s2g(dst, oring + (size_t)os * P.W, row_bytes);
+          bulk_commit();
+          bulk_wait_read<0>();                 // the staging row has been read: the consumers may overwrite it
+          mbar_arrive(&out_empty[os]);
+        }
+        __syncwarp();
+      }
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  } else if (warp == NCW) {
     // ===================== producer =====================
     // The producer is latency bound on its own metadata reads, so they are software pipelined: the record (and
     // the pre-permuted scale) of batch i+1 and the boundaries of the next work unit are requested before batch i
@@ -153,6 +187,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) seg_stream_kernel(const __grid_co
     float4 acc[NA];
 #pragma unroll
     for (int a = 0; a < NA; ++a) acc[a] = f4_zero();
+    int oc = 0;                                  // rows handed to the pusher so far (same value in every consumer thread)
+    const uint32_t oring_s = smem_u32(oring);
     for (int k = 0;; ++k) {
       const int st = k % nst;
       const uint32_t ph = (uint32_t)(k / nst) & 1u;
@@ -171,11 +207,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) seg_stream_kernel(const __grid_co
 #pragma unroll
       for (int a = 0; a < NA; ++a) {
         const int col = t + a * NCT;
-        if (col >= WV) continue;
+        const bool active = col < WV;
+        if (!active && !pushing) continue;       // (when pushing, every consumer thread takes part in the slot handshake)
         const uint32_t col_s = rows_s + (uint32_t)col * 16u;
         float4 v[SR];
 #pragma unroll
-        for (int e = 0; e < SR; ++e) v[e] = (e < count) ? lds_f4(col_s + (uint32_t)e * row_bytes) : f4_zero();
+        for (int e = 0; e < SR; ++e) v[e] = (active && e < count) ? lds_f4(col_s + (uint32_t)e * row_bytes) : f4_zero();
 #pragma unroll
         for (int e = 0; e < SR; ++e) {
           if (e < count) {
@@ -190,6 +227,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) seg_stream_kernel(const __grid_co
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(row) : "r"(h + (uint32_t)offsetof(StageHdr, row) + 4u * e));
                 float *dst = (MODE == RS_UPD_GRAD ? (P.routes.n > 0 ? route_row(P.routes, row, P.W) : P.dense_grad + (int64_t)row * P.W)
                                                   : P.table + (int64_t)row * P.W);
+                if (pushing) {
+                  const int os = oc % out_slots;
+                  mbar_wait(&out_empty[os], ((uint32_t)(oc / out_slots) & 1u) ^ 1u);
+                  if (active)
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(oring_s + (uint32_t)os * row_bytes + (uint32_t)col * 16u),
+                                 "f"(acc[a].x), "f"(acc[a].y), "f"(acc[a].z), "f"(acc[a].w)
+                                 : "memory");
+                  if (t == 0) out_dst[os] = dst;
+                  fence_proxy_async();
+                  __syncwarp();
+                  if (lane == 0) mbar_arrive(&out_full[os]);
+                  ++oc;
+                  acc[a] = f4_zero();
+                  continue;
+                }
                 if (dst) dst += col * 4;   // nullptr: the routed destination is beyond the receiver's capacity (flagged there)
                 if (MODE == RS_UPD_SGD) {
                   int ts;
@@ -213,7 +265,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) seg_stream_kernel(const __grid_co
               } else {
                 int ps;
                 asm volatile("ld.shared.s32 %0, [%1];" : "=r"(ps) : "r"(h + (uint32_t)offsetof(StageHdr, pslot) + 4u * e));
-                stg_f4(P.partial + (int64_t)ps * P.W + col * 4, acc[a]);
+                if (active) stg_f4(P.partial + (int64_t)ps * P.W + col * 4, acc[a]);
               }
               acc[a] = f4_zero();
             }
@@ -222,6 +274,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) seg_stream_kernel(const __grid_co
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[st]);
+    }
+    if (pushing) {   // tell the pusher warp that no more rows will come
+      const int os = oc % out_slots;
+      mbar_wait(&out_empty[os], ((uint32_t)(oc / out_slots) & 1u) ^ 1u);
+      if (t == 0) out_dst[os] = OUT_DONE;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&out_full[os]);
     }
   }
 }
@@ -235,13 +294,16 @@ __global__ void __launch_bounds__(256) scale_sorted_kernel(const int4 *__restric
 template <int NA>
 int launch_na(const UpdParams &P, int n, int mode, cudaStream_t st) {
   const size_t stage_bytes = (size_t)2 * SR * P.W * 4;
-  int nst = (int)((200 * 1024) / stage_bytes);
+  // routed gradient rows leave through the pusher warp (see the kernel); RS_NO_PUSHER=1 keeps the consumers' own stores
+  const int out_slots = (mode == RS_UPD_GRAD && NA == 1 && P.routes.n > 0 && !getenv("RS_NO_PUSHER")) ? OUT_SLOTS : 0;
+  const size_t out_bytes = (size_t)out_slots * P.W * 4;
+  int nst = (int)((200 * 1024 - out_bytes) / stage_bytes);
   if (nst > MAX_ST) nst = MAX_ST;
   if (nst < BATCH + 1) {
     set_error("rs_segment_update: row of %d floats too wide for the streaming kernel", P.W);
     return RS_E_UNSUPPORTED;
   }
-  const size_t smem = stage_bytes * nst;
+  const size_t smem = stage_bytes * nst + out_bytes;
   RS_CUDA(cudaMemsetAsync(P.work_counter, 0, sizeof(int32_t), st));
   if (P.scale) {  // per-sample scale gathered into sorted-lookup order: the producer then reads it coalesced
     scale_sorted_kernel<<<(n + 255) / 256, 256, 0, st>>>(P.lookup_desc, P.scale, P.F, n, P.scale_sorted);
@@ -251,7 +313,7 @@ int launch_na(const UpdParams &P, int n, int mode, cudaStream_t st) {
 #define RS_LAUNCH_STREAM(M)                                                                                        \
   do {                                                                                                             \
     RS_CUDA(cudaFuncSetAttribute(seg_stream_kernel<NA, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    seg_stream_kernel<NA, M><<<grid, NTHREADS, smem, st>>>(P, n, nst);                                             \
+    seg_stream_kernel<NA, M><<<grid, NTHREADS + (out_slots ? 32 : 0), smem, st>>>(P, n, nst, out_slots);           \
   } while (0)
   switch (mode) {
     case RS_UPD_GRAD: RS_LAUNCH_STREAM(RS_UPD_GRAD); break;

@@ -162,16 +162,16 @@ class _FieldModel(nn.Module):
     def clear_pending(self):
         self._pending.clear()
 
-    def _row_update(self, opt, segs, F, **src):
+    def _row_update(self, opt, segs, F, tag="", **src):
         """Apply the optimizer to the rows of self.weight named by `segs` (gradient source in **src)."""
         if opt.kind == "sgd":
-            ops.segment_update(segs, ops.RS_UPD_SGD, self.width, F, table=self.weight.data, lr=opt.lr, wd=opt.weight_decay, **src)
+            ops.segment_update(segs, ops.RS_UPD_SGD, self.width, F, table=self.weight.data, lr=opt.lr, wd=opt.weight_decay, tag=tag, **src)
         else:
             if self.adam_m is None:
                 self.adam_m = torch.zeros_like(self.weight.data)
                 self.adam_v = torch.zeros_like(self.weight.data)
             ops.segment_update(segs, ops.RS_UPD_ADAM, self.width, F, table=self.weight.data, m=self.adam_m, v=self.adam_v,
-                               lr=opt.lr, wd=opt.weight_decay, betas=opt.betas, eps=opt.eps, step=opt.step_count, **src)
+                               lr=opt.lr, wd=opt.weight_decay, betas=opt.betas, eps=opt.eps, step=opt.step_count, tag=tag, **src)
 
     def apply_pending(self, opt):
         for rec in self._pending.values():
@@ -197,10 +197,10 @@ class _FieldModel(nn.Module):
                 # NVLink (device-resident routes); after the barrier the owner runs the same sort / segment-reduce /
                 # update kernels over what it received (the fill level of that buffer is a device scalar: n_valid)
                 routes, ent = ex.grad_routes(plan, self.weight.data, rec["g"].device)
-                ops.segment_update(segs, ops.RS_UPD_GRAD, self.width, self.F, grad_routes=routes, **src)
+                ops.segment_update(segs, ops.RS_UPD_GRAD, self.width, self.F, grad_routes=routes, tag="/push", **src)
                 recv = ex.finish_push(plan, ent)
                 osegs = ex.owner_segments(plan, self.weight.shape[0], self.width)
-                self._row_update(opt, osegs, 1, dense=recv)
+                self._row_update(opt, osegs, 1, tag="/owner", dense=recv)
                 continue
             # NCCL formulation: every fetched row has at least one lookup in this batch, so RS_UPD_GRAD writes every row
             block_grad = torch.empty(plan.n_uniq, self.width, dtype=torch.float32, device=rec["g"].device)

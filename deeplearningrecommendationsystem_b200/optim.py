@@ -16,12 +16,16 @@ from . import ops
 
 
 class FusedRowOptimizer:
-    def __init__(self, model, dense_optimizer=None, lr=0.01, kind="sgd", weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8):
+    def __init__(self, model, dense_optimizer=None, lr=0.01, kind="sgd", weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8,
+                 data_parallel=True):
+        """data_parallel: average the dense parameters' gradients over the process group before the dense step (the
+        replicated-parameter half of the multi-GPU partition); False for a model that lives on one rank only."""
         if kind not in ("sgd", "adam"):
             raise ValueError("kind must be 'sgd' or 'adam'")
         self.model, self.dense = model, dense_optimizer
         self.lr, self.kind, self.weight_decay, self.betas, self.eps = lr, kind, weight_decay, betas, eps
         self.step_count = 0
+        self.data_parallel = data_parallel
 
     def _sparse_modules(self):
         return [m for m in self.model.modules() if hasattr(m, "apply_pending")]
@@ -36,7 +40,9 @@ class FusedRowOptimizer:
         self.step_count += 1
         for m in self._sparse_modules():
             m.apply_pending(self)
-        if self.dense is not None:
+        if self.dense is not None and not self.data_parallel:
+            self.dense.step()
+        elif self.dense is not None:
             from .dist import allreduce_dense_grads
             fabric = next((m.exchange.fabric for m in self._sparse_modules()
                            if getattr(m, "exchange", None) is not None and hasattr(m.exchange, "fabric")), None)
