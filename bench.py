@@ -439,7 +439,7 @@ def build_c2(cards, dev, world, exchange=None, fabric=None):
     from deeplearningrecommendationsystem_b200.nfield import FieldFFM, FieldFM
     from deeplearningrecommendationsystem_b200.optim import FusedRowOptimizer
     from deeplearningrecommendationsystem_b200.trainer import Trainer
-    sharded = world > 1 or exchange is not None
+    sharded = world > 1 or exchange is not None or os.environ.get("RS_BENCH_FORCE_SHARDED") == "1"   # world 1: same kernels, local "peers"
     if sharded and exchange is None:
         from deeplearningrecommendationsystem_b200 import dist as rsdist
         exchange = rsdist.DeviceRowExchange(fabric) if os.environ.get("RS_PEER_EXCHANGE", "1") == "1" else None

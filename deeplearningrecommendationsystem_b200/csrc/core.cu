@@ -121,6 +121,9 @@ __global__ void __launch_bounds__(256) gather_rows_peer_kernel(const float *__re
                                                               const __grid_constant__ rs::Routes R, int32_t *status) {
   // Remote stores are latency bound, so every thread keeps four independent 16-byte pieces in flight: the four
   // loads are issued before the four stores.
+  __shared__ int64_t rtab[rs::ROUTE_TAB];
+  rs::route_tab_load(rtab, R);
+  __syncthreads();
   const int64_t total = m * wv;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e0 < total; e0 += 4 * stride) {
@@ -135,7 +138,7 @@ __global__ void __launch_bounds__(256) gather_rows_peer_kernel(const float *__re
         const int v = (int)(e - i * wv);
         const int64_t id = rs::clamp_id(idx[i], rows, status);
         val[u] = rs::ldg_nc_f4(table + (id * wv + v) * 4);
-        dst[u] = rs::route_row(R, i, wv * 4);
+        dst[u] = rs::route_row(R, rtab, i, wv * 4);
         if (dst[u]) dst[u] += v * 4;
       }
     }

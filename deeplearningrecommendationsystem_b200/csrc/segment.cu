@@ -388,12 +388,13 @@ struct Vec<1> {
 };
 
 template <int VEC, int MODE>
-__device__ __forceinline__ void apply_row(const UpdParams &P, int64_t row, int e /* element (in VEC units) */, typename Vec<VEC>::T g) {
+__device__ __forceinline__ void apply_row(const UpdParams &P, const int64_t *rtab, int64_t row, int e /* element (in VEC units) */,
+                                          typename Vec<VEC>::T g) {
   using V = Vec<VEC>;
   int64_t off = (row * P.W) + (int64_t)e * VEC;
   if (MODE == RS_UPD_GRAD) {
     if (P.routes.n > 0) {
-      float *d = rs::route_row(P.routes, row, P.W);
+      float *d = rs::route_row(P.routes, rtab, row, P.W);
       if (d) V::st(d + (int64_t)e * VEC, g);
     } else
       V::st(P.dense_grad + off, g);
@@ -421,6 +422,11 @@ template <int VEC, int GS, int NA, int MODE>
 __global__ void __launch_bounds__(256, (NA <= 4) ? 4 : 1) seg_chunk_kernel(const __grid_constant__ UpdParams P, int64_t n) {
   using V = Vec<VEC>;
   constexpr int GPB = 256 / GS;
+  __shared__ int64_t rtab[rs::ROUTE_TAB];
+  if (MODE == RS_UPD_GRAD && P.routes.n > 0) {
+    rs::route_tab_load(rtab, P.routes);
+    __syncthreads();
+  }
   const int lane = threadIdx.x % GS;
   const int WV = P.W / VEC;
   const int nchunks = *P.n_chunks;
@@ -469,7 +475,7 @@ __global__ void __launch_bounds__(256, (NA <= 4) ? 4 : 1) seg_chunk_kernel(const
 #pragma unroll
       for (int a = 0; a < NA; ++a) {
         const int e = lane + a * GS;
-        if (e < WV) apply_row<VEC, MODE>(P, row, e, acc[a]);
+        if (e < WV) apply_row<VEC, MODE>(P, rtab, row, e, acc[a]);
       }
     } else {
       float *dst = P.partial + (int64_t)partial_slot(s0, s1 - s0) * P.W;
@@ -491,6 +497,11 @@ __global__ void __launch_bounds__(256) seg_combine_kernel(const __grid_constant_
   using V = Vec<VEC>;
   constexpr int GPB = 256 / GS;
   extern __shared__ __align__(16) float s_grp[];  // [GPB][W]
+  __shared__ int64_t rtab[rs::ROUTE_TAB];
+  if (MODE == RS_UPD_GRAD && P.routes.n > 0) {
+    rs::route_tab_load(rtab, P.routes);
+    __syncthreads();
+  }
   const int lane = threadIdx.x % GS, grp = threadIdx.x / GS;
   const int WV = P.W / VEC;
   const int nm = *P.n_multi;
@@ -536,7 +547,7 @@ __global__ void __launch_bounds__(256) seg_combine_kernel(const __grid_constant_
         if (e < WV) {
           typename V::T t = V::ld(s_grp + e * VEC);
           for (int q = 1; q < used; ++q) t = V::add(t, V::ld(s_grp + (size_t)q * P.W + e * VEC));
-          apply_row<VEC, MODE>(P, P.uniq[g], e, t);
+          apply_row<VEC, MODE>(P, rtab, P.uniq[g], e, t);
         }
       }
     }

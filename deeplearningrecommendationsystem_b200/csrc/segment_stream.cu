@@ -25,7 +25,7 @@ constexpr int NCT = NCW * 32;  // consumer threads: thread t owns float4 columns
 constexpr int NTHREADS = NCT + 32;
 constexpr int UNIT = RS_UNIT;   // sorted lookups per work unit
 constexpr int MAX_ST = 12;
-constexpr int OUT_SLOTS = 4;   // staging rows of the pusher warp (routed RS_UPD_GRAD)
+constexpr int OUT_SLOTS = 64;    // most staging rows of the pusher warp (routed RS_UPD_GRAD); runs of out_slots / 4 rows
 
 struct __align__(16) StageHdr {
   int flags[SR];      // 1 first | 2 last lookup of its chunk | 4 segment is a single chunk
@@ -33,6 +33,8 @@ struct __align__(16) StageHdr {
   uint32_t row[SR];   // global table row
   int pslot[SR];      // chunk-partial slot (multi-chunk segments)
   int tslot[SR];      // table-row slot inside the stage (single-chunk segments, SGD)
+  float *dst[SR];     // where the finished row of a single-chunk segment goes (table row / gradient row / routed peer row);
+                      // resolved once by the producer lane instead of by every consumer thread
   int count, done, pad0, pad1;
 };
 
@@ -49,16 +51,20 @@ __device__ __forceinline__ int4 lds_i4(uint32_t addr) {
 
 // out_slots > 0 (routed RS_UPD_GRAD, NA == 1): reduced rows leave through a PUSHER warp.  Remote (NVLink peer) stores issued
 // by the consumer warps themselves stall those warps until the link accepts them, which backs the whole ring up -- the
-// kernel then costs HBM time PLUS link time.  Instead the consumers drop each finished row into a small shared-memory
-// staging ring and the pusher warp sends it with one cp.async.bulk shared -> (peer) global, so the link transfer overlaps
-// the gradient stream.
-template <int NA, int MODE>
-__global__ void __launch_bounds__(NTHREADS + 32, 1) seg_stream_kernel(const __grid_constant__ UpdParams P, int n, int nst, int out_slots) {
+// kernel then costs HBM time PLUS link time (measured at N = 2: 1.7-2.0 ms against 0.95 ms unsharded).  Instead the
+// consumers drop each finished row into a shared-memory staging ring and the pusher warp sends RUNS of rows with one
+// cp.async.bulk shared -> (peer) global each: consecutive unique rows of a work unit are consecutive rows of the owner's
+// buffer, and a bulk store to peer memory costs ~1.4 us of the SM's copy engine whatever its size (measured: one store
+// per 1664-byte row ran at 175 GB/s chip-wide), so the rows have to leave several at a time.
+template <int NA, int MODE, bool PUSH>
+__global__ void __launch_bounds__(NTHREADS + (PUSH ? 32 : 0), 1) seg_stream_kernel(const __grid_constant__ UpdParams P, int n, int nst, int out_slots) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t full_bar[MAX_ST], empty_bar[MAX_ST];
   __shared__ uint64_t out_full[OUT_SLOTS], out_empty[OUT_SLOTS];
   __shared__ float *out_dst[OUT_SLOTS];
   __shared__ StageHdr hdr[MAX_ST];
+  __shared__ int64_t rtab[ROUTE_TAB];
+  if (MODE == RS_UPD_GRAD && P.routes.n > 0) route_tab_load(rtab, P.routes);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int WV = P.W >> 2;
   const uint32_t row_bytes = (uint32_t)P.W * 4u;
@@ -79,24 +85,42 @@ __global__ void __launch_bounds__(NTHREADS + 32, 1) seg_stream_kernel(const __gr
   const float *src = P.stash ? P.stash : P.dense;
   float *oring = ring + (size_t)nst * stage_floats;        // OUT_SLOTS staging rows behind the stage ring
   float *const OUT_DONE = reinterpret_cast<float *>(uintptr_t(1));
-  const bool pushing = MODE == RS_UPD_GRAD && NA == 1 && out_slots > 0;
+  constexpr bool pushing = PUSH;   // compile-time: the handshake code must not weigh on the plain instantiations
 
   if (warp == NCW + 1) {
     // ===================== pusher =====================
     if (pushing) {
-      for (int oc = 0;; ++oc) {
-        const int os = oc % out_slots;
-        mbar_wait(&out_full[os], (uint32_t)(oc / out_slots) & 1u);
-        float *dst = *reinterpret_cast<float *volatile *>(&out_dst[os]);
-        if (dst == OUT_DONE) break;
-        if (lane == 0) {
-          if (dst) bulk_s2g(dst, oring + (size_t)os * P.W, row_bytes);
+      if (lane == 0) {
+        const int RUN = out_slots / 4;       // rows per bulk store at most; <= 2 RUN rows are unreleased at any time, so
+        int oc = 0, rel = 0;                 // the consumers always find free slots and the pusher can wait for rows
+        int run_len = 0, run_slot = 0, prev_rows = 0;
+        float *run_dst = nullptr;
+        auto flush = [&]() {
+          if (run_len == 0) return;
+          if (run_dst) bulk_s2g(run_dst, oring + (size_t)run_slot * P.W, row_bytes * (uint32_t)run_len);
           bulk_commit();
-          bulk_wait_read<0>();                 // the staging row has been read: the consumers may overwrite it
-          mbar_arrive(&out_empty[os]);
+          bulk_wait_read<1>();               // every store but the newest has read its staging rows: recycle them
+          for (int i = 0; i < prev_rows; ++i, rel = (rel + 1 == out_slots ? 0 : rel + 1)) mbar_arrive(&out_empty[rel]);
+          prev_rows = run_len;
+          run_len = 0;
+        };
+        int os = 0;
+        uint32_t oph = 0;
+        for (;; ++oc, os = (os + 1 == out_slots ? 0 : os + 1), oph ^= (os == 0 ? 1u : 0u)) {
+          mbar_wait(&out_full[os], oph);
+          float *dst = *reinterpret_cast<float *volatile *>(&out_dst[os]);
+          if (dst == OUT_DONE) break;
+          const bool extend = run_len > 0 && run_len < RUN && os != 0 && run_dst != nullptr && dst == run_dst + (size_t)run_len * P.W;
+          if (extend) {
+            ++run_len;
+          } else {
+            flush();
+            run_slot = os, run_dst = dst, run_len = 1;
+          }
         }
-        __syncwarp();
+        flush();
       }
+      __syncwarp();
       if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
   } else if (warp == NCW) {
@@ -104,7 +128,8 @@ __global__ void __launch_bounds__(NTHREADS + 32, 1) seg_stream_kernel(const __gr
     // The producer is latency bound on its own metadata reads, so they are software pipelined: the record (and
     // the pre-permuted scale) of batch i+1 and the boundaries of the next work unit are requested before batch i
     // is issued.
-    int k = 0;  // running stage counter
+    int pst = 0;        // next stage of the ring and its phase, advanced without divisions
+    uint32_t pph = 0;
     int u = 0;
     if (lane == 0) u = atomicAdd(P.work_counter, 1);
     u = __shfl_sync(0xffffffffu, u, 0);
@@ -130,6 +155,14 @@ __global__ void __launch_bounds__(NTHREADS + 32, 1) seg_stream_kernel(const __gr
           if (P.scale) sc_nxt = P.scale_sorted[sn];
         }
         const bool want_table = valid && MODE == RS_UPD_SGD && (d.y & 6) == 6;  // last lookup of a single-chunk segment
+        float *dptr = nullptr;
+        if (valid && (d.y & 6) == 6) {
+          const int64_t row = (int64_t)(uint32_t)d.z;
+          if (MODE == RS_UPD_GRAD)
+            dptr = P.routes.n > 0 ? route_row(P.routes, rtab, row, P.W) : P.dense_grad + row * P.W;
+          else
+            dptr = P.table + row * P.W;
+        }
         const int sub = lane >> 3, e = lane & 7;                                 // stage within the batch, entry within the stage
         const unsigned tmask = __ballot_sync(0xffffffffu, want_table);
         const unsigned vmask = __ballot_sync(0xffffffffu, valid);
@@ -139,8 +172,10 @@ __global__ void __launch_bounds__(NTHREADS + 32, 1) seg_stream_kernel(const __gr
 #pragma unroll
         for (int b = 0; b < BATCH; ++b) {
           // every lane walks the four stages in order so the empty-waits are warp-uniform
-          const int st = (k + b) % nst;
-          const uint32_t ph = (uint32_t)((k + b) / nst) & 1u;
+          const int st = pst;
+          const uint32_t ph = pph;
+          pst = (pst + 1 == nst) ? 0 : pst + 1;
+          pph ^= (pst == 0) ? 1u : 0u;
           mbar_wait(&empty_bar[st], ph ^ 1u);
           if (sub == b) {
             if (valid) {
@@ -149,6 +184,7 @@ __global__ void __launch_bounds__(NTHREADS + 32, 1) seg_stream_kernel(const __gr
               hdr[st].row[e] = (uint32_t)d.z;
               hdr[st].pslot[e] = d.w;
               hdr[st].tslot[e] = tslot;
+              hdr[st].dst[e] = dptr;
             }
             if (e == 0) {
               hdr[st].count = nval;
@@ -164,13 +200,12 @@ __global__ void __launch_bounds__(NTHREADS + 32, 1) seg_stream_kernel(const __gr
             if (want_table) bulk_g2s(dst + (size_t)(SR + tslot) * P.W, P.table + (int64_t)(uint32_t)d.z * P.W, row_bytes, &full_bar[st]);
           }
         }
-        k += BATCH;
       }
       u = __shfl_sync(0xffffffffu, un, 0);
     }
     // terminator stage
-    const int st = k % nst;
-    const uint32_t ph = (uint32_t)(k / nst) & 1u;
+    const int st = pst;
+    const uint32_t ph = pph;
     mbar_wait(&empty_bar[st], ph ^ 1u);
     if (lane == 0) {
       hdr[st].count = 0;
@@ -187,11 +222,12 @@ __global__ void __launch_bounds__(NTHREADS + 32, 1) seg_stream_kernel(const __gr
     float4 acc[NA];
 #pragma unroll
     for (int a = 0; a < NA; ++a) acc[a] = f4_zero();
-    int oc = 0;                                  // rows handed to the pusher so far (same value in every consumer thread)
+    int os = 0;                                  // next staging slot handed to the pusher and its phase (same in every thread)
+    uint32_t oph = 0;
     const uint32_t oring_s = smem_u32(oring);
-    for (int k = 0;; ++k) {
-      const int st = k % nst;
-      const uint32_t ph = (uint32_t)(k / nst) & 1u;
+    int st = 0;
+    uint32_t ph = 0;
+    for (;; st = (st + 1 == nst ? 0 : st + 1), ph ^= (st == 0 ? 1u : 0u)) {
       mbar_wait(&full_bar[st], ph);
       const uint32_t h = hdr_s + (uint32_t)st * (uint32_t)sizeof(StageHdr);
       const int4 tail = lds_i4(h + offsetof(StageHdr, count));
@@ -223,13 +259,10 @@ __global__ void __launch_bounds__(NTHREADS + 32, 1) seg_stream_kernel(const __gr
             acc[a].w = __fadd_rn(acc[a].w, __fmul_rn(v[e].w, sc[e]));
             if (fl[e] & 2) {  // chunk ends here
               if (fl[e] & 4) {
-                uint32_t row;
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(row) : "r"(h + (uint32_t)offsetof(StageHdr, row) + 4u * e));
-                float *dst = (MODE == RS_UPD_GRAD ? (P.routes.n > 0 ? route_row(P.routes, row, P.W) : P.dense_grad + (int64_t)row * P.W)
-                                                  : P.table + (int64_t)row * P.W);
+                float *dst;
+                asm volatile("ld.shared.u64 %0, [%1];" : "=l"(dst) : "r"(h + (uint32_t)offsetof(StageHdr, dst) + 8u * e));
                 if (pushing) {
-                  const int os = oc % out_slots;
-                  mbar_wait(&out_empty[os], ((uint32_t)(oc / out_slots) & 1u) ^ 1u);
+                  mbar_wait(&out_empty[os], oph ^ 1u);
                   if (active)
                     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(oring_s + (uint32_t)os * row_bytes + (uint32_t)col * 16u),
                                  "f"(acc[a].x), "f"(acc[a].y), "f"(acc[a].z), "f"(acc[a].w)
@@ -238,7 +271,8 @@ __global__ void __launch_bounds__(NTHREADS + 32, 1) seg_stream_kernel(const __gr
                   fence_proxy_async();
                   __syncwarp();
                   if (lane == 0) mbar_arrive(&out_full[os]);
-                  ++oc;
+                  os = (os + 1 == out_slots) ? 0 : os + 1;
+                  oph ^= (os == 0) ? 1u : 0u;
                   acc[a] = f4_zero();
                   continue;
                 }
@@ -251,6 +285,8 @@ __global__ void __launch_bounds__(NTHREADS + 32, 1) seg_stream_kernel(const __gr
                 } else if (MODE == RS_UPD_GRAD) {
                   if (dst) stg_f4(dst, acc[a]);
                 } else {
+                  uint32_t row;
+                  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(row) : "r"(h + (uint32_t)offsetof(StageHdr, row) + 4u * e));
                   float wv[4], mv[4], vv[4], gv[4];
                   *reinterpret_cast<float4 *>(wv) = ldg_f4(dst);
                   *reinterpret_cast<float4 *>(mv) = ldg_f4(P.m + (int64_t)row * P.W + col * 4);
@@ -276,8 +312,7 @@ __global__ void __launch_bounds__(NTHREADS + 32, 1) seg_stream_kernel(const __gr
       if (lane == 0) mbar_arrive(&empty_bar[st]);
     }
     if (pushing) {   // tell the pusher warp that no more rows will come
-      const int os = oc % out_slots;
-      mbar_wait(&out_empty[os], ((uint32_t)(oc / out_slots) & 1u) ^ 1u);
+      mbar_wait(&out_empty[os], oph ^ 1u);
       if (t == 0) out_dst[os] = OUT_DONE;
       __syncwarp();
       if (lane == 0) mbar_arrive(&out_full[os]);
@@ -295,7 +330,11 @@ template <int NA>
 int launch_na(const UpdParams &P, int n, int mode, cudaStream_t st) {
   const size_t stage_bytes = (size_t)2 * SR * P.W * 4;
   // routed gradient rows leave through the pusher warp (see the kernel); RS_NO_PUSHER=1 keeps the consumers' own stores
-  const int out_slots = (mode == RS_UPD_GRAD && NA == 1 && P.routes.n > 0 && !getenv("RS_NO_PUSHER")) ? OUT_SLOTS : 0;
+  int out_slots = 0;
+  if (mode == RS_UPD_GRAD && NA == 1 && P.routes.n > 0 && !getenv("RS_NO_PUSHER")) {
+    out_slots = (int)((26 * 1024) / ((size_t)P.W * 4)) / 4 * 4;          // ~26 KB of staging rows, a multiple of 4
+    out_slots = out_slots > OUT_SLOTS ? OUT_SLOTS : (out_slots < 8 ? 8 : out_slots);
+  }
   const size_t out_bytes = (size_t)out_slots * P.W * 4;
   int nst = (int)((200 * 1024 - out_bytes) / stage_bytes);
   if (nst > MAX_ST) nst = MAX_ST;
@@ -310,15 +349,17 @@ int launch_na(const UpdParams &P, int n, int mode, cudaStream_t st) {
     RS_CHECK_LAUNCH();
   }
   const int grid = num_sms();
-#define RS_LAUNCH_STREAM(M)                                                                                        \
-  do {                                                                                                             \
-    RS_CUDA(cudaFuncSetAttribute(seg_stream_kernel<NA, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    seg_stream_kernel<NA, M><<<grid, NTHREADS + (out_slots ? 32 : 0), smem, st>>>(P, n, nst, out_slots);           \
+#define RS_LAUNCH_STREAM(M, PUSH)                                                                                          \
+  do {                                                                                                                     \
+    RS_CUDA(cudaFuncSetAttribute(seg_stream_kernel<NA, M, PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    seg_stream_kernel<NA, M, PUSH><<<grid, NTHREADS + (PUSH ? 32 : 0), smem, st>>>(P, n, nst, out_slots);                  \
   } while (0)
   switch (mode) {
-    case RS_UPD_GRAD: RS_LAUNCH_STREAM(RS_UPD_GRAD); break;
-    case RS_UPD_SGD: RS_LAUNCH_STREAM(RS_UPD_SGD); break;
-    default: RS_LAUNCH_STREAM(RS_UPD_ADAM); break;
+    case RS_UPD_GRAD:
+      if (NA == 1 && out_slots > 0) RS_LAUNCH_STREAM(RS_UPD_GRAD, (NA == 1)); else RS_LAUNCH_STREAM(RS_UPD_GRAD, false);
+      break;
+    case RS_UPD_SGD: RS_LAUNCH_STREAM(RS_UPD_SGD, false); break;
+    default: RS_LAUNCH_STREAM(RS_UPD_ADAM, false); break;
   }
 #undef RS_LAUNCH_STREAM
   return RS_OK;
