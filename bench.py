@@ -442,7 +442,9 @@ def build_c2(cards, dev, world, exchange=None, fabric=None):
     sharded = world > 1 or exchange is not None or os.environ.get("RS_BENCH_FORCE_SHARDED") == "1"   # world 1: same kernels, local "peers"
     if sharded and exchange is None:
         from deeplearningrecommendationsystem_b200 import dist as rsdist
-        exchange = rsdist.DeviceRowExchange(fabric) if os.environ.get("RS_PEER_EXCHANGE", "1") == "1" else None
+        from deeplearningrecommendationsystem_b200.nfield import direct_ranges
+        direct = direct_ranges(cards) if os.environ.get("RS_DIRECT", "1") == "1" else ()
+        exchange = rsdist.DeviceRowExchange(fabric, direct=direct) if os.environ.get("RS_PEER_EXCHANGE", "1") == "1" else None
     kw = dict(fused=True, device=dev, sharded=sharded, exchange=exchange)
     fm = FieldFM(cards, D, seed=1, **kw)
     ffm = FieldFFM(cards, D, seed=2, **kw)

@@ -26,7 +26,7 @@ RS_MAX_RANKS = 64
 
 class rs_routes(C.Structure):
     _fields_ = [("n", C.c_int32), ("start", C.c_int64 * (RS_MAX_RANKS + 1)), ("base", C.c_void_p * RS_MAX_RANKS),
-                ("row0", C.c_int64 * RS_MAX_RANKS), ("dyn_start", C.c_void_p), ("dyn_row0", C.c_void_p), ("cap_rows", C.c_int64)]
+                ("row0", C.c_int64 * RS_MAX_RANKS), ("dyn_start", C.c_void_p), ("dyn_row0", C.c_void_p), ("cap_rows", C.c_int64), ("self", C.c_int32)]
 
 
 class rs_dedup_opts(C.Structure):
@@ -37,9 +37,17 @@ RS_SHARD_CTL_WORDS = 384
 RS_CTL_CNT_IN, RS_CTL_BLK0_IN, RS_CTL_G0_IN, RS_CTL_SEND_START, RS_CTL_RECV_START, RS_CTL_M_TOTAL = 0, 64, 128, 192, 257, 322
 
 
+RS_MAX_DIRECT = 8
+
+
 class rs_shard(C.Structure):
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("rows_per_rank", C.c_int64), ("cap_req", C.c_int64),
-                ("cap_recv", C.c_int64), ("req", C.c_void_p * RS_MAX_RANKS), ("ctl", C.c_void_p * RS_MAX_RANKS)]
+                ("cap_recv", C.c_int64), ("req", C.c_void_p * RS_MAX_RANKS), ("ctl", C.c_void_p * RS_MAX_RANKS),
+                ("n_direct", C.c_int32), ("direct_lo", C.c_int64 * RS_MAX_DIRECT), ("direct_hi", C.c_int64 * RS_MAX_DIRECT)]
+
+
+class rs_peer_tables(C.Structure):
+    _fields_ = [("world", C.c_int32), ("direct_mask", C.c_uint64), ("shard", C.c_void_p * RS_MAX_RANKS), ("total_rows", C.c_int64)]
 
 
 class rs_fields_io(C.Structure):
@@ -101,8 +109,9 @@ SIGNATURES = {
     "rs_dedup_sort_ex": [_P, _L, _I, _PP(_L), _L, _PP(rs_dedup_opts), _P, _Z, _PP(rs_segments), _P, _P],
     "rs_segments_relabel": [_PP(rs_segments), _L, _P],
     "rs_shard_post": [_PP(rs_shard), _PP(rs_segments), _L, _P, _P],
-    "rs_shard_collect": [_PP(rs_shard), _P, _P, _P, _P],
-    "rs_shard_serve": [_PP(rs_shard), _P, _L, _I, _P, _PP(_P), _L, _P, _P],
+    "rs_shard_collect": [_PP(rs_shard), _P, _P, _P, _P, _P],
+    "rs_shard_serve": [_PP(rs_shard), _P, _L, _I, _P, _P, _PP(_P), _L, _P, _P],
+    "rs_ffm_fwd_peer": [_PP(rs_tables), _P, _L, _I, _PP(rs_peer_tables), _P, _P, _P, _P],
     "rs_segment_update": [_PP(rs_segments), _L, _PP(rs_update), _P],
     "rs_adam_dense": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P],
     "rs_xembed_fwd": [_PP(rs_xslots), _P, _L, _P, _P, _P],

@@ -148,7 +148,12 @@ struct Routes {
   int64_t row0[RS_MAX_RANKS];
   const int64_t *dyn_start, *dyn_row0;  // device-resident ranges (host-sync-free sharded step), else nullptr
   int64_t cap_rows;                     // > 0: destination rows >= cap_rows are dropped
+  int self;                             // own index among the destinations (all-to-all schedule rotation), -1 unknown
 };
+// rotation of a walk over `count` items so that rank `self` of n starts self/n of the way through
+__device__ __forceinline__ int64_t route_rotation(const Routes &R, int64_t count) {
+  return (R.n > 1 && R.self > 0) ? count * R.self / R.n : 0;
+}
 // The ranges are staged ONCE per CTA into shared memory (route_tab_load + __syncthreads): the device-resident ones live in
 // symmetric (peer-mapped) memory, where every load is a round trip to L2/HBM -- three dependent ones per routed row cost
 // ~0.7 us per row when read in place.  tab[0..n] = start, tab[RS_MAX_RANKS+1 ..] = row0.

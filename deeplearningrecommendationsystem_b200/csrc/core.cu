@@ -109,6 +109,7 @@ int fill_routes(Routes &R, const rs_routes *r, const char *who) {
   R.dyn_start = r->dyn_start;
   R.dyn_row0 = r->dyn_row0;
   R.cap_rows = r->cap_rows;
+  R.self = r->self;
   RS_CHECK_ARG(!r->dyn_start || r->dyn_row0, RS_E_ARG, "%s: dyn_start without dyn_row0", who);
   return RS_OK;
 }

@@ -26,6 +26,11 @@ struct FfmParams {
   int pitchv;  // float4 per padded row in shared memory
   int nst;     // ring stages
   int32_t *status;
+  // row-sharded "direct" fields (rs_ffm_fwd_peer): read from the owner's shard over NVLink, ids are global rows
+  int world;
+  uint64_t direct_mask;
+  const float *shard[RS_MAX_RANKS];
+  int64_t total_rows;
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1) ffm_fwd_kernel(const __grid_constant__ FfmParams P) {
@@ -78,8 +83,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) ffm_fwd_kernel(const __grid_const
       for (int h = 0; h < 2; ++h) {
         const int f = lane + 32 * h;
         if (f < P.F) {
-          const int64_t id = rs::clamp_id(id_cur[h], s_rows[f], P.status);
-          rs::bulk_g2s(dst + (size_t)f * P.pitchv, s_base[f] + id * (int64_t)P.rowv * 4, row_bytes, &full_bar[s]);
+          const float *src;
+          if ((P.direct_mask >> f) & 1ull) {   // global row g of a direct field: rank g % world holds it at local row g / world
+            const int64_t g = rs::clamp_id(id_cur[h], P.total_rows, P.status);
+            const int64_t l = g / P.world;
+            src = P.shard[(int)(g - l * P.world)] + l * (int64_t)P.rowv * 4;
+          } else {
+            src = s_base[f] + rs::clamp_id(id_cur[h], s_rows[f], P.status) * (int64_t)P.rowv * 4;
+          }
+          rs::bulk_g2s(dst + (size_t)f * P.pitchv, src, row_bytes, &full_bar[s]);
         }
       }
       id_cur[0] = id_nxt[0];
@@ -197,6 +209,11 @@ int dense_launch(const float *Tin, const float *g, int64_t B, int F, int NF, int
 
 RS_API int rs_ffm_fwd(const rs_tables *T, const int64_t *ids, int64_t B, int32_t D, float *cross, float *stash, int32_t *status,
                       void *stream) {
+  return rs_ffm_fwd_peer(T, ids, B, D, nullptr, cross, stash, status, stream);
+}
+
+RS_API int rs_ffm_fwd_peer(const rs_tables *T, const int64_t *ids, int64_t B, int32_t D, const rs_peer_tables *PT, float *cross,
+                           float *stash, int32_t *status, void *stream) {
   RS_CHECK_ARG(T && ids && cross, RS_E_ARG, "rs_ffm_fwd: null argument");
   const int F = T->num_fields;
   RS_CHECK_ARG(F >= 2 && F <= RS_MAX_FIELDS, RS_E_SHAPE, "rs_ffm_fwd: F=%d out of range", F);
@@ -204,8 +221,20 @@ RS_API int rs_ffm_fwd(const rs_tables *T, const int64_t *ids, int64_t B, int32_t
   RS_CHECK_ARG(T->width == F * D, RS_E_SHAPE, "rs_ffm_fwd: table width %d != F*D = %d", T->width, F * D);
   if (B == 0) return RS_OK;
   FfmParams P = {};
+  P.world = 1;
+  if (PT && PT->direct_mask) {
+    RS_CHECK_ARG(PT->world >= 1 && PT->world <= RS_MAX_RANKS && PT->total_rows > 0, RS_E_ARG, "rs_ffm_fwd_peer: bad world / total_rows");
+    P.world = PT->world;
+    P.direct_mask = PT->direct_mask;
+    P.total_rows = PT->total_rows;
+    for (int k = 0; k < PT->world; ++k) {
+      RS_CHECK_ARG(PT->shard[k], RS_E_ARG, "rs_ffm_fwd_peer: null shard pointer for rank %d", k);
+      P.shard[k] = PT->shard[k];
+    }
+  }
   for (int f = 0; f < F; ++f) {
-    RS_CHECK_ARG(T->base[f] && T->rows[f] > 0, RS_E_ARG, "rs_ffm_fwd: table %d missing", f);
+    const bool direct = (P.direct_mask >> f) & 1ull;
+    RS_CHECK_ARG(direct || (T->base[f] && T->rows[f] > 0), RS_E_ARG, "rs_ffm_fwd: table %d missing", f);
     P.base[f] = T->base[f];
     P.rows[f] = T->rows[f];
   }

@@ -430,7 +430,9 @@ __global__ void __launch_bounds__(256, (NA <= 4) ? 4 : 1) seg_chunk_kernel(const
   const int lane = threadIdx.x % GS;
   const int WV = P.W / VEC;
   const int nchunks = *P.n_chunks;
-  for (int64_t c = (int64_t)blockIdx.x * GPB + threadIdx.x / GS; c < nchunks; c += (int64_t)gridDim.x * GPB) {
+  const int64_t crot = (MODE == RS_UPD_GRAD && P.routes.n > 0) ? rs::route_rotation(P.routes, nchunks) : 0;
+  for (int64_t c0 = (int64_t)blockIdx.x * GPB + threadIdx.x / GS; c0 < nchunks; c0 += (int64_t)gridDim.x * GPB) {
+    const int64_t c = c0 + crot < nchunks ? c0 + crot : c0 + crot - nchunks;   // all-to-all schedule (see rs_routes.self)
     const int s0 = P.chunk_start[c], s1 = P.chunk_start[c + 1];
     const int g = P.chunk_seg[c];
     // everything that depends only on g is requested now, so it is in flight together with the gradient rows
@@ -631,6 +633,7 @@ RS_API int rs_segment_update(const rs_segments *seg, int64_t n, const rs_update 
   P.routes.n = 0;
   P.routes.dyn_start = P.routes.dyn_row0 = nullptr;
   P.routes.cap_rows = 0;
+  P.routes.self = -1;
   if (u->mode == RS_UPD_GRAD && u->grad_routes) {
     int rc = rs::fill_routes(P.routes, u->grad_routes, "rs_segment_update");
     if (rc) return rc;

@@ -134,8 +134,12 @@ __global__ void __launch_bounds__(NTHREADS + (PUSH ? 32 : 0), 1) seg_stream_kern
     if (lane == 0) u = atomicAdd(P.work_counter, 1);
     u = __shfl_sync(0xffffffffu, u, 0);
     const int nunits = n / UNIT + 1;
+    // routed rows: every rank starts its walk over the (owner-major) units at its own share, so that at any moment the
+    // ranks push to different owners instead of all to the same one (rs_routes.self)
+    const int urot = (MODE == RS_UPD_GRAD && P.routes.n > 0) ? (int)route_rotation(P.routes, nunits) : 0;
     while (u < nunits) {
-      const int sA = P.unit_start[u], sB = P.unit_start[u + 1];
+      const int uu = u + urot < nunits ? u + urot : u + urot - nunits;
+      const int sA = P.unit_start[uu], sB = P.unit_start[uu + 1];
       int un = 0;                                    // claim the next unit now; its latency hides behind this one
       if (lane == 0) un = atomicAdd(P.work_counter, 1);
       int4 d_nxt = make_int4(0, 0, 0, 0);
@@ -329,9 +333,11 @@ __global__ void __launch_bounds__(256) scale_sorted_kernel(const int4 *__restric
 template <int NA>
 int launch_na(const UpdParams &P, int n, int mode, cudaStream_t st) {
   const size_t stage_bytes = (size_t)2 * SR * P.W * 4;
-  // routed gradient rows leave through the pusher warp (see the kernel); RS_NO_PUSHER=1 keeps the consumers' own stores
+  // RS_PUSHER=1: routed gradient rows leave through the pusher warp (see the kernel).  Measured at N = 2 on the C2 shape the
+  // consumers' own 128-bit stores are faster (1.07 ms vs 1.43 ms: the per-row staging handshake costs more than the link
+  // stalls it removes), so direct stores are the default.
   int out_slots = 0;
-  if (mode == RS_UPD_GRAD && NA == 1 && P.routes.n > 0 && !getenv("RS_NO_PUSHER")) {
+  if (mode == RS_UPD_GRAD && NA == 1 && P.routes.n > 0 && getenv("RS_PUSHER")) {
     out_slots = (int)((26 * 1024) / ((size_t)P.W * 4)) / 4 * 4;          // ~26 KB of staging rows, a multiple of 4
     out_slots = out_slots > OUT_SLOTS ? OUT_SLOTS : (out_slots < 8 ? 8 : out_slots);
   }

@@ -23,6 +23,8 @@ struct ShardDev {
   int64_t R, cap_req, cap_recv;
   int32_t *req[RS_MAX_RANKS];
   int64_t *ctl[RS_MAX_RANKS];
+  int n_direct;
+  int64_t direct_lo[RS_MAX_DIRECT], direct_hi[RS_MAX_DIRECT];
 };
 
 int fill_shard(ShardDev &D, const rs_shard *S, const char *who) {
@@ -34,6 +36,10 @@ int fill_shard(ShardDev &D, const rs_shard *S, const char *who) {
     D.req[k] = S->req[k];
     D.ctl[k] = S->ctl[k];
   }
+  RS_CHECK_ARG(S->n_direct >= 0 && S->n_direct <= RS_MAX_DIRECT, RS_E_ARG, "%s: at most %d direct ranges", who, RS_MAX_DIRECT);
+  RS_CHECK_ARG(S->n_direct == 0 || S->rows_per_rank < (1ll << 31), RS_E_SHAPE, "%s: direct ranges need rows_per_rank < 2^31", who);
+  D.n_direct = S->n_direct;
+  for (int k = 0; k < S->n_direct; ++k) D.direct_lo[k] = S->direct_lo[k], D.direct_hi[k] = S->direct_hi[k];
   return RS_OK;
 }
 
@@ -65,13 +71,21 @@ __global__ void __launch_bounds__(256) shard_post_kernel(const __grid_constant__
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nu; j += (int64_t)gridDim.x * blockDim.x) {
     const int64_t key = uniq[j];
     const int o = (int)(key / S.R);
-    S.req[o][(int64_t)S.rank * S.cap_req + (j - bounds[o])] = (int32_t)(key - (int64_t)o * S.R);
+    const int64_t l = key - (int64_t)o * S.R;
+    uint32_t e = (uint32_t)l;
+    if (S.n_direct > 0) {          // flag rows of the direct ranges: the owner will not copy them (bit 31)
+      const int64_t g = l * S.world + o;
+      for (int k = 0; k < S.n_direct; ++k)
+        if (g >= S.direct_lo[k] && g < S.direct_hi[k]) e |= 0x80000000u;
+    }
+    S.req[o][(int64_t)S.rank * S.cap_req + (j - bounds[o])] = (int32_t)e;
   }
 }
 
 // ------------------------------------------------------------------ owner: prefix of the counts + compact receive list
 __global__ void __launch_bounds__(256) shard_collect_kernel(const __grid_constant__ ShardDev S, int64_t *__restrict__ recv_local,
-                                                           int32_t *__restrict__ m_total, int32_t *status) {
+                                                           uint8_t *__restrict__ recv_skip, int32_t *__restrict__ m_total,
+                                                           int32_t *status) {
   __shared__ int64_t start[RS_MAX_RANKS + 1];
   int64_t *ctl = S.ctl[S.rank];
   if (threadIdx.x == 0) {
@@ -100,7 +114,9 @@ __global__ void __launch_bounds__(256) shard_collect_kernel(const __grid_constan
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
     int r = 0;
     while (r + 1 < S.world && i >= start[r + 1]) ++r;
-    recv_local[i] = (int64_t)req[(int64_t)r * S.cap_req + (i - start[r])];
+    const uint32_t e = (uint32_t)req[(int64_t)r * S.cap_req + (i - start[r])];
+    recv_local[i] = (int64_t)(e & 0x7fffffffu);
+    if (recv_skip) recv_skip[i] = (uint8_t)(e >> 31);
   }
 }
 
@@ -112,7 +128,8 @@ struct Blocks {
 // generic 128-bit path (any width that is a multiple of 4 floats): one 16-byte piece per thread iteration, four in flight
 __global__ void __launch_bounds__(256) shard_serve_kernel(const __grid_constant__ ShardDev S, const float *__restrict__ table, int64_t rows,
                                                          int wv, const int64_t *__restrict__ recv_local,
-                                                         const __grid_constant__ Blocks B, int64_t cap_block, int32_t *status) {
+                                                         const uint8_t *__restrict__ skip, const __grid_constant__ Blocks B,
+                                                         int64_t cap_block, int32_t *status) {
   __shared__ int64_t start[RS_MAX_RANKS + 1], blk0[RS_MAX_RANKS];
   const int64_t *ctl = S.ctl[S.rank];
   if (threadIdx.x <= S.world) start[threadIdx.x] = ctl[RS_CTL_RECV_START + threadIdx.x];
@@ -120,14 +137,17 @@ __global__ void __launch_bounds__(256) shard_serve_kernel(const __grid_constant_
   __syncthreads();
   const int64_t total = start[S.world] * wv;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  // all-to-all schedule: owner o serves requester o+1 first, then o+2, ... so the owners never gang up on one receiver
+  const int64_t rot = start[(S.rank + 1) % S.world] * wv;
   for (int64_t e0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e0 < total; e0 += 4 * stride) {
     float4 val[4];
     float *dst[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int64_t e = e0 + u * stride;
+      const int64_t ev = e0 + u * stride;
+      const int64_t e = ev + rot < total ? ev + rot : ev + rot - total;
       dst[u] = nullptr;
-      if (e < total) {
+      if (ev < total && !(skip && skip[e / wv])) {
         const int64_t i = e / wv;
         const int v = (int)(e - i * wv);
         int r = 0;
@@ -150,6 +170,7 @@ constexpr int SERVE_C = 16, SERVE_NST = 2, SERVE_WARPS = 4;
 
 __global__ void __launch_bounds__(SERVE_WARPS * 32, 1) shard_serve_tma_kernel(const __grid_constant__ ShardDev S, const float *__restrict__ table,
                                                                              int64_t rows, int W, const int64_t *__restrict__ recv_local,
+                                                                             const uint8_t *__restrict__ skip,
                                                                              const __grid_constant__ Blocks B, int64_t cap_block,
                                                                              int32_t *status) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -163,9 +184,12 @@ __global__ void __launch_bounds__(SERVE_WARPS * 32, 1) shard_serve_tma_kernel(co
   if (threadIdx.x < SERVE_WARPS * SERVE_NST) rs::mbar_init(&full_bar[threadIdx.x / SERVE_NST][threadIdx.x % SERVE_NST], 1);
   __syncthreads();
   if (threadIdx.x == 0) {
+    // chunk numbering follows the all-to-all schedule: position i of the walk serves requester (rank + 1 + i) % world, so
+    // the owners never gang up on one receiver's NVLink ingress
     int64_t acc = 0;
-    for (int r = 0; r < S.world; ++r) {
-      cstart[r] = acc;
+    for (int i = 0; i < S.world; ++i) {
+      const int r = (S.rank + 1 + i) % S.world;
+      cstart[i] = acc;
       acc += (start[r + 1] - start[r] + SERVE_C - 1) / SERVE_C;
     }
     cstart[S.world] = acc;
@@ -180,9 +204,10 @@ __global__ void __launch_bounds__(SERVE_WARPS * 32, 1) shard_serve_tma_kernel(co
   // chunk k of this warp -> (first compact row, row count, destination)
   auto describe = [&](int64_t k, int64_t &i0, int &cnt, float *&dst) {
     const int64_t c = gw + k * nw;
-    int r = 0;
-    while (r + 1 < S.world && c >= cstart[r + 1]) ++r;
-    i0 = start[r] + (c - cstart[r]) * SERVE_C;
+    int i = 0;
+    while (i + 1 < S.world && c >= cstart[i + 1]) ++i;
+    const int r = (S.rank + 1 + i) % S.world;
+    i0 = start[r] + (c - cstart[i]) * SERVE_C;
     const int64_t left = start[r + 1] - i0;
     cnt = (int)(left < SERVE_C ? left : SERVE_C);
     const int64_t drow = blk0[r] + (i0 - start[r]);
@@ -192,7 +217,9 @@ __global__ void __launch_bounds__(SERVE_WARPS * 32, 1) shard_serve_tma_kernel(co
 
   // iteration k: [stage k % NST is free once the store of chunk k - NST has read it] -> loads of chunk k ->
   // [wait for the loads of chunk k - 1] -> store of chunk k - 1.  The store of chunk k - NST was committed NST - 2
-  // groups ago, so at most NST - 2 newer groups may still be reading.
+  // groups ago, so at most NST - 2 newer groups may still be reading.  live[st]: rows of the chunk that are copied at all
+  // (rows of a "direct" range are skipped); a fully live chunk leaves in one bulk store, a mixed one in one store per run.
+  uint32_t live[SERVE_NST];
   for (int64_t k = 0; k <= mine; ++k) {
     if (k < mine) {
       const int st = (int)(k % SERVE_NST);
@@ -202,9 +229,11 @@ __global__ void __launch_bounds__(SERVE_WARPS * 32, 1) shard_serve_tma_kernel(co
       int cnt;
       float *dst;
       describe(k, i0, cnt, dst);
-      if (lane == 0) rs::mbar_arrive_expect_tx(&full_bar[warp][st], row_bytes * (uint32_t)cnt);
+      const bool on = lane < cnt && !(skip && skip[i0 + lane]);
+      live[st] = __ballot_sync(0xffffffffu, on);
+      if (lane == 0) rs::mbar_arrive_expect_tx(&full_bar[warp][st], row_bytes * (uint32_t)__popc(live[st]));
       __syncwarp();
-      if (lane < cnt) {
+      if (on) {
         const int64_t id = rs::clamp_id(recv_local[i0 + lane], rows, status);
         rs::bulk_g2s(ring + ((size_t)st * SERVE_C + lane) * W, table + id * W, row_bytes, &full_bar[warp][st]);
       }
@@ -217,7 +246,14 @@ __global__ void __launch_bounds__(SERVE_WARPS * 32, 1) shard_serve_tma_kernel(co
       float *dst;
       describe(j, i0, cnt, dst);
       rs::mbar_wait(&full_bar[warp][st], (uint32_t)(j / SERVE_NST) & 1u);
-      if (cnt > 0) rs::bulk_s2g(dst, ring + (size_t)st * SERVE_C * W, row_bytes * (uint32_t)cnt);
+      uint32_t m = live[st];
+      while (m) {                                   // maximal runs of copied rows (one run in the common case)
+        const int a = __ffs(m) - 1;
+        const uint32_t rest = ~(m >> a);
+        const int len = rest ? __ffs(rest) - 1 : 32 - a;
+        rs::bulk_s2g(dst + (size_t)a * W, ring + ((size_t)st * SERVE_C + a) * W, row_bytes * (uint32_t)len);
+        m = (len + a >= 32) ? 0u : (m >> (a + len)) << (a + len);
+      }
       rs::bulk_commit();
     }
     __syncwarp();
@@ -241,19 +277,21 @@ RS_API int rs_shard_post(const rs_shard *S, const rs_segments *seg, int64_t n, i
   return RS_OK;
 }
 
-RS_API int rs_shard_collect(const rs_shard *S, int64_t *recv_local, int32_t *m_total, int32_t *status, void *stream) {
+RS_API int rs_shard_collect(const rs_shard *S, int64_t *recv_local, uint8_t *recv_skip, int32_t *m_total, int32_t *status,
+                            void *stream) {
   ShardDev D;
   if (int rc = fill_shard(D, S, "rs_shard_collect")) return rc;
   RS_CHECK_ARG(recv_local && m_total, RS_E_ARG, "rs_shard_collect: null output");
+  RS_CHECK_ARG(recv_skip || S->n_direct == 0, RS_E_ARG, "rs_shard_collect: recv_skip is required with direct ranges");
   int64_t blocks = (S->cap_recv + 255) / 256;
   const int cap = rs::num_sms() * 8;
-  shard_collect_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(D, recv_local, m_total, status);
+  shard_collect_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(D, recv_local, recv_skip, m_total, status);
   RS_CHECK_LAUNCH();
   return RS_OK;
 }
 
 RS_API int rs_shard_serve(const rs_shard *S, const float *table, int64_t rows, int32_t width, const int64_t *recv_local,
-                          float *const *block, int64_t cap_block_rows, int32_t *status, void *stream) {
+                          const uint8_t *skip, float *const *block, int64_t cap_block_rows, int32_t *status, void *stream) {
   ShardDev D;
   if (int rc = fill_shard(D, S, "rs_shard_serve")) return rc;
   RS_CHECK_ARG(table && rows > 0 && width >= 4 && width % 4 == 0 && recv_local && block && cap_block_rows > 0, RS_E_ARG,
@@ -268,12 +306,12 @@ RS_API int rs_shard_serve(const rs_shard *S, const float *table, int64_t rows, i
   const size_t smem = (size_t)SERVE_WARPS * SERVE_NST * SERVE_C * width * 4;
   if (width * 4 >= 512 && smem <= 220 * 1024 && !(mode && !strcmp(mode, "st"))) {
     RS_CUDA(cudaFuncSetAttribute(shard_serve_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    shard_serve_tma_kernel<<<rs::num_sms(), SERVE_WARPS * 32, smem, st>>>(D, table, rows, width, recv_local, B, cap_block_rows, status);
+    shard_serve_tma_kernel<<<rs::num_sms(), SERVE_WARPS * 32, smem, st>>>(D, table, rows, width, recv_local, skip, B, cap_block_rows, status);
   } else {
     const int wv = width / 4;
     int64_t blocks = (S->cap_recv * wv + 1023) / 1024;
     const int cap = rs::num_sms() * 8;
-    shard_serve_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(D, table, rows, wv, recv_local, B, cap_block_rows, status);
+    shard_serve_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(D, table, rows, wv, recv_local, skip, B, cap_block_rows, status);
   }
   RS_CHECK_LAUNCH();
   return RS_OK;

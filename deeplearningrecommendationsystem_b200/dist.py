@@ -333,7 +333,11 @@ class DeviceRowExchange:
 
     device_plan = True
 
-    def __init__(self, fabric=None, recv_slack=1.25):
+    def __init__(self, fabric=None, recv_slack=1.25, direct=()):
+        """direct: global-row ranges [(lo, hi), ...] that a forward kernel reads from the owners' shards by itself
+        (nfield.FieldFFM over symmetric table shards); their rows are requested (the owner needs the list for its update)
+        but flagged, and fetch(..., skip_direct=True) does not copy them."""
+        self.direct = tuple((int(lo), int(hi)) for lo, hi in direct)
         if fabric is None:
             fabric = SymmFabric() if dist.is_initialized() and dist.get_world_size() > 1 else LocalFabric()
         self.fabric, self.world, self.rank, self.recv_slack = fabric, fabric.world, fabric.rank, recv_slack
@@ -360,8 +364,9 @@ class DeviceRowExchange:
         req, req_ptrs = self.fabric.alloc((self.world * cap_req,), torch.int32, device)
         ctl, ctl_ptrs = self.fabric.alloc((_lib.RS_SHARD_CTL_WORDS,), torch.int64, device)
         self._ctl = {"cap_req": cap_req, "cap_recv": cap_recv, "R": R, "req": req, "ctl": ctl,
-                     "S": ops.make_shard(self.world, self.rank, R, cap_req, cap_recv, req_ptrs, ctl_ptrs),
+                     "S": ops.make_shard(self.world, self.rank, R, cap_req, cap_recv, req_ptrs, ctl_ptrs, self.direct),
                      "recv_local": torch.zeros(cap_recv, dtype=torch.int64, device=device),
+                     "recv_skip": torch.zeros(cap_recv, dtype=torch.uint8, device=device),
                      "m_total": torch.zeros(1, dtype=torch.int32, device=device)}
         self.fabric.barrier()                      # every rank's buffers exist (and are zeroed) before anyone writes to them
         return self._ctl
@@ -402,7 +407,7 @@ class DeviceRowExchange:
         segs = ops.dedup_sort(ids, F, list(offsets) if F > 1 or offsets else None, total_rows, shard=(self.world, c["R"]))
         ops.shard_post(c["S"], segs)
         self.fabric.barrier()
-        ops.shard_collect(c["S"], c["recv_local"], c["m_total"])
+        ops.shard_collect(c["S"], c["recv_local"], c["m_total"], c["recv_skip"])
         self._gen += 1
         return DevPlan(self._gen, n, segs, segs.inverse().long(), c["recv_local"], c["m_total"])
 
@@ -410,12 +415,14 @@ class DeviceRowExchange:
         if plan.gen != self._gen:
             raise RuntimeError("stale exchange plan: the exchange has planned another batch since (one batch in flight per exchange)")
 
-    def fetch(self, plan, local_table):
-        """-> (cap, W) block; rows [0, n_uniq) hold the rows this rank's batch needs, in the order `local_ids` indexes."""
+    def fetch(self, plan, local_table, skip_direct=False):
+        """-> (cap, W) block; rows [0, n_uniq) hold the rows this rank's batch needs, in the order `local_ids` indexes.
+        skip_direct: rows of the direct ranges are left out (the caller's forward kernel reads them from the shards)."""
         from . import ops
         self._check(plan)
         c, ent = self._ctl, self._buffers(local_table, local_table.device)
-        ops.shard_serve(c["S"], local_table, plan.recv_local, ent["block_ptrs"], c["cap_req"])
+        ops.shard_serve(c["S"], local_table, plan.recv_local, ent["block_ptrs"], c["cap_req"],
+                        skip=c["recv_skip"] if (skip_direct and self.direct) else None)
         with _phase("exchange_barrier"):
             self.fabric.barrier()
         return ent["block"]
@@ -456,7 +463,7 @@ class DeviceRowExchange:
         c, ent = self._ctl, self._bufs[(table.shape[1], table.data_ptr())]
         base = c["ctl"].data_ptr()
         return ops.make_routes(None, ent["grad_ptrs"], None, dyn_start=base + 8 * _lib.RS_CTL_SEND_START,
-                               dyn_row0=base + 8 * _lib.RS_CTL_G0_IN, cap_rows=c["cap_recv"]), ent
+                               dyn_row0=base + 8 * _lib.RS_CTL_G0_IN, cap_rows=c["cap_recv"], self_index=self.rank), ent
 
     def finish_push(self, plan, ent):
         with _phase("exchange_barrier"):

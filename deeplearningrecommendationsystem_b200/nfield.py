@@ -38,6 +38,24 @@ def _xavier_concat(cards, width, row_dim, device=None, seed=None):
     return out
 
 
+DIRECT_ROWS = 1 << 20      # fields with at least this many rows are read from the peers' shards by the FFM forward itself
+
+
+def direct_ranges(cardinalities, threshold=DIRECT_ROWS):
+    """Global-row ranges of the fields large enough that a batch's lookups into them are (nearly) all distinct: fetching
+    those rows into the block first cannot save traffic, so the row-sharded FieldFFM pulls them over NVLink inside its
+    forward kernel (dist.DeviceRowExchange(direct=...), rs_ffm_fwd_peer).  At most 8 ranges (the largest fields)."""
+    if not threshold:
+        return ()
+    off, out = 0, []
+    for c in cardinalities:
+        if c >= threshold:
+            out.append((off, off + int(c)))
+        off += int(c)
+    out.sort(key=lambda r: r[0] - r[1])
+    return tuple(sorted(out[:8]))
+
+
 class _CrossFn(torch.autograd.Function):
     """Routes dL/dcross into the owning module; the table itself is updated by the fused optimizer."""
 
@@ -99,7 +117,7 @@ class _EmbedFn(torch.autograd.Function):
 
 class _FieldModel(nn.Module):
     def __init__(self, cardinalities, width, row_dim, fused=True, seed=None, device=None, sharded=False, group=None,
-                 fabric=None, exchange=None):
+                 fabric=None, exchange=None, direct_threshold=0):
         super().__init__()
         self.cards = [int(c) for c in cardinalities]
         self.F, self.width, self.fused = len(self.cards), width, fused
@@ -120,12 +138,20 @@ class _FieldModel(nn.Module):
             if exchange is not None:
                 self.exchange = exchange
             elif os.environ.get("RS_PEER_EXCHANGE", "1") == "1":
-                self.exchange = rsdist.DeviceRowExchange(fabric)
+                direct = direct_ranges(self.cards, direct_threshold) if os.environ.get("RS_DIRECT", "1") == "1" else ()
+                self.exchange = rsdist.DeviceRowExchange(fabric, direct=direct)
             else:
                 self.exchange = rsdist.RowExchange(rsdist.cuda_prims(), group)
             rows = self.exchange.local_rows(self.total_rows)
             std = math.sqrt(2.0 / (self.total_rows / self.F + row_dim))
-            w = torch.empty(rows, width, dtype=torch.float32, device=device)
+            self.shard_ptrs = None
+            if getattr(self.exchange, "device_plan", False) and torch.device(device if device is not None else "cpu").type == "cuda":
+                # the shard lives in symmetric (peer-mapped) memory, so that kernels of other ranks can read its rows directly
+                R = (self.total_rows + self.exchange.world - 1) // self.exchange.world
+                full, self.shard_ptrs = self.exchange.fabric.alloc((R, width), torch.float32, torch.device(device))
+                w = full[:rows]
+            else:
+                w = torch.empty(rows, width, dtype=torch.float32, device=device)
             g = torch.Generator(device=w.device).manual_seed((seed or 0) * 1000 + self.exchange.rank)
             self.weight = nn.Parameter(w.normal_(0.0, std, generator=g), requires_grad=False)
             self.register_buffer("offsets_dev", torch.tensor(self.offsets_host, dtype=torch.int64, device=device), persistent=False)
@@ -257,9 +283,13 @@ class _FieldModel(nn.Module):
         rec = {}
         if self.sharded:
             plan = self._plan(ids, train and self.fused)
-            block = self.exchange.fetch(plan, self.weight.data)
-            ids = plan.local_ids.view(ids.shape)
-            cross, stash = self._interact(ops.make_tables([block] * self.F), ids, want_stash=train)
+            direct = bool(getattr(self, "direct_fields", None))
+            if direct:
+                block = self.exchange.fetch(plan, self.weight.data, skip_direct=True)
+            else:
+                block = self.exchange.fetch(plan, self.weight.data)
+            orig, ids = ids, plan.local_ids.view(ids.shape)
+            cross, stash = self._interact(ops.make_tables([block] * self.F), ids, want_stash=train, **({"orig_ids": orig} if direct else {}))
             rec = {"plan": plan}
         else:
             if train and self.fused:      # the sort depends only on the ids: overlap it with the forward kernels
@@ -295,12 +325,32 @@ class FieldFM(_FieldModel):
 class FieldFFM(_FieldModel):
     """sigmoid(b + sum_{i<j} <v_{i,j}, v_{j,i}>): feature i's table row is (F, D), slot j aimed at field j."""
 
-    def __init__(self, cardinalities, num_vector, fused=True, seed=None, device=None, sharded=False, group=None, **kw):
+    def __init__(self, cardinalities, num_vector, fused=True, seed=None, device=None, sharded=False, group=None,
+                 direct_threshold=DIRECT_ROWS, **kw):
         F = len(cardinalities)
-        super().__init__(cardinalities, F * num_vector, num_vector, fused, seed, device, sharded, group, **kw)
+        super().__init__(cardinalities, F * num_vector, num_vector, fused, seed, device, sharded, group,
+                         direct_threshold=direct_threshold, **kw)
         self.D = num_vector
+        # fields whose whole row range is one of the exchange's direct ranges: the forward kernel reads their rows from the
+        # owners' shards itself (see direct_ranges); needs the shard in symmetric memory
+        self.direct_fields = []
+        ranges = set(getattr(self.exchange, "direct", ()) or ()) if self.sharded and self.shard_ptrs is not None else set()
+        for f, (o, c) in enumerate(zip(self.offsets_host, self.cards)):
+            if (o, o + c) in ranges:
+                self.direct_fields.append(f)
+        if self.direct_fields:
+            dev = self.weight.device
+            self._direct_cols = torch.tensor(self.direct_fields, dtype=torch.int64, device=dev)
+            self._direct_offs = torch.tensor([self.offsets_host[f] for f in self.direct_fields], dtype=torch.int64, device=dev)
+            self._direct_mask = sum(1 << f for f in self.direct_fields)
 
-    def _interact(self, T, ids, want_stash):
+    def _interact(self, T, ids, want_stash, orig_ids=None):
+        if orig_ids is not None and self.direct_fields:
+            # block rows for the fetched fields, GLOBAL rows for the direct ones
+            mix = ids.clone()
+            mix[:, self._direct_cols] = orig_ids[:, self._direct_cols] + self._direct_offs
+            return ops.ffm_fwd(T, mix, self.D, want_stash=want_stash,
+                               peer=(self.exchange.world, self._direct_mask, self.shard_ptrs, self.total_rows))
         return ops.ffm_fwd(T, ids, self.D, want_stash=want_stash)
 
 

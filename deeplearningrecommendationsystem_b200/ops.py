@@ -210,8 +210,10 @@ def fields_bwd(T, B, device, ids=None, dense_in=None, g_cross=None, g_bi=None, g
     return dE
 
 
-def ffm_fwd(T, ids, D, want_stash=True):
-    """cross (B,), stash (B, F, F*D) | None for an F-field FFM whose table rows are (F, D)."""
+def ffm_fwd(T, ids, D, want_stash=True, peer=None):
+    """cross (B,), stash (B, F, F*D) | None for an F-field FFM whose table rows are (F, D).
+    peer=(world, direct_mask, shard_ptrs, total_rows): row-sharded tables, the fields of direct_mask are read straight from
+    the owning rank's shard over NVLink (ids of those fields are GLOBAL rows) -- rs_ffm_fwd_peer."""
     ids = _i64(ids)
     _need_cuda(ids)
     F = T.num_fields
@@ -220,9 +222,16 @@ def ffm_fwd(T, ids, D, want_stash=True):
     stash = torch.empty(B, F, F * D, dtype=torch.float32, device=ids.device) if want_stash else None
     if B == 0:
         return cross, stash
+    PT = None
+    if peer is not None:
+        PT = _lib.rs_peer_tables()
+        PT.world, PT.direct_mask, PT.total_rows = int(peer[0]), int(peer[1]), int(peer[3])
+        for k, ptr in enumerate(peer[2]):
+            PT.shard[k] = int(ptr)
+        PT = C.byref(PT)
     with _timed("ffm_fwd"):
-        _lib.check(_lib.load().rs_ffm_fwd(C.byref(T), ids.data_ptr(), B, D, cross.data_ptr(), _p(stash),
-                                          status_word(ids.device).data_ptr(), _stream()), "rs_ffm_fwd")
+        _lib.check(_lib.load().rs_ffm_fwd_peer(C.byref(T), ids.data_ptr(), B, D, PT, cross.data_ptr(), _p(stash),
+                                               status_word(ids.device).data_ptr(), _stream()), "rs_ffm_fwd")
     _count()
     return cross, stash
 
@@ -412,7 +421,7 @@ def prefetch_dedup(ids, F=1, row_offset=None, total_rows=None):
         _prefetching = False
 
 
-def make_routes(starts, bases, row0s, dyn_start=None, dyn_row0=None, cap_rows=0):
+def make_routes(starts, bases, row0s, dyn_start=None, dyn_row0=None, cap_rows=0, self_index=-1):
     """rs_routes: logical rows [starts[k], starts[k+1]) go to bases[k] (device pointer, peer-mapped or local) at row
     offset row0s[k].  len(starts) == len(bases) + 1.  dyn_start / dyn_row0: device addresses of the same two arrays
     (int64) when they only exist on the device (host-sync-free sharded step); starts / row0s are then ignored."""
@@ -427,15 +436,22 @@ def make_routes(starts, bases, row0s, dyn_start=None, dyn_row0=None, cap_rows=0)
     else:
         R.dyn_start, R.dyn_row0 = int(dyn_start), int(dyn_row0)
     R.cap_rows = int(cap_rows)
+    R.self = int(self_index)
     return R
 
 
-def make_shard(world, rank, rows_per_rank, cap_req, cap_recv, req_ptrs, ctl_ptrs):
-    """rs_shard: the per-exchange constants + the peer-mapped request / control buffers of every rank."""
+def make_shard(world, rank, rows_per_rank, cap_req, cap_recv, req_ptrs, ctl_ptrs, direct=()):
+    """rs_shard: the per-exchange constants + the peer-mapped request / control buffers of every rank.
+    direct: global-row ranges [(lo, hi), ...] whose rows are read by the forward kernel itself (not fetched)."""
     S = _lib.rs_shard()
     S.world, S.rank, S.rows_per_rank, S.cap_req, S.cap_recv = world, rank, int(rows_per_rank), int(cap_req), int(cap_recv)
     for k in range(world):
         S.req[k], S.ctl[k] = int(req_ptrs[k]), int(ctl_ptrs[k])
+    if len(direct) > _lib.RS_MAX_DIRECT:
+        raise ValueError(f"at most {_lib.RS_MAX_DIRECT} direct row ranges")
+    S.n_direct = len(direct)
+    for k, (lo, hi) in enumerate(direct):
+        S.direct_lo[k], S.direct_hi[k] = int(lo), int(hi)
     return S
 
 
@@ -447,22 +463,23 @@ def shard_post(S, segs):
     _count()
 
 
-def shard_collect(S, recv_local, m_total):
-    """owner: prefix of the received counts, compact receive list (first m_total entries of recv_local), gradient
-    offsets sent back to the requesters"""
+def shard_collect(S, recv_local, m_total, recv_skip=None):
+    """owner: prefix of the received counts, compact receive list (first m_total entries of recv_local; recv_skip flags the
+    requests that lie in a direct range), gradient offsets sent back to the requesters"""
     _need_cuda(recv_local, m_total)
     with _timed("shard_collect"):
-        _lib.check(_lib.load().rs_shard_collect(C.byref(S), recv_local.data_ptr(), m_total.data_ptr(),
+        _lib.check(_lib.load().rs_shard_collect(C.byref(S), recv_local.data_ptr(), _p(recv_skip), m_total.data_ptr(),
                                                 status_word(recv_local.device).data_ptr(), _stream()), "rs_shard_collect")
     _count()
 
 
-def shard_serve(S, table, recv_local, block_ptrs, cap_block_rows):
-    """owner: table[recv_local[i]] -> the requesters' blocks over NVLink (follow with a cross-rank barrier)"""
+def shard_serve(S, table, recv_local, block_ptrs, cap_block_rows, skip=None):
+    """owner: table[recv_local[i]] -> the requesters' blocks over NVLink (follow with a cross-rank barrier); rows flagged in
+    `skip` (uint8) are not copied"""
     _need_cuda(table, recv_local)
     ptrs = (C.c_void_p * S.world)(*[int(p) for p in block_ptrs])
     with _timed(f"shard_serve[w{table.shape[1]}]"):
-        _lib.check(_lib.load().rs_shard_serve(C.byref(S), table.data_ptr(), table.shape[0], table.shape[1], recv_local.data_ptr(), ptrs,
+        _lib.check(_lib.load().rs_shard_serve(C.byref(S), table.data_ptr(), table.shape[0], table.shape[1], recv_local.data_ptr(), _p(skip), ptrs,
                                               int(cap_block_rows), status_word(table.device).data_ptr(), _stream()), "rs_shard_serve")
     _count()
 

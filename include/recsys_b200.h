@@ -57,6 +57,11 @@ typedef struct rs_routes {
   const int64_t *dyn_start;
   const int64_t *dyn_row0;
   int64_t cap_rows;
+  /* Own index among the n destinations (-1 = unknown).  When every rank pushes to the destinations in the same order
+   * (rows are sorted owner-major), all of them hit destination 0 first, then 1, ...: an n-way incast on one NVLink ingress
+   * at a time.  Knowing `self`, the kernels start their walk over the rows at self/n of the way through, so that at any
+   * moment rank r is sending to rank (r + t) % n -- the classic all-to-all schedule.  Results do not depend on it. */
+  int32_t self;
 } rs_routes;
 
 int rs_version(void);
@@ -115,6 +120,17 @@ int rs_fields_bwd(const rs_tables *T, const rs_fields_grad *g, int64_t B, void *
  * Rows travel global->shared with cp.async.bulk (TMA bulk copy) through an mbarrier ring. */
 int rs_ffm_fwd(const rs_tables *T /* width = F*D */, const int64_t *ids, int64_t B, int32_t D, float *cross,
                float *stash, int32_t *status, void *stream);
+/* Row-sharded variant: fields whose bit is set in direct_mask are read straight from the owning rank's shard
+ * (shard[g % world] + (g / world) * width, peer-mapped pointers) with ids[b, f] = GLOBAL row g; the other fields are read
+ * from T as in rs_ffm_fwd (ids = row of T->base[f], typically the fetched block).  Same outputs. */
+typedef struct rs_peer_tables {
+  int32_t world;
+  uint64_t direct_mask;
+  const float *shard[RS_MAX_RANKS];
+  int64_t total_rows; /* bound for the global rows of the direct fields */
+} rs_peer_tables;
+int rs_ffm_fwd_peer(const rs_tables *T /* width = F*D */, const int64_t *ids, int64_t B, int32_t D, const rs_peer_tables *PT,
+                    float *cross, float *stash, int32_t *status, void *stream);
 /* Dense small-F variant used by the MovieLens FFM module: Tin (B, F, NF, D), field_of[F] (host). */
 int rs_ffm_dense_fwd(const float *Tin, int64_t B, int32_t F, int32_t NF, int32_t D, const int32_t *field_of,
                      float *cross, void *stream);
@@ -214,6 +230,7 @@ int rs_segment_update(const rs_segments *seg, int64_t n, const rs_update *u, voi
  * Bit 4 (16) of `status` is set when an owner is asked for more rows than cap_recv. */
 #define RS_SHARD_CTL_WORDS 384
 enum { RS_CTL_CNT_IN = 0, RS_CTL_BLK0_IN = 64, RS_CTL_G0_IN = 128, RS_CTL_SEND_START = 192, RS_CTL_RECV_START = 257, RS_CTL_M_TOTAL = 322 };
+#define RS_MAX_DIRECT 8
 typedef struct rs_shard {
   int32_t world, rank;
   int64_t rows_per_rank; /* R = ceil(total_rows / world) */
@@ -221,13 +238,21 @@ typedef struct rs_shard {
   int64_t cap_recv;      /* rows one owner can receive per step */
   int32_t *req[RS_MAX_RANKS];
   int64_t *ctl[RS_MAX_RANKS];
+  /* "Direct" global-row ranges [direct_lo[k], direct_hi[k]): fields so large that a batch's lookups are (nearly) all
+   * distinct, so fetching their rows into the block first saves nothing.  Their requests are flagged (recv_skip) and a
+   * forward kernel that can read peer shards itself (rs_ffm_fwd_peer) pulls those rows straight over NVLink inside its
+   * own TMA pipeline -- the transfer then overlaps the forward's HBM traffic instead of preceding it. */
+  int32_t n_direct;
+  int64_t direct_lo[RS_MAX_DIRECT], direct_hi[RS_MAX_DIRECT];
 } rs_shard;
 int rs_shard_post(const rs_shard *S, const rs_segments *seg, int64_t n, int32_t *status, void *stream);
-int rs_shard_collect(const rs_shard *S, int64_t *recv_local /* [cap_recv] */, int32_t *m_total /* device */,
+/* recv_skip [cap_recv] (may be NULL when n_direct == 0): 1 for received requests that lie in a direct range. */
+int rs_shard_collect(const rs_shard *S, int64_t *recv_local /* [cap_recv] */, uint8_t *recv_skip, int32_t *m_total /* device */,
                      int32_t *status, void *stream);
-/* block[r]: base of rank r's receive block (cap_block_rows x width fp32), peer-mapped. */
+/* block[r]: base of rank r's receive block (cap_block_rows x width fp32), peer-mapped.  skip != NULL: rows flagged there
+ * are not copied (their block slots stay untouched). */
 int rs_shard_serve(const rs_shard *S, const float *table, int64_t rows, int32_t width, const int64_t *recv_local,
-                   float *const *block, int64_t cap_block_rows, int32_t *status, void *stream);
+                   const uint8_t *skip, float *const *block, int64_t cap_block_rows, int32_t *status, void *stream);
 
 
 /* Fused DENSE Adam sweep with torch.optim.Adam's exact arithmetic order ("reference-Adam" mode for the

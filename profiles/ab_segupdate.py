@@ -44,8 +44,8 @@ blk = ops.block_segments(blk, nu, W)
 grad = torch.zeros(ids.numel(), W, device=dev)
 print("GRAD -> compact dense_grad  %.3f ms" % timeit(lambda: ops.segment_update(blk, ops.RS_UPD_GRAD, W, F, stash=stash, scale=scale, dense_grad=grad)))
 routes = ops.make_routes([0, ids.numel()], [grad.data_ptr()], [0])
-os.environ["RS_NO_PUSHER"] = "1"
 print("GRAD routed (direct stores) %.3f ms" % timeit(lambda: ops.segment_update(blk, ops.RS_UPD_GRAD, W, F, stash=stash, scale=scale, grad_routes=routes)))
-del os.environ["RS_NO_PUSHER"]
+os.environ["RS_PUSHER"] = "1"
 print("GRAD routed (pusher warp)   %.3f ms" % timeit(lambda: ops.segment_update(blk, ops.RS_UPD_GRAD, W, F, stash=stash, scale=scale, grad_routes=routes)))
+del os.environ["RS_PUSHER"]
 print("SGD fused, relabelled segs  %.3f ms" % timeit(lambda: ops.segment_update(blk, ops.RS_UPD_SGD, W, F, stash=stash, scale=scale, table=grad, lr=0.01)))

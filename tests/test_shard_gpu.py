@@ -63,7 +63,7 @@ def test_owner_major_keys():
     assert torch.equal(segs.uniq().cpu(), u) and torch.equal(segs.inverse().cpu().long(), inv)
 
 
-def _sharded_run(world, kind, D, B, steps, lr, cards, share_exchange=False):
+def _sharded_run(world, kind, D, B, steps, lr, cards, direct_threshold=None):
     from deeplearningrecommendationsystem_b200 import dist as rsdist, ops
     from deeplearningrecommendationsystem_b200.nfield import FieldFFM, FieldFM
     from deeplearningrecommendationsystem_b200.optim import FusedRowOptimizer
@@ -72,7 +72,10 @@ def _sharded_run(world, kind, D, B, steps, lr, cards, share_exchange=False):
     ref = cls(cards, D, fused=True, seed=4, device="cpu")
 
     def rank_fn(fab):
-        m = cls(cards, D, fused=True, seed=4, device="cuda", sharded=True, fabric=fab)
+        kw = {} if direct_threshold is None else {"direct_threshold": direct_threshold}
+        m = cls(cards, D, fused=True, seed=4, device="cuda", sharded=True, fabric=fab, **kw)
+        if direct_threshold:
+            assert m.direct_fields, "expected some fields to be read directly from the peers' shards"
         m.load_global(ref.weight.data)
         tr = Trainer(m, torch.nn.BCELoss(), FusedRowOptimizer(m, torch.optim.SGD([m.bias], lr=lr), lr=lr))
         ids, y = _batch(fab.rank, B, cards)
@@ -111,6 +114,20 @@ def _sharded_run(world, kind, D, B, steps, lr, cards, share_exchange=False):
 @pytest.mark.parametrize("kind,D", [("fm", 16), ("ffm", 8)])
 def test_virtual_ranks_equal_single_gpu(world, kind, D):
     _sharded_run(world, kind, D, 300, 3, 0.5, CARDS)
+
+
+@pytest.mark.parametrize("world", [1, 3, 4])
+def test_virtual_ranks_direct_fields(world):
+    """FieldFFM with its big fields read straight from the owners' shards inside the forward kernel (rs_ffm_fwd_peer; the
+    exchange flags those requests and rs_shard_serve skips them) == the unsharded step.  Fields of >= 100 rows are direct."""
+    _sharded_run(world, "ffm", 8, 300, 3, 0.5, CARDS, direct_threshold=100)
+    _sharded_run(world, "ffm", 16, 300, 2, 0.5, CARDS, direct_threshold=100)     # 512-byte rows: the TMA serve kernel with skipped runs
+
+
+def test_virtual_ranks_c2_shape_direct():
+    cards = [min(c, 2000) for c in [1460, 583, 10131227, 2202608, 305, 24, 12517, 633, 3, 93145, 5683, 8351593, 3194, 27, 14992,
+                                    5461306, 10, 5652, 2173, 4, 7046547, 18, 15, 286181, 105, 142572]]
+    _sharded_run(4, "ffm", 16, 700, 2, 0.5, cards, direct_threshold=2000)
 
 
 def test_virtual_ranks_c2_shape():
