@@ -24,9 +24,18 @@ def short(name):
     return name.split("(")[0][:70]
 
 
-def launches(path):
+def launches(path, anchor=None, lo=0, hi=None):
+    """anchor: only the launches from the lo-th to the hi-th occurrence of a kernel whose name contains `anchor` (the
+    timed steps of bench.py: every step starts with the same kernel)"""
     rows = [r for r in csv.reader(l for l in open(path) if not l.startswith("==")) if r]
     hdr = rows[0]
+    if anchor:
+        ki = hdr.index("Kernel Name")
+        # one row per launch here (a single metric), so occurrences can be counted on the rows directly
+        occ = [i for i, r in enumerate(rows[1:], 1) if anchor in r[ki]]
+        a = occ[lo]
+        b = occ[hi] if hi is not None and hi < len(occ) else len(rows)
+        rows = [hdr] + rows[a:b]
     ki, vi, mi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Name")
     ui = hdr.index("Metric Unit")
     agg = OrderedDict()
@@ -62,4 +71,7 @@ def full(path):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "launches" and len(sys.argv) > 3:
+        launches(sys.argv[2], sys.argv[3], int(sys.argv[4]), int(sys.argv[5]))
+    else:
+        {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
