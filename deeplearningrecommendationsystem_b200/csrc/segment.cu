@@ -357,10 +357,7 @@ RS_API int rs_segments_relabel(const rs_segments *seg, int64_t n, void *stream) 
 // =================================================================== segment reduce + update
 namespace {
 
-// Slot of a chunk's partial sum.  Full chunks are disjoint runs of RS_CHUNK sorted lookups, so start/RS_CHUNK is
-// unique among them; a tail chunk (len < RS_CHUNK) is preceded by at least one full chunk of its own segment, so
-// start/RS_CHUNK is unique among tails as well.  Even slots hold full chunks, odd slots tails.
-__device__ __forceinline__ int partial_slot(int start, int len) { return 2 * (start / RS_CHUNK) + (len < RS_CHUNK ? 1 : 0); }
+using rs::partial_slot;
 
 template <int VEC>
 struct Vec;
@@ -563,7 +560,9 @@ int launch_update(const UpdParams &P, int64_t n, cudaStream_t st) {
   int64_t blocks64 = (n + GPB - 1) / GPB;
   int cap = rs::num_sms() * 64;
   int blocks = (int)(blocks64 < cap ? blocks64 : cap);
-  if (P.use_stream) {
+  if (P.combine_only) {
+    // the chunk pass was done by another kernel (ffm_train.cu) that left the partials of the multi-chunk segments in P.partial
+  } else if (P.use_stream) {
     int rc = rs::launch_seg_stream(P, n, MODE, st);   // chunk pass as a TMA-fed streaming kernel (segment_stream.cu)
     if (rc) return rc;
   } else {
@@ -594,20 +593,12 @@ int launch_mode(const UpdParams &P, int mode, int64_t n, cudaStream_t st) {
 
 }  // namespace
 
-RS_API int rs_segment_update(const rs_segments *seg, int64_t n, const rs_update *u, void *stream) {
-  RS_CHECK_ARG(seg && u, RS_E_ARG, "rs_segment_update: null argument");
-  RS_CHECK_ARG(n > 0 && n < (1ll << 31), RS_E_SHAPE, "rs_segment_update: bad n");
-  RS_CHECK_ARG(u->width >= 1 && u->width <= 2048 && u->F >= 1 && n % u->F == 0, RS_E_SHAPE, "rs_segment_update: bad width/F");
-  RS_CHECK_ARG(u->stash || u->dense, RS_E_ARG, "rs_segment_update: need stash and/or dense gradient source");
-  RS_CHECK_ARG(!u->scale || (u->stash && (u->scale_width == 1 || u->scale_width == u->width)), RS_E_ARG,
-               "rs_segment_update: scale needs stash and scale_width in {1,width}");
-  if (u->mode == RS_UPD_GRAD) RS_CHECK_ARG(u->dense_grad || u->grad_routes, RS_E_ARG, "rs_segment_update: dense_grad is NULL");
-  if (u->mode != RS_UPD_GRAD) RS_CHECK_ARG(u->table, RS_E_ARG, "rs_segment_update: table is NULL");
-  if (u->mode == RS_UPD_ADAM) RS_CHECK_ARG(u->m && u->v && u->step >= 1, RS_E_ARG, "rs_segment_update: Adam needs m, v, step>=1");
+namespace rs {
+
+int make_upd_params(const rs_segments *seg, int64_t n, const rs_update *u, UpdParams &P) {
   RS_CHECK_ARG((int64_t)(2 * (n / RS_CHUNK + 2)) * u->width <= seg->partial_floats, RS_E_WORKSPACE,
                "rs_segment_update: dedup workspace was sized for a narrower row (need %lld floats of partials, have %lld)",
                (long long)((int64_t)(2 * (n / RS_CHUNK + 2)) * u->width), (long long)seg->partial_floats);
-  UpdParams P;
   P.sorted_pos = seg->sorted_pos;
   P.seg_start = seg->seg_start;
   P.seg_first_chunk = seg->seg_first_chunk;
@@ -650,11 +641,14 @@ RS_API int rs_segment_update(const rs_segments *seg, int64_t n, const rs_update 
   double bc2 = 1.0 - pow((double)u->beta2, (double)u->step);
   P.step_size = (float)((double)u->lr / (bc1 > 0 ? bc1 : 1.0));
   P.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2 > 0 ? bc2 : 1.0));
-  cudaStream_t st = (cudaStream_t)stream;
-  const int W = u->width, mode = u->mode;
-  // wide rows (>= 256 B) with one gradient source and at most a per-sample scalar scale take the TMA-fed streaming kernel
-  P.use_stream = (W % 4 == 0 && W >= 64 && W <= 640 && !(u->stash && u->dense) && (!u->scale || u->scale_width == 1) &&
-                  !getenv("RS_NO_STREAM")) ? 1 : 0;
+  P.use_stream = 0;
+  P.combine_only = 0;
+  return RS_OK;
+}
+
+// chunk pass + combine pass (or the combine pass alone when P.combine_only) for rows of P.W floats
+int dispatch_update(const UpdParams &P, int mode, int64_t n, cudaStream_t st) {
+  const int W = P.W;
   if (W % 4 == 0) {
     const int wv = W / 4;
     if (wv <= 1) return launch_mode<4, 1, 1>(P, mode, n, st);
@@ -674,6 +668,28 @@ RS_API int rs_segment_update(const rs_segments *seg, int64_t n, const rs_update 
   if (W <= 512) return launch_mode<1, 32, 16>(P, mode, n, st);
   rs::set_error("rs_segment_update: width %d not a multiple of 4 and > 512", W);
   return RS_E_UNSUPPORTED;
+}
+
+}  // namespace rs
+
+RS_API int rs_segment_update(const rs_segments *seg, int64_t n, const rs_update *u, void *stream) {
+  RS_CHECK_ARG(seg && u, RS_E_ARG, "rs_segment_update: null argument");
+  RS_CHECK_ARG(n > 0 && n < (1ll << 31), RS_E_SHAPE, "rs_segment_update: bad n");
+  RS_CHECK_ARG(u->width >= 1 && u->width <= 2048 && u->F >= 1 && n % u->F == 0, RS_E_SHAPE, "rs_segment_update: bad width/F");
+  RS_CHECK_ARG(u->stash || u->dense, RS_E_ARG, "rs_segment_update: need stash and/or dense gradient source");
+  RS_CHECK_ARG(!u->scale || (u->stash && (u->scale_width == 1 || u->scale_width == u->width)), RS_E_ARG,
+               "rs_segment_update: scale needs stash and scale_width in {1,width}");
+  if (u->mode == RS_UPD_GRAD) RS_CHECK_ARG(u->dense_grad || u->grad_routes, RS_E_ARG, "rs_segment_update: dense_grad is NULL");
+  if (u->mode != RS_UPD_GRAD) RS_CHECK_ARG(u->table, RS_E_ARG, "rs_segment_update: table is NULL");
+  if (u->mode == RS_UPD_ADAM) RS_CHECK_ARG(u->m && u->v && u->step >= 1, RS_E_ARG, "rs_segment_update: Adam needs m, v, step>=1");
+  UpdParams P;
+  int rc = rs::make_upd_params(seg, n, u, P);
+  if (rc) return rc;
+  const int W = u->width;
+  // wide rows (>= 256 B) with one gradient source and at most a per-sample scalar scale take the TMA-fed streaming kernel
+  P.use_stream = (W % 4 == 0 && W >= 64 && W <= 640 && !(u->stash && u->dense) && (!u->scale || u->scale_width == 1) &&
+                  !getenv("RS_NO_STREAM")) ? 1 : 0;
+  return rs::dispatch_update(P, u->mode, n, (cudaStream_t)stream);
 }
 
 // =================================================================== dense Adam sweep

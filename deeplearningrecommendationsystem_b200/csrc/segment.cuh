@@ -15,6 +15,7 @@ struct UpdParams {
   const float *stash, *scale, *dense;
   float *table, *m, *v, *dense_grad;
   int W, F, scale_width, use_stream;
+  int combine_only;  // the chunk pass already ran elsewhere (ffm_train.cu): only add the partials of the multi-chunk segments
   Routes routes;  // routes.n > 0: RS_UPD_GRAD writes row r to a peer instead of dense_grad[r]
   float lr, wd, beta1, beta2, eps, step_size, inv_sqrt_bc2;
 };
@@ -32,7 +33,14 @@ __device__ __forceinline__ void adam1(float &w, float &m, float &v, float g, con
   w = w - P.step_size * (m / denom);
 }
 
+// Slot of a chunk's partial sum.  Full chunks are disjoint runs of RS_CHUNK sorted lookups, so start/RS_CHUNK is
+// unique among them; a tail chunk (len < RS_CHUNK) is preceded by at least one full chunk of its own segment, so
+// start/RS_CHUNK is unique among tails as well.  Even slots hold full chunks, odd slots tails.
+__device__ __forceinline__ int partial_slot(int start, int len) { return 2 * (start / RS_CHUNK) + (len < RS_CHUNK ? 1 : 0); }
+
 int fill_routes(Routes &R, const rs_routes *r, const char *who);
 int launch_seg_stream(const UpdParams &P, int64_t n, int mode, cudaStream_t st);
+int make_upd_params(const rs_segments *seg, int64_t n, const rs_update *u, UpdParams &P);   // segment.cu
+int dispatch_update(const UpdParams &P, int mode, int64_t n, cudaStream_t st);
 
 }  // namespace rs

@@ -206,6 +206,11 @@ class _FieldModel(nn.Module):
             src = {"dense": rec["g"]} if rec.get("stash") is None else {"stash": rec["stash"], "scale": rec["g"]}
             if not self.sharded:
                 segs = ops.dedup_sort(rec["ids"], self.F, self.offsets_host, self.total_rows, max_width=self.width)
+                if rec.get("recompute"):      # FieldFFM without a Jacobian stash: gradient rows rebuilt from the table itself
+                    if opt.kind != "sgd":
+                        raise RuntimeError("this forward ran without a Jacobian stash (row optimizer bound as SGD); step it with that optimizer")
+                    ops.ffm_bwd_update(self.tables(), rec["ids"], self.D, segs, rec["g"], self.weight.data, opt.lr, opt.weight_decay)
+                    continue
                 self._row_update(opt, segs, self.F, **src)
                 continue
             # row-sharded: reduce the batch's gradients per fetched row, send them to the owners, update there
@@ -299,6 +304,8 @@ class _FieldModel(nn.Module):
             if self._anchor is None or self._anchor.device != ids.device:
                 self._anchor = torch.zeros(1, device=ids.device, requires_grad=True)
             self._token += 1
+            if stash is None:
+                rec = {**rec, "recompute": True}
             self._pending[self._token] = {"ids": ids, "stash": stash, **rec}
             cross = _CrossFn.apply(self._anchor, cross, self, self._token)
         elif train:
@@ -344,7 +351,18 @@ class FieldFFM(_FieldModel):
             self._direct_offs = torch.tensor([self.offsets_host[f] for f in self.direct_fields], dtype=torch.int64, device=dev)
             self._direct_mask = sum(1 << f for f in self.direct_fields)
 
+    def bind_row_optimizer(self, opt):
+        """Called by FusedRowOptimizer: with plain SGD on an unsharded table the training forward writes no Jacobian stash
+        and the step rebuilds the gradient rows from the table (ops.ffm_bwd_update) -- the stash is 5.6 of the 8.8 GB the
+        stash-based FFM step moves at the C2 shape.  RS_FFM_RECOMPUTE=0 keeps the stash."""
+        import os
+        self._recompute = (opt.kind == "sgd" and self.fused and not self.sharded and self.width // 4 <= 256
+                           and os.environ.get("RS_FFM_RECOMPUTE", "1") == "1")
+
     def _interact(self, T, ids, want_stash, orig_ids=None):
+        if want_stash and getattr(self, "_recompute", False) and self.fused and not self._pending:
+            # (a second forward before the step keeps its stash: its gradients must not see the first one's update)
+            return ops.ffm_fwd(T, ids, self.D, want_stash=False)
         if orig_ids is not None and self.direct_fields:
             # block rows for the fetched fields, GLOBAL rows for the direct ones
             mix = ids.clone()

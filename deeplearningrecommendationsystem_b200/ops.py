@@ -519,6 +519,37 @@ def segment_update(segs, mode, width, F, stash=None, scale=None, dense=None, tab
     _count(2)
 
 
+_ffm_bwd_ws = {}
+
+
+def ffm_bwd_update(T, ids, D, segs, g_cross, table, lr, wd=0.0, tag=""):
+    """FFM backward + fused SGD row update recomputed from the table (rs_ffm_bwd_update): no Jacobian stash.
+    T: rs_tables over `table` (the concatenated (total_rows, F*D) tensor), ids (B, F) the batch the forward ran on,
+    segs = dedup_sort(ids, ..., max_width=F*D), g_cross (B,) = dL/dcross.  The table must be unchanged since the forward."""
+    ids, g_cross = _i64(ids), _f32(g_cross)
+    _need_cuda(ids, g_cross, table)
+    F = T.num_fields
+    B = ids.numel() // F
+    if B == 0:
+        return
+    lib = _lib.load()
+    nbytes = C.c_size_t(0)
+    _lib.check(lib.rs_ffm_bwd_ws_bytes(B * F, B, F * D, C.byref(nbytes)), "rs_ffm_bwd_ws_bytes")
+    key = (ids.device, B * F, F * D)
+    ws = _ffm_bwd_ws.get(key)
+    if ws is None or ws.numel() < nbytes.value:
+        _ffm_bwd_ws.clear()                                  # one shape at a time: the buffer is ~half a stash
+        ws = _ffm_bwd_ws[key] = torch.empty(nbytes.value, dtype=torch.uint8, device=ids.device)
+    u = _lib.rs_update()
+    u.mode, u.width, u.F, u.scale_width = RS_UPD_SGD, F * D, F, 1
+    u.scale, u.table = g_cross.data_ptr(), table.data_ptr()
+    u.lr, u.wd, u.step = lr, wd, 1
+    with _timed(f"ffm_bwd_update{tag}"):
+        _lib.check(lib.rs_ffm_bwd_update(C.byref(T), ids.data_ptr(), B, D, C.byref(segs.seg), C.byref(u), ws.data_ptr(), ws.numel(),
+                                         status_word(ids.device).data_ptr(), _stream()), "rs_ffm_bwd_update")
+    _count(5)
+
+
 def adam_dense(p, g, m, v, step, lr=1e-3, wd=0.0, betas=(0.9, 0.999), eps=1e-8):
     _need_cuda(p, g, m, v)
     _lib.check(_lib.load().rs_adam_dense(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, wd, betas[0],

@@ -26,6 +26,9 @@ class FusedRowOptimizer:
         self.lr, self.kind, self.weight_decay, self.betas, self.eps = lr, kind, weight_decay, betas, eps
         self.step_count = 0
         self.data_parallel = data_parallel
+        for m in self._sparse_modules():
+            if hasattr(m, "bind_row_optimizer"):
+                m.bind_row_optimizer(self)
 
     def _sparse_modules(self):
         return [m for m in self.model.modules() if hasattr(m, "apply_pending")]

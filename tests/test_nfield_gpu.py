@@ -249,3 +249,62 @@ def test_graphed_step_equals_eager(kind):
         pred, loss = gs(*ins, rating=y)
         assert torch.equal(pred, tr.predictions_train) and torch.equal(loss, tr.train_loss)
     assert torch.equal(m1.weight, m2.weight) and torch.equal(m1.bias, m2.bias)
+
+
+@pytest.mark.parametrize("cards,D,B,wd", [
+    ([min(c, 3000) for c in C2_CARDS], 16, 4096, 0.0),          # the C2 row shape (416 floats), heavy duplicates + single rows
+    ([min(c, 200000) for c in C2_CARDS], 16, 3000, 1e-3),       # mostly rows looked up once, weight decay
+    ([3, 50, 7, 1000, 24], 4, 700, 0.0),                        # 20-float rows
+    ([5 + 37 * k for k in range(40)], 8, 1500, 0.0),            # F = 40 > 32 fields (two id registers per lane)
+    ([2, 3], 64, 10000, 0.0),                                   # two tiny tables: every row spans many chunks
+])
+def test_ffm_stash_free_step_is_bit_identical_to_stash_step(cards, D, B, wd, monkeypatch):
+    """rs_ffm_bwd_update (gradient rows recomputed from the table: no Jacobian stash) against rs_ffm_fwd(stash) +
+    rs_segment_update: same per-element arithmetic, chunking and combine order => the same bits after every step."""
+    from deeplearningrecommendationsystem_b200 import ops
+    from deeplearningrecommendationsystem_b200.nfield import FieldFFM
+    from deeplearningrecommendationsystem_b200.optim import FusedRowOptimizer
+    from deeplearningrecommendationsystem_b200.trainer import Trainer
+    g = torch.Generator().manual_seed(3)
+    ids = torch.stack([torch.randint(0, c, (B,), generator=g) for c in cards], dim=1).cuda()
+    y = (torch.rand(B, 1, generator=g) < 0.3).float().cuda()
+    lr = 0.3
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("RS_FFM_RECOMPUTE", mode)
+        m = FieldFFM(cards, D, fused=True, seed=11, device="cuda")
+        tr = Trainer(m, torch.nn.BCELoss(), FusedRowOptimizer(m, torch.optim.SGD([m.bias], lr=lr), lr=lr, weight_decay=wd))
+        assert m._recompute == (mode == "1")
+        launches = ops.launches()
+        for _ in range(3):
+            tr.train_loop(ids, train_rating=y)
+        out[mode] = (m.weight.detach().clone(), tr.predictions_train.detach().clone(), ops.launches() - launches)
+    ops.check_status()
+    assert torch.equal(out["1"][1], out["0"][1])
+    assert torch.equal(out["1"][0], out["0"][0])
+    assert out["1"][2] != out["0"][2]           # the two runs really took different kernels
+
+
+def test_ffm_second_forward_before_step_keeps_its_stash():
+    """two forwards, one step: the second record must not be recomputed from a table the first record already updated"""
+    from deeplearningrecommendationsystem_b200.nfield import FieldFFM
+    from deeplearningrecommendationsystem_b200.optim import FusedRowOptimizer
+    g = torch.Generator().manual_seed(4)
+    B = 500
+    ids = [torch.stack([torch.randint(0, c, (B,), generator=g) for c in CARDS], dim=1).cuda() for _ in range(2)]
+    y = (torch.rand(B, 1, generator=g) < 0.3).float().cuda()
+    res = []
+    for rec in ("1", "0"):
+        import os
+        os.environ["RS_FFM_RECOMPUTE"] = rec
+        try:
+            m = FieldFFM(CARDS, 8, fused=True, seed=2, device="cuda")
+            opt = FusedRowOptimizer(m, torch.optim.SGD([m.bias], lr=0.2), lr=0.2)
+        finally:
+            os.environ.pop("RS_FFM_RECOMPUTE")
+        opt.zero_grad()
+        loss = torch.nn.BCELoss()(m(ids[0]), y) + torch.nn.BCELoss()(m(ids[1]), y)
+        loss.backward()
+        opt.step()
+        res.append(m.weight.detach().clone())
+    assert torch.equal(res[0], res[1])
