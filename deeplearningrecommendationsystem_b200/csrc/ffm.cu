@@ -12,7 +12,10 @@
 namespace {
 
 constexpr int NCW = 8;                 // consumer warps
-constexpr int NTHREADS = (NCW + 1) * 32;
+constexpr int NPW = 2;                 // producer warps: one warp issues a bulk copy every ~70 cycles (profiles/tma_rate_micro.cu:
+                                       // 44 ns per 1664-byte row from one warp, 31-35 ns from two), so the rows of a sample are
+                                       // split over two issuing warps
+constexpr int NTHREADS = (NCW + NPW) * 32;
 constexpr int MAX_STAGES = 8;
 
 struct FfmParams {
@@ -31,6 +34,10 @@ struct FfmParams {
   uint64_t direct_mask;
   const float *shard[RS_MAX_RANKS];
   int64_t total_rows;
+  // "cold-slice" stash (rs_ffm_fwd_train): mini[b][i][c][:] = v_{cold_c, i}(b) for the nC fields flagged cold
+  float *mini;
+  int nC;
+  signed char cidx[RS_MAX_FIELDS];   // index of field j among the cold fields, -1 = not cold
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1) ffm_fwd_kernel(const __grid_constant__ FfmParams P) {
@@ -39,16 +46,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) ffm_fwd_kernel(const __grid_const
   __shared__ float s_part[MAX_STAGES][NCW];
   __shared__ const float *s_base[RS_MAX_FIELDS];
   __shared__ int64_t s_rows[RS_MAX_FIELDS];
+  __shared__ int s_cidx[RS_MAX_FIELDS];
   for (int i = threadIdx.x; i < P.F; i += blockDim.x) {
     s_base[i] = P.base[i];
     s_rows[i] = P.rows[i];
+    s_cidx[i] = P.cidx[i];
   }
   float4 *tiles = reinterpret_cast<float4 *>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int stage_v = P.F * P.pitchv;
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.nst; ++s) {
-      rs::mbar_init(&full_bar[s], 1);
+      rs::mbar_init(&full_bar[s], NPW);
       rs::mbar_init(&empty_bar[s], NCW);
     }
     rs::mbar_fence_init();
@@ -56,51 +65,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) ffm_fwd_kernel(const __grid_const
   __syncthreads();
   const uint32_t row_bytes = (uint32_t)P.rowv * 16u;
 
-  if (warp == 0) {
-    // ===== producer: one bulk copy per table row =====
-    // The id reads sit on the producer's critical path (one dependent global load per sample), so the ids of sample
-    // k+1 are requested before the copies of sample k are issued.
+  if (warp < NPW) {
+    // ===== producers: one bulk copy per table row; lane l of producer warp w owns field f = l * NPW + w =====
+    // The id reads sit on the producers' critical path (one dependent global load per sample), so the id of sample
+    // k+1 is requested before the copies of sample k are issued.
+    const int f = lane * NPW + warp;
+    const bool has = f < P.F;
+    const uint32_t nmine = (uint32_t)((P.F - warp + NPW - 1) / NPW);
     int k = 0;
     int64_t b = blockIdx.x;
-    int64_t id_cur[2] = {0, 0}, id_nxt[2] = {0, 0};  // lane f holds the ids of fields f and f+32
-    if (b < P.B) {
-      if (lane < P.F) id_cur[0] = P.ids[b * P.F + lane];
-      if (lane + 32 < P.F) id_cur[1] = P.ids[b * P.F + lane + 32];
-    }
+    int64_t id_cur = 0, id_nxt = 0;
+    if (b < P.B && has) id_cur = P.ids[b * P.F + f];
     for (; b < P.B; b += gridDim.x, ++k) {
       const int64_t bn = b + gridDim.x;
-      if (bn < P.B) {
-        if (lane < P.F) id_nxt[0] = P.ids[bn * P.F + lane];
-        if (lane + 32 < P.F) id_nxt[1] = P.ids[bn * P.F + lane + 32];
-      }
+      if (bn < P.B && has) id_nxt = P.ids[bn * P.F + f];
       const int s = k % P.nst;
       const uint32_t ph = (uint32_t)(k / P.nst) & 1u;
       rs::mbar_wait(&empty_bar[s], ph ^ 1u);
-      if (lane == 0) rs::mbar_arrive_expect_tx(&full_bar[s], row_bytes * (uint32_t)P.F);
+      if (lane == 0) rs::mbar_arrive_expect_tx(&full_bar[s], row_bytes * nmine);
       __syncwarp();
       float4 *dst = tiles + (size_t)s * stage_v;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int f = lane + 32 * h;
-        if (f < P.F) {
-          const float *src;
-          if ((P.direct_mask >> f) & 1ull) {   // global row g of a direct field: rank g % world holds it at local row g / world
-            const int64_t g = rs::clamp_id(id_cur[h], P.total_rows, P.status);
-            const int64_t l = g / P.world;
-            src = P.shard[(int)(g - l * P.world)] + l * (int64_t)P.rowv * 4;
-          } else {
-            src = s_base[f] + rs::clamp_id(id_cur[h], s_rows[f], P.status) * (int64_t)P.rowv * 4;
-          }
-          rs::bulk_g2s(dst + (size_t)f * P.pitchv, src, row_bytes, &full_bar[s]);
+      if (has) {
+        const float *src;
+        if ((P.direct_mask >> f) & 1ull) {   // global row g of a direct field: rank g % world holds it at local row g / world
+          const int64_t g = rs::clamp_id(id_cur, P.total_rows, P.status);
+          const int64_t l = g / P.world;
+          src = P.shard[(int)(g - l * P.world)] + l * (int64_t)P.rowv * 4;
+        } else {
+          src = s_base[f] + rs::clamp_id(id_cur, s_rows[f], P.status) * (int64_t)P.rowv * 4;
         }
+        rs::bulk_g2s(dst + (size_t)f * P.pitchv, src, row_bytes, &full_bar[s]);
       }
-      id_cur[0] = id_nxt[0];
-      id_cur[1] = id_nxt[1];
+      id_cur = id_nxt;
     }
   } else {
     // ===== consumers =====
-    const int cw = warp - 1;
-    const int ct = threadIdx.x - 32;
+    const int cw = warp - NPW;
+    const int ct = threadIdx.x - 32 * NPW;
     int k = 0;
     for (int64_t b = blockIdx.x; b < P.B; b += gridDim.x, ++k) {
       const int s = k % P.nst;
@@ -108,11 +109,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) ffm_fwd_kernel(const __grid_const
       rs::mbar_wait(&full_bar[s], ph);
       const float4 *T = tiles + (size_t)s * stage_v;
       float4 *st_out = P.stash ? reinterpret_cast<float4 *>(P.stash) + b * (int64_t)P.F * P.rowv : nullptr;
+      float4 *mini_b = P.mini ? reinterpret_cast<float4 *>(P.mini) + b * (int64_t)P.F * P.nC * P.dv : nullptr;
       float acc = 0.f;
       for (int i = cw; i < P.F; i += NCW) {
         const float4 *Ti = T + (size_t)i * P.pitchv;
         const float4 *Tcol = T + i * P.dv;  // + j*pitchv + d4 -> v_{j,i}
         float4 *out_i = st_out ? st_out + (size_t)i * P.rowv : nullptr;
+        float4 *mini_i = mini_b ? mini_b + (size_t)i * P.nC * P.dv : nullptr;
         for (int w0 = lane; w0 < P.rowv; w0 += 128) {
           float4 tr[4], own[4];
 #pragma unroll
@@ -128,6 +131,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) ffm_fwd_kernel(const __grid_const
             const int w = w0 + 32 * u;
             acc += rs::f4_dot(own[u], tr[u]);
             if (out_i && w < P.rowv) rs::stg_cs_f4(reinterpret_cast<float *>(out_i + w), tr[u]);
+            if (mini_i && w < P.rowv) {
+              const int j = w >> P.dvs;
+              const int c = s_cidx[j];
+              if (c >= 0 && j != i) rs::stg_cs_f4(reinterpret_cast<float *>(mini_i + c * P.dv + (w & (P.dv - 1))), tr[u]);
+            }
           }
         }
       }
@@ -207,13 +215,27 @@ int dense_launch(const float *Tin, const float *g, int64_t B, int F, int NF, int
 
 }  // namespace
 
+static int ffm_fwd_launch(const rs_tables *T, const int64_t *ids, int64_t B, int32_t D, const rs_peer_tables *PT, float *cross,
+                          float *stash, uint64_t cold_mask, float *mini, int32_t *status, void *stream);
+
 RS_API int rs_ffm_fwd(const rs_tables *T, const int64_t *ids, int64_t B, int32_t D, float *cross, float *stash, int32_t *status,
                       void *stream) {
-  return rs_ffm_fwd_peer(T, ids, B, D, nullptr, cross, stash, status, stream);
+  return ffm_fwd_launch(T, ids, B, D, nullptr, cross, stash, 0, nullptr, status, stream);
 }
 
 RS_API int rs_ffm_fwd_peer(const rs_tables *T, const int64_t *ids, int64_t B, int32_t D, const rs_peer_tables *PT, float *cross,
                            float *stash, int32_t *status, void *stream) {
+  return ffm_fwd_launch(T, ids, B, D, PT, cross, stash, 0, nullptr, status, stream);
+}
+
+RS_API int rs_ffm_fwd_train(const rs_tables *T, const int64_t *ids, int64_t B, int32_t D, uint64_t cold_mask, float *cross,
+                            float *cold_stash, int32_t *status, void *stream) {
+  RS_CHECK_ARG(!cold_mask || cold_stash, RS_E_ARG, "rs_ffm_fwd_train: cold_stash is NULL");
+  return ffm_fwd_launch(T, ids, B, D, nullptr, cross, nullptr, cold_mask, cold_stash, status, stream);
+}
+
+static int ffm_fwd_launch(const rs_tables *T, const int64_t *ids, int64_t B, int32_t D, const rs_peer_tables *PT, float *cross,
+                          float *stash, uint64_t cold_mask, float *mini, int32_t *status, void *stream) {
   RS_CHECK_ARG(T && ids && cross, RS_E_ARG, "rs_ffm_fwd: null argument");
   const int F = T->num_fields;
   RS_CHECK_ARG(F >= 2 && F <= RS_MAX_FIELDS, RS_E_SHAPE, "rs_ffm_fwd: F=%d out of range", F);
@@ -241,6 +263,10 @@ RS_API int rs_ffm_fwd_peer(const rs_tables *T, const int64_t *ids, int64_t B, in
   P.ids = ids;
   P.cross = cross;
   P.stash = stash;
+  if (F < 64) cold_mask &= (1ull << F) - 1ull;
+  P.mini = cold_mask ? mini : nullptr;
+  P.nC = 0;
+  for (int f = 0; f < RS_MAX_FIELDS; ++f) P.cidx[f] = (f < F && ((cold_mask >> f) & 1ull)) ? (signed char)P.nC++ : (signed char)-1;
   P.B = B;
   P.F = F;
   P.D = D;
@@ -253,7 +279,7 @@ RS_API int rs_ffm_fwd_peer(const rs_tables *T, const int64_t *ids, int64_t B, in
   if (P.dv < 8) pad = (((P.dv * 16 - row_bytes) % 128) + 128) % 128;  // rows of consecutive j land 16*dv bytes apart mod 128
   P.pitchv = (row_bytes + pad) / 16;
   const size_t stage_bytes = (size_t)F * P.pitchv * 16;
-  int nst = (int)((220 * 1024) / stage_bytes);  // 227 KB per CTA minus the static barriers/pointer tables
+  int nst = (int)((232448 - 2048) / stage_bytes);  // 227 KB per CTA minus the static barriers / pointer tables (1.4 KB)
   RS_CHECK_ARG(nst >= 1, RS_E_UNSUPPORTED, "rs_ffm_fwd: F*F*D tile (%zu B) does not fit in shared memory", stage_bytes);
   if (nst > MAX_STAGES) nst = MAX_STAGES;
   P.nst = nst;

@@ -6,18 +6,21 @@
 // at F = 26, D = 16, B = 65536).  Here it is recomputed from the table instead, which is possible because the lookups
 // split into two classes with different hazards:
 //
-//   rows looked up ONCE in the batch (nearly every row of the large fields): only their own sample reads them, so the
-//     CTA that holds the sample's tile in shared memory (same TMA ring as the forward) updates them in place
-//     -- ffm_single_kernel; traffic = tile read + row write, nothing else;
-//   rows looked up several times (the small, L2-resident fields): their lookups are reduced in sorted (= ascending
+//   rows of the COLD fields (cold_mask: the large tables) looked up ONCE in the batch -- nearly all of their rows: only
+//     their own sample reads them, so the CTA that holds the sample's tile in shared memory (same TMA ring as the
+//     forward) updates them in place -- ffm_single_kernel; traffic = tile read + row write, nothing else;
+//   every other row (looked up several times, or in a small field): its lookups are reduced in sorted (= ascending
 //     position) order, RS_CHUNK at a time exactly as rs_segment_update does, but each lookup's gradient row is GATHERED
-//     as F slices of D floats from the other rows of its sample (ffm_multi_kernel: mostly L2 hits); results go to a small
-//     gradient buffer, because a table row may still be read by other chunks / by the single-row pass;
+//     slice by slice (ffm_multi_kernel): the slices that live in rows of the small fields straight from the table
+//     (the lookups of one field need slot i of every small table: a few MB, L2 resident), the slices that live in rows
+//     of the cold fields from the "cold-slice stash" rs_ffm_fwd_train wrote (nC of F slices per lookup; a random 64-byte
+//     read into a 56 GB table costs a TLB miss each -- measured 1.2 ms for the 10 M of them at the C2 shape).  Results
+//     go to a small gradient buffer, because a table row may still be read by other chunks;
 //   ffm_apply_kernel + the combine pass of segment.cu then apply the buffered gradients.
 //
-// Order: multi (reads only) -> single (writes rows nobody else reads) -> apply (all reads are over).  The arithmetic per
-// element is the stash path's (explicit mul, add in sorted order, same chunking, same combine), so the two paths
-// produce identical bits.
+// Order: multi (reads only) -> single (writes cold-field rows nobody else reads) -> apply (all reads are over).  The
+// arithmetic per element is the stash path's (explicit mul, add in sorted order, same chunking, same combine), so the
+// two paths produce identical bits.
 #include "segment.cuh"
 
 namespace {
@@ -25,7 +28,8 @@ namespace {
 using rs::UpdParams;
 
 constexpr int NCW = 8;                 // consumer warps of the single-row pass
-constexpr int NTHREADS = (NCW + 1) * 32;
+constexpr int NPW = 2;                 // producer warps (see ffm.cu)
+constexpr int NTHREADS = (NCW + NPW) * 32;
 constexpr int MAX_STAGES = 8;
 
 struct TrainParams {
@@ -44,6 +48,10 @@ struct TrainParams {
   int F, D, dv, dvs, rowv, W, pitchv, nst;
   float lr, wd;
   int32_t *status;
+  unsigned long long cold_mask;      // fields whose once-looked-up rows are updated in place / whose slices come from `mini`
+  const float *mini;                 // (B, F, nC, D) cold-slice stash written by rs_ffm_fwd_train
+  int nC;
+  signed char cidx[RS_MAX_FIELDS];
 };
 
 __device__ __forceinline__ float upd_sgd1(float w, float g, float lr, float wd) { return w - lr * (g + wd * w); }
@@ -67,12 +75,15 @@ __global__ void __launch_bounds__(256) ffm_classify_kernel(const __grid_constant
     const int s0 = P.chunk_start[c], s1 = P.chunk_start[c + 1];
     const int g = P.chunk_seg[c];
     const bool one_chunk = (P.seg_first_chunk[g + 1] - P.seg_first_chunk[g]) == 1;
+    multi = true;
     if (one_chunk && s1 - s0 == 1) {
       const int p = P.sorted_pos[s0];
       const int b = p / P.F;
-      atomicOr(P.single_mask + b, 1ull << (p - b * P.F));
-    } else {
-      multi = true;
+      const int i = p - b * P.F;
+      if ((P.cold_mask >> i) & 1ull) {
+        atomicOr(P.single_mask + b, 1ull << i);
+        multi = false;
+      }
     }
   }
   const unsigned m = __ballot_sync(0xffffffffu, multi);
@@ -96,7 +107,7 @@ __global__ void __launch_bounds__(256, (NA * UNR <= 8) ? 3 : 2) ffm_multi_kernel
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int nlist = *P.n_list;
-  int jj[NA], qq[NA];
+  int jj[NA], qq[NA], cj[NA];
   bool inrow[NA];
 #pragma unroll
   for (int a = 0; a < NA; ++a) {
@@ -104,6 +115,7 @@ __global__ void __launch_bounds__(256, (NA * UNR <= 8) ? 3 : 2) ffm_multi_kernel
     jj[a] = w >> P.dvs;
     qq[a] = w & (P.dv - 1);
     inrow[a] = w < P.rowv;
+    cj[a] = inrow[a] ? P.cidx[jj[a]] : -1;     // >= 0: this column's slices come from the cold-slice stash
   }
   const float *base0 = lane < P.F ? P.base[lane] : nullptr;
   const int64_t rows0 = lane < P.F ? P.rows[lane] : 1;
@@ -127,6 +139,7 @@ __global__ void __launch_bounds__(256, (NA * UNR <= 8) ? 3 : 2) ffm_multi_kernel
       const int cnt = (s1 - sb) < 32 ? (s1 - sb) : 32;
       for (int u0 = 0; u0 < cnt; u0 += UNR) {
         const float *ptr0[UNR], *ptr1[UNR];
+        const float *mu[UNR];
         int iu[UNR];
         float gu[UNR];
 #pragma unroll
@@ -134,10 +147,13 @@ __global__ void __launch_bounds__(256, (NA * UNR <= 8) ? 3 : 2) ffm_multi_kernel
           const int b = __shfl_sync(0xffffffffu, my_b, u0 + u);
           iu[u] = __shfl_sync(0xffffffffu, my_i, u0 + u);
           gu[u] = __shfl_sync(0xffffffffu, my_g, u0 + u);
+          mu[u] = P.mini + ((int64_t)b * P.F + iu[u]) * P.nC * P.D;
           ptr0[u] = ptr1[u] = nullptr;
-          if (u0 + u < cnt) {
-            if (lane < P.F) ptr0[u] = base0 + rs::clamp_id(__ldg(P.ids + (int64_t)b * P.F + lane), rows0, P.status) * P.W;
-            if (BIGF && lane + 32 < P.F) ptr1[u] = base1 + rs::clamp_id(__ldg(P.ids + (int64_t)b * P.F + lane + 32), rows1, P.status) * P.W;
+          if (u0 + u < cnt) {   // (lanes of cold fields need no row pointer)
+            if (lane < P.F && !((P.cold_mask >> lane) & 1ull))
+              ptr0[u] = base0 + rs::clamp_id(__ldg(P.ids + (int64_t)b * P.F + lane), rows0, P.status) * P.W;
+            if (BIGF && lane + 32 < P.F && !((P.cold_mask >> (lane + 32)) & 1ull))
+              ptr1[u] = base1 + rs::clamp_id(__ldg(P.ids + (int64_t)b * P.F + lane + 32), rows1, P.status) * P.W;
           }
         }
         float4 val[UNR][NA];
@@ -151,7 +167,9 @@ __global__ void __launch_bounds__(256, (NA * UNR <= 8) ? 3 : 2) ffm_multi_kernel
               if (jj[a] >= 32) src = hi;
             }
             const bool ok = (u0 + u < cnt) && inrow[a] && jj[a] != iu[u];
-            val[u][a] = ok ? rs::ldg_nc_f4(reinterpret_cast<const float *>(src) + (iu[u] * P.dv + qq[a]) * 4) : rs::f4_zero();
+            const float *from = cj[a] >= 0 ? mu[u] + (cj[a] * P.dv + qq[a]) * 4
+                                           : reinterpret_cast<const float *>(src) + (iu[u] * P.dv + qq[a]) * 4;
+            val[u][a] = ok ? rs::ldg_nc_f4(from) : rs::f4_zero();
           }
         }
 #pragma unroll
@@ -190,7 +208,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ffm_single_kernel(const __grid_co
   const int stage_v = P.F * P.pitchv;
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.nst; ++s) {
-      rs::mbar_init(&full_bar[s], 1);
+      rs::mbar_init(&full_bar[s], NPW);
       rs::mbar_init(&empty_bar[s], NCW);
     }
     rs::mbar_fence_init();
@@ -198,24 +216,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) ffm_single_kernel(const __grid_co
   __syncthreads();
   const uint32_t row_bytes = (uint32_t)P.rowv * 16u;
 
-  if (warp == 0) {
-    // ===== producer =====
+  if (warp < NPW) {
+    // ===== producers: lane l of producer warp w owns field f = l * NPW + w =====
+    const int f = lane * NPW + warp;
+    const bool has = f < P.F;
+    const uint32_t nmine = (uint32_t)((P.F - warp + NPW - 1) / NPW);
     int k = 0;      // stages handed out so far
     int64_t b = blockIdx.x;
-    int64_t id_cur[2] = {0, 0}, id_nxt[2] = {0, 0};
+    int64_t id_cur = 0, id_nxt = 0;
     unsigned long long m_cur = 0, m_nxt = 0;
     float g_cur = 0.f, g_nxt = 0.f;
     if (b < P.B) {
-      if (lane < P.F) id_cur[0] = P.ids[b * P.F + lane];
-      if (lane + 32 < P.F) id_cur[1] = P.ids[b * P.F + lane + 32];
+      if (has) id_cur = P.ids[b * P.F + f];
       m_cur = P.single_mask[b];
       g_cur = P.g[b];
     }
     for (; b < P.B; b += gridDim.x) {
       const int64_t bn = b + gridDim.x;
       if (bn < P.B) {
-        if (lane < P.F) id_nxt[0] = P.ids[bn * P.F + lane];
-        if (lane + 32 < P.F) id_nxt[1] = P.ids[bn * P.F + lane + 32];
+        if (has) id_nxt = P.ids[bn * P.F + f];
         m_nxt = P.single_mask[bn];
         g_nxt = P.g[bn];
       }
@@ -224,31 +243,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) ffm_single_kernel(const __grid_co
         const uint32_t ph = (uint32_t)(k / P.nst) & 1u;
         ++k;
         rs::mbar_wait(&empty_bar[s], ph ^ 1u);
-        const float *src[2] = {nullptr, nullptr};
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int f = lane + 32 * h;
-          if (f < P.F) {
-            src[h] = s_base[f] + rs::clamp_id(id_cur[h], s_rows[f], P.status) * (int64_t)P.rowv * 4;
-            s_row[s][f] = const_cast<float *>(src[h]);
-          }
+        const float *src = nullptr;
+        if (has) {
+          src = s_base[f] + rs::clamp_id(id_cur, s_rows[f], P.status) * (int64_t)P.rowv * 4;
+          s_row[s][f] = const_cast<float *>(src);
         }
-        if (lane == 0) {
+        if (warp == 0 && lane == 0) {
           s_mask[s] = m_cur;
           s_g[s] = g_cur;
         }
         __syncwarp();
-        if (lane == 0) rs::mbar_arrive_expect_tx(&full_bar[s], row_bytes * (uint32_t)P.F);
+        if (lane == 0) rs::mbar_arrive_expect_tx(&full_bar[s], row_bytes * nmine);
         __syncwarp();
-        float4 *dst = tiles + (size_t)s * stage_v;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int f = lane + 32 * h;
-          if (f < P.F) rs::bulk_g2s(dst + (size_t)f * P.pitchv, src[h], row_bytes, &full_bar[s]);
-        }
+        if (has) rs::bulk_g2s(tiles + (size_t)s * stage_v + (size_t)f * P.pitchv, src, row_bytes, &full_bar[s]);
       }
-      id_cur[0] = id_nxt[0];
-      id_cur[1] = id_nxt[1];
+      id_cur = id_nxt;
       m_cur = m_nxt;
       g_cur = g_nxt;
     }
@@ -257,12 +266,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) ffm_single_kernel(const __grid_co
     const uint32_t ph = (uint32_t)(k / P.nst) & 1u;
     rs::mbar_wait(&empty_bar[s], ph ^ 1u);
     if (lane == 0) {
-      s_mask[s] = 0ull;
+      if (warp == 0) s_mask[s] = 0ull;
       rs::mbar_arrive(&full_bar[s]);
     }
   } else {
     // ===== consumers: warp cw takes the cw-th, (cw + NCW)-th, ... row of the mask =====
-    const int cw = warp - 1;
+    const int cw = warp - NPW;
     for (int k = 0;; ++k) {
       const int s = k % P.nst;
       const uint32_t ph = (uint32_t)(k / P.nst) & 1u;
@@ -365,8 +374,10 @@ int launch_train(const TrainParams &P, const UpdParams &U, int64_t n, int mode, 
   const size_t stage_bytes = (size_t)P.F * P.pitchv * 16;
   const size_t smem = stage_bytes * P.nst;
   RS_CUDA(cudaFuncSetAttribute(ffm_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ffm_single_kernel<<<(int)(P.B < sms ? P.B : sms), NTHREADS, smem, st>>>(P);
-  RS_CHECK_LAUNCH();
+  if (P.cold_mask) {
+    ffm_single_kernel<<<(int)(P.B < sms ? P.B : sms), NTHREADS, smem, st>>>(P);
+    RS_CHECK_LAUNCH();
+  }
   ffm_apply_kernel<NA><<<sms * 8, 256, 0, st>>>(P);
   RS_CHECK_LAUNCH();
   return rs::dispatch_update(U, mode, n, st);   // combine pass only (U.combine_only): multi-chunk segments, in place
@@ -380,13 +391,14 @@ RS_API int rs_ffm_bwd_ws_bytes(int64_t n, int64_t B, int32_t width, size_t *byte
   return RS_OK;
 }
 
-RS_API int rs_ffm_bwd_update(const rs_tables *T, const int64_t *ids, int64_t B, int32_t D, const rs_segments *seg, const rs_update *u,
-                             void *ws, size_t ws_bytes, int32_t *status, void *stream) {
+RS_API int rs_ffm_bwd_update(const rs_tables *T, const int64_t *ids, int64_t B, int32_t D, uint64_t cold_mask, const float *cold_stash,
+                             const rs_segments *seg, const rs_update *u, void *ws, size_t ws_bytes, int32_t *status, void *stream) {
   RS_CHECK_ARG(T && ids && seg && u && ws, RS_E_ARG, "rs_ffm_bwd_update: null argument");
   const int F = T->num_fields;
   RS_CHECK_ARG(F >= 2 && F <= RS_MAX_FIELDS, RS_E_SHAPE, "rs_ffm_bwd_update: F=%d out of range", F);
   RS_CHECK_ARG(D >= 4 && D <= 256 && (D & (D - 1)) == 0, RS_E_UNSUPPORTED, "rs_ffm_bwd_update: D=%d must be a power of two in [4,256]", D);
   RS_CHECK_ARG(T->width == F * D && u->width == F * D && u->F == F, RS_E_SHAPE, "rs_ffm_bwd_update: table width must be F*D = %d", F * D);
+  RS_CHECK_ARG(!cold_mask || cold_stash, RS_E_ARG, "rs_ffm_bwd_update: cold fields need the cold-slice stash of rs_ffm_fwd_train");
   RS_CHECK_ARG(u->mode == RS_UPD_SGD, RS_E_UNSUPPORTED, "rs_ffm_bwd_update: only RS_UPD_SGD (use the stash + rs_segment_update for other modes)");
   RS_CHECK_ARG(u->table && u->scale && !u->stash && !u->dense, RS_E_ARG,
                "rs_ffm_bwd_update: needs table and scale (= dL/dcross per sample); stash / dense must be NULL");
@@ -443,6 +455,10 @@ RS_API int rs_ffm_bwd_update(const rs_tables *T, const int64_t *ids, int64_t B, 
   P.lr = u->lr;
   P.wd = u->wd;
   P.status = status;
+  P.cold_mask = F < 64 ? (cold_mask & ((1ull << F) - 1ull)) : cold_mask;
+  P.mini = cold_stash;
+  P.nC = 0;
+  for (int f = 0; f < RS_MAX_FIELDS; ++f) P.cidx[f] = (f < F && ((P.cold_mask >> f) & 1ull)) ? (signed char)P.nC++ : (signed char)-1;
   cudaStream_t st = (cudaStream_t)stream;
   if (rowv <= 32) return launch_train<1>(P, U, n, u->mode, st);
   if (rowv <= 64) return launch_train<2>(P, U, n, u->mode, st);

@@ -38,6 +38,7 @@ def _xavier_concat(cards, width, row_dim, device=None, seed=None):
     return out
 
 
+COLD_ROWS = 1 << 16        # stash-free FFM step: fields with at least this many rows are "cold" (see FieldFFM.bind_row_optimizer)
 DIRECT_ROWS = 1 << 20      # fields with at least this many rows are read from the peers' shards by the FFM forward itself
 
 
@@ -209,7 +210,8 @@ class _FieldModel(nn.Module):
                 if rec.get("recompute"):      # FieldFFM without a Jacobian stash: gradient rows rebuilt from the table itself
                     if opt.kind != "sgd":
                         raise RuntimeError("this forward ran without a Jacobian stash (row optimizer bound as SGD); step it with that optimizer")
-                    ops.ffm_bwd_update(self.tables(), rec["ids"], self.D, segs, rec["g"], self.weight.data, opt.lr, opt.weight_decay)
+                    ops.ffm_bwd_update(self.tables(), rec["ids"], self.D, segs, rec["g"], self.weight.data, opt.lr, opt.weight_decay,
+                                       cold_mask=self.cold_mask, cold_stash=rec["stash"])
                     continue
                 self._row_update(opt, segs, self.F, **src)
                 continue
@@ -304,7 +306,7 @@ class _FieldModel(nn.Module):
             if self._anchor is None or self._anchor.device != ids.device:
                 self._anchor = torch.zeros(1, device=ids.device, requires_grad=True)
             self._token += 1
-            if stash is None:
+            if getattr(self, "_stash_is_cold_slices", False):
                 rec = {**rec, "recompute": True}
             self._pending[self._token] = {"ids": ids, "stash": stash, **rec}
             cross = _CrossFn.apply(self._anchor, cross, self, self._token)
@@ -352,17 +354,24 @@ class FieldFFM(_FieldModel):
             self._direct_mask = sum(1 << f for f in self.direct_fields)
 
     def bind_row_optimizer(self, opt):
-        """Called by FusedRowOptimizer: with plain SGD on an unsharded table the training forward writes no Jacobian stash
-        and the step rebuilds the gradient rows from the table (ops.ffm_bwd_update) -- the stash is 5.6 of the 8.8 GB the
-        stash-based FFM step moves at the C2 shape.  RS_FFM_RECOMPUTE=0 keeps the stash."""
+        """Called by FusedRowOptimizer.  RS_FFM_RECOMPUTE=1 (opt-in; plain SGD, unsharded table): the training forward
+        writes only a cold-slice stash and the step rebuilds the gradient rows from the table (ops.ffm_fwd_train /
+        ops.ffm_bwd_update), bit-identical to the default.  It moves about half the DRAM bytes of the full-stash step but
+        is SLOWER on B200 (4.5 vs 2.2 ms per C2 step): its 64-byte slice gathers run at ~27 G accesses/s, while the
+        full-stash kernels stream 1664-byte rows through TMA at 5 TB/s (profiles/r2_ffm_stash_free.md)."""
         import os
         self._recompute = (opt.kind == "sgd" and self.fused and not self.sharded and self.width // 4 <= 256
-                           and os.environ.get("RS_FFM_RECOMPUTE", "1") == "1")
+                           and os.environ.get("RS_FFM_RECOMPUTE", "0") == "1")
+        # "cold" fields: tables too large to stay in L2.  Their once-looked-up rows are updated in place, and slices that
+        # live in their rows travel through the cold-slice stash instead of being gathered at random from a many-GB table.
+        self.cold_mask = sum(1 << f for f, c in enumerate(self.cards) if c >= COLD_ROWS)
 
     def _interact(self, T, ids, want_stash, orig_ids=None):
+        self._stash_is_cold_slices = False
         if want_stash and getattr(self, "_recompute", False) and self.fused and not self._pending:
-            # (a second forward before the step keeps its stash: its gradients must not see the first one's update)
-            return ops.ffm_fwd(T, ids, self.D, want_stash=False)
+            # (a second forward before the step keeps its full stash: its gradients must not see the first one's update)
+            self._stash_is_cold_slices = True
+            return ops.ffm_fwd_train(T, ids, self.D, self.cold_mask)
         if orig_ids is not None and self.direct_fields:
             # block rows for the fetched fields, GLOBAL rows for the direct ones
             mix = ids.clone()

@@ -236,6 +236,25 @@ def ffm_fwd(T, ids, D, want_stash=True, peer=None):
     return cross, stash
 
 
+def ffm_fwd_train(T, ids, D, cold_mask):
+    """Training forward of the stash-free FFM step: cross (B,) and the cold-slice stash (B, F, nC, D) -- slot i of the rows
+    of the nC fields flagged in cold_mask, for every lookup (b, i) -- that ffm_bwd_update consumes (rs_ffm_fwd_train)."""
+    ids = _i64(ids)
+    _need_cuda(ids)
+    F = T.num_fields
+    B = ids.numel() // F
+    nC = bin(cold_mask & ((1 << F) - 1)).count("1")
+    cross = torch.empty(B, dtype=torch.float32, device=ids.device)
+    mini = torch.empty(B, F, nC, D, dtype=torch.float32, device=ids.device) if nC else None
+    if B == 0:
+        return cross, mini
+    with _timed("ffm_fwd"):
+        _lib.check(_lib.load().rs_ffm_fwd_train(C.byref(T), ids.data_ptr(), B, D, int(cold_mask), cross.data_ptr(), _p(mini),
+                                                status_word(ids.device).data_ptr(), _stream()), "rs_ffm_fwd_train")
+    _count()
+    return cross, mini
+
+
 def _field_of(field_of):
     return (C.c_int32 * len(field_of))(*field_of)
 
@@ -522,12 +541,13 @@ def segment_update(segs, mode, width, F, stash=None, scale=None, dense=None, tab
 _ffm_bwd_ws = {}
 
 
-def ffm_bwd_update(T, ids, D, segs, g_cross, table, lr, wd=0.0, tag=""):
-    """FFM backward + fused SGD row update recomputed from the table (rs_ffm_bwd_update): no Jacobian stash.
+def ffm_bwd_update(T, ids, D, segs, g_cross, table, lr, wd=0.0, cold_mask=0, cold_stash=None, tag=""):
+    """FFM backward + fused SGD row update rebuilt from the table (rs_ffm_bwd_update): no full Jacobian stash.
     T: rs_tables over `table` (the concatenated (total_rows, F*D) tensor), ids (B, F) the batch the forward ran on,
-    segs = dedup_sort(ids, ..., max_width=F*D), g_cross (B,) = dL/dcross.  The table must be unchanged since the forward."""
+    segs = dedup_sort(ids, ..., max_width=F*D), g_cross (B,) = dL/dcross, (cold_mask, cold_stash) as given to / returned by
+    ffm_fwd_train.  The table must be unchanged since the forward."""
     ids, g_cross = _i64(ids), _f32(g_cross)
-    _need_cuda(ids, g_cross, table)
+    _need_cuda(ids, g_cross, table, cold_stash)
     F = T.num_fields
     B = ids.numel() // F
     if B == 0:
@@ -545,7 +565,7 @@ def ffm_bwd_update(T, ids, D, segs, g_cross, table, lr, wd=0.0, tag=""):
     u.scale, u.table = g_cross.data_ptr(), table.data_ptr()
     u.lr, u.wd, u.step = lr, wd, 1
     with _timed(f"ffm_bwd_update{tag}"):
-        _lib.check(lib.rs_ffm_bwd_update(C.byref(T), ids.data_ptr(), B, D, C.byref(segs.seg), C.byref(u), ws.data_ptr(), ws.numel(),
+        _lib.check(lib.rs_ffm_bwd_update(C.byref(T), ids.data_ptr(), B, D, int(cold_mask), _p(cold_stash), C.byref(segs.seg), C.byref(u), ws.data_ptr(), ws.numel(),
                                          status_word(ids.device).data_ptr(), _stream()), "rs_ffm_bwd_update")
     _count(5)
 

@@ -212,19 +212,27 @@ typedef struct rs_update {
 } rs_update;
 int rs_segment_update(const rs_segments *seg, int64_t n, const rs_update *u, void *stream);
 
-/* ---- FFM backward + row update WITHOUT the Jacobian stash (autograd of model/ffm.py:61-82 + embedding_dense_backward +
+/* ---- FFM training step WITHOUT the full Jacobian stash (autograd of model/ffm.py:61-82 + embedding_dense_backward +
  * optimizer.step(), trainer/trainer.py:38-39).  The gradient of table row (b, i) is dL/dcross[b] * [v_{j,i}(b)]_j, i.e.
- * slot i of the other rows of sample b, so it can be recomputed from the (not yet updated) table instead of being
- * written out by rs_ffm_fwd (stash = NULL there): rows looked up once in the batch are updated in place by the CTA that
- * holds their sample's tile; rows looked up several times are reduced in sorted order from gathered slices, buffered,
- * and applied after every read is over.  Same per-element arithmetic, chunking and combine order as
- * rs_segment_update(stash, scale) => identical bits.  `seg` = rs_dedup_sort of the same ids (with the partial scratch
- * sized for width F*D); `u`: mode RS_UPD_SGD, width = F*D, F, table = the concatenated table the T->base[f] point
- * into, scale = dL/dcross (B), lr, wd; stash / dense must be NULL.  The table must not have changed since the forward.
- * ws: rs_ffm_bwd_ws_bytes(n = B*F, B, width). */
+ * slot i of the other rows of sample b, so it can be rebuilt from the (not yet updated) table instead of being written
+ * out whole by rs_ffm_fwd.  Fields are split by `cold_mask` (bit f set = field f is a LARGE table):
+ *   rs_ffm_fwd_train   forward; writes only the "cold-slice stash" cold_stash[b, i, c, :] = v_{cold_c, i}(b)
+ *                      (B, F, nC, D), nC = popcount(cold_mask): the slices that live in rows of the large tables
+ *                      (nC/F of a full stash; random 64-byte reads into a many-GB table are TLB-miss bound);
+ *   rs_ffm_bwd_update  rows of cold fields looked up once in the batch are updated in place by the CTA that holds their
+ *                      sample's tile; every other row is reduced in sorted order from gathered slices (small-field
+ *                      slices straight from the table -- L2 resident --, cold ones from cold_stash), buffered, and
+ *                      applied after every read is over.
+ * Same per-element arithmetic, chunking and combine order as rs_ffm_fwd(stash) + rs_segment_update(stash, scale)
+ * => identical bits.  `seg` = rs_dedup_sort of the same ids (partial scratch sized for width F*D); `u`: mode RS_UPD_SGD,
+ * width = F*D, F, table = the concatenated table the T->base[f] point into, scale = dL/dcross (B), lr, wd; stash /
+ * dense must be NULL.  The table must not have changed since the forward.  ws: rs_ffm_bwd_ws_bytes(n = B*F, B, width). */
+int rs_ffm_fwd_train(const rs_tables *T /* width = F*D */, const int64_t *ids, int64_t B, int32_t D, uint64_t cold_mask,
+                     float *cross, float *cold_stash, int32_t *status, void *stream);
 int rs_ffm_bwd_ws_bytes(int64_t n, int64_t B, int32_t width, size_t *bytes);
-int rs_ffm_bwd_update(const rs_tables *T /* width = F*D */, const int64_t *ids, int64_t B, int32_t D, const rs_segments *seg,
-                      const rs_update *u, void *ws, size_t ws_bytes, int32_t *status, void *stream);
+int rs_ffm_bwd_update(const rs_tables *T /* width = F*D */, const int64_t *ids, int64_t B, int32_t D, uint64_t cold_mask,
+                      const float *cold_stash, const rs_segments *seg, const rs_update *u, void *ws, size_t ws_bytes,
+                      int32_t *status, void *stream);
 
 /* ---- row-sharded tables: the exchange plan lives on the DEVICE (no reference counterpart).
  * Global row g is owned by rank g % world at local index g / world.  Every rank owns two small symmetric (peer-mapped)

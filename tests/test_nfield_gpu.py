@@ -257,6 +257,9 @@ def test_graphed_step_equals_eager(kind):
     ([3, 50, 7, 1000, 24], 4, 700, 0.0),                        # 20-float rows
     ([5 + 37 * k for k in range(40)], 8, 1500, 0.0),            # F = 40 > 32 fields (two id registers per lane)
     ([2, 3], 64, 10000, 0.0),                                   # two tiny tables: every row spans many chunks
+    ([70000 if k % 7 == 0 else 5 + 37 * k for k in range(40)], 8, 1200, 0.0),   # F > 32 with six cold (>= 2^16 rows) fields
+    ([70000, 90000, 66000, 131072, 80000], 8, 3000, 1e-3),      # every field cold: all slices come from the cold-slice stash
+    ([65536, 9, 100000], 32, 2500, 0.0),                        # D = 32
 ])
 def test_ffm_stash_free_step_is_bit_identical_to_stash_step(cards, D, B, wd, monkeypatch):
     """rs_ffm_bwd_update (gradient rows recomputed from the table: no Jacobian stash) against rs_ffm_fwd(stash) +
