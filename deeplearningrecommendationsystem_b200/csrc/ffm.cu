@@ -7,6 +7,8 @@
 // sum_{i<j} <T[i][j], T[j][i]> from shared memory and stream out the transposed tile
 // stash[b][i][j] = T[j][i] (the Jacobian d cross / d v_{i,j}) that the segment-reduce/update kernel later
 // scales by dL/dcross[b].  Rows are padded in shared memory so the transposed reads are bank-conflict free.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -17,6 +19,7 @@ constexpr int NPW = 2;                 // producer warps: one warp issues a bulk
                                        // split over two issuing warps
 constexpr int NTHREADS = (NCW + NPW) * 32;
 constexpr int MAX_STAGES = 8;
+constexpr int64_t HOT_TABLE_BYTES = 32ll << 20;
 
 struct FfmParams {
   const float *base[RS_MAX_FIELDS];
@@ -36,6 +39,7 @@ struct FfmParams {
   int64_t total_rows;
   // "cold-slice" stash (rs_ffm_fwd_train): mini[b][i][c][:] = v_{cold_c, i}(b) for the nC fields flagged cold
   float *mini;
+  int hint;   // use the L2 eviction hints (RS_FFM_L2HINT=0 turns them off)
   int nC;
   signed char cidx[RS_MAX_FIELDS];   // index of field j among the cold fields, -1 = not cold
 };
@@ -72,6 +76,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) ffm_fwd_kernel(const __grid_const
     const int f = lane * NPW + warp;
     const bool has = f < P.F;
     const uint32_t nmine = (uint32_t)((P.F - warp + NPW - 1) / NPW);
+    // L2 residency hint per field: a table of at most HOT_TABLE_BYTES is re-read many times per batch (keep it), a large
+    // one is touched about once per row (let it go first); the stash stores are streaming (st.global.cs) already
+    const bool hot = has && !((P.direct_mask >> f) & 1ull) && P.hint && s_rows[f] * (int64_t)P.rowv * 16 <= HOT_TABLE_BYTES;
+    const uint64_t policy = hot ? rs::l2_policy_evict_last() : rs::l2_policy_evict_first();
     int k = 0;
     int64_t b = blockIdx.x;
     int64_t id_cur = 0, id_nxt = 0;
@@ -94,7 +102,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) ffm_fwd_kernel(const __grid_const
         } else {
           src = s_base[f] + rs::clamp_id(id_cur, s_rows[f], P.status) * (int64_t)P.rowv * 4;
         }
-        rs::bulk_g2s(dst + (size_t)f * P.pitchv, src, row_bytes, &full_bar[s]);
+        if (P.hint)
+          rs::bulk_g2s_hint(dst + (size_t)f * P.pitchv, src, row_bytes, &full_bar[s], policy);
+        else
+          rs::bulk_g2s(dst + (size_t)f * P.pitchv, src, row_bytes, &full_bar[s]);
       }
       id_cur = id_nxt;
     }
@@ -265,6 +276,10 @@ static int ffm_fwd_launch(const rs_tables *T, const int64_t *ids, int64_t B, int
   P.stash = stash;
   if (F < 64) cold_mask &= (1ull << F) - 1ull;
   P.mini = cold_mask ? mini : nullptr;
+  {
+    const char *e = getenv("RS_FFM_L2HINT");
+    P.hint = !(e && e[0] == '0');
+  }
   P.nC = 0;
   for (int f = 0; f < RS_MAX_FIELDS; ++f) P.cidx[f] = (f < F && ((cold_mask >> f) & 1ull)) ? (signed char)P.nC++ : (signed char)-1;
   P.B = B;

@@ -197,7 +197,9 @@ class SymmFabric(Fabric):
     def allreduce_mean(self, grads):
         """Average a SMALL set of dense gradients (the FM/FFM/MF bias, a few floats) through a symmetric buffer: every rank
         copies its flat bucket into slot [rank] of every peer, barrier, fixed-order sum.  No NCCL call, so the sharded
-        step stays one launch sequence.  Returns False (caller falls back to NCCL) for big buckets."""
+        step stays one launch sequence.  Two buffers are used alternately, so ONE barrier per call is enough: nobody can
+        overwrite the buffer a slow rank is still summing before that rank has passed the next call's barrier.
+        Returns False (caller falls back to NCCL) for big buckets."""
         K = sum(g.numel() for g in grads)
         if K == 0:
             return True
@@ -206,25 +208,29 @@ class SymmFabric(Fabric):
         dev = grads[0].device
         if getattr(self, "_ar", None) is None:
             try:
-                buf, _ = self.alloc((self.world, self.AR_MAX), torch.float32, dev)
+                buf, _ = self.alloc((2, self.world, self.AR_MAX), torch.float32, dev)
                 h = self._handles[-1]
-                views = [h.get_buffer(r, (self.world, self.AR_MAX), torch.float32) for r in range(self.world)]
-                self._ar = (buf, views)
+                views = [h.get_buffer(r, (2, self.world, self.AR_MAX), torch.float32) for r in range(self.world)]
+                self._ar, self._ar_flip = (buf, views), 0
                 self.barrier()
             except Exception:                      # symmetric-memory API without get_buffer: use NCCL
                 self._ar_broken = True
                 return False
         buf, views = self._ar
+        flip = self._ar_flip
+        if not torch.cuda.is_current_stream_capturing():
+            self._ar_flip ^= 1         # (a captured step always replays the buffer it was captured with: see below)
         flat = torch.cat([g.reshape(-1) for g in grads])
         for r in range(self.world):
-            views[r][self.rank, :K].copy_(flat)
+            views[r][flip, self.rank, :K].copy_(flat)
         self.barrier()
-        mean = buf[:, :K].sum(0) / self.world
+        mean = buf[flip, :, :K].sum(0) / self.world
         off = 0
         for g in grads:
             g.copy_(mean[off:off + g.numel()].view_as(g))
             off += g.numel()
-        self.barrier()
+        if torch.cuda.is_current_stream_capturing():
+            self.barrier()             # a replayed graph cannot alternate buffers: keep the second barrier there
         return True
 
 

@@ -35,11 +35,16 @@ class GraphedTrainStep:
     def _eager(self, inputs, rating):
         outs = []
         for model, loss_fn, optimizer in self.jobs:
+            from .trainer.trainer import fused_bce_step
             model.train()
             optimizer.zero_grad()
-            pred = model(*inputs)
-            loss = loss_fn(pred, rating)
-            loss.backward()
+            fused = fused_bce_step(model, loss_fn, inputs, rating)
+            if fused is not None:
+                pred, loss = fused
+            else:
+                pred = model(*inputs)
+                loss = loss_fn(pred, rating)
+                loss.backward()
             optimizer.step()
             outs.append((pred, loss))
         self.all_losses = [l for _, l in outs]

@@ -319,6 +319,10 @@ class _FieldModel(nn.Module):
     def forward(self, ids):
         return torch.sigmoid(self.logit(ids)).unsqueeze(1)
 
+    def train_logit(self, ids):
+        """(pre-sigmoid logit (B,), shape of forward()'s output) -- lets the Trainer fuse sigmoid + BCELoss + their backward"""
+        return self.logit(ids), (ids.shape[0], 1)
+
 
 class FieldFM(_FieldModel):
     """sigmoid(b + 0.5 * sum_d[(sum_f e_f)^2 - sum_f e_f^2]) over F id-fields, D-dim rows."""
@@ -401,8 +405,17 @@ class FieldMF(_FieldModel):
         ids = torch.stack([user_indices, item_indices], dim=1)
         return torch.sigmoid(self.logit(ids))                       # (B,)
 
+    def train_logit(self, user_indices, item_indices):
+        ids = torch.stack([user_indices, item_indices], dim=1)
+        return self.logit(ids), (ids.shape[0],)
 
-class FieldPNN(_FieldModel):
+
+class _EmbedModel(_FieldModel):
+    """models that use the table through embed() and put dense layers on top: forward() is not sigmoid(logit())"""
+    train_logit = None
+
+
+class FieldPNN(_EmbedModel):
     """Inner-product PNN over F id-fields (reference model/pnn.py:55-77,111-131 generalised from six features):
     lz = Linear(F*D, H0)(concat), lp = Linear(F(F-1)/2, H0)(inner products), ReLU tower, Linear(H[-1], 1), sigmoid."""
 
@@ -425,7 +438,7 @@ class FieldPNN(_FieldModel):
         return torch.sigmoid(self.output(h)).view(-1, 1)
 
 
-class FieldAFM(_FieldModel):
+class FieldAFM(_EmbedModel):
     """Attentional pooling over the F(F-1)/2 pairwise products of F id-fields (reference model/afm.py:55-66):
     sigmoid(Linear(D,1)(sum_p softmax_p(h.relu(P_p W + b)) P_p))."""
 
@@ -447,7 +460,7 @@ class FieldAFM(_FieldModel):
         return torch.sigmoid(self.output_layer(pooled))
 
 
-class _PairTable(_FieldModel):
+class _PairTable(_EmbedModel):
     """user + item tables of one embedding width in one concatenated (optionally row-sharded) buffer; only embed() is used"""
     use_bias = False
 

@@ -33,6 +33,31 @@ def _check_ids(model):
 _binary_metrics = binary_metrics
 
 
+def fused_bce_step(model, loss_fn, args, rating):
+    """forward -> sigmoid -> BCELoss(mean) -> backward with the sigmoid, the loss, its mean and both of their backward
+    passes in ONE kernel pair (rs_sigmoid_bce: same op sequence as autograd, fixed-order mean), for models that expose
+    their pre-sigmoid logit through ``train_logit`` (the nfield FM / FFM / MF models) under a plain ``nn.BCELoss()``.
+    Returns (predictions, loss) exactly as ``loss_fn(model(*args), rating)`` would (loss detached), or None when the
+    combination does not apply -- the caller then runs the generic path.  RS_FUSED_BCE=0 disables it."""
+    if os.environ.get("RS_FUSED_BCE", "1") != "1" or type(loss_fn) is not torch.nn.BCELoss:
+        return None
+    if loss_fn.reduction != "mean" or loss_fn.weight is not None:
+        return None
+    fn = getattr(model, "train_logit", None)
+    if fn is None or not torch.is_grad_enabled() or not args[0].is_cuda or rating.dtype != torch.float32:
+        return None
+    if rating.numel() != args[0].shape[0] or torch.is_tensor(rating) and rating.requires_grad:
+        return None
+    from .. import ops
+    logit, shape = fn(*args)
+    if tuple(rating.shape) != tuple(shape):           # BCELoss would raise / warn: let it
+        raise ValueError(f"Using a target size ({tuple(rating.shape)}) that is different to the input size ({tuple(shape)}) is deprecated. "
+                         "Please ensure they have the same size.")
+    pred, loss, g = ops.sigmoid_bce(logit.detach(), rating)
+    logit.backward(g)
+    return pred.view(shape), loss
+
+
 class Trainer:
     def __init__(self, model, loss_fn, optimizer):
         self.model, self.loss_fn, self.optimizer = model, loss_fn, optimizer
@@ -49,9 +74,15 @@ class Trainer:
     def train_loop(self, *args, train_rating):
         self.model.train()
         self.optimizer.zero_grad()
-        self.predictions_train = self._forward(args, "train_loop")
-        self.train_loss = self.loss_fn(self.predictions_train, train_rating)
-        self.train_loss.backward()
+        if len(args) not in (1, 2):
+            raise ValueError("Invalid number of arguments provided to train_loop")
+        fused = fused_bce_step(self.model, self.loss_fn, args, train_rating)
+        if fused is not None:
+            self.predictions_train, self.train_loss = fused
+        else:
+            self.predictions_train = self._forward(args, "train_loop")
+            self.train_loss = self.loss_fn(self.predictions_train, train_rating)
+            self.train_loss.backward()
         self.optimizer.step()
         self.train_rating = train_rating
         self._steps += 1

@@ -311,3 +311,36 @@ def test_ffm_second_forward_before_step_keeps_its_stash():
         opt.step()
         res.append(m.weight.detach().clone())
     assert torch.equal(res[0], res[1])
+
+
+@pytest.mark.parametrize("kind", ["fm", "ffm", "mf"])
+def test_trainer_fused_sigmoid_bce_matches_generic_path(kind, monkeypatch):
+    """Trainer.train_loop with nn.BCELoss on a model that exposes train_logit runs sigmoid + loss + both backward passes as
+    rs_sigmoid_bce; the generic autograd path (RS_FUSED_BCE=0) must give the same predictions, loss and updated rows."""
+    from deeplearningrecommendationsystem_b200.nfield import FieldFFM, FieldFM, FieldMF
+    from deeplearningrecommendationsystem_b200.optim import FusedRowOptimizer
+    from deeplearningrecommendationsystem_b200.trainer import Trainer
+    g = torch.Generator().manual_seed(12)
+    B = 900
+    out = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("RS_FUSED_BCE", fused)
+        if kind == "mf":
+            m = FieldMF(300, 500, 16, seed=4, device="cuda")
+            ins = (torch.randint(0, 300, (B,), generator=torch.Generator().manual_seed(1)).cuda(),
+                   torch.randint(0, 500, (B,), generator=torch.Generator().manual_seed(2)).cuda())
+            y = (torch.rand(B, generator=torch.Generator().manual_seed(3)) < 0.3).float().cuda()
+            opt = FusedRowOptimizer(m, None, lr=0.3)
+        else:
+            m = (FieldFM if kind == "fm" else FieldFFM)(CARDS, 8, seed=4, device="cuda")
+            ins = (torch.stack([torch.randint(0, c, (B,), generator=torch.Generator().manual_seed(c)) for c in CARDS], dim=1).cuda(),)
+            y = (torch.rand(B, 1, generator=torch.Generator().manual_seed(3)) < 0.3).float().cuda()
+            opt = FusedRowOptimizer(m, torch.optim.SGD([m.bias], lr=0.3), lr=0.3)
+        tr = Trainer(m, torch.nn.BCELoss(), opt)
+        for _ in range(2):
+            tr.train_loop(*ins, train_rating=y)
+        assert tr.predictions_train.shape == y.shape
+        out[fused] = (tr.predictions_train.detach().cpu().numpy(), float(tr.train_loss), m.weight.detach().cpu().numpy(),
+                      m.bias.detach().cpu().numpy())
+    for a, b in zip(out["1"], out["0"]):
+        np.testing.assert_allclose(a, b, rtol=2e-6, atol=1e-7)
