@@ -40,3 +40,18 @@ def catalogue_frame(g, num_users, num_items, shuffle=True):
     df["user_id"] = df["user_id"].astype(np.int64)
     df["item_id"] = df["item_id"].astype(np.int64)
     return df
+
+
+def feature_matrix_fast(g, B, nu, ni):
+    """vectorised feature_matrix for large B (same column layout; n distinct random genres per row)"""
+    x = torch.zeros(B, 45)
+    x[:, 0] = torch.randint(0, nu, (B,), generator=g).float()
+    x[:, 1] = torch.randint(0, ni, (B,), generator=g).float()
+    x[:, 2] = torch.rand(B, generator=g)
+    r = torch.arange(B)
+    x[r, 3 + torch.randint(0, 2, (B,), generator=g)] = 1.0
+    x[r, 5 + torch.randint(0, 21, (B,), generator=g)] = 1.0
+    n_genre = torch.randint(0, 7, (B, 1), generator=g)
+    order = torch.rand(B, 19, generator=g).argsort(dim=1)
+    x[:, 26:] = (order < n_genre).float()
+    return x

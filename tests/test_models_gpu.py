@@ -209,3 +209,38 @@ def test_din_attention_tc_equals_fused(pool):
         else:
             assert float((a - b).norm()) <= 1e-4 * float(b.norm()) + tol, k
     assert float(res["tc"][-1].abs().max()) < 1e-4 and float(res["fused"][-1].abs().max()) < 1e-4
+
+
+def test_c1_shape_deepfm_matches_oracle():
+    """BASELINE.json configs[0] at its own shape (scripts/deepfm.py:52-55): DeepFM(943, 1682, [512, 256, 128, 1], 128) on one
+    full batch of 87 909 ML-100k-shaped rows, dense Adam(1e-3, weight_decay=1e-5) through Trainer.train_loop.  Predictions,
+    loss and every gradient against the CPU oracle (oracle/ml100k.py, pinned to the reference's golden outputs at the
+    small shape); then the second step's loss, which only agrees if the first Adam step did.
+    Bar: 1e-5 relative; gradients relative to the largest entry of their tensor (a full-batch sum of 87 909 terms)."""
+    from helpers import feature_matrix_fast
+    from deeplearningrecommendationsystem_b200 import model as M
+    from deeplearningrecommendationsystem_b200.trainer import Trainer
+    from oracle import optim as oo
+    g = torch.Generator().manual_seed(7)
+    B = 87909
+    x = feature_matrix_fast(g, B, 943, 1682)
+    y = (torch.rand(B, 1, generator=g) < 0.3).float()
+    torch.manual_seed(0)
+    m = M.DeepFM(943, 1682, [512, 256, 128, 1], 128)
+    sd0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    pred, loss, grads = ml100k.loss_and_grads("deepfm", sd0, [x], y)
+    m = m.cuda()
+    tr = Trainer(m, torch.nn.BCELoss(), torch.optim.Adam(m.parameters(), lr=1e-3, weight_decay=1e-5))
+    tr.train_loop(x.cuda(), train_rating=y.cuda())
+    close(tr.predictions_train, pred.numpy(), 1e-6)
+    np.testing.assert_allclose(tr.train_loss.item(), loss.item(), rtol=RTOL)
+    for k, v in m.named_parameters():
+        want = grads[k].numpy()
+        np.testing.assert_allclose(v.grad.cpu().numpy(), want, rtol=RTOL, atol=RTOL * float(np.abs(want).max()) + 1e-9, err_msg=k)
+    # oracle Adam step (torch.optim.Adam single-tensor arithmetic, oracle/optim.adam_dense), then the second forward
+    sd1 = {}
+    for k, p in sd0.items():
+        sd1[k] = oo.adam_dense(p, grads[k], torch.zeros_like(p), torch.zeros_like(p), 1, lr=1e-3, wd=1e-5)[0]
+    _, loss1, _ = ml100k.loss_and_grads("deepfm", sd1, [x], y)
+    tr.train_loop(x.cuda(), train_rating=y.cuda())
+    np.testing.assert_allclose(tr.train_loss.item(), loss1.item(), rtol=RTOL)
