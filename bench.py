@@ -442,8 +442,12 @@ def build_c2(cards, dev, world, exchange=None, fabric=None):
     sharded = world > 1 or exchange is not None or os.environ.get("RS_BENCH_FORCE_SHARDED") == "1"   # world 1: same kernels, local "peers"
     if sharded and exchange is None:
         from deeplearningrecommendationsystem_b200 import dist as rsdist
-        from deeplearningrecommendationsystem_b200.nfield import direct_ranges
-        direct = direct_ranges(cards) if os.environ.get("RS_DIRECT", "1") == "1" else ()
+        from deeplearningrecommendationsystem_b200.nfield import REPLICATE_ROWS, direct_ranges
+        # default placement: tables under REPLICATE_ROWS rows are replicated, the others row-sharded (nfield._FieldModel);
+        # RS_REPLICATE_ROWS=0 row-shards every table (then the largest fields are read directly by the FFM forward)
+        rep = int(os.environ.get("RS_REPLICATE_ROWS", REPLICATE_ROWS))
+        hybrid = any(c < rep for c in cards) and any(c >= rep for c in cards)
+        direct = direct_ranges(cards) if (os.environ.get("RS_DIRECT", "1") == "1" and not hybrid) else ()
         exchange = rsdist.DeviceRowExchange(fabric, direct=direct) if os.environ.get("RS_PEER_EXCHANGE", "1") == "1" else None
     kw = dict(fused=True, device=dev, sharded=sharded, exchange=exchange)
     fm = FieldFM(cards, D, seed=1, **kw)
@@ -517,27 +521,32 @@ def verify_sharded(dev, world, rank):
     dist.all_gather(all_ids, ids)
     dist.all_gather(all_y, y)
     out = {}
-    for name in ("device", "nccl"):
-        progress(f"  verify: {name} exchange")
-        os.environ["RS_PEER_EXCHANGE"] = "1" if name == "device" else "0"
-        ex = rsdist.DeviceRowExchange() if name == "device" else None
+    label = {"hybrid": "small tables (< 4096 rows) replicated + rs_replica_sgd, large ones row-sharded over dist.DeviceRowExchange (the bench's placement)",
+             "device": "every table row-sharded, dist.DeviceRowExchange (peer-memory kernels, no host sync)",
+             "nccl": "every table row-sharded, dist.RowExchange (NCCL all_to_all_single)"}
+    for name in ("hybrid", "device", "nccl"):
+        progress(f"  verify: {name}")
+        os.environ["RS_PEER_EXCHANGE"] = "0" if name == "nccl" else "1"
+        ex = rsdist.DeviceRowExchange() if name != "nccl" else None
         errs = []
         for cls, width in ((FieldFFM, F * D), (FieldFM, D)):
             glob = _xavier_concat(cards, width, D, dev, seed=5)                  # same bits on every rank (same device type, same seed)
-            m = cls(cards, D, seed=5, device=dev, sharded=True, exchange=ex)
+            m = cls(cards, D, seed=5, device=dev, sharded=True, exchange=ex, replicate_below=4096 if name == "hybrid" else 0)
+            assert m.hybrid == (name == "hybrid")
             m.load_global(glob)
             tr = Trainer(m, torch.nn.BCELoss(), FusedRowOptimizer(m, torch.optim.SGD([m.bias], lr=lr), lr=lr))
             preds = []
             for _ in range(steps):
                 tr.train_loop(ids, train_rating=y)
                 preds.append(tr.predictions_train.detach().clone())
-            rows = [(m.total_rows - r + world - 1) // world for r in range(world)]
+            sh_total = m.big_total
+            rows = [(sh_total - r + world - 1) // world for r in range(world)]
             pad = torch.zeros(max(rows), width, device=dev)
             pad[: m.weight.shape[0]] = m.weight.data
             got = [torch.empty_like(pad) for _ in range(world)]
             dist.all_gather(got, pad)
             if rank == 0:
-                full = rsdist.unshard_rows([got[r][: rows[r]] for r in range(world)])
+                full = m.assemble_global([got[r][: rows[r]] for r in range(world)])
                 s = cls(cards, D, seed=5, device=dev)
                 s.weight.data.copy_(glob)
                 ts = Trainer(s, torch.nn.BCELoss(), FusedRowOptimizer(s, torch.optim.SGD([s.bias], lr=lr), lr=lr, data_parallel=False))
@@ -554,8 +563,7 @@ def verify_sharded(dev, world, rank):
             torch.cuda.empty_cache()
         ops.check_status(dev)
         if rank == 0:
-            out[name] = {"max_rel_err": max(errs), "exchange": "dist.DeviceRowExchange (peer-memory kernels, no host sync)" if name == "device"
-                         else "dist.RowExchange (NCCL all_to_all_single)", "ok": max(errs) <= 1e-4}
+            out[name] = {"max_rel_err": max(errs), "placement": label[name], "ok": max(errs) <= 1e-4}
     os.environ["RS_PEER_EXCHANGE"] = "1"
     if rank == 0:
         out["what"] = (f"{world} ranks x B={B}, 26 fields capped at 2^13 rows, {steps} SGD steps of FFM and FM: predictions (relative) and final "
@@ -591,9 +599,10 @@ def run_c2(args):
                       "l2": "8 distinct id batches cycled; per-step traffic (>8 GB) far exceeds the 126 MB L2",
                       "unique_rows_per_batch": n_uniq})
     if world > 1:
-        line["config"]["parallelism"] = (f"dp{world}: batch split, tables row-sharded (row r on rank r % {world}); per step the DISTINCT rows of the "
-                                         "batch are exchanged by this package's kernels over NVLink peer memory (rows: owner's TMA gather -> "
-                                         "requester's block; gradients: requester's segment-reduce -> owner's buffer), no NCCL and no host sync in the step")
+        line["config"]["parallelism"] = (f"dp{world}: batch split; tables under 65536 rows replicated (per-rank dense gradient, reduced + SGD + "
+                                         f"re-broadcast by rs_replica_sgd over NVLink peer memory), the larger ones row-sharded (row r on rank "
+                                         f"r % {world}): the FFM forward reads their rows straight from the owners' shards, gradients go "
+                                         "requester's segment-reduce -> owner's buffer; no NCCL and no host sync in the step")
     tag = f"{'light' if args.light else 'full'}-{args.dist}"
     roofs = c2_rooflines(legs, B, n_uniq, tag)
     line["roofline"] = roofs.get("segment_update")

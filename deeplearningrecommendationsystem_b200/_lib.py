@@ -47,7 +47,8 @@ class rs_shard(C.Structure):
 
 
 class rs_peer_tables(C.Structure):
-    _fields_ = [("world", C.c_int32), ("direct_mask", C.c_uint64), ("shard", C.c_void_p * RS_MAX_RANKS), ("total_rows", C.c_int64)]
+    _fields_ = [("world", C.c_int32), ("direct_mask", C.c_uint64), ("shard", C.c_void_p * RS_MAX_RANKS), ("total_rows", C.c_int64),
+                ("split_mask", C.c_uint64), ("stash_split", C.c_void_p)]
 
 
 class rs_fields_io(C.Structure):
@@ -116,6 +117,7 @@ SIGNATURES = {
     "rs_ffm_bwd_ws_bytes": [_L, _L, _I, _PP(_Z)],
     "rs_ffm_fwd_train": [_PP(rs_tables), _P, _L, _I, C.c_uint64, _P, _P, _P, _P],
     "rs_ffm_bwd_update": [_PP(rs_tables), _P, _L, _I, C.c_uint64, _P, _PP(rs_segments), _PP(rs_update), _P, _Z, _P, _P],
+    "rs_replica_sgd": [_PP(_P), _PP(_P), _L, _I, _I, _F, _F, _P],
     "rs_adam_dense": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P],
     "rs_xembed_fwd": [_PP(rs_xslots), _P, _L, _P, _P, _P],
     "rs_xembed_bag_bwd": [_PP(rs_xslots), _P, _P, _L, _PP(_P), _P, _Z, _P],

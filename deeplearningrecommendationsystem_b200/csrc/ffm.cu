@@ -39,6 +39,10 @@ struct FfmParams {
   int64_t total_rows;
   // "cold-slice" stash (rs_ffm_fwd_train): mini[b][i][c][:] = v_{cold_c, i}(b) for the nC fields flagged cold
   float *mini;
+  // split stash (rs_peer_tables.stash_split): rows of the fields in split_mask go to stash2, the others to stash
+  float *stash2;
+  int F1, F2;                            // number of fields whose rows go to stash / stash2
+  unsigned char st_slot[RS_MAX_FIELDS];  // position of field i inside its stash; bit 7 set = stash2
   int hint;   // use the L2 eviction hints (RS_FFM_L2HINT=0 turns them off)
   int nC;
   signed char cidx[RS_MAX_FIELDS];   // index of field j among the cold fields, -1 = not cold
@@ -51,10 +55,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) ffm_fwd_kernel(const __grid_const
   __shared__ const float *s_base[RS_MAX_FIELDS];
   __shared__ int64_t s_rows[RS_MAX_FIELDS];
   __shared__ int s_cidx[RS_MAX_FIELDS];
+  __shared__ int s_slot[RS_MAX_FIELDS];
   for (int i = threadIdx.x; i < P.F; i += blockDim.x) {
     s_base[i] = P.base[i];
     s_rows[i] = P.rows[i];
     s_cidx[i] = P.cidx[i];
+    s_slot[i] = P.st_slot[i];
   }
   float4 *tiles = reinterpret_cast<float4 *>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -126,6 +132,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) ffm_fwd_kernel(const __grid_const
         const float4 *Ti = T + (size_t)i * P.pitchv;
         const float4 *Tcol = T + i * P.dv;  // + j*pitchv + d4 -> v_{j,i}
         float4 *out_i = st_out ? st_out + (size_t)i * P.rowv : nullptr;
+        if (P.stash2) {   // split stash: (B, F1, W) and (B, F2, W)
+          const int sl = s_slot[i];
+          out_i = (sl & 128) ? reinterpret_cast<float4 *>(P.stash2) + (b * P.F2 + (sl & 127)) * (int64_t)P.rowv
+                             : (P.stash ? reinterpret_cast<float4 *>(P.stash) + (b * P.F1 + sl) * (int64_t)P.rowv : nullptr);
+        }
         float4 *mini_i = mini_b ? mini_b + (size_t)i * P.nC * P.dv : nullptr;
         for (int w0 = lane; w0 < P.rowv; w0 += 128) {
           float4 tr[4], own[4];
@@ -255,7 +266,7 @@ static int ffm_fwd_launch(const rs_tables *T, const int64_t *ids, int64_t B, int
   if (B == 0) return RS_OK;
   FfmParams P = {};
   P.world = 1;
-  if (PT && PT->direct_mask) {
+  if (PT && (PT->direct_mask || PT->stash_split)) {
     RS_CHECK_ARG(PT->world >= 1 && PT->world <= RS_MAX_RANKS && PT->total_rows > 0, RS_E_ARG, "rs_ffm_fwd_peer: bad world / total_rows");
     P.world = PT->world;
     P.direct_mask = PT->direct_mask;
@@ -274,6 +285,16 @@ static int ffm_fwd_launch(const rs_tables *T, const int64_t *ids, int64_t B, int
   P.ids = ids;
   P.cross = cross;
   P.stash = stash;
+  P.stash2 = nullptr;
+  P.F1 = F, P.F2 = 0;
+  if (PT && PT->stash_split) {
+    P.stash2 = PT->stash_split;
+    P.F1 = P.F2 = 0;
+    for (int f = 0; f < F; ++f) {
+      if ((PT->split_mask >> f) & 1ull) P.st_slot[f] = (unsigned char)(128 | P.F2++); else P.st_slot[f] = (unsigned char)P.F1++;
+    }
+    RS_CHECK_ARG(P.F2 > 0 && P.F2 < 128 && (P.F1 == 0 || stash), RS_E_ARG, "rs_ffm_fwd_peer: bad stash split");
+  }
   if (F < 64) cold_mask &= (1ull << F) - 1ull;
   P.mini = cold_mask ? mini : nullptr;
   {

@@ -261,7 +261,57 @@ __global__ void __launch_bounds__(SERVE_WARPS * 32, 1) shard_serve_tma_kernel(co
   if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// ------------------------------------------------------------------ replicated small tables: all-reduce fused with the SGD step
+// Every rank holds the same copy `w` of the small tables and its own dense gradient `g` (both in symmetric memory).  Rank r
+// owns the r-th slice of the elements: it adds the N gradient slices in rank order (peer loads over NVLink), applies the
+// SGD step to its own copy's values and stores the new values into EVERY rank's copy (peer stores).  One kernel is the
+// reduce-scatter, the optimizer step and the all-gather; each element is computed once, so the replicas stay bit-identical.
+struct Replicas {
+  float *w[RS_MAX_RANKS];
+  const float *g[RS_MAX_RANKS];
+};
+
+__global__ void __launch_bounds__(256) replica_sgd_kernel(const __grid_constant__ Replicas R, int world, int rank, int64_t lo4, int64_t hi4,
+                                                         float lr, float wd) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = lo4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi4; i += stride) {
+    float4 acc = rs::f4_zero();
+    for (int r0 = 0; r0 < world; r0 += 8) {      // eight peer loads in flight, added in rank order
+      float4 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = (r0 + k < world) ? rs::ldg_f4(R.g[r0 + k] + i * 4) : rs::f4_zero();
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (r0 + k < world) acc = rs::f4_add(acc, v[k]);
+    }
+    const float4 w = rs::ldg_f4(R.w[rank] + i * 4);
+    const float4 n = make_float4(w.x - lr * (acc.x + wd * w.x), w.y - lr * (acc.y + wd * w.y), w.z - lr * (acc.z + wd * w.z),
+                                 w.w - lr * (acc.w + wd * w.w));
+    for (int r = 0; r < world; ++r) rs::stg_f4(R.w[(rank + r) % world] + i * 4, n);
+  }
+}
+
 }  // namespace
+
+RS_API int rs_replica_sgd(float *const *w, const float *const *g, int64_t numel, int32_t world, int32_t rank, float lr, float wd,
+                          void *stream) {
+  RS_CHECK_ARG(w && g && world >= 1 && world <= RS_MAX_RANKS && rank >= 0 && rank < world, RS_E_ARG, "rs_replica_sgd: bad argument");
+  RS_CHECK_ARG(numel >= 0 && numel % 4 == 0, RS_E_SHAPE, "rs_replica_sgd: numel must be a multiple of 4");
+  Replicas R;
+  for (int k = 0; k < world; ++k) {
+    RS_CHECK_ARG(w[k] && g[k], RS_E_ARG, "rs_replica_sgd: null buffer for rank %d", k);
+    R.w[k] = w[k];
+    R.g[k] = g[k];
+  }
+  const int64_t n4 = numel / 4, per = (n4 + world - 1) / world;
+  const int64_t lo4 = per * rank < n4 ? per * rank : n4, hi4 = lo4 + per < n4 ? lo4 + per : n4;
+  if (hi4 <= lo4) return RS_OK;
+  int64_t blocks = (hi4 - lo4 + 255) / 256;
+  const int cap = rs::num_sms() * 8;
+  replica_sgd_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(R, world, rank, lo4, hi4, lr, wd);
+  RS_CHECK_LAUNCH();
+  return RS_OK;
+}
 
 RS_API int rs_shard_post(const rs_shard *S, const rs_segments *seg, int64_t n, int32_t *status, void *stream) {
   ShardDev D;

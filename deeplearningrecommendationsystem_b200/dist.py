@@ -318,6 +318,7 @@ class DevPlan:
     def __init__(self, gen, n, segs, local_ids, recv_local, m_total):
         self.gen, self.n, self.segs, self.local_ids, self.recv_local, self.m_total = gen, n, segs, local_ids, recv_local, m_total
         self.osegs, self.osegs_ready = None, None
+        self.ready = None            # event: the plan was built on a side stream (plan_for(on_side=True))
 
     @property
     def n_uniq(self):             # capacity stand-in: callers only use it to size things
@@ -351,6 +352,7 @@ class DeviceRowExchange:
         self._bufs = {}
         self._gen, self._memo = 0, None
         self._side, self._unjoined = None, None
+        self._derived = None
 
     def local_rows(self, total_rows):
         return (total_rows - self.rank + self.world - 1) // self.world
@@ -377,30 +379,73 @@ class DeviceRowExchange:
         self.fabric.barrier()                      # every rank's buffers exist (and are zeroed) before anyone writes to them
         return self._ctl
 
-    def _buffers(self, table, device):
+    def _buffers(self, table, device, need_block=True):
         """block / grads buffers of one table (keyed by the table, not just its width: the fetched block must survive
-        until that table's backward, and a model may shard two tables of equal width)"""
+        until that table's backward, and a model may shard two tables of equal width).  need_block=False: the table's rows
+        are never fetched (its forward reads the shards directly), only the gradient buffer is needed."""
         width, key = table.shape[1], (table.shape[1], table.data_ptr())
         ent = self._bufs.get(key)
         if ent is None:
             c = self._ctl
-            block, block_ptrs = self.fabric.alloc((c["cap_req"], width), torch.float32, device)
+            block, block_ptrs = self.fabric.alloc((c["cap_req"], width), torch.float32, device) if need_block else (None, None)
             grads, grad_ptrs = self.fabric.alloc((c["cap_recv"], width), torch.float32, device)
             ent = self._bufs[key] = {"block": block, "block_ptrs": block_ptrs, "grads": grads, "grad_ptrs": grad_ptrs}
+            self.fabric.barrier()
+        elif need_block and ent["block"] is None:
+            ent["block"], ent["block_ptrs"] = self.fabric.alloc((self._ctl["cap_req"], width), torch.float32, device)
             self.fabric.barrier()
         return ent
 
     # ---- forward
-    def plan_for(self, ids, offsets, total_rows):
+    def derived(self, ids, name, make):
+        """A tensor derived from the batch's id matrix (e.g. the columns of the row-sharded fields), built once per batch and
+        shared by every model stepping on that batch -- so that their plans and sorts are shared as well."""
+        d = self._derived
+        if d is None or d[0] is not ids or d[1] != ids._version:
+            d = self._derived = (ids, ids._version, {})
+        if name not in d[2]:
+            d[2][name] = make()
+        return d[2][name]
+
+    def plan_for(self, ids, offsets, total_rows, on_side=False, prefetch_rows=None, wait=True):
         """ids (B, F) local ids, offsets: HOST list of the F row offsets.  Memoised on the identity of `ids` while it is
-        the exchange's latest plan (the FM and the FFM model of one batch share it)."""
+        the exchange's latest plan (the FM and the FFM model of one batch share it).
+        on_side: build the plan on the exchange's side stream (the caller's forward does not need it: it overlaps);
+        prefetch_rows: also run the owner-side sort there (training); wait=False: do not order the current stream after a
+        plan that is still being built -- the caller does that later with wait_plan()."""
         m = self._memo
         if m is not None and m[0] is ids and m[1] == ids._version and m[2] == total_rows and m[3] == tuple(offsets):
-            return m[4]
-        with _phase("exchange_plan"):
-            plan = self._plan(ids, offsets, total_rows)
+            plan = m[4]
+            if wait:
+                self.wait_plan(plan)
+            if prefetch_rows is not None and plan.osegs is None:
+                self.wait_plan(plan)
+                self.prefetch_owner_segments(plan, prefetch_rows)
+            return plan
+        cur = torch.cuda.current_stream(ids.device)
+        if on_side:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=ids.device)
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                with _phase("exchange_plan"):
+                    plan = self._plan(ids, offsets, total_rows)
+                if prefetch_rows is not None:
+                    self.prefetch_owner_segments(plan, prefetch_rows)
+                plan.ready = torch.cuda.Event()
+                plan.ready.record(self._side)
+        else:
+            with _phase("exchange_plan"):
+                plan = self._plan(ids, offsets, total_rows)
+            if prefetch_rows is not None:
+                self.prefetch_owner_segments(plan, prefetch_rows)
         self._memo = (ids, ids._version, total_rows, tuple(offsets), plan)
         return plan
+
+    def wait_plan(self, plan):
+        """order the current stream after a plan built on the side stream"""
+        if plan is not None and plan.ready is not None:
+            torch.cuda.current_stream().wait_event(plan.ready)
 
     def _plan(self, ids, offsets, total_rows):
         from . import ops
@@ -458,7 +503,6 @@ class DeviceRowExchange:
             torch.cuda.current_stream().wait_event(plan.osegs_ready)
             if self._unjoined is plan.osegs_ready:
                 self._unjoined = None
-            plan.osegs_ready = None
         return ops.attach_partial(plan.osegs, width)
 
     def grad_routes(self, plan, table, device):
@@ -466,7 +510,7 @@ class DeviceRowExchange:
         o's `grads` buffer at the offset o announced during rs_shard_collect."""
         from . import _lib, ops
         self._check(plan)
-        c, ent = self._ctl, self._bufs[(table.shape[1], table.data_ptr())]
+        c, ent = self._ctl, self._buffers(table, device, need_block=False)
         base = c["ctl"].data_ptr()
         return ops.make_routes(None, ent["grad_ptrs"], None, dyn_start=base + 8 * _lib.RS_CTL_SEND_START,
                                dyn_row0=base + 8 * _lib.RS_CTL_G0_IN, cap_rows=c["cap_recv"], self_index=self.rank), ent

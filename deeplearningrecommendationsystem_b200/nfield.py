@@ -38,6 +38,7 @@ def _xavier_concat(cards, width, row_dim, device=None, seed=None):
     return out
 
 
+REPLICATE_ROWS = 1 << 16   # multi-GPU: fields with fewer rows are REPLICATED on every rank, the others row-sharded (see _FieldModel)
 COLD_ROWS = 1 << 16        # stash-free FFM step: fields with at least this many rows are "cold" (see FieldFFM.bind_row_optimizer)
 DIRECT_ROWS = 1 << 20      # fields with at least this many rows are read from the peers' shards by the FFM forward itself
 
@@ -117,8 +118,10 @@ class _EmbedFn(torch.autograd.Function):
 
 
 class _FieldModel(nn.Module):
+    supports_hybrid = False
+
     def __init__(self, cardinalities, width, row_dim, fused=True, seed=None, device=None, sharded=False, group=None,
-                 fabric=None, exchange=None, direct_threshold=0):
+                 fabric=None, exchange=None, direct_threshold=0, replicate_below=None):
         super().__init__()
         self.cards = [int(c) for c in cardinalities]
         self.F, self.width, self.fused = len(self.cards), width, fused
@@ -126,7 +129,7 @@ class _FieldModel(nn.Module):
         for c in self.cards:
             offs.append(offs[-1] + c)
         self.offsets_host, self.total_rows = offs[:-1], offs[-1]
-        self.sharded, self.exchange = sharded, None
+        self.sharded, self.exchange, self.hybrid = sharded, None, False
         if sharded:
             if not fused:
                 raise ValueError("sharded tables are updated by the fused row optimizer (fused=True)")
@@ -136,19 +139,35 @@ class _FieldModel(nn.Module):
             # RS_PEER_EXCHANGE=0 selects the NCCL all-to-all formulation (dist.RowExchange, host-synchronised split sizes),
             # which is also what the gloo CPU tests drive.  `exchange` may also be passed in (shared by several models).
             import os
+            on_cuda = torch.device(device if device is not None else "cpu").type == "cuda"
+            rep = int(os.environ.get("RS_REPLICATE_ROWS", REPLICATE_ROWS)) if replicate_below is None else int(replicate_below)
+            small = [f for f, c in enumerate(self.cards) if c < rep]
+            big = [f for f, c in enumerate(self.cards) if c >= rep]
+            peer_default = os.environ.get("RS_PEER_EXCHANGE", "1") == "1"
+            # HYBRID placement: small tables are replicated (dense gradient reduced over the ranks by
+            # rs_replica_sgd), only the large ones are row-sharded.  Needs the device-side exchange.
+            self.hybrid = bool(self.supports_hybrid and small and big and on_cuda and
+                               (getattr(exchange, "device_plan", False) if exchange is not None else peer_default))
             if exchange is not None:
                 self.exchange = exchange
-            elif os.environ.get("RS_PEER_EXCHANGE", "1") == "1":
-                direct = direct_ranges(self.cards, direct_threshold) if os.environ.get("RS_DIRECT", "1") == "1" else ()
+            elif peer_default:
+                direct = direct_ranges(self.cards, direct_threshold) if (os.environ.get("RS_DIRECT", "1") == "1" and not self.hybrid) else ()
                 self.exchange = rsdist.DeviceRowExchange(fabric, direct=direct)
             else:
                 self.exchange = rsdist.RowExchange(rsdist.cuda_prims(), group)
-            rows = self.exchange.local_rows(self.total_rows)
-            std = math.sqrt(2.0 / (self.total_rows / self.F + row_dim))
+            if self.hybrid and getattr(self.exchange, "direct", ()):
+                raise ValueError("hybrid placement (replicated small tables) takes an exchange without direct ranges")
+            self.small_fields, self.big_fields = (small, big) if self.hybrid else ([], list(range(self.F)))
+            sh_cards = [self.cards[f] for f in self.big_fields]          # the row-sharded sub-table
+            sh_total = sum(sh_cards)
+            self.big_cards, self.big_total = sh_cards, sh_total
+            self.big_offsets_host = [sum(sh_cards[:k]) for k in range(len(sh_cards))]
+            rows = self.exchange.local_rows(sh_total)
+            std = math.sqrt(2.0 / (sh_total / len(sh_cards) + row_dim))
             self.shard_ptrs = None
-            if getattr(self.exchange, "device_plan", False) and torch.device(device if device is not None else "cpu").type == "cuda":
+            if getattr(self.exchange, "device_plan", False) and on_cuda:
                 # the shard lives in symmetric (peer-mapped) memory, so that kernels of other ranks can read its rows directly
-                R = (self.total_rows + self.exchange.world - 1) // self.exchange.world
+                R = (sh_total + self.exchange.world - 1) // self.exchange.world
                 full, self.shard_ptrs = self.exchange.fabric.alloc((R, width), torch.float32, torch.device(device))
                 w = full[:rows]
             else:
@@ -156,6 +175,23 @@ class _FieldModel(nn.Module):
             g = torch.Generator(device=w.device).manual_seed((seed or 0) * 1000 + self.exchange.rank)
             self.weight = nn.Parameter(w.normal_(0.0, std, generator=g), requires_grad=False)
             self.register_buffer("offsets_dev", torch.tensor(self.offsets_host, dtype=torch.int64, device=device), persistent=False)
+            if self.hybrid:
+                dev, fab = torch.device(device), self.exchange.fabric
+                self.small_cards = [self.cards[f] for f in small]
+                self.small_total = sum(self.small_cards)
+                self.small_offsets_host = [sum(self.small_cards[:k]) for k in range(len(small))]
+                ws, self.small_ptrs = fab.alloc((self.small_total, width), torch.float32, dev)
+                ws.copy_(_xavier_concat(self.small_cards, width, row_dim, dev, (seed or 0) + 7919))     # same bits on every rank
+                self.weight_small = nn.Parameter(ws, requires_grad=False)
+                self.gsmall, self.gsmall_ptrs = fab.alloc((self.small_total, width), torch.float32, dev)
+                self._big_cols_t = torch.tensor(big, dtype=torch.int64, device=dev)
+                self._small_cols_t = torch.tensor(small, dtype=torch.int64, device=dev)
+                add = [0] * self.F
+                for k, f in enumerate(big):
+                    add[f] = self.big_offsets_host[k]
+                self._mix_add = torch.tensor(add, dtype=torch.int64, device=dev)
+                self._big_mask = sum(1 << f for f in big)
+                fab.barrier()
         else:
             self.weight = nn.Parameter(_xavier_concat(self.cards, width, row_dim, device, seed), requires_grad=not fused)
         self.bias = nn.Parameter(torch.zeros(1, device=device))
@@ -173,10 +209,33 @@ class _FieldModel(nn.Module):
             _FieldModel._offset_cache[key] = t
         return t
 
+    def _field_rows(self, table, fields):
+        return torch.cat([table[self.offsets_host[f]:self.offsets_host[f] + self.cards[f]] for f in fields])
+
     def load_global(self, global_weight):
-        """sharded mode: take this rank's rows (r % N == rank) of a full (total_rows, W) table."""
+        """sharded mode: take this rank's share of a full (total_rows, W) table -- the rows r % N == rank of the row-sharded
+        fields (all of them unless the placement is hybrid) and a full copy of the replicated small fields."""
         from . import dist as rsdist
-        self.weight.data.copy_(rsdist.shard_rows(global_weight.to(self.weight.device), self.exchange.rank, self.exchange.world))
+        gw = global_weight.to(self.weight.device)
+        big = self._field_rows(gw, self.big_fields) if self.hybrid else gw
+        self.weight.data.copy_(rsdist.shard_rows(big, self.exchange.rank, self.exchange.world))
+        if self.hybrid:
+            self.weight_small.data.copy_(self._field_rows(gw, self.small_fields))
+
+    def assemble_global(self, shards):
+        """inverse of load_global (tests / verification): list of every rank's weight shard -> the full (total_rows, W) table
+        (the replicated fields are taken from this rank's copy)."""
+        from . import dist as rsdist
+        big = rsdist.unshard_rows(list(shards))
+        if not self.hybrid:
+            return big
+        out = torch.empty(self.total_rows, self.width, dtype=big.dtype, device=big.device)
+        for k, f in enumerate(self.big_fields):
+            out[self.offsets_host[f]:self.offsets_host[f] + self.cards[f]] = big[self.big_offsets_host[k]:self.big_offsets_host[k] + self.cards[f]]
+        for k, f in enumerate(self.small_fields):
+            out[self.offsets_host[f]:self.offsets_host[f] + self.cards[f]] = \
+                self.weight_small.data[self.small_offsets_host[k]:self.small_offsets_host[k] + self.cards[f]].to(big.device)
+        return out
 
     def tables(self):
         return ops.tables_from_concat(self.weight.data, self.offsets_host, self.cards)
@@ -215,6 +274,9 @@ class _FieldModel(nn.Module):
                     continue
                 self._row_update(opt, segs, self.F, **src)
                 continue
+            if rec.get("hybrid"):
+                self._apply_hybrid(opt, rec)
+                continue
             # row-sharded: reduce the batch's gradients per fetched row, send them to the owners, update there
             plan, ex = rec["plan"], self.exchange
             if plan.segs is not None:      # the plan already sorted these lookups by row: no second sort
@@ -243,6 +305,64 @@ class _FieldModel(nn.Module):
                 osegs = ops.dedup_sort(plan.recv_local, 1, None, self.weight.shape[0], max_width=self.width)
                 self._row_update(opt, osegs, 1, dense=recv)
         self._pending.clear()
+
+    # ---- hybrid placement: replicated small tables + row-sharded large ones
+    def _hybrid_tables(self, block):
+        """rs_tables of the F fields: small fields -> this rank's replica, large fields -> `block` (rows fetched by the
+        exchange; None when the forward kernel reads them from the owners' shards itself)."""
+        T = ops._lib.rs_tables()
+        T.num_fields, T.width = self.F, self.width
+        small_base = self.weight_small.data_ptr()
+        for k, f in enumerate(self.small_fields):
+            T.base[f] = small_base + self.small_offsets_host[k] * self.width * 4
+            T.rows[f] = self.cards[f]
+        for f in self.big_fields:
+            T.base[f] = block.data_ptr() if block is not None else self.weight.data_ptr()
+            T.rows[f] = block.shape[0] if block is not None else 1
+        return T
+
+    def _hybrid_forward(self, ids, train):
+        ex = self.exchange
+        ids_big = ex.derived(ids, "big", lambda: ids[:, self._big_cols_t].contiguous())
+        rec = {"hybrid": True}
+        plan = None
+        if train or not self.hybrid_direct:
+            # the plan (sort of the large-field lookups, request lists to the owners) is only needed before the forward if
+            # rows have to be fetched; otherwise it runs on a side stream under the forward kernel
+            plan = ex.plan_for(ids_big, self.big_offsets_host, self.big_total, on_side=self.hybrid_direct,
+                               prefetch_rows=self.weight.shape[0] if train else None, wait=not self.hybrid_direct)
+        if train:
+            ids_small = ex.derived(ids, "small", lambda: ids[:, self._small_cols_t].contiguous())
+            ops.prefetch_dedup(ids_small, len(self.small_fields), self.small_offsets_host, self.small_total)
+            rec.update(plan=plan, ids_small=ids_small)
+        cross, st_small, st_big = self._hybrid_interact(ids, plan, train)
+        rec.update(stash_small=st_small, stash_big=st_big)
+        return cross, rec
+
+    def _apply_hybrid(self, opt, rec):
+        if opt.kind != "sgd" or opt.weight_decay != 0.0:
+            raise RuntimeError("replicated small tables (hybrid placement) are updated with plain SGD, weight_decay = 0; "
+                               "build the model with replicate_below=0 to row-shard every table instead")
+        ex, W = self.exchange, self.width
+        plan = rec["plan"]
+        ex.wait_plan(plan)                       # (before this step's first barrier on this stream)
+        g = rec["g"] * (1.0 / ex.world)          # gradients are averaged over the ranks
+        Fs, Fb = len(self.small_fields), len(self.big_fields)
+        # replicated tables: this rank's batch reduced into its dense gradient (symmetric memory)
+        segs_s = ops.dedup_sort(rec["ids_small"], Fs, self.small_offsets_host, self.small_total, max_width=W)
+        self.gsmall.zero_()
+        ops.segment_update(segs_s, ops.RS_UPD_GRAD, W, Fs, stash=rec["stash_small"], scale=g, dense_grad=self.gsmall, tag="/small")
+        # row-sharded tables: reduce per distinct row, store straight into the owners' buffers
+        segs_b = ops.block_segments(plan.segs, plan.n_uniq, W)
+        routes, ent = ex.grad_routes(plan, self.weight.data, g.device)
+        ops.segment_update(segs_b, ops.RS_UPD_GRAD, W, Fb, grad_routes=routes, stash=rec["stash_big"], scale=g, tag="/push")
+        recv = ex.finish_push(plan, ent)         # barrier: pushed rows have landed, every rank's dense gradient is complete
+        ops.replica_sgd(self.small_ptrs, self.gsmall_ptrs, self.small_total * W, ex.world, ex.rank, opt.lr)
+        osegs = ex.owner_segments(plan, self.weight.shape[0], W)
+        self._row_update(opt, osegs, 1, tag="/owner", dense=recv)
+        from .dist import _phase
+        with _phase("exchange_barrier"):
+            ex.fabric.barrier()                  # replicas rewritten and gradients read before anyone's next step
 
     def _plan(self, ids, train):
         ex = self.exchange
@@ -288,7 +408,10 @@ class _FieldModel(nn.Module):
             raise ValueError(f"ids must be (B, {self.F})")
         train = torch.is_grad_enabled()
         rec = {}
-        if self.sharded:
+        if self.sharded and self.hybrid:
+            cross, rec = self._hybrid_forward(ids, train and self.fused)
+            stash = rec.get("stash_small")
+        elif self.sharded:
             plan = self._plan(ids, train and self.fused)
             direct = bool(getattr(self, "direct_fields", None))
             if direct:
@@ -330,9 +453,22 @@ class FieldFM(_FieldModel):
     def __init__(self, cardinalities, embedding_dim, fused=True, seed=None, device=None, sharded=False, group=None, **kw):
         super().__init__(cardinalities, embedding_dim, embedding_dim, fused, seed, device, sharded, group, **kw)
 
+    supports_hybrid = True
+    hybrid_direct = False        # the large-field rows are fetched into a block before the forward
+
     def _interact(self, T, ids, want_stash):
         out = ops.fields_fwd(T, ids.shape[0], ids.device, ids=ids, cross=True, stash=want_stash)
         return out["cross"], out.get("stash")
+
+    def _hybrid_interact(self, ids, plan, want_stash):
+        block = self.exchange.fetch(plan, self.weight.data)
+        mix = ids.clone()
+        mix[:, self._big_cols_t] = plan.local_ids.view(ids.shape[0], len(self.big_fields))
+        out = ops.fields_fwd(self._hybrid_tables(block), ids.shape[0], ids.device, ids=mix, cross=True, stash=want_stash)
+        if not want_stash:
+            return out["cross"], None, None
+        st = out["stash"]                                   # (B, F, D): 64-byte rows, split by a gather
+        return out["cross"], st[:, self._small_cols_t].contiguous(), st[:, self._big_cols_t].contiguous()
 
 
 class FieldFFM(_FieldModel):
@@ -356,6 +492,17 @@ class FieldFFM(_FieldModel):
             self._direct_cols = torch.tensor(self.direct_fields, dtype=torch.int64, device=dev)
             self._direct_offs = torch.tensor([self.offsets_host[f] for f in self.direct_fields], dtype=torch.int64, device=dev)
             self._direct_mask = sum(1 << f for f in self.direct_fields)
+
+    supports_hybrid = True
+    hybrid_direct = True         # the forward kernel reads the large-field rows from the owners' shards itself
+
+    def _hybrid_interact(self, ids, plan, want_stash):
+        mix = ids + self._mix_add                           # large fields: global row inside the sharded sub-table
+        peer = (self.exchange.world, self._big_mask, self.shard_ptrs, self.big_total)
+        if not want_stash:
+            cross, _ = ops.ffm_fwd(self._hybrid_tables(None), mix, self.D, want_stash=False, peer=peer)
+            return cross, None, None
+        return ops.ffm_fwd(self._hybrid_tables(None), mix, self.D, want_stash=True, peer=peer, split_mask=self._big_mask)
 
     def bind_row_optimizer(self, opt):
         """Called by FusedRowOptimizer.  RS_FFM_RECOMPUTE=1 (opt-in; plain SGD, unsharded table): the training forward

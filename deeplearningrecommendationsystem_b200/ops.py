@@ -210,30 +210,37 @@ def fields_bwd(T, B, device, ids=None, dense_in=None, g_cross=None, g_bi=None, g
     return dE
 
 
-def ffm_fwd(T, ids, D, want_stash=True, peer=None):
+def ffm_fwd(T, ids, D, want_stash=True, peer=None, split_mask=0):
     """cross (B,), stash (B, F, F*D) | None for an F-field FFM whose table rows are (F, D).
     peer=(world, direct_mask, shard_ptrs, total_rows): row-sharded tables, the fields of direct_mask are read straight from
-    the owning rank's shard over NVLink (ids of those fields are GLOBAL rows) -- rs_ffm_fwd_peer."""
+    the owning rank's shard over NVLink (ids of those fields are GLOBAL rows) -- rs_ffm_fwd_peer.
+    split_mask != 0 (with peer): returns (cross, stash_rest (B, F - k, W), stash_split (B, k, W)) -- the Jacobian rows of the
+    k fields in split_mask are written to their own tensor (the row-sharded tables), the others' (replicated tables) to
+    stash_rest."""
     ids = _i64(ids)
     _need_cuda(ids)
     F = T.num_fields
     B = ids.numel() // F
     cross = torch.empty(B, dtype=torch.float32, device=ids.device)
-    stash = torch.empty(B, F, F * D, dtype=torch.float32, device=ids.device) if want_stash else None
+    k = bin(split_mask & ((1 << F) - 1)).count("1") if split_mask else 0
+    stash = torch.empty(B, F - k, F * D, dtype=torch.float32, device=ids.device) if want_stash else None
+    stash2 = torch.empty(B, k, F * D, dtype=torch.float32, device=ids.device) if (want_stash and k) else None
     if B == 0:
-        return cross, stash
+        return (cross, stash, stash2) if split_mask else (cross, stash)
     PT = None
     if peer is not None:
         PT = _lib.rs_peer_tables()
         PT.world, PT.direct_mask, PT.total_rows = int(peer[0]), int(peer[1]), int(peer[3])
-        for k, ptr in enumerate(peer[2]):
-            PT.shard[k] = int(ptr)
+        for r, ptr in enumerate(peer[2]):
+            PT.shard[r] = int(ptr)
+        if stash2 is not None:
+            PT.split_mask, PT.stash_split = int(split_mask), stash2.data_ptr()
         PT = C.byref(PT)
     with _timed("ffm_fwd"):
         _lib.check(_lib.load().rs_ffm_fwd_peer(C.byref(T), ids.data_ptr(), B, D, PT, cross.data_ptr(), _p(stash),
                                                status_word(ids.device).data_ptr(), _stream()), "rs_ffm_fwd")
     _count()
-    return cross, stash
+    return (cross, stash, stash2) if split_mask else (cross, stash)
 
 
 def ffm_fwd_train(T, ids, D, cold_mask):
@@ -568,6 +575,17 @@ def ffm_bwd_update(T, ids, D, segs, g_cross, table, lr, wd=0.0, cold_mask=0, col
         _lib.check(lib.rs_ffm_bwd_update(C.byref(T), ids.data_ptr(), B, D, int(cold_mask), _p(cold_stash), C.byref(segs.seg), C.byref(u), ws.data_ptr(), ws.numel(),
                                          status_word(ids.device).data_ptr(), _stream()), "rs_ffm_bwd_update")
     _count(5)
+
+
+def replica_sgd(w_ptrs, g_ptrs, numel, world, rank, lr, wd=0.0):
+    """Replicated table: sum the ranks' dense gradients in rank order, SGD step, result stored into every rank's copy
+    (rs_replica_sgd).  w_ptrs / g_ptrs: per-rank device addresses (symmetric memory).  Barriers before and after are the
+    caller's."""
+    W = (C.c_void_p * world)(*[int(p) for p in w_ptrs])
+    G = (C.c_void_p * world)(*[int(p) for p in g_ptrs])
+    with _timed("replica_sgd"):
+        _lib.check(_lib.load().rs_replica_sgd(W, G, int(numel), world, rank, lr, wd, _stream()), "rs_replica_sgd")
+    _count()
 
 
 def adam_dense(p, g, m, v, step, lr=1e-3, wd=0.0, betas=(0.9, 0.999), eps=1e-8):

@@ -128,6 +128,11 @@ typedef struct rs_peer_tables {
   uint64_t direct_mask;
   const float *shard[RS_MAX_RANKS];
   int64_t total_rows; /* bound for the global rows of the direct fields */
+  /* optional split stash: when stash_split != NULL the Jacobian rows of the fields in split_mask go to
+   * stash_split (B, popcount(split_mask), F*D), field order preserved, and `stash` holds only the other fields'
+   * rows (B, F - popcount, F*D) -- the replicated and the row-sharded tables of one model are reduced separately */
+  uint64_t split_mask;
+  float *stash_split;
 } rs_peer_tables;
 int rs_ffm_fwd_peer(const rs_tables *T /* width = F*D */, const int64_t *ids, int64_t B, int32_t D, const rs_peer_tables *PT,
                     float *cross, float *stash, int32_t *status, void *stream);
@@ -276,6 +281,14 @@ int rs_shard_collect(const rs_shard *S, int64_t *recv_local /* [cap_recv] */, ui
 int rs_shard_serve(const rs_shard *S, const float *table, int64_t rows, int32_t width, const int64_t *recv_local,
                    const uint8_t *skip, float *const *block, int64_t cap_block_rows, int32_t *status, void *stream);
 
+/* Replicated small tables ("small tables + all dense params: replicated; gradients all-reduced"): every rank
+ * holds the same copy w[k] of the table and its own dense gradient g[k] (symmetric memory, peer-mapped pointers indexed
+ * by rank; numel floats each).  Rank `rank` owns the rank-th slice of the elements: it adds the `world` gradient slices
+ * in rank order, applies w -= lr * (sum + wd * w) to that slice and stores the result into every rank's copy -- the
+ * reduce-scatter, the SGD step and the all-gather in one kernel; replicas stay bit-identical.  Cross-rank barriers must
+ * precede (all g complete) and follow (before g or w are touched again) the call. */
+int rs_replica_sgd(float *const *w, const float *const *g, int64_t numel, int32_t world, int32_t rank, float lr, float wd,
+                   void *stream);
 
 /* Fused DENSE Adam sweep with torch.optim.Adam's exact arithmetic order ("reference-Adam" mode for the
  * MovieLens-sized tables; scripts/deepfm.py:55). */

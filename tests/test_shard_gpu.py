@@ -63,7 +63,7 @@ def test_owner_major_keys():
     assert torch.equal(segs.uniq().cpu(), u) and torch.equal(segs.inverse().cpu().long(), inv)
 
 
-def _sharded_run(world, kind, D, B, steps, lr, cards, direct_threshold=None):
+def _sharded_run(world, kind, D, B, steps, lr, cards, direct_threshold=None, replicate_below=0, shared_exchange=False):
     from deeplearningrecommendationsystem_b200 import dist as rsdist, ops
     from deeplearningrecommendationsystem_b200.nfield import FieldFFM, FieldFM
     from deeplearningrecommendationsystem_b200.optim import FusedRowOptimizer
@@ -73,9 +73,11 @@ def _sharded_run(world, kind, D, B, steps, lr, cards, direct_threshold=None):
 
     def rank_fn(fab):
         kw = {} if direct_threshold is None else {"direct_threshold": direct_threshold}
+        kw["replicate_below"] = replicate_below
         m = cls(cards, D, fused=True, seed=4, device="cuda", sharded=True, fabric=fab, **kw)
         if direct_threshold:
             assert m.direct_fields, "expected some fields to be read directly from the peers' shards"
+        assert m.hybrid == bool(replicate_below)
         m.load_global(ref.weight.data)
         tr = Trainer(m, torch.nn.BCELoss(), FusedRowOptimizer(m, torch.optim.SGD([m.bias], lr=lr), lr=lr))
         ids, y = _batch(fab.rank, B, cards)
@@ -86,11 +88,14 @@ def _sharded_run(world, kind, D, B, steps, lr, cards, direct_threshold=None):
             preds.append(tr.predictions_train.detach().clone())
         with torch.no_grad():
             ev = m(ids).clone()                       # inference path: plan + fetch only
-        return m.weight.data.clone(), m.bias.detach().clone(), torch.stack(preds), ev
+        return m.weight.data.clone(), m.bias.detach().clone(), torch.stack(preds), ev, m
 
     outs = rsdist.ThreadFabric.run(world, rank_fn)
     ops.check_status()
-    full = rsdist.unshard_rows([o[0] for o in outs])
+    full = outs[0][4].assemble_global([o[0] for o in outs])
+    if replicate_below:     # the replicas must be bit-identical
+        for r in range(1, world):
+            assert torch.equal(outs[r][4].weight_small.data, outs[0][4].weight_small.data)
     m = cls(cards, D, fused=True, seed=4, device="cpu").cuda()
     tr = Trainer(m, torch.nn.BCELoss(), FusedRowOptimizer(m, torch.optim.SGD([m.bias], lr=lr), lr=lr))
     batches = [_batch(r, B, cards) for r in range(world)]
@@ -122,6 +127,22 @@ def test_virtual_ranks_direct_fields(world):
     exchange flags those requests and rs_shard_serve skips them) == the unsharded step.  Fields of >= 100 rows are direct."""
     _sharded_run(world, "ffm", 8, 300, 3, 0.5, CARDS, direct_threshold=100)
     _sharded_run(world, "ffm", 16, 300, 2, 0.5, CARDS, direct_threshold=100)     # 512-byte rows: the TMA serve kernel with skipped runs
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+@pytest.mark.parametrize("kind,D", [("fm", 16), ("ffm", 8), ("ffm", 16)])
+def test_virtual_ranks_hybrid_placement(world, kind, D):
+    """small tables replicated (dense gradient reduced over the ranks + SGD in rs_replica_sgd), tables of >= 100 rows
+    row-sharded (FFM: read from the owners' shards inside the forward kernel, plan built on a side stream; FM: fetched
+    into a block) == the unsharded step on the concatenated batch"""
+    _sharded_run(world, kind, D, 300, 3, 0.5, CARDS, replicate_below=100)
+
+
+def test_virtual_ranks_c2_shape_hybrid():
+    cards = [min(c, 2000) for c in [1460, 583, 10131227, 2202608, 305, 24, 12517, 633, 3, 93145, 5683, 8351593, 3194, 27, 14992,
+                                    5461306, 10, 5652, 2173, 4, 7046547, 18, 15, 286181, 105, 142572]]
+    _sharded_run(4, "ffm", 16, 700, 2, 0.5, cards, replicate_below=2000)
+    _sharded_run(4, "fm", 16, 700, 2, 0.5, cards, replicate_below=2000)
 
 
 def test_virtual_ranks_c2_shape_direct():
