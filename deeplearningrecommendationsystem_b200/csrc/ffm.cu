@@ -315,7 +315,15 @@ static int ffm_fwd_launch(const rs_tables *T, const int64_t *ids, int64_t B, int
   if (P.dv < 8) pad = (((P.dv * 16 - row_bytes) % 128) + 128) % 128;  // rows of consecutive j land 16*dv bytes apart mod 128
   P.pitchv = (row_bytes + pad) / 16;
   const size_t stage_bytes = (size_t)F * P.pitchv * 16;
-  int nst = (int)((232448 - 2048) / stage_bytes);  // 227 KB per CTA minus the static barriers / pointer tables (1.4 KB)
+  // Shared memory: 227 KB per SM.  TWO resident CTAs per SM with a 2-stage ring each (four producer and sixteen consumer
+  // warps per SM) beat one CTA with a 5-stage ring: 0.73 vs 0.88 ms at the C2 shape -- one producer warp issues a bulk copy
+  // every ~70 cycles and each stage hand-shake costs ~430 ns (profiles/tma_rate_micro.cu), so issue parallelism matters
+  // more than ring depth.  RS_FFM_CTAS=1 restores the single deep ring.
+  int want_ctas = 2;
+  if (const char *e = getenv("RS_FFM_CTAS")) want_ctas = atoi(e) == 1 ? 1 : 2;
+  const size_t budget = 232448 / want_ctas - 2048 - 1024;      // static shared memory + the per-CTA reservation
+  int nst = (int)(budget / stage_bytes);
+  if (nst < 2 && want_ctas == 2) nst = (int)((232448 - 2048 - 1024) / stage_bytes);   // tile too large for two CTAs: one deep ring
   RS_CHECK_ARG(nst >= 1, RS_E_UNSUPPORTED, "rs_ffm_fwd: F*F*D tile (%zu B) does not fit in shared memory", stage_bytes);
   if (nst > MAX_STAGES) nst = MAX_STAGES;
   P.nst = nst;

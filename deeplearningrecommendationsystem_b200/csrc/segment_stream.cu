@@ -19,7 +19,6 @@ namespace rs {
 namespace {
 
 constexpr int SR = 8;          // gradient rows per stage (and table-row slots per stage)
-constexpr int BATCH = 4;       // stages the producer fills per iteration (32 lanes = 4 x 8 lookups)
 constexpr int NCW = 4;         // consumer warps
 constexpr int NCT = NCW * 32;  // consumer threads: thread t owns float4 columns t, t+128, ...
 constexpr int NTHREADS = NCT + 32;
@@ -56,7 +55,8 @@ __device__ __forceinline__ int4 lds_i4(uint32_t addr) {
 // cp.async.bulk shared -> (peer) global each: consecutive unique rows of a work unit are consecutive rows of the owner's
 // buffer, and a bulk store to peer memory costs ~1.4 us of the SM's copy engine whatever its size (measured: one store
 // per 1664-byte row ran at 175 GB/s chip-wide), so the rows have to leave several at a time.
-template <int NA, int MODE, bool PUSH>
+// BATCH = stages the producer fills per iteration (BATCH x 8 lanes each own one lookup); the ring needs BATCH + 1 stages
+template <int NA, int MODE, bool PUSH, int BATCH>
 __global__ void __launch_bounds__(NTHREADS + (PUSH ? 32 : 0), 1) seg_stream_kernel(const __grid_constant__ UpdParams P, int n, int nst, int out_slots) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t full_bar[MAX_ST], empty_bar[MAX_ST];
@@ -144,17 +144,18 @@ __global__ void __launch_bounds__(NTHREADS + (PUSH ? 32 : 0), 1) seg_stream_kern
       if (lane == 0) un = atomicAdd(P.work_counter, 1);
       int4 d_nxt = make_int4(0, 0, 0, 0);
       float sc_nxt = 1.0f;
-      if (sA + lane < sB) {
+      const bool mine = lane < SR * BATCH;            // lanes beyond the batch carry no lookup
+      if (mine && sA + lane < sB) {
         d_nxt = P.lookup_desc[sA + lane];
         if (P.scale) sc_nxt = P.scale_sorted[sA + lane];
       }
       for (int s0 = sA; s0 < sB; s0 += SR * BATCH) {
         const int s = s0 + lane;
-        const bool valid = s < sB;
+        const bool valid = mine && s < sB;
         const int4 d = d_nxt;
         const float sc = sc_nxt;
         const int sn = s + SR * BATCH;               // prefetch the next batch of this unit
-        if (sn < sB) {
+        if (mine && sn < sB) {
           d_nxt = P.lookup_desc[sn];
           if (P.scale) sc_nxt = P.scale_sorted[sn];
         }
@@ -342,9 +343,21 @@ int launch_na(const UpdParams &P, int n, int mode, cudaStream_t st) {
     out_slots = out_slots > OUT_SLOTS ? OUT_SLOTS : (out_slots < 8 ? 8 : out_slots);
   }
   const size_t out_bytes = (size_t)out_slots * P.W * 4;
-  int nst = (int)((200 * 1024 - out_bytes) / stage_bytes);
+  // Two resident CTAs per SM (each: one producer warp, four consumer warps, a ring of >= 3 stages filled two at a time) when
+  // two such rings fit in the 227 KB, else one CTA with a deep ring filled four stages at a time.  One producer warp
+  // issues a bulk copy every ~70 cycles and pays ~430 ns per stage hand-shake (profiles/tma_rate_micro.cu): two issuing
+  // warps per SM stream the 1664-byte rows faster than one, whatever the ring depth.  RS_SEG_CTAS=1 forces one CTA.
+  const size_t static_bytes = 6 * 1024;
+  int per_sm = (out_slots == 0) ? 2 : 1;
+  if (const char *e = getenv("RS_SEG_CTAS")) per_sm = (atoi(e) == 1) ? 1 : per_sm;
+  int nst = 0;
+  if (per_sm == 2) {
+    nst = (int)((232448 / 2 - static_bytes - 1024) / stage_bytes);
+    if (nst < 3) per_sm = 1;
+  }
+  if (per_sm == 1) nst = (int)((200 * 1024 - out_bytes) / stage_bytes);
   if (nst > MAX_ST) nst = MAX_ST;
-  if (nst < BATCH + 1) {
+  if (nst < (per_sm == 2 ? 3 : 5)) {
     set_error("rs_segment_update: row of %d floats too wide for the streaming kernel", P.W);
     return RS_E_UNSUPPORTED;
   }
@@ -354,19 +367,24 @@ int launch_na(const UpdParams &P, int n, int mode, cudaStream_t st) {
     scale_sorted_kernel<<<(n + 255) / 256, 256, 0, st>>>(P.lookup_desc, P.scale, P.F, n, P.scale_sorted);
     RS_CHECK_LAUNCH();
   }
-  const int grid = num_sms();
-#define RS_LAUNCH_STREAM(M, PUSH)                                                                                          \
-  do {                                                                                                                     \
-    RS_CUDA(cudaFuncSetAttribute(seg_stream_kernel<NA, M, PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    seg_stream_kernel<NA, M, PUSH><<<grid, NTHREADS + (PUSH ? 32 : 0), smem, st>>>(P, n, nst, out_slots);                  \
+  const int grid = num_sms() * per_sm;
+#define RS_LAUNCH_STREAM(M, PUSH, BT)                                                                                          \
+  do {                                                                                                                         \
+    RS_CUDA(cudaFuncSetAttribute(seg_stream_kernel<NA, M, PUSH, BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    seg_stream_kernel<NA, M, PUSH, BT><<<grid, NTHREADS + (PUSH ? 32 : 0), smem, st>>>(P, n, nst, out_slots);                  \
+  } while (0)
+#define RS_LAUNCH_BT(M, PUSH)                                      \
+  do {                                                             \
+    if (per_sm == 2) RS_LAUNCH_STREAM(M, PUSH, 2); else RS_LAUNCH_STREAM(M, PUSH, 4); \
   } while (0)
   switch (mode) {
     case RS_UPD_GRAD:
-      if (NA == 1 && out_slots > 0) RS_LAUNCH_STREAM(RS_UPD_GRAD, (NA == 1)); else RS_LAUNCH_STREAM(RS_UPD_GRAD, false);
+      if (NA == 1 && out_slots > 0) RS_LAUNCH_STREAM(RS_UPD_GRAD, (NA == 1), 4); else RS_LAUNCH_BT(RS_UPD_GRAD, false);
       break;
-    case RS_UPD_SGD: RS_LAUNCH_STREAM(RS_UPD_SGD, false); break;
-    default: RS_LAUNCH_STREAM(RS_UPD_ADAM, false); break;
+    case RS_UPD_SGD: RS_LAUNCH_BT(RS_UPD_SGD, false); break;
+    default: RS_LAUNCH_BT(RS_UPD_ADAM, false); break;
   }
+#undef RS_LAUNCH_BT
 #undef RS_LAUNCH_STREAM
   return RS_OK;
 }
