@@ -72,7 +72,7 @@ class rs_update(C.Structure):
                 ("stash", C.c_void_p), ("scale", C.c_void_p), ("dense", C.c_void_p),
                 ("table", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("dense_grad", C.c_void_p),
                 ("lr", C.c_float), ("wd", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
-                ("step", C.c_int32), ("grad_routes", C.POINTER(rs_routes))]
+                ("step", C.c_int32), ("grad_routes", C.POINTER(rs_routes)), ("half_sm", C.c_int32)]
 
 
 class rs_xslots(C.Structure):

@@ -643,6 +643,7 @@ int make_upd_params(const rs_segments *seg, int64_t n, const rs_update *u, UpdPa
   P.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2 > 0 ? bc2 : 1.0));
   P.use_stream = 0;
   P.combine_only = 0;
+  P.half_sm = u->half_sm;
   return RS_OK;
 }
 

@@ -15,6 +15,7 @@ struct UpdParams {
   const float *stash, *scale, *dense;
   float *table, *m, *v, *dense_grad;
   int W, F, scale_width, use_stream;
+  int half_sm;       // streaming kernel: one CTA with a half-size ring per SM (leave room for a concurrent kernel)
   int combine_only;  // the chunk pass already ran elsewhere (ffm_train.cu): only add the partials of the multi-chunk segments
   Routes routes;  // routes.n > 0: RS_UPD_GRAD writes row r to a peer instead of dense_grad[r]
   float lr, wd, beta1, beta2, eps, step_size, inv_sqrt_bc2;

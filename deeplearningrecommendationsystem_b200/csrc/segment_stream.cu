@@ -351,13 +351,15 @@ int launch_na(const UpdParams &P, int n, int mode, cudaStream_t st) {
   int per_sm = (out_slots == 0) ? 2 : 1;
   if (const char *e = getenv("RS_SEG_CTAS")) per_sm = (atoi(e) == 1) ? 1 : per_sm;
   int nst = 0;
+  bool small_ring = per_sm == 2;           // half-size ring filled two stages at a time
   if (per_sm == 2) {
     nst = (int)((232448 / 2 - static_bytes - 1024) / stage_bytes);
-    if (nst < 3) per_sm = 1;
+    if (nst < 3) per_sm = 1, small_ring = false;
+    else if (P.half_sm) per_sm = 1;        // same ring, one CTA per SM: the other half of the SM is left to a concurrent kernel
   }
-  if (per_sm == 1) nst = (int)((200 * 1024 - out_bytes) / stage_bytes);
+  if (!small_ring) nst = (int)((200 * 1024 - out_bytes) / stage_bytes);
   if (nst > MAX_ST) nst = MAX_ST;
-  if (nst < (per_sm == 2 ? 3 : 5)) {
+  if (nst < (small_ring ? 3 : 5)) {
     set_error("rs_segment_update: row of %d floats too wide for the streaming kernel", P.W);
     return RS_E_UNSUPPORTED;
   }
@@ -375,7 +377,7 @@ int launch_na(const UpdParams &P, int n, int mode, cudaStream_t st) {
   } while (0)
 #define RS_LAUNCH_BT(M, PUSH)                                      \
   do {                                                             \
-    if (per_sm == 2) RS_LAUNCH_STREAM(M, PUSH, 2); else RS_LAUNCH_STREAM(M, PUSH, 4); \
+    if (small_ring) RS_LAUNCH_STREAM(M, PUSH, 2); else RS_LAUNCH_STREAM(M, PUSH, 4); \
   } while (0)
   switch (mode) {
     case RS_UPD_GRAD:

@@ -129,7 +129,7 @@ class _FieldModel(nn.Module):
         for c in self.cards:
             offs.append(offs[-1] + c)
         self.offsets_host, self.total_rows = offs[:-1], offs[-1]
-        self.sharded, self.exchange, self.hybrid = sharded, None, False
+        self.sharded, self.exchange, self.hybrid, self._hstream = sharded, None, False, None
         if sharded:
             if not fused:
                 raise ValueError("sharded tables are updated by the fused row optimizer (fused=True)")
@@ -348,14 +348,25 @@ class _FieldModel(nn.Module):
         ex.wait_plan(plan)                       # (before this step's first barrier on this stream)
         g = rec["g"] * (1.0 / ex.world)          # gradients are averaged over the ranks
         Fs, Fb = len(self.small_fields), len(self.big_fields)
-        # replicated tables: this rank's batch reduced into its dense gradient (symmetric memory)
-        segs_s = ops.dedup_sort(rec["ids_small"], Fs, self.small_offsets_host, self.small_total, max_width=W)
-        self.gsmall.zero_()
-        ops.segment_update(segs_s, ops.RS_UPD_GRAD, W, Fs, stash=rec["stash_small"], scale=g, dense_grad=self.gsmall, tag="/small")
+        # The two reductions run side by side: the replicated tables' (HBM-bound, local) on a side stream, the sharded
+        # tables' (bound by the NVLink stores to the owners) on this one; each streaming kernel takes half of every SM.
+        cur = torch.cuda.current_stream()
+        if self._hstream is None:
+            self._hstream = torch.cuda.Stream(device=g.device)
+        self._hstream.wait_stream(cur)
+        with torch.cuda.stream(self._hstream):
+            # replicated tables: this rank's batch reduced into its dense gradient (symmetric memory)
+            segs_s = ops.dedup_sort(rec["ids_small"], Fs, self.small_offsets_host, self.small_total, max_width=W)
+            self.gsmall.zero_()
+            ops.segment_update(segs_s, ops.RS_UPD_GRAD, W, Fs, stash=rec["stash_small"], scale=g, dense_grad=self.gsmall, tag="/small",
+                               half_sm=True)
+            small_done = torch.cuda.Event()
+            small_done.record()
         # row-sharded tables: reduce per distinct row, store straight into the owners' buffers
         segs_b = ops.block_segments(plan.segs, plan.n_uniq, W)
         routes, ent = ex.grad_routes(plan, self.weight.data, g.device)
-        ops.segment_update(segs_b, ops.RS_UPD_GRAD, W, Fb, grad_routes=routes, stash=rec["stash_big"], scale=g, tag="/push")
+        ops.segment_update(segs_b, ops.RS_UPD_GRAD, W, Fb, grad_routes=routes, stash=rec["stash_big"], scale=g, tag="/push", half_sm=True)
+        cur.wait_event(small_done)
         recv = ex.finish_push(plan, ent)         # barrier: pushed rows have landed, every rank's dense gradient is complete
         ops.replica_sgd(self.small_ptrs, self.gsmall_ptrs, self.small_total * W, ex.world, ex.rank, opt.lr)
         osegs = ex.owner_segments(plan, self.weight.shape[0], W)

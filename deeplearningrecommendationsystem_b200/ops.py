@@ -525,7 +525,7 @@ def gather_rows_peer(table, idx, routes):
 
 
 def segment_update(segs, mode, width, F, stash=None, scale=None, dense=None, table=None, m=None, v=None, dense_grad=None,
-                   lr=0.0, wd=0.0, betas=(0.9, 0.999), eps=1e-8, step=1, grad_routes=None, tag=""):
+                   lr=0.0, wd=0.0, betas=(0.9, 0.999), eps=1e-8, step=1, grad_routes=None, tag="", half_sm=False):
     """Segment-reduce the per-lookup row gradients (scale*stash + dense) and apply `mode` to the touched rows."""
     u = _lib.rs_update()
     u.mode, u.width, u.F = mode, width, F
@@ -540,6 +540,7 @@ def segment_update(segs, mode, width, F, stash=None, scale=None, dense=None, tab
     u.lr, u.wd, u.beta1, u.beta2, u.eps, u.step = lr, wd, betas[0], betas[1], eps, step
     if grad_routes is not None:
         u.grad_routes = C.pointer(grad_routes)
+    u.half_sm = 1 if half_sm else 0
     with _timed(f"segment_update{tag}[w{width}]"):
         _lib.check(_lib.load().rs_segment_update(C.byref(segs.seg), segs.n, C.byref(u), _stream()), "rs_segment_update")
     _count(2)

@@ -214,6 +214,9 @@ typedef struct rs_update {
   int32_t step;       /* 1-based */
   const rs_routes *grad_routes; /* RS_UPD_GRAD only, optional: write row r of the reduced gradient to a peer
                                    (routes) instead of dense_grad[r] -- segment-reduce fused with the gradient push */
+  int32_t half_sm;    /* != 0: the streaming kernel takes one CTA and half of the shared memory per SM, so that a second
+                         streaming update launched on another stream runs beside it (an NVLink-bound gradient push next to
+                         an HBM-bound local reduce) */
 } rs_update;
 int rs_segment_update(const rs_segments *seg, int64_t n, const rs_update *u, void *stream);
 
