@@ -807,11 +807,14 @@ def run_other(args):
             legs = run_legs(step, pool, B, args, world, dev, local, graph_step=gstep, extra_warmup=3 if world > 1 else 0)
             k = legs["kern"]
             if w == "c1":
-                name = max((n for n in k), key=lambda n: k[n]) if k else None
-                if "xembed_fwd" in k:
-                    roof = hbm_roofline("xembed_fwd_kernel (feature-vector lookups: 2 id gathers + 4 one-/multi-hot bags -> (B, 6, 128))",
-                                        f"{B} x (45 x 4 B features + 6 x 128 x 4 B embeddings written)", B * (45 * 4 + 6 * 128 * 4), k["xembed_fwd"],
-                                        note="the C1 step itself is dominated by the cuBLAS fp32 towers (768->512->256->128->1, scoped out by SURVEY 2.2)")
+                # the embedding backward of the two id tables is the largest of this package's kernels in the C1 step
+                if "segment_update[w128]" in k:
+                    roof = hbm_roofline("rs_segment_update[w128] (deterministic embedding backward of the user / item tables: 2 x B gradient rows "
+                                        "of 128 floats segment-reduced into dense gradients)",
+                                        f"2 x {B} x 512 B gradient rows read + (943 + 1682) x 512 B dense gradient written + 2 x {B} x 16 B records",
+                                        2 * B * 512 + (943 + 1682) * 512 + 2 * B * 16, k["segment_update[w128]"],
+                                        note="the C1 step itself is dominated by the cuBLAS fp32 towers (768->512->256->128->1) and the dense "
+                                             "torch Adam sweep, scoped out by SURVEY 2.2: this package's kernels account for ~0.3 of its ~8.9 ms")
             elif w == "c3" and model == "PNN-inner":
                 if "fields_fwd" in k:
                     roof = hbm_roofline("fields_fwd_kernel (39-field gather + 741 inner products + concat)",
