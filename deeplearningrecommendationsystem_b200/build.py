@@ -35,10 +35,25 @@ def _digest():
 
 
 def build(force=False, verbose=False):
-    """Compile if sources changed.  Returns the path of the shared library."""
+    """Compile if sources changed.  Returns the path of the shared library.  Serialised across processes with a file lock
+    (N torchrun ranks importing the package at once must not write the same .o / .so files concurrently): the first one
+    in builds, the others find the fresh stamp."""
     dig = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
         return LIB
+    import fcntl
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    with open(os.path.join(HERE, "build", ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
+                return LIB          # another process built it while this one waited
+            return _build_locked(dig, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(dig, verbose):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)

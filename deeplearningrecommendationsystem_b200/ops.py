@@ -402,6 +402,17 @@ def dedup_sort(ids, F=1, row_offset=None, total_rows=None, max_width=1, reuse_wo
     return segs
 
 
+def invalidate_dedup(device=None):
+    """Forget the memoised sorts (of `device`, or of every device).  The memo recognises an id tensor by (storage pointer,
+    version counter, identity): writes that bypass the version counter -- `ids.data.copy_()`, a kernel or a CUDA-graph
+    replay writing through the pointer -- are invisible to it, so call this after such a write if the same tensor object
+    is then handed to an op again eagerly."""
+    if device is None:
+        _seg_memo.clear()
+    else:
+        _seg_memo.pop(torch.device(device), None)
+
+
 def attach_partial(segs, width):
     """(Re)attach the chunk-partial scratch for rows of `width` floats to finished segments."""
     part = _partial_buffer(segs.device, segs.n, int(width))
