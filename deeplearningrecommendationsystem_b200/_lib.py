@@ -124,6 +124,7 @@ SIGNATURES = {
     "rs_xembed_bag_ws_bytes": [_PP(rs_xslots), _L, _PP(_Z)],
     "rs_xcol_to_ids": [_P, _L, _I, _I, _P, _P],
     "rs_sigmoid_bce": [_P, _P, _L, _P, _P, _P, _P, _P],
+    "rs_sigmoid_bce_bias": [_P, _P, _P, _L, _P, _P, _P, _P, _P, _P],
     "rs_sample_negatives": [_P, _L, _L, _L, _I, C.c_uint64, C.c_uint32, _P, _P, _P, _P],
     "rs_assemble_features": [_P, _P, _P, _L, _I, _P, _L, _I, _L, _P, _P, _P],
     "rs_rank_segments": [_P, _P, _L, _L, _I, _P, _P, _P, _P],

@@ -179,15 +179,18 @@ RS_API int rs_xcol_to_ids(const float *x, int64_t B, int32_t xcols, int32_t col,
 }
 
 // ------------------------------------------------------------------ sigmoid + BCE (mean) fwd/bwd
-// pass 1: per-block partial sums in a fixed tree order; pass 2: one block sums the partials in index order.
-__global__ void __launch_bounds__(256) sigmoid_bce_kernel(const float *__restrict__ logit, const float *__restrict__ y, int64_t B,
-                                                         float *__restrict__ pred, float *__restrict__ g_logit,
-                                                         float *__restrict__ partial) {
-  __shared__ float red[8];
-  float acc = 0.f;
-  float invB = 1.0f / (float)B;
+// pass 1: per-block partial sums in a fixed tree order; pass 2: one warp adds the partials (lane-strided, then a fixed
+// shuffle tree): deterministic.  Optional: the logit is cross[b] + *bias (the models' `cross + self.bias`), and the sum of
+// d loss / d logit (= the bias gradient) is reduced alongside the loss.
+__global__ void __launch_bounds__(256) sigmoid_bce_kernel(const float *__restrict__ logit, const float *__restrict__ bias,
+                                                         const float *__restrict__ y, int64_t B, float *__restrict__ pred,
+                                                         float *__restrict__ g_logit, float *__restrict__ partial, int want_gsum) {
+  __shared__ float red[8], redg[8];
+  float acc = 0.f, accg = 0.f;
+  const float invB = 1.0f / (float)B;
+  const float bz = bias ? __ldg(bias) : 0.f;
   for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (int64_t)gridDim.x * blockDim.x) {
-    float z = logit[b];
+    float z = bias ? logit[b] + bz : logit[b];
     float p = 1.0f / (1.0f + expf(-z));
     float t = y[b];
     float lp = fmaxf(logf(p), -100.f);
@@ -196,33 +199,48 @@ __global__ void __launch_bounds__(256) sigmoid_bce_kernel(const float *__restric
     if (pred) pred[b] = p;
     // autograd's exact sequence (binary_cross_entropy_backward then sigmoid_backward), so that saturated
     // probabilities (p == 0 or 1 in fp32) give the same gradient as the reference, not the analytic (p-t)/B
-    if (g_logit) g_logit[b] = (invB * (p - t) / fmaxf((1.0f - p) * p, 1e-12f)) * ((1.0f - p) * p);
+    const float g = (invB * (p - t) / fmaxf((1.0f - p) * p, 1e-12f)) * ((1.0f - p) * p);
+    if (g_logit) g_logit[b] = g;
+    accg += g;
   }
   acc = rs::warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  accg = rs::warp_sum(accg);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc, redg[threadIdx.x >> 5] = accg;
   __syncthreads();
   if (threadIdx.x == 0) {
-    float s = 0.f;
-    for (int i = 0; i < 8; ++i) s += red[i];
+    float s = 0.f, sg = 0.f;
+    for (int i = 0; i < 8; ++i) s += red[i], sg += redg[i];
     partial[blockIdx.x] = s;
+    if (want_gsum) partial[1024 + blockIdx.x] = sg;
   }
 }
-__global__ void bce_finish_kernel(const float *__restrict__ partial, int nparts, int64_t B, float *__restrict__ loss) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    float s = 0.f;
-    for (int i = 0; i < nparts; ++i) s += partial[i];
+__global__ void __launch_bounds__(32) bce_finish_kernel(const float *__restrict__ partial, int nparts, int64_t B, float *__restrict__ loss,
+                                                       float *__restrict__ g_sum) {
+  float s = 0.f, sg = 0.f;
+  for (int i = threadIdx.x; i < nparts; i += 32) {
+    s += partial[i];
+    if (g_sum) sg += partial[1024 + i];
+  }
+  s = rs::warp_sum(s);
+  sg = rs::warp_sum(sg);
+  if (threadIdx.x == 0) {
     *loss = s / (float)B;
+    if (g_sum) *g_sum = sg;
   }
 }
-RS_API int rs_sigmoid_bce(const float *logit, const float *y, int64_t B, float *pred, float *g_logit, float *loss_mean, float *ws,
-                          void *stream) {
-  RS_CHECK_ARG(logit && y && loss_mean && ws && B > 0, RS_E_ARG, "rs_sigmoid_bce: bad argument");
+RS_API int rs_sigmoid_bce_bias(const float *cross, const float *bias, const float *y, int64_t B, float *pred, float *g_logit,
+                               float *loss_mean, float *g_sum, float *ws, void *stream) {
+  RS_CHECK_ARG(cross && y && loss_mean && ws && B > 0, RS_E_ARG, "rs_sigmoid_bce: bad argument");
   int blocks = (int)((B + 255) / 256);
   if (blocks > 1024) blocks = 1024;
   cudaStream_t st = (cudaStream_t)stream;
-  sigmoid_bce_kernel<<<blocks, 256, 0, st>>>(logit, y, B, pred, g_logit, ws);
+  sigmoid_bce_kernel<<<blocks, 256, 0, st>>>(cross, bias, y, B, pred, g_logit, ws, g_sum ? 1 : 0);
   RS_CHECK_LAUNCH();
-  bce_finish_kernel<<<1, 32, 0, st>>>(ws, blocks, B, loss_mean);
+  bce_finish_kernel<<<1, 32, 0, st>>>(ws, blocks, B, loss_mean, g_sum);
   RS_CHECK_LAUNCH();
   return RS_OK;
+}
+RS_API int rs_sigmoid_bce(const float *logit, const float *y, int64_t B, float *pred, float *g_logit, float *loss_mean, float *ws,
+                          void *stream) {
+  return rs_sigmoid_bce_bias(logit, nullptr, y, B, pred, g_logit, loss_mean, nullptr, ws, stream);
 }

@@ -416,7 +416,7 @@ __device__ __forceinline__ void apply_row(const UpdParams &P, const int64_t *rta
 // sorted (= ascending position) order; loads for UNR lookups are issued before their adds so the dependent FADD
 // chain does not serialise the memory latency.
 template <int VEC, int GS, int NA, int MODE>
-__global__ void __launch_bounds__(256, (NA <= 4) ? 4 : 1) seg_chunk_kernel(const __grid_constant__ UpdParams P, int64_t n) {
+__global__ void __launch_bounds__(256, (NA == 1) ? 6 : ((NA <= 4) ? 4 : 1)) seg_chunk_kernel(const __grid_constant__ UpdParams P, int64_t n) {
   using V = Vec<VEC>;
   constexpr int GPB = 256 / GS;
   __shared__ int64_t rtab[rs::ROUTE_TAB];

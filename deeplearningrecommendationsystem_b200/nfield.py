@@ -414,7 +414,7 @@ class _FieldModel(nn.Module):
         concat, pairs = _EmbedFn.apply(self._anchor, self, self._token, T, ids, want_pairs)
         return concat, (pairs if want_pairs else None)
 
-    def logit(self, ids):
+    def logit(self, ids, add_bias=True):
         if ids.dim() != 2 or ids.shape[1] != self.F:
             raise ValueError(f"ids must be (B, {self.F})")
         train = torch.is_grad_enabled()
@@ -446,7 +446,7 @@ class _FieldModel(nn.Module):
             cross = _CrossFn.apply(self._anchor, cross, self, self._token)
         elif train:
             cross = _DenseGradFn.apply(self.weight, cross, self, ids, stash)
-        return cross + self.bias if self.use_bias else cross
+        return cross + self.bias if (self.use_bias and add_bias) else cross
 
     use_bias = True
 
@@ -454,8 +454,9 @@ class _FieldModel(nn.Module):
         return torch.sigmoid(self.logit(ids)).unsqueeze(1)
 
     def train_logit(self, ids):
-        """(pre-sigmoid logit (B,), shape of forward()'s output) -- lets the Trainer fuse sigmoid + BCELoss + their backward"""
-        return self.logit(ids), (ids.shape[0], 1)
+        """(cross (B,), bias parameter | None, shape of forward()'s output) with logit = cross + bias -- lets the Trainer fuse
+        the bias add, sigmoid, BCELoss, their backward and the bias-gradient sum into one kernel pair"""
+        return self.logit(ids, add_bias=False), (self.bias if self.use_bias else None), (ids.shape[0], 1)
 
 
 class FieldFM(_FieldModel):
@@ -565,7 +566,7 @@ class FieldMF(_FieldModel):
 
     def train_logit(self, user_indices, item_indices):
         ids = torch.stack([user_indices, item_indices], dim=1)
-        return self.logit(ids), (ids.shape[0],)
+        return self.logit(ids, add_bias=False), None, (ids.shape[0],)
 
 
 class _EmbedModel(_FieldModel):

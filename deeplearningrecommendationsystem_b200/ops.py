@@ -668,19 +668,22 @@ def xcol_to_ids(x, col):
     return ids
 
 
-def sigmoid_bce(logit, y, want_grad=True):
-    """pred, mean BCE loss (0-d tensor), d loss / d logit -- one fused pass + fixed-order reduction."""
+def sigmoid_bce(logit, y, want_grad=True, bias=None, want_gsum=False):
+    """pred, mean BCE loss (0-d tensor), d loss / d logit -- one fused pass + fixed-order reduction.
+    bias (1-element tensor): the logit is `logit + bias` (the models' last step, folded in); want_gsum: also return
+    sum(d loss / d logit) (the bias gradient, shape (1,)) as a fourth value."""
     logit, y = _f32(logit).view(-1), _f32(y).view(-1)
-    _need_cuda(logit, y)
+    _need_cuda(logit, y, bias)
     B = logit.numel()
     pred = torch.empty_like(logit)
     g = torch.empty_like(logit) if want_grad else None
     loss = torch.empty((), dtype=torch.float32, device=logit.device)
-    ws = torch.empty(1024, dtype=torch.float32, device=logit.device)
-    _lib.check(_lib.load().rs_sigmoid_bce(logit.data_ptr(), y.data_ptr(), B, pred.data_ptr(), _p(g), loss.data_ptr(), ws.data_ptr(),
-                                          _stream()), "rs_sigmoid_bce")
+    gsum = torch.empty(1, dtype=torch.float32, device=logit.device) if want_gsum else None
+    ws = torch.empty(2048, dtype=torch.float32, device=logit.device)
+    _lib.check(_lib.load().rs_sigmoid_bce_bias(logit.data_ptr(), _p(_f32(bias)), y.data_ptr(), B, pred.data_ptr(), _p(g), loss.data_ptr(),
+                                               _p(gsum), ws.data_ptr(), _stream()), "rs_sigmoid_bce")
     _count(2)
-    return pred, loss, g
+    return (pred, loss, g, gsum) if want_gsum else (pred, loss, g)
 
 
 def gru_fwd(gi, w_hh, b_hh, want_gates=True):

@@ -36,7 +36,8 @@ _binary_metrics = binary_metrics
 def fused_bce_step(model, loss_fn, args, rating):
     """forward -> sigmoid -> BCELoss(mean) -> backward with the sigmoid, the loss, its mean and both of their backward
     passes in ONE kernel pair (rs_sigmoid_bce: same op sequence as autograd, fixed-order mean), for models that expose
-    their pre-sigmoid logit through ``train_logit`` (the nfield FM / FFM / MF models) under a plain ``nn.BCELoss()``.
+    their pre-sigmoid logit through ``train_logit`` -> (cross, bias parameter | None, output shape) with logit = cross + bias
+    (the nfield FM / FFM / MF models) under a plain ``nn.BCELoss()``.
     Returns (predictions, loss) exactly as ``loss_fn(model(*args), rating)`` would (loss detached), or None when the
     combination does not apply -- the caller then runs the generic path.  RS_FUSED_BCE=0 disables it."""
     if os.environ.get("RS_FUSED_BCE", "1") != "1" or type(loss_fn) is not torch.nn.BCELoss:
@@ -49,12 +50,17 @@ def fused_bce_step(model, loss_fn, args, rating):
     if rating.numel() != args[0].shape[0] or torch.is_tensor(rating) and rating.requires_grad:
         return None
     from .. import ops
-    logit, shape = fn(*args)
+    cross, bias, shape = fn(*args)                    # logit = cross + bias (bias may be None)
     if tuple(rating.shape) != tuple(shape):           # BCELoss would raise / warn: let it
         raise ValueError(f"Using a target size ({tuple(rating.shape)}) that is different to the input size ({tuple(shape)}) is deprecated. "
                          "Please ensure they have the same size.")
-    pred, loss, g = ops.sigmoid_bce(logit.detach(), rating)
-    logit.backward(g)
+    want_gsum = bias is not None and bias.requires_grad
+    out = ops.sigmoid_bce(cross.detach(), rating, bias=None if bias is None else bias.detach(), want_gsum=want_gsum)
+    pred, loss, g = out[:3]
+    cross.backward(g)
+    if want_gsum:                                     # d loss / d bias = sum of d loss / d logit, reduced inside the loss kernel
+        gb = out[3].view_as(bias)
+        bias.grad = gb if bias.grad is None else bias.grad + gb
     return pred.view(shape), loss
 
 

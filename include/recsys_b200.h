@@ -417,6 +417,11 @@ int rs_gemm_nt_3xtf32(const rs_gemm_nt *g, void *stream);
  * saturates.  loss_mean is a device scalar produced by a fixed-order two-pass reduce. */
 int rs_sigmoid_bce(const float *logit, const float *y, int64_t B, float *pred, float *g_logit, float *loss_mean,
                    float *ws /* >= 1024 floats */, void *stream);
+/* Same with the models' last step folded in: logit[b] = cross[b] + *bias (bias: device scalar or NULL), and
+ * *g_sum = sum_b g_logit[b] (the bias gradient; NULL = not wanted), reduced in the same fixed order as the loss.
+ * ws >= 2048 floats. */
+int rs_sigmoid_bce_bias(const float *cross, const float *bias, const float *y, int64_t B, float *pred, float *g_logit,
+                        float *loss_mean, float *g_sum, float *ws /* >= 2048 floats */, void *stream);
 
 /* ---- catalogue ranking: the per-user `torch.topk(scores, k, dim=0)` of every recommendation() method
  * (model/deepfm.py:85-95, model/din.py:55-66, model/neuralcf.py:61-72, model/pnn.py:133-143 ...), all users in one launch.
