@@ -3,6 +3,8 @@
 // optimizer.step() for embedding tables (reference trainer/trainer.py:38-39).
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
 
 #include <stdlib.h>
 #include <string.h>
@@ -24,12 +26,17 @@ struct Offsets {
 __global__ void __launch_bounds__(256) make_keys_kernel(const int64_t *__restrict__ ids, int64_t n, int F, const __grid_constant__ Offsets O,
                                                        int64_t total_rows, uint32_t *__restrict__ keys, int32_t *__restrict__ pos,
                                                        int32_t *status, const int32_t *__restrict__ n_valid, int shard_world,
-                                                       int64_t shard_rows, uint32_t pad_key) {
+                                                       int64_t shard_rows, uint32_t pad_key, int32_t *__restrict__ scalars,
+                                                       int32_t *__restrict__ seg_start) {
   __shared__ int64_t s_off[RS_MAX_FIELDS + 1];
   for (int i = threadIdx.x; i < F; i += blockDim.x) s_off[i] = O.off[i];
   if (threadIdx.x == 0) s_off[F] = total_rows;
   __syncthreads();
   int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p == 0) {   // the device scalars (n_uniq, n_chunks, n_multi, work counter) start at zero: an empty (all padding) list
+    scalars[0] = scalars[1] = scalars[2] = scalars[3] = 0;   // then leaves n_uniq = n_chunks = 0 and seg_start[0] = 0
+    seg_start[0] = 0;
+  }
   if (p >= n) return;
   pos[p] = (int32_t)p;
   if (n_valid && p >= *n_valid) {
@@ -47,6 +54,27 @@ __global__ void __launch_bounds__(256) make_keys_kernel(const int64_t *__restric
 
 #define RS_NV(nvp, n) ((nvp) ? (int64_t) * (nvp) : (n))   /* number of real (non-padding) lookups */
 
+// head of a segment / of a chunk, recomputed where needed instead of being stored (nv = number of real lookups)
+__device__ __forceinline__ bool is_head(const uint32_t *__restrict__ k, int64_t s, int64_t nv) {
+  return s < nv && (s == 0 || k[s] != k[s - 1]);
+}
+__device__ __forceinline__ bool is_chunk_head(const int32_t *__restrict__ segidx1, const int32_t *__restrict__ seg_start, int64_t s,
+                                              int64_t nv) {
+  return s < nv && (((int)s - seg_start[segidx1[s] - 1]) % RS_CHUNK) == 0;
+}
+// scan inputs computed on the fly (cub::TransformInputIterator over a counting iterator)
+struct HeadOp {
+  const uint32_t *k;
+  const int32_t *nvp;
+  int64_t n;
+  __device__ __forceinline__ int32_t operator()(int32_t s) const { return is_head(k, s, RS_NV(nvp, n)) ? 1 : 0; }
+};
+struct ChunkHeadOp {
+  const int32_t *segidx1, *seg_start, *nvp;
+  int64_t n;
+  __device__ __forceinline__ int32_t operator()(int32_t s) const { return is_chunk_head(segidx1, seg_start, s, RS_NV(nvp, n)) ? 1 : 0; }
+};
+
 __global__ void __launch_bounds__(256) head_flags_kernel(const uint32_t *__restrict__ k, int64_t n, int32_t *__restrict__ head,
                                                         const int32_t *__restrict__ nvp) {
   int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -56,7 +84,7 @@ __global__ void __launch_bounds__(256) head_flags_kernel(const uint32_t *__restr
 
 // segidx1 = inclusive scan of head flags (1-based segment index)
 __global__ void __launch_bounds__(256) seg_scatter_kernel(const uint32_t *__restrict__ k, const int32_t *__restrict__ pos,
-                                                         const int32_t *__restrict__ head, const int32_t *__restrict__ segidx1, int64_t n,
+                                                         const int32_t *__restrict__ segidx1, int64_t n,
                                                          int64_t *__restrict__ uniq, int32_t *__restrict__ seg_start,
                                                          int32_t *__restrict__ inverse, int32_t *__restrict__ n_uniq,
                                                          const int32_t *__restrict__ nvp) {
@@ -64,7 +92,7 @@ __global__ void __launch_bounds__(256) seg_scatter_kernel(const uint32_t *__rest
   n = RS_NV(nvp, n);
   if (s >= n) return;
   int g = segidx1[s] - 1;
-  if (head[s]) {
+  if (is_head(k, s, n)) {
     uniq[g] = (int64_t)k[s];
     seg_start[g] = (int32_t)s;
   }
@@ -75,35 +103,32 @@ __global__ void __launch_bounds__(256) seg_scatter_kernel(const uint32_t *__rest
   }
 }
 
-__global__ void __launch_bounds__(256) chunk_flags_kernel(const int32_t *__restrict__ head, const int32_t *__restrict__ segidx1,
-                                                         const int32_t *__restrict__ seg_start, int64_t n, int32_t *__restrict__ chead,
-                                                         int32_t *__restrict__ counts, const int32_t *__restrict__ nvp) {
+// (only the hand-written scan of sort.cu needs the flags in memory; the cub path scans them on the fly)
+__global__ void __launch_bounds__(256) chunk_flags_kernel(const int32_t *__restrict__ segidx1, const int32_t *__restrict__ seg_start,
+                                                         int64_t n, int32_t *__restrict__ chead, const int32_t *__restrict__ nvp) {
   int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
-  if (s >= RS_NV(nvp, n)) {
-    chead[s] = 0;
-    return;
-  }
-  int g = segidx1[s] - 1;
-  int st = seg_start[g];
-  chead[s] = (((int)s - st) % RS_CHUNK == 0) ? 1 : 0;
-  if (head[s]) counts[g] = seg_start[g + 1] - st;
+  chead[s] = is_chunk_head(segidx1, seg_start, s, RS_NV(nvp, n)) ? 1 : 0;
 }
 
-__global__ void __launch_bounds__(256) chunk_scatter_kernel(const int32_t *__restrict__ head, const int32_t *__restrict__ segidx1,
-                                                           const int32_t *__restrict__ chead, const int32_t *__restrict__ chunkidx1,
+__global__ void __launch_bounds__(256) chunk_scatter_kernel(const int32_t *__restrict__ segidx1, const int32_t *__restrict__ seg_start,
+                                                           const int32_t *__restrict__ chunkidx1,
                                                            int64_t n, int32_t *__restrict__ chunk_start, int32_t *__restrict__ chunk_seg,
                                                            int32_t *__restrict__ seg_first_chunk, int32_t *__restrict__ n_chunks,
-                                                           const int32_t *__restrict__ nvp) {
+                                                           int32_t *__restrict__ counts, const int32_t *__restrict__ nvp) {
   int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   n = RS_NV(nvp, n);
   if (s >= n) return;
   int g = segidx1[s] - 1;
   int c = chunkidx1[s] - 1;
-  if (chead[s]) {
+  const int st = seg_start[g];
+  if ((((int)s - st) % RS_CHUNK) == 0) {          // chunk head
     chunk_start[c] = (int32_t)s;
     chunk_seg[c] = g;
-    if (head[s]) seg_first_chunk[g] = c;
+    if ((int)s == st) {                           // segment head
+      seg_first_chunk[g] = c;
+      counts[g] = seg_start[g + 1] - st;
+    }
   }
   if (s == n - 1) {
     *n_chunks = c + 1;
@@ -112,44 +137,39 @@ __global__ void __launch_bounds__(256) chunk_scatter_kernel(const int32_t *__res
   }
 }
 
-// segments cut into more than one chunk need a second pass; list them (order is irrelevant to the numerics)
-__global__ void __launch_bounds__(256) multi_list_kernel(const int32_t *__restrict__ seg_first_chunk, const int32_t *__restrict__ n_uniq,
-                                                        int32_t *__restrict__ multi_seg, int32_t *__restrict__ n_multi) {
-  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= *n_uniq) return;
-  if (seg_first_chunk[g + 1] - seg_first_chunk[g] > 1) multi_seg[atomicAdd(n_multi, 1)] = (int32_t)g;
-}
-
-// One 16-byte record per sorted lookup so the streaming update kernel needs a single coalesced read per lookup
-// instead of chasing chunk -> segment -> row through three arrays.
-__global__ void __launch_bounds__(256) lookup_desc_kernel(const int32_t *__restrict__ sorted_pos, const int32_t *__restrict__ chunkidx1,
-                                                         const int32_t *__restrict__ chunk_start, const int32_t *__restrict__ chunk_seg,
-                                                         const int32_t *__restrict__ seg_first_chunk, const int64_t *__restrict__ uniq,
-                                                         int64_t n, int4 *__restrict__ desc, const int32_t *__restrict__ nvp) {
-  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n) return;
-  if (s >= RS_NV(nvp, n)) {
-    desc[s] = make_int4(0, 0, 0, 0);
-    return;
+// Last pass, three independent jobs in one launch:
+//  (a) segments cut into more than one chunk need a second pass; list them (order is irrelevant to the numerics);
+//  (b) one 16-byte record per sorted lookup so the streaming update kernel needs a single coalesced read per lookup
+//      instead of chasing chunk -> segment -> row through three arrays;
+//  (c) work units of the streaming kernel start on chunk boundaries: unit u = chunks whose first lookup is in
+//      [u*RS_UNIT, (u+1)*RS_UNIT).  unit_start[u] = first chunk start >= u*RS_UNIT (n past the end).
+__global__ void __launch_bounds__(256) dedup_finish_kernel(const int32_t *__restrict__ sorted_pos, const int32_t *__restrict__ segidx1,
+                                                          const int32_t *__restrict__ chunkidx1, const int32_t *__restrict__ seg_start,
+                                                          const int32_t *__restrict__ chunk_start, const int32_t *__restrict__ chunk_seg,
+                                                          const int32_t *__restrict__ seg_first_chunk, const int64_t *__restrict__ uniq,
+                                                          int64_t n, int nunits, int4 *__restrict__ desc, int32_t *__restrict__ unit_start,
+                                                          const int32_t *__restrict__ n_uniq, int32_t *__restrict__ multi_seg,
+                                                          int32_t *__restrict__ n_multi, const int32_t *__restrict__ nvp) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nv = RS_NV(nvp, n);
+  if (s < *n_uniq && seg_first_chunk[s + 1] - seg_first_chunk[s] > 1) multi_seg[atomicAdd(n_multi, 1)] = (int32_t)s;     // (a)
+  if (s < n) {                                                                                                           // (b)
+    if (s >= nv) {
+      desc[s] = make_int4(0, 0, 0, 0);
+    } else {
+      const int c = chunkidx1[s] - 1;
+      const int s0 = chunk_start[c], s1 = chunk_start[c + 1];
+      const int g = chunk_seg[c];
+      const bool single = (seg_first_chunk[g + 1] - seg_first_chunk[g]) == 1;
+      int flags = (s == s0 ? 1 : 0) | (s + 1 == s1 ? 2 : 0) | (single ? 4 : 0);
+      desc[s] = make_int4(sorted_pos[s], flags, (int)(uint32_t)uniq[g], 2 * (s0 / RS_CHUNK) + ((s1 - s0) < RS_CHUNK ? 1 : 0));
+    }
   }
-  const int c = chunkidx1[s] - 1;
-  const int s0 = chunk_start[c], s1 = chunk_start[c + 1];
-  const int g = chunk_seg[c];
-  const bool single = (seg_first_chunk[g + 1] - seg_first_chunk[g]) == 1;
-  int flags = (s == s0 ? 1 : 0) | (s + 1 == s1 ? 2 : 0) | (single ? 4 : 0);
-  desc[s] = make_int4(sorted_pos[s], flags, (int)(uint32_t)uniq[g], 2 * (s0 / RS_CHUNK) + ((s1 - s0) < RS_CHUNK ? 1 : 0));
-}
-
-// Work units of the streaming kernel start on chunk boundaries: unit u = chunks whose first lookup is in
-// [u*RS_UNIT, (u+1)*RS_UNIT).  unit_start[u] = first chunk start >= u*RS_UNIT (n past the end).
-__global__ void __launch_bounds__(256) unit_start_kernel(const int4 *__restrict__ desc, int64_t n, int nunits, int32_t *__restrict__ unit_start,
-                                                        const int32_t *__restrict__ nvp) {
-  int u = blockIdx.x * blockDim.x + threadIdx.x;
-  if (u > nunits) return;
-  n = RS_NV(nvp, n);
-  int64_t s = (int64_t)u * RS_UNIT;
-  while (s < n && !(desc[s].y & 1)) ++s;  // a chunk has at most RS_CHUNK lookups, so this stops within RS_CHUNK steps
-  unit_start[u] = (int32_t)(s < n ? s : n);
+  if (s <= nunits) {                                                                                                     // (c)
+    int64_t t = s * RS_UNIT;
+    while (t < nv && !is_chunk_head(segidx1, seg_start, t, nv)) ++t;   // a chunk has at most RS_CHUNK lookups: stops within RS_CHUNK steps
+    unit_start[s] = (int32_t)(t < nv ? t : nv);
+  }
 }
 
 // Rename the rows of a finished sort to their rank among the distinct keys (row of segment g := g).
@@ -212,6 +232,16 @@ WsLayout layout(int64_t n, int max_width) {
   cub::DeviceRadixSort::SortPairs(nullptr, sort_b, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const int32_t *)nullptr,
                                   (int32_t *)nullptr, (int)n, 0, 32);
   cub::DeviceScan::InclusiveSum(nullptr, scan_b, (const int32_t *)nullptr, (int32_t *)nullptr, (int)n);
+  {
+    using Count = cub::CountingInputIterator<int32_t>;
+    size_t b1 = 0, b2 = 0;
+    cub::TransformInputIterator<int32_t, HeadOp, Count> heads(Count(0), HeadOp{nullptr, nullptr, n});
+    cub::TransformInputIterator<int32_t, ChunkHeadOp, Count> cheads(Count(0), ChunkHeadOp{nullptr, nullptr, nullptr, n});
+    cub::DeviceScan::InclusiveSum(nullptr, b1, heads, (int32_t *)nullptr, (int)n);
+    cub::DeviceScan::InclusiveSum(nullptr, b2, cheads, (int32_t *)nullptr, (int)n);
+    scan_b = scan_b > b1 ? scan_b : b1;
+    scan_b = scan_b > b2 ? scan_b : b2;
+  }
   L.cub_bytes = sort_b > scan_b ? sort_b : scan_b;
   L.cub = take(L.cub_bytes);
   L.sort_hist = take(rs::radix_sort_ws_ints(n) * 4);   // per-tile digit counts of the hand-written radix sort
@@ -292,55 +322,51 @@ RS_API int rs_dedup_sort_ex(const int64_t *ids, int64_t n, int32_t F, const int6
   if (!row_offset) RS_CHECK_ARG(F == 1, RS_E_ARG, "rs_dedup_sort: row_offset required when F > 1");
   cudaStream_t st = (cudaStream_t)stream;
   int blocks = (int)((n + 255) / 256);
-  // scalars start at zero so that an empty (all padding) list leaves n_uniq = n_chunks = 0 and seg_start[0] = 0
-  RS_CUDA(cudaMemsetAsync(seg->n_uniq, 0, 4 * sizeof(int32_t), st));
-  if (nvp) RS_CUDA(cudaMemsetAsync(seg->seg_start, 0, sizeof(int32_t), st));
   make_keys_kernel<<<blocks, 256, 0, st>>>(ids, n, F, O, total_rows, keys_in, pos_in, status, nvp, shard_world, shard_rows,
-                                           (uint32_t)(key_space - 1));
+                                           (uint32_t)(key_space - 1), seg->n_uniq, seg->seg_start);
   RS_CHECK_LAUNCH();
   int end_bit = 1;
   while (end_bit < 32 && (1ull << end_bit) < (uint64_t)key_space) ++end_bit;
   // Stable sort by row key.  Default: cub::DeviceRadixSort (onesweep) + cub::DeviceScan -- library plumbing, like cuBLAS
   // for the towers.  RS_SORT=own selects the hand-written LSD radix sort and prefix sums of sort.cu: bit-identical
-  // results (tests/test_kernels_gpu.py), but 15 small launches per sort instead of 4, which measured 3 % slower on the
-  // whole C2 step, so it is not the default yet.  head / segidx1 are free until the sort ends (its scratch).
+  // results (tests/test_kernels_gpu.py), but more and smaller launches, which measured 4 % slower on the whole C2 step
+  // and 17 % on C5, so it is not the default.  head / segidx1 are free until the sort ends (its scratch).
+  // The segment / chunk head flags are never stored on the cub path: the scans read them through transform iterators and
+  // the later kernels recompute them (14 launches per dedup instead of 20 -- the small-batch configs are launch bound).
   const bool use_cub = !(getenv("RS_SORT") && !strcmp(getenv("RS_SORT"), "own"));
   int32_t *sort_hist = (int32_t *)(w + L.sort_hist), *scan_ws = (int32_t *)(w + L.scan_ws);
+  using Count = cub::CountingInputIterator<int32_t>;
   if (use_cub) {
     RS_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, keys_in, seg->sorted_key, pos_in, seg->sorted_pos, (int)n, 0, end_bit, st));
+    cub::TransformInputIterator<int32_t, HeadOp, Count> heads(Count(0), HeadOp{seg->sorted_key, nvp, n});
+    RS_CUDA(cub::DeviceScan::InclusiveSum(cub_ws, cub_bytes, heads, segidx1, (int)n, st));
   } else {
     int rc = rs::radix_sort_pairs(keys_in, pos_in, seg->sorted_key, seg->sorted_pos, (uint32_t *)head, segidx1, sort_hist, n, end_bit, st);
     if (rc) return rc;
-  }
-  head_flags_kernel<<<blocks, 256, 0, st>>>(seg->sorted_key, n, head, nvp);
-  RS_CHECK_LAUNCH();
-  if (use_cub) {
-    RS_CUDA(cub::DeviceScan::InclusiveSum(cub_ws, cub_bytes, head, segidx1, (int)n, st));
-  } else {
-    int rc = rs::inclusive_sum_i32(head, segidx1, n, scan_ws, st);
+    head_flags_kernel<<<blocks, 256, 0, st>>>(seg->sorted_key, n, head, nvp);
+    RS_CHECK_LAUNCH();
+    rc = rs::inclusive_sum_i32(head, segidx1, n, scan_ws, st);
     if (rc) return rc;
   }
-  seg_scatter_kernel<<<blocks, 256, 0, st>>>(seg->sorted_key, seg->sorted_pos, head, segidx1, n, seg->uniq, seg->seg_start,
+  seg_scatter_kernel<<<blocks, 256, 0, st>>>(seg->sorted_key, seg->sorted_pos, segidx1, n, seg->uniq, seg->seg_start,
                                              seg->inverse, seg->n_uniq, nvp);
   RS_CHECK_LAUNCH();
-  chunk_flags_kernel<<<blocks, 256, 0, st>>>(head, segidx1, seg->seg_start, n, chead, seg->counts, nvp);
-  RS_CHECK_LAUNCH();
   if (use_cub) {
-    RS_CUDA(cub::DeviceScan::InclusiveSum(cub_ws, cub_bytes, chead, chunkidx1, (int)n, st));
+    cub::TransformInputIterator<int32_t, ChunkHeadOp, Count> cheads(Count(0), ChunkHeadOp{segidx1, seg->seg_start, nvp, n});
+    RS_CUDA(cub::DeviceScan::InclusiveSum(cub_ws, cub_bytes, cheads, chunkidx1, (int)n, st));
   } else {
+    chunk_flags_kernel<<<blocks, 256, 0, st>>>(segidx1, seg->seg_start, n, chead, nvp);
+    RS_CHECK_LAUNCH();
     int rc = rs::inclusive_sum_i32(chead, chunkidx1, n, scan_ws, st);
     if (rc) return rc;
   }
-  chunk_scatter_kernel<<<blocks, 256, 0, st>>>(head, segidx1, chead, chunkidx1, n, seg->chunk_start, seg->chunk_seg,
-                                               seg->seg_first_chunk, seg->n_chunks, nvp);
-  RS_CHECK_LAUNCH();
-  multi_list_kernel<<<blocks, 256, 0, st>>>(seg->seg_first_chunk, seg->n_uniq, seg->multi_seg, seg->n_multi);
-  RS_CHECK_LAUNCH();
-  lookup_desc_kernel<<<blocks, 256, 0, st>>>(seg->sorted_pos, chunkidx1, seg->chunk_start, seg->chunk_seg, seg->seg_first_chunk,
-                                             seg->uniq, n, (int4 *)seg->lookup_desc, nvp);
+  chunk_scatter_kernel<<<blocks, 256, 0, st>>>(segidx1, seg->seg_start, chunkidx1, n, seg->chunk_start, seg->chunk_seg,
+                                               seg->seg_first_chunk, seg->n_chunks, seg->counts, nvp);
   RS_CHECK_LAUNCH();
   const int nunits = (int)(n / RS_UNIT + 1);
-  unit_start_kernel<<<(nunits + 256) / 256, 256, 0, st>>>((const int4 *)seg->lookup_desc, n, nunits, seg->unit_start, nvp);
+  dedup_finish_kernel<<<blocks, 256, 0, st>>>(seg->sorted_pos, segidx1, chunkidx1, seg->seg_start, seg->chunk_start, seg->chunk_seg,
+                                              seg->seg_first_chunk, seg->uniq, n, nunits, (int4 *)seg->lookup_desc, seg->unit_start,
+                                              seg->n_uniq, seg->multi_seg, seg->n_multi, nvp);
   RS_CHECK_LAUNCH();
   return RS_OK;
 }
