@@ -654,3 +654,84 @@ def test_gemm_nt_grouped_rows():
     got = ops.gemm_nt(rows, W, M=B * L, a_rows=(L, (L + 1) * D, D))
     want = (rows[:, :L].reshape(B * L, D).double() @ W.double().t())
     assert float((got.double() - want).abs().max()) <= 1e-5 * float((rows.abs().max() * W.abs().sum(1).max()))
+
+
+# ------------------------------------------------------------------ round-2 entry points
+def test_sigmoid_bce_with_bias_and_gradient_sum():
+    """rs_sigmoid_bce_bias: logit = cross + bias folded in, bias gradient = sum of d loss / d logit reduced beside the loss"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(9)
+    for B in (1, 37, 5000, 300000):                   # 300000 > 1024 blocks x 256 threads: the grid-stride path
+        cross = (torch.randn(B, generator=g) * 2).requires_grad_(True)
+        bias = torch.tensor([0.37], requires_grad=True)
+        y = (torch.rand(B, generator=g) < 0.3).float()
+        loss = torch.nn.BCELoss()(torch.sigmoid(cross + bias), y)
+        gc, gb = torch.autograd.grad(loss, (cross, bias))
+        pred, l, gz, gsum = ops.sigmoid_bce(cross.detach().cuda(), y.cuda(), bias=bias.detach().cuda(), want_gsum=True)
+        close(pred, torch.sigmoid(cross + bias).detach(), rtol=1e-6, atol=1e-7)
+        close(l, loss.detach(), rtol=1e-5)
+        close(gz, gc, rtol=1e-4, atol=1e-9)
+        close(gsum, gb, rtol=1e-5, atol=1e-7)
+        pred0, l0, gz0 = ops.sigmoid_bce((cross + bias).detach().cuda(), y.cuda())        # the plain entry point agrees
+        assert torch.equal(pred0, pred) and torch.equal(gz0, gz) and torch.equal(l0, l)
+
+
+@pytest.mark.parametrize("world,numel", [(1, 64), (2, 4 * 1000), (3, 4 * 333), (8, 4 * 4099)])
+def test_replica_sgd_equals_allreduce_plus_sgd(world, numel):
+    """rs_replica_sgd run by every rank in turn (the peers are just other buffers): every replica ends up with
+    w - lr * (sum of the ranks' gradients), and the replicas are bit-identical."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(world)
+    w0 = torch.randn(numel, generator=g)
+    grads = [torch.randn(numel, generator=g) for _ in range(world)]
+    W = [w0.clone().cuda() for _ in range(world)]
+    G = [x.cuda() for x in grads]
+    for r in range(world):
+        ops.replica_sgd([t.data_ptr() for t in W], [t.data_ptr() for t in G], numel, world, r, 0.25)
+    want = w0.double()
+    acc = torch.zeros(numel, dtype=torch.float32)
+    for x in grads:
+        acc = acc + x                                   # rank order, fp32: the kernel's order
+    want = w0 - 0.25 * acc
+    for r in range(world):
+        assert torch.equal(W[r], W[0])
+        close(W[r], want, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("mode", ["grad", "sgd"])
+def test_streaming_update_half_sm_is_bit_identical(mode):
+    """half_sm (one CTA per SM, room for a concurrent kernel) only changes the launch geometry"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    rows, n, W = 500, 20000, 416
+    ids = (torch.rand(n, generator=g) ** 3 * rows).long().clamp_(max=rows - 1)
+    G = torch.randn(n, W, generator=g).cuda()
+    table = torch.randn(rows, W, generator=g)
+    segs = ops.dedup_sort(ids.cuda(), 1, None, rows, max_width=W, reuse_workspace=False)
+    outs = []
+    for half in (False, True):
+        if mode == "grad":
+            out = torch.zeros(rows, W).cuda()
+            ops.segment_update(segs, ops.RS_UPD_GRAD, W, 1, dense=G, dense_grad=out, half_sm=half)
+        else:
+            out = table.clone().cuda()
+            ops.segment_update(segs, ops.RS_UPD_SGD, W, 1, dense=G, table=out, lr=0.1, half_sm=half)
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("F,D,B,mask", [(26, 16, 300, 0b10100000000100000000000100), (6, 8, 500, 0b100001), (40, 8, 100, (1 << 39) | (1 << 3) | 1)])
+def test_ffm_split_stash(F, D, B, mask):
+    """rs_ffm_fwd_peer with stash_split: the Jacobian rows of the masked fields go to their own tensor, field order kept"""
+    ops = _ops()
+    rows = [5 + 3 * f for f in range(F)]
+    tabs, ids = make_fields(F, F * D, rows, B, seed=F + D)
+    keep = [t.cuda() for t in tabs]
+    T = ops.make_tables(keep)
+    cross, full = ops.ffm_fwd(T, ids.cuda(), D, want_stash=True)
+    peer = (1, 0, [keep[0].data_ptr()], 1)            # no direct fields: only the split is exercised
+    c2, rest, split = ops.ffm_fwd(T, ids.cuda(), D, want_stash=True, peer=peer, split_mask=mask)
+    big = [f for f in range(F) if (mask >> f) & 1]
+    small = [f for f in range(F) if not (mask >> f) & 1]
+    assert torch.equal(c2, cross)
+    assert torch.equal(split, full[:, big]) and torch.equal(rest, full[:, small])
