@@ -688,7 +688,6 @@ def test_replica_sgd_equals_allreduce_plus_sgd(world, numel):
     G = [x.cuda() for x in grads]
     for r in range(world):
         ops.replica_sgd([t.data_ptr() for t in W], [t.data_ptr() for t in G], numel, world, r, 0.25)
-    want = w0.double()
     acc = torch.zeros(numel, dtype=torch.float32)
     for x in grads:
         acc = acc + x                                   # rank order, fp32: the kernel's order
